@@ -1,0 +1,191 @@
+/* r3_layouts.h — byte-exact std430 records shared by rend3's Rust managers and this library.
+ *
+ * These are the buffers the reference's managers already upload to wgpu; the C ABI in
+ * rend3_b200.h consumes the very same bytes, so the Rust side needs no repacking.
+ * Every struct cites the reference definition it mirrors (paths relative to the reference
+ * repository root) and is checked with static_assert against the encase/std430 offsets.
+ *
+ * Plain C99 / C++11 / CUDA compatible.  No pointers, no torch types.
+ */
+#ifndef R3_LAYOUTS_H
+#define R3_LAYOUTS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+#define R3_STATIC_ASSERT(c, m) static_assert(c, m)
+#else
+#define R3_STATIC_ASSERT(c, m) _Static_assert(c, m)
+#endif
+
+#define R3_INVALID_VERTEX 0x00FFFFFFu        /* rend3/shaders/vertex_attributes.wgsl:15 */
+#define R3_CAMERA_VIEWPORT 0xFFFFFFFFu       /* CameraSpecifier::Viewport -> shadow_index u32::MAX (culler.rs:166-169) */
+#define R3_ATTR_ABSENT 0xFFFFFFFFu           /* missing vertex attribute (managers/object.rs:263) */
+#define R3_BATCH_SIZE 256u                   /* rend3-routine/src/culling/mod.rs:1 */
+#define R3_WORKGROUP_SIZE 256u               /* rend3-routine/src/culling/mod.rs:2 */
+#define R3_NO_PREVIOUS 0xFFFFFFFFu           /* batching.rs:226 */
+
+/* PerCameraUniform.flags (culler.rs:151-156, structures.wgsl:64-72) */
+#define R3_PCU_POSITIVE_AREA_VISIBLE 0x1u
+#define R3_PCU_MULTISAMPLED 0x2u
+
+/* PbrMaterial flags (rend3-routine/shaders/src/material.wgsl:1-15) */
+#define R3_MAT_ALBEDO_ACTIVE 0x0001u
+#define R3_MAT_ALBEDO_BLEND 0x0002u
+#define R3_MAT_ALBEDO_VERTEX_SRGB 0x0004u
+#define R3_MAT_AOMR_COMBINED 0x0040u
+#define R3_MAT_CC_GLTF_COMBINED 0x0400u
+#define R3_MAT_UNLIT 0x2000u
+#define R3_MAT_NEAREST 0x4000u
+
+/* vertex attribute slot order of PbrMaterial::supported_attributes (pbr/material.rs:486-495) */
+enum { R3_ATTR_POSITION = 0, R3_ATTR_NORMAL, R3_ATTR_TANGENT, R3_ATTR_UV0, R3_ATTR_UV1, R3_ATTR_COLOR0, R3_ATTR_COUNT };
+
+/* ShaderObject<PbrMaterial> — rend3/src/managers/object.rs:23-36, structures_object.wgsl:3-12. stride 128 */
+typedef struct r3_object {
+    float transform[16];          /* @0   model->world, column major */
+    float sphere_center[3];       /* @64  world-space bounding sphere (object.rs:269) */
+    float sphere_radius;          /* @76 */
+    uint32_t first_index;         /* @80  word index into the mesh buffer (object.rs:279) */
+    uint32_t index_count;         /* @84 */
+    uint32_t material_index;      /* @88 */
+    uint32_t attr_offset[6];      /* @92  byte offsets into the mesh buffer, R3_ATTR_ABSENT if missing */
+    uint32_t enabled;             /* @116 */
+    uint32_t _pad[2];             /* @120 */
+} r3_object;
+R3_STATIC_ASSERT(sizeof(r3_object) == 128, "Object stride");
+R3_STATIC_ASSERT(offsetof(r3_object, sphere_center) == 64, "sphere");
+R3_STATIC_ASSERT(offsetof(r3_object, first_index) == 80, "first_index");
+R3_STATIC_ASSERT(offsetof(r3_object, attr_offset) == 92, "attr offsets");
+R3_STATIC_ASSERT(offsetof(r3_object, enabled) == 116, "enabled");
+
+/* PerCameraUniform header — rend3-routine/src/culling/culler.rs:158-175, structures.wgsl:47-62.
+ * `objects[]` (r3_object_matrices, stride 128) follows at byte 240. */
+typedef struct r3_camera_header {
+    float view[16];               /* @0 */
+    float view_proj[16];          /* @64 */
+    uint32_t shadow_index;        /* @128 R3_CAMERA_VIEWPORT for the viewport camera */
+    uint32_t _pad0[3];
+    float frustum[5][4];          /* @144 left,right,top,bottom,near: (abc, d) normalised (util/frustum.rs:96-145) */
+    float resolution[2];          /* @224 */
+    uint32_t flags;               /* @232 R3_PCU_* */
+    uint32_t object_count;        /* @236 capacity of the object buffer (culler.rs:446-447) */
+} r3_camera_header;
+R3_STATIC_ASSERT(sizeof(r3_camera_header) == 240, "PerCameraUniform header");
+R3_STATIC_ASSERT(offsetof(r3_camera_header, frustum) == 144, "frustum");
+R3_STATIC_ASSERT(offsetof(r3_camera_header, resolution) == 224, "resolution");
+R3_STATIC_ASSERT(offsetof(r3_camera_header, object_count) == 236, "object_count");
+
+/* PerCameraUniformObjectData — culler.rs:177-183 */
+typedef struct r3_object_matrices {
+    float model_view[16];
+    float model_view_proj[16];
+} r3_object_matrices;
+R3_STATIC_ASSERT(sizeof(r3_object_matrices) == 128, "PerCameraUniformObjectData");
+
+/* ShaderObjectCullingInformation — culling/batching.rs:90-100 */
+typedef struct r3_object_culling_info {
+    uint32_t invocation_start;
+    uint32_t invocation_end;
+    uint32_t object_id;
+    uint32_t region_id;
+    uint32_t base_region_invocation;
+    uint32_t local_region_id;
+    uint32_t previous_global_invocation;
+    uint32_t atomic_capable;
+} r3_object_culling_info;
+R3_STATIC_ASSERT(sizeof(r3_object_culling_info) == 32, "ObjectCullingInformation");
+
+/* ShaderBatchData — culling/batching.rs:81-88 (#[align(256)] => 8448 bytes) */
+typedef struct r3_batch_data {
+    uint32_t total_objects;
+    uint32_t total_invocations;
+    uint32_t batch_base_invocation;
+    r3_object_culling_info object_culling_information[256];
+    uint32_t _pad[61];
+} r3_batch_data;
+R3_STATIC_ASSERT(sizeof(r3_batch_data) == 8448, "ShaderBatchData");
+R3_STATIC_ASSERT(offsetof(r3_batch_data, object_culling_information) == 12, "batch table");
+
+/* JobSubRegion + ShaderJobKey — culling/batching.rs:22-32 (host side only) */
+typedef struct r3_region {
+    uint32_t job_index;           /* batch this region's draw call binds (DrawCall::batch_index) */
+    uint32_t bind_group_index;    /* TextureBindGroupIndex (DUMMY = 0 in the GpuDriven profile) */
+    uint64_t material_key;
+} r3_region;
+R3_STATIC_ASSERT(sizeof(r3_region) == 16, "region");
+
+/* IndirectCall — structures.wgsl:20-26 (20 bytes) */
+typedef struct r3_indirect_call {
+    uint32_t vertex_count;
+    uint32_t instance_count;
+    uint32_t base_index;
+    int32_t vertex_offset;
+    uint32_t base_instance;
+} r3_indirect_call;
+R3_STATIC_ASSERT(sizeof(r3_indirect_call) == 20, "IndirectCall");
+
+/* FrameUniforms — rend3-routine/src/uniforms.rs:16-27, structures.wgsl:28-38 (uniform buffer, 496 B) */
+typedef struct r3_frame_uniforms {
+    float view[16];
+    float view_proj[16];
+    float origin_view_proj[16];
+    float inv_view[16];
+    float inv_view_proj[16];
+    float inv_origin_view_proj[16];
+    float frustum[5][4];          /* @384 */
+    float ambient[4];             /* @464 */
+    uint32_t resolution[2];       /* @480 */
+    uint32_t _pad[2];
+} r3_frame_uniforms;
+R3_STATIC_ASSERT(sizeof(r3_frame_uniforms) == 496, "FrameUniforms");
+R3_STATIC_ASSERT(offsetof(r3_frame_uniforms, ambient) == 464, "ambient");
+
+/* ShaderDirectionalLight — rend3/src/managers/directional.rs:38-53; buffer = u32 count @0, array @16 */
+typedef struct r3_directional_light {
+    float view_proj[16];          /* @0 */
+    float color[3];               /* @64 color*intensity */
+    float _pad0;
+    float direction[3];           /* @80 un-normalised (directional.rs:145) */
+    float _pad1;
+    float inv_resolution[2];      /* @96 1/atlas size */
+    float atlas_offset[2];        /* @104 */
+    float atlas_size[2];          /* @112 */
+    float _pad2[2];
+} r3_directional_light;
+R3_STATIC_ASSERT(sizeof(r3_directional_light) == 128, "DirectionalLight");
+R3_STATIC_ASSERT(offsetof(r3_directional_light, atlas_offset) == 104, "atlas_offset");
+
+/* ShaderPointLight — rend3/src/managers/point.rs:21-26; buffer = u32 count @0, array @16 */
+typedef struct r3_point_light {
+    float position[4];
+    float color[3];
+    float radius;
+} r3_point_light;
+R3_STATIC_ASSERT(sizeof(r3_point_light) == 32, "PointLight");
+
+/* GpuPoweredShaderWrapper<PbrMaterial> — managers/material.rs:25-29 + pbr/material.rs:526-543,
+ * material.wgsl:21-57 (208 bytes) */
+typedef struct r3_material {
+    uint32_t textures[10];        /* @0 0 = none */
+    uint32_t _pad0[2];
+    float uv_transform0[3][4];    /* @48 mat3x3 columns padded to vec4 */
+    float uv_transform1[3][4];    /* @96 */
+    float albedo[4];              /* @144 */
+    float emissive[3];            /* @160 */
+    float roughness;              /* @172 */
+    float metallic;               /* @176 */
+    float reflectance;            /* @180 */
+    float clear_coat;             /* @184 */
+    float clear_coat_roughness;   /* @188 */
+    float anisotropy;             /* @192 */
+    float ambient_occlusion;      /* @196 */
+    float alpha_cutout;           /* @200 */
+    uint32_t flags;               /* @204 */
+} r3_material;
+R3_STATIC_ASSERT(sizeof(r3_material) == 208, "GpuMaterialData");
+R3_STATIC_ASSERT(offsetof(r3_material, albedo) == 144, "albedo");
+R3_STATIC_ASSERT(offsetof(r3_material, flags) == 204, "flags");
+
+#endif /* R3_LAYOUTS_H */

@@ -1,0 +1,150 @@
+/* rend3_b200.h — C ABI of librend3_b200.so: rend3's GPU-driven per-object hot path on B200.
+ *
+ * The library replaces, beneath rend3's public Renderer/Object/Material/RenderGraph API, the
+ * work that `rend3-routine` records into wgpu for:
+ *     GpuCuller::object_uniform_upload  + uniform_prep.wgsl     (culling/culler.rs:427-529)
+ *     batch_objects                                              (culling/batching.rs:120-250)
+ *     GpuCuller::cull                   + cull.wgsl              (culling/culler.rs:531-659)
+ *     ForwardRoutine::add_forward_to_graph + opaque.wgsl/depth.wgsl (forward.rs:192-315)
+ *     HiZRoutine::add_hi_z_to_graph     + hi_z.wgsl              (hi_z.rs:161-234)
+ *     TonemappingRoutine::add_to_graph  + blit.wgsl              (tonemapping.rs:108-147)
+ * in the node order of BaseRenderGraph::add_to_graph (base.rs:129-185).
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, a negative R3_E_* code otherwise; the message is
+ *     available from r3_last_error().  Nothing unwinds, aborts or exits across the boundary
+ *     (the reference panics inside graph nodes, culler.rs:439,572 — a C ABI cannot).
+ *   - host pointers are borrowed for the duration of the call only; the library owns all
+ *     device memory.  Buffers are the std430 bytes rend3's managers already produce
+ *     (r3_layouts.h), so the Rust side uploads exactly what it uploads to wgpu today.
+ *   - one context per GPU; calls on a context must be externally serialised (this is the
+ *     `data_core` mutex of the reference, rend3/src/graph/graph.rs:265).  Work is
+ *     stream-ordered and asynchronous; only r3_sync() and r3_readback_*() block.
+ *   - `camera` is R3_CAMERA_VIEWPORT or a shadow index 0..R3_MAX_SHADOWS-1
+ *     (CameraSpecifier, rend3-routine/src/common/camera.rs).
+ */
+#ifndef REND3_B200_H
+#define REND3_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "r3_layouts.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R3_ABI_VERSION 1u
+#define R3_MAX_SHADOWS 63u
+
+enum {
+    R3_OK = 0,
+    R3_E_INVALID = -1,   /* bad argument / call order (the reference's assert!/unwrap sites) */
+    R3_E_CUDA = -2,      /* CUDA runtime failure; message carries cudaGetErrorString */
+    R3_E_OOM = -3,       /* allocation failed (MeshCreationError::BufferAllocationFailed analogue) */
+    R3_E_NO_DEVICE = -4, /* RendererInitializationError::MissingAdapter analogue */
+    R3_E_STATE = -5      /* required earlier stage has not run for this camera/frame */
+};
+
+typedef struct r3_ctx r3_ctx;
+
+/* ------------------------------------------------------------------ context */
+uint32_t r3_abi_version(void);
+/* replaces rend3::create_iad + GpuCuller::new/PbrRoutine::new pipeline creation (base.rs:111-124) */
+int r3_ctx_create(int device, r3_ctx** out);
+int r3_ctx_destroy(r3_ctx* ctx);
+const char* r3_last_error(const r3_ctx* ctx);
+int r3_sync(r3_ctx* ctx);
+/* the CUDA stream all work of this context is enqueued on (cudaStream_t as void*) */
+int r3_get_stream(r3_ctx* ctx, void** stream);
+/* number of kernel launches issued by this context since creation (bench.py gpu_launches) */
+int r3_launch_count(r3_ctx* ctx, uint64_t* launches);
+
+/* ------------------------------------------------------------------ world data
+ * same bytes as the wgpu buffers named on the right */
+int r3_set_objects(r3_ctx*, const r3_object* records, uint32_t n_slots);           /* object_manager.buffer::<M>() (object.rs:193) */
+int r3_update_objects(r3_ctx*, const uint32_t* slots, const r3_object* records, uint32_t n); /* ScatterCopy (object.rs:344-364) */
+/* borrow an object buffer that already lives in device memory (zero copy; caller keeps it alive) */
+int r3_set_objects_device(r3_ctx*, const void* device_records, uint32_t n_slots);
+/* facts batch_objects reads from the object/material managers (batching.rs:144-167):
+ * flags bit0 = slot is live (enumerated_objects), bit1 = SortingReason::Optimization
+ * ("atomic capable"), bit2 = SortingOrder::BackToFront.  location = InternalObject::location. */
+int r3_set_object_sort_info(r3_ctx*, const uint64_t* material_key, const uint8_t* flags,
+                            const float* location_xyz, uint32_t n_slots);
+int r3_set_mesh_buffer(r3_ctx*, const void* bytes, uint64_t nbytes);               /* eval_output.mesh_buffer (mesh.rs:99) */
+int r3_set_materials(r3_ctx*, const r3_material* records, uint32_t count);         /* material_manager.archetype_view::<M>().buffer() */
+int r3_set_directional_lights(r3_ctx*, const void* bytes, uint64_t nbytes,
+                              uint32_t atlas_width, uint32_t atlas_height);         /* directional.rs:135-156 */
+int r3_set_point_lights(r3_ctx*, const void* bytes, uint64_t nbytes);              /* point.rs:58-74 */
+int r3_set_frame_uniforms(r3_ctx*, const r3_frame_uniforms* uniforms);             /* uniforms.rs:94-106 */
+
+/* ------------------------------------------------------------------ per-object cull + uniform bake
+ * GpuCuller::object_uniform_upload (culler.rs:427-529) fused with the sphere-frustum test of
+ * batch_objects (batching.rs:144-148, util/frustum.rs:148-161): for every slot < object_count
+ * bakes MV/MVP when `enabled`, and appends the slot to the camera's ascending visible list when
+ * it is live and its world sphere is inside the 5 planes. */
+#define R3_CB_BAKE 1u
+#define R3_CB_CULL 2u
+int r3_object_uniform_upload(r3_ctx*, uint32_t camera, const r3_camera_header* header, uint32_t mode);
+int r3_visible_count(r3_ctx*, uint32_t camera, uint32_t* count);
+int r3_readback_visible(r3_ctx*, uint32_t camera, uint32_t* out, uint32_t capacity, uint32_t* count);
+int r3_readback_object_matrices(r3_ctx*, uint32_t camera, r3_object_matrices* out, uint32_t first, uint32_t n);
+
+/* ------------------------------------------------------------------ batching + per-triangle cull
+ * batch_objects (batching.rs:120-250) over the camera's visible list: sort by ShaderJobSortingKey,
+ * pack <=256 objects per ShaderBatchData, split regions on key change, remember each object's
+ * global invocation for next frame.  `viewport_location` = viewport_camera_state.location(). */
+int r3_batch_objects(r3_ctx*, uint32_t camera, const float viewport_location[3], uint32_t max_dispatch_count);
+int r3_batch_counts(r3_ctx*, uint32_t camera, uint32_t* n_batches, uint32_t* n_regions, uint32_t* total_invocations);
+int r3_readback_batches(r3_ctx*, uint32_t camera, r3_batch_data* batches, r3_region* regions);
+/* GpuCuller::cull (culler.rs:531-659) + cull.wgsl.  batches/regions == NULL uses the jobs of the last
+ * r3_batch_objects call; otherwise the caller's own ShaderBatchDatas (a Rust batch_objects). */
+int r3_cull(r3_ctx*, uint32_t camera, const r3_batch_data* batches, uint32_t n_batches,
+            const r3_region* regions, uint32_t n_regions);
+/* CullingBuffers readback (culler.rs:88-125).  `partition`: 0 = Output (predicted, kept for next
+ * frame), 1 = Input (residual / previous frame).  Sizes in elements. */
+int r3_readback_indices(r3_ctx*, uint32_t camera, int partition, uint32_t* out, uint64_t capacity, uint64_t* count);
+int r3_readback_draw_calls(r3_ctx*, uint32_t camera, int partition, r3_indirect_call* out, uint32_t capacity, uint32_t* count);
+int r3_readback_culling_results(r3_ctx*, uint32_t camera, int partition, uint32_t* out, uint64_t capacity, uint64_t* count);
+
+/* ------------------------------------------------------------------ forward path
+ * render targets of BaseRenderGraphIntermediateState::new (base.rs:212-290): hdr colour rgba16f,
+ * depth32f (reverse-Z, cleared to 0.0, compare GreaterEqual), shadow atlas depth32f. */
+int r3_set_render_target(r3_ctx*, uint32_t width, uint32_t height, uint32_t samples, const float clear_color[4]);
+int r3_clear_shadow_atlas(r3_ctx*);                                                /* clear.rs / base.rs:293-295 */
+/* pbr_shadow_rendering (base.rs:366-396): depth.wgsl over the shadow camera's culled list, into
+ * the atlas viewport (offset, size). */
+int r3_shadow_pass(r3_ctx*, uint32_t shadow_index, uint32_t offset_x, uint32_t offset_y, uint32_t size);
+/* begin the primary render pass: colour = clear colour, depth = 0.0 (base.rs:257-264) */
+int r3_forward_begin(r3_ctx*);
+/* ForwardRoutine::add_forward_to_graph for the opaque + cutout routines.
+ * source 0 = CullingSource::Predicted (last frame's list, forward.rs:224-232),
+ *        1 = CullingSource::Residual (this frame's residual list, forward.rs:212-222). */
+int r3_forward_pass(r3_ctx*, int source);
+int r3_hiz_build(r3_ctx*);                                                          /* hi_z.rs:161-234 */
+/* run opaque.wgsl::fs_main for the winning fragment of every covered pixel */
+int r3_forward_resolve(r3_ctx*);
+int r3_tonemap(r3_ctx*, int srgb_target);                                           /* tonemapping.rs:108-147 */
+
+int r3_readback_hdr_f32(r3_ctx*, float* rgba, uint64_t capacity_floats);            /* pre-f16 shading result (parity) */
+int r3_readback_hdr_f16(r3_ctx*, uint16_t* rgba, uint64_t capacity_halfs);          /* the Rgba16Float target */
+int r3_readback_depth(r3_ctx*, float* depth, uint64_t capacity);
+int r3_readback_ldr(r3_ctx*, uint8_t* rgba8, uint64_t capacity);
+int r3_readback_shadow_atlas(r3_ctx*, float* depth, uint64_t capacity);
+int r3_readback_hiz(r3_ctx*, uint32_t mip, float* depth, uint64_t capacity, uint32_t* width, uint32_t* height);
+/* forward statistics of the last frame: [0] triangles set up, [1] fragments that passed the depth
+ * test when rasterised, [2] pixels shaded by r3_forward_resolve */
+int r3_forward_stats(r3_ctx*, uint64_t stats[4]);
+
+/* ------------------------------------------------------------------ multi-GPU plumbing
+ * raw device views so torch.distributed / NCCL can move the visible list and tile rows without a
+ * host bounce.  which: 0 visible list (u32), 1 hdr f16 colour, 2 object matrices */
+int r3_device_ptr(r3_ctx*, uint32_t camera, int which, void** device_ptr, uint64_t* nbytes);
+/* restrict rasterisation + shading to pixel rows [row_begin, row_end) (screen-tile split) */
+int r3_set_scissor_rows(r3_ctx*, uint32_t row_begin, uint32_t row_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REND3_B200_H */

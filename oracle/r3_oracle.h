@@ -1,0 +1,58 @@
+/* r3_oracle.h — internal declarations of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+ *
+ * The oracle is a plain-C restatement of the reference's arithmetic for the hot path.  It exists
+ * so tests/ can check the CUDA path; nothing in rend3_b200/ may include, link or call it.
+ * It exports the same entry points as include/rend3_b200.h with the prefix r3o_ instead of r3_.
+ */
+#ifndef R3_ORACLE_H
+#define R3_ORACLE_H
+
+#include <stdint.h>
+#include "../include/r3_layouts.h"
+
+#define R3O_MAX_CAMERAS 64
+
+/* InputOutputBuffer — rend3-routine/src/culling/suballoc.rs:17-223 (header kept out of `data`) */
+typedef struct {
+    uint8_t* data;
+    uint64_t capacity_elements, out_elems, in_elems, elem_size;
+    int flipped, clear_on_swap, created;
+} r3o_iobuf;
+
+typedef struct {
+    int header_set;
+    r3_camera_header header;
+    r3_object_matrices* matrices; uint32_t matrices_cap;
+    uint32_t* visible; uint32_t visible_count, visible_cap;
+    /* batch_objects products (this frame) and the cached DrawCallSet of the previous frame (forward.rs:219) */
+    r3_batch_data* batches; uint32_t n_batches;
+    r3_region* regions; uint32_t n_regions; uint32_t total_invocations;
+    r3_batch_data* prev_batches; uint32_t prev_n_batches;
+    r3_region* prev_regions; uint32_t prev_n_regions; uint32_t prev_total_invocations;
+    int has_draw_call_set, has_prev_draw_call_set;
+    uint32_t* prev_invocation; uint32_t prev_invocation_cap;   /* PerCameraPreviousInvocationsMap */
+    r3o_iobuf index_buffer, draw_call_buffer, results_buffer;  /* CullingBuffers (culler.rs:88-125) */
+} r3o_camera;
+
+typedef struct r3o_ctx {
+    char err[256];
+    r3_object* objects; uint32_t n_slots;
+    uint64_t* sort_key; uint8_t* sort_flags; float* sort_loc; uint32_t sort_n;
+    uint32_t* mesh; uint64_t mesh_words;
+    r3_material* materials; uint32_t n_materials;
+    r3_directional_light* dir_lights; uint32_t n_dir; uint32_t atlas_w, atlas_h;
+    r3_point_light* point_lights; uint32_t n_point;
+    r3_frame_uniforms uniforms;
+    r3o_camera cams[R3O_MAX_CAMERAS];
+    /* render targets */
+    uint32_t width, height, samples; float clear_color[4];
+    uint32_t row_begin, row_end;
+    uint64_t* vis;            /* per pixel (depth bits << 32) | (pass << 31) | triangle record */
+    float* hdr; uint16_t* hdr16; float* depth; uint8_t* ldr;
+    float* atlas;
+    float** hiz; uint32_t* hiz_w; uint32_t* hiz_h; uint32_t hiz_mips;
+    struct r3o_tri* tris[2]; uint64_t n_tris[2], cap_tris[2];
+    uint64_t stats[4];
+} r3o_ctx;
+
+#endif
