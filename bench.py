@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — rend3 hot path on B200: culled objects/s (cull + uniform bake) and shaded Mfrag/s (PBR forward).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU arithmetic (oracle port) on the host cores
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic input:
+  * headline workload (BASELINE config 4, the one the target metric is quoted on): fused per-object frustum cull +
+    object-uniform bake over 10 M object records PER GPU (weak scaling), 1% disabled, visible list ascending;
+    at N > 1 the visible lists are all-gathered with NCCL (counts, then padded lists) as north_star asks;
+  * `value` = objects culled+baked per second, inputs resident in HBM, CUDA events on the library's stream;
+  * `e2e`   = the same through the C ABI with HOST buffers: r3_set_objects (pinned H2D of every record) +
+    r3_object_uniform_upload + r3_readback_visible (D2H) inside the timed region;
+  * `forward` = BASELINE config 5 (4K, ~500k triangles, 64 point lights + 4 shadow-mapped directional lights):
+    whole frames through BaseRenderGraph.add_to_graph; Mfrag/s = fs_main invocations / frame time; at N > 1 the
+    screen is split in row tiles, one per rank, and the rgba16f rows are all-gathered.
+Inputs (1.28 GB of records + 1.28 GB of matrices per step) exceed the 126 MB L2, so no explicit flush is needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from rend3_b200.backend import CAMERA_VIEWPORT, CB_BAKE, CB_CULL  # noqa: E402
+from rend3_b200.routines import BaseRenderGraph, BaseRenderGraphSettings, per_camera_header  # noqa: E402
+from rend3_b200.scenes import cloud_camera, cube_field_scene, object_cloud_records  # noqa: E402
+
+METRIC = "culled objects/s (fused frustum cull + object-uniform bake)"
+BYTES_PER_OBJECT = 212   # 84 B read (transform 64 + sphere 16 + enabled 4) + 128 B MV/MVP written
+BYTES_PER_VISIBLE = 4
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+class DeviceView:
+    """__cuda_array_interface__ wrapper so torch.distributed can move library-owned device memory without a host bounce."""
+
+    def __init__(self, ptr, nbytes, typestr="|u1", itemsize=1):
+        self.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def reference_arm(args):
+    """The reference's own CPU arithmetic for the path.  The reference (Rust + wgpu) cannot be built or run here (no
+    cargo, no Vulkan ICD: SURVEY 8c), so this arm times the oracle port — uniform_prep.wgsl + batch_objects' frustum filter
+    restated in C — with every host thread, on bounded samples of the same workload."""
+    import oracle
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = min(args.objects, 2_000_000)   # bounded sample: 2 M of the 10 M records per step
+    cores = os.cpu_count() or 1
+    rec = object_cloud_records(n, seed=4)
+    header = per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (1920, 1080), 1, n)
+    b = oracle.load_oracle_backend()
+    b.set_objects(rec)
+    for _ in range(args.warmup):
+        b.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        b.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE config 4: cull + uniform bake over 10 M object records per GPU", "objects_per_step_sampled": n,
+                   "note": "reference itself (Rust/wgpu) cannot run here; CPU oracle port of uniform_prep.wgsl + Frustum::contains_sphere"},
+        "cpu_baseline": {"value": value, "unit": "objects/s", "cores": cores, "kind": "port", "sample": f"{n} of {args.objects} records per step, OpenMP over all host cores"},
+        "e2e": {"value": value, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(n_total):
+    import oracle
+
+    n = min(n_total, 2_000_000)
+    rec = object_cloud_records(n, seed=4)
+    header = per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (1920, 1080), 1, n)
+    b = oracle.load_oracle_backend()
+    b.set_objects(rec)
+    b.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t0 < 5.0 and reps < 50):
+        b.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n / dt, "unit": "objects/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{n} of {n_total} records, {reps} repetitions, OpenMP over all host cores (oracle/r3_oracle.c)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--objects", type=int, default=10_000_000, help="object records per GPU")
+    ap.add_argument("--no-forward", action="store_true")
+    ap.add_argument("--forward-steps", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from rend3_b200 import load_cuda_backend   # fails loudly when librend3_b200.so is missing: no CPU fallback
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.objects
+    backend = load_cuda_backend(local)
+    stream = torch.cuda.ExternalStream(backend.stream(), device=torch.device("cuda", local))
+
+    # ---- inputs: this rank's shard of the object set, built on the host, staged in pinned memory
+    rec = object_cloud_records(n, seed=4 + rank)
+    pinned = torch.empty(n * 128, dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = rec.view(np.uint8).reshape(-1)
+    host_rec = pinned.numpy().view(rec.dtype)
+    del rec
+    header = per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (1920, 1080), 1, n)
+    backend.set_objects(host_rec)
+    vis_host = torch.empty(n, dtype=torch.int32, pin_memory=True)
+
+    def gather_visible():
+        if world == 1:
+            return
+        cptr, _ = backend.device_ptr(CAMERA_VIEWPORT, 3)
+        vptr, vbytes = backend.device_ptr(CAMERA_VIEWPORT, 0)
+        with torch.cuda.stream(stream):
+            cnt = torch.as_tensor(DeviceView(cptr, 4, "<i4", 4), device=f"cuda:{local}")
+            counts = torch.empty(world, dtype=torch.int32, device=f"cuda:{local}")
+            dist.all_gather_into_tensor(counts, cnt)
+            m = int(counts.max().item())
+            mine = torch.as_tensor(DeviceView(vptr, vbytes, "<i4", 4), device=f"cuda:{local}")[:max(m, 1)]
+            out = torch.empty(world * max(m, 1), dtype=torch.int32, device=f"cuda:{local}")
+            dist.all_gather_into_tensor(out, mine)
+
+    def step_resident():
+        backend.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+        gather_visible()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    launches0 = backend.launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            starts[i].record(stream)
+            backend.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+            ends[i].record(stream)
+            gather_visible()
+        barrier()
+        wall = time.perf_counter() - t_wall0
+    kernel_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = starts[0].elapsed_time(ends[-1]) if world == 1 else wall * 1e3
+    launches = backend.launch_count() - launches0
+    n_vis = backend.visible_count(CAMERA_VIEWPORT)
+    t = torch.tensor([total_ms], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    kern_s = float(np.mean(kernel_ms)) * 1e-3
+    achieved = (BYTES_PER_OBJECT * n + BYTES_PER_VISIBLE * n_vis) / kern_s / 1e9
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region
+    e2e_steps = max(3, min(args.steps, 5))
+    backend.set_objects(host_rec)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        backend.set_objects(host_rec)                                         # pinned H2D of every record
+        backend.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+        nv = backend.visible_count(CAMERA_VIEWPORT)
+        backend._call("readback_visible", __import__("ctypes").c_uint32(CAMERA_VIEWPORT), __import__("ctypes").c_void_p(vis_host.data_ptr()),
+                      __import__("ctypes").c_uint32(n), None)               # D2H of the visible list into pinned memory
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * n / float(te.item()), "unit": "objects/s", "h2d_bytes_per_step": n * 128 + 240, "d2h_bytes_per_step": 4 * nv + 4}
+
+    # ---- forward: BASELINE config 5
+    forward = None
+    if not args.no_forward:
+        res = (3840, 2160)
+        ev = cube_field_scene(n_objects=4400, seed=5, resolution=res, extent=30.0, pull_back=14.0, n_point_lights=64, n_dir_lights=4,
+                              shadow_resolution=2048, shadow_distance=200.0, subdivisions=(2, 3, 3, 4), scale_range=(0.6, 2.4))
+        fb = load_cuda_backend(local)
+        fstream = torch.cuda.ExternalStream(fb.stream(), device=torch.device("cuda", local))
+        graph = BaseRenderGraph(fb)
+        settings = BaseRenderGraphSettings(clear_color=(0.1, 0.05, 0.1, 1.0))
+        rows = (res[1] * rank // world, res[1] * (rank + 1) // world)
+
+        def frame(upload):
+            graph.add_to_graph(ev, res, 1, settings, upload=upload, scissor_rows=rows if world > 1 else None)
+            if world > 1:
+                ptr, nbytes = fb.device_ptr(CAMERA_VIEWPORT, 1)
+                with torch.cuda.stream(fstream):
+                    img = torch.as_tensor(DeviceView(ptr, nbytes), device=f"cuda:{local}")
+                    row_bytes = res[0] * 8
+                    mine = img[rows[0] * row_bytes:rows[1] * row_bytes]
+                    if res[1] % world == 0:
+                        dist.all_gather_into_tensor(img, mine.clone())
+        frame(True)
+        for _ in range(2):
+            frame(False)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = fb.launch_count()
+        tw = time.perf_counter()
+        f0.record(fstream)
+        for _ in range(args.forward_steps):
+            frame(False)
+        f1.record(fstream)
+        barrier()
+        frame_ms = (time.perf_counter() - tw) * 1e3 / args.forward_steps
+        tf = torch.tensor([frame_ms], device=f"cuda:{local}")
+        st = torch.tensor([float(x) for x in fb.forward_stats()[:3]], device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            dist.all_reduce(st, op=dist.ReduceOp.SUM)
+        frame_ms = float(tf.item())
+        tris = int(fb.readback_draw_calls(CAMERA_VIEWPORT, 0)["vertex_count"].sum()) // 3
+        forward = {"workload": "BASELINE config 5: 3840x2160, 4400 meshes / ~500k triangles, 64 point lights + 4 directional lights with 2048^2 shadow maps",
+                   "frame_ms": frame_ms, "shaded_mfrag_s": float(st[2].item()) / frame_ms / 1e3, "raster_mfrag_s": float(st[1].item()) / frame_ms / 1e3,
+                   "shaded_fragments": int(st[2].item()), "depth_passing_fragments": int(st[1].item()), "triangles_after_cull": tris,
+                   "gpu_launches_per_frame": (fb.launch_count() - l0) // max(args.forward_steps, 1),
+                   "split": f"{world} row tiles, rgba16f rows all-gathered" if world > 1 else "single GPU"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 4: fused frustum cull + uniform bake, 10 M object records per GPU (128 B std430 records, 1% disabled)",
+                       "objects_per_gpu": n, "visible_fraction": n_vis / n, "parallelism": f"object-range shards x{world}, NCCL all-gather of the visible lists" if world > 1 else "single GPU",
+                       "l2": "inputs (1.28 GB) + outputs (1.28 GB) per step exceed the 126 MB L2; no explicit flush"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "cull_bake_kernel<bake,cull>", "kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_launch": BYTES_PER_OBJECT * n + BYTES_PER_VISIBLE * n_vis,
+                         "peak_source": peak_src},
+            "cpu_baseline": cpu_baseline(n),
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "forward": forward,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

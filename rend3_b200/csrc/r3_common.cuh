@@ -1,0 +1,153 @@
+// r3_common.cuh — shared declarations of librend3_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rend3_b200.h"
+
+#define R3_EXPORT extern "C" __attribute__((visibility("default")))
+
+constexpr int R3_MAX_CAMERAS = 64;          // slot 0 = viewport, 1+i = shadow i
+constexpr int R3_SM_COUNT = 148;            // B200: 2 dies x 74 SMs
+
+struct r3_iobuf {                           // InputOutputBuffer, rend3-routine/src/culling/suballoc.rs:17-223
+    uint8_t* d = nullptr;
+    uint64_t capacity_elements = 0, out_elems = 0, in_elems = 0, elem_size = 0;
+    bool flipped = false, clear_on_swap = false, created = false;
+    uint64_t out_off() const { return flipped ? capacity_elements / 2 : 0; }
+    uint64_t in_off() const { return flipped ? 0 : capacity_elements / 2; }
+};
+
+// device-side description of the draw calls of one camera/frame (what forward.rs:290-313 walks)
+struct r3_jobs {
+    r3_batch_data* d_batches = nullptr; uint32_t batches_cap = 0, n_batches = 0;
+    r3_region* d_regions = nullptr; uint32_t regions_cap = 0, n_regions = 0;
+    uint32_t* d_region_first_inv = nullptr;   // [n_regions+1] first global invocation of each region
+    uint32_t total_invocations = 0;
+    std::vector<r3_batch_data> batches;      // host copies (batch_objects builds these on the CPU)
+    std::vector<r3_region> regions;
+    bool valid = false;
+};
+
+struct r3_camera {
+    bool header_set = false;
+    r3_camera_header header{};
+    r3_object_matrices* d_matrices = nullptr; uint32_t matrices_cap = 0;
+    uint32_t* d_visible = nullptr; uint32_t visible_cap = 0;
+    uint32_t* d_visible_count = nullptr;      // device scalar
+    unsigned long long* d_tile_state = nullptr; uint32_t tile_state_cap = 0;   // decoupled look-back descriptors (+ticket)
+    int visible_count_host = -1;              // cached after a readback, -1 = unknown
+    r3_jobs jobs[2]; int cur = 0;             // jobs[cur] = this frame, jobs[cur^1] = cached DrawCallSet (forward.rs:219)
+    bool has_draw_call_set = false; int cache_idx = -1;   // cache_idx: which jobs[] the forward routine cached, -1 = none
+    std::vector<uint32_t> prev_invocation;    // PerCameraPreviousInvocationsMap (batching.rs:102-118)
+    r3_iobuf index_buffer, draw_call_buffer, results_buffer;   // CullingBuffers (culler.rs:88-125)
+    // scratch of the ordered triangle compaction
+    uint32_t* d_resid_bits = nullptr; uint64_t resid_bits_cap = 0;
+    unsigned long long* d_word_scan = nullptr; uint64_t word_scan_cap = 0;
+    unsigned long long* d_block_sums = nullptr; uint64_t block_sums_cap = 0;
+};
+
+struct r3_tri_record { float xyw[3][3]; uint32_t object_id; uint32_t vid[3]; uint32_t _pad[3]; };   // 64 B
+static_assert(sizeof(r3_tri_record) == 64, "triangle record");
+
+struct r3_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    // world
+    r3_object* d_objects = nullptr; uint32_t n_slots = 0, objects_cap = 0; bool objects_borrowed = false;
+    std::vector<uint64_t> sort_key; std::vector<uint8_t> sort_flags; std::vector<float> sort_loc;
+    uint32_t* d_live_bits = nullptr; uint32_t live_bits_cap = 0; bool have_live = false;
+    uint32_t* d_mesh = nullptr; uint64_t mesh_words = 0, mesh_cap = 0;
+    r3_material* d_materials = nullptr; uint32_t n_materials = 0, materials_cap = 0;
+    r3_directional_light* d_dir = nullptr; uint32_t n_dir = 0, dir_cap = 0;
+    r3_point_light* d_point = nullptr; uint32_t n_point = 0, point_cap = 0;
+    float* d_light_mats = nullptr; uint64_t light_mats_cap = 0;   // view-space light tables built by light_prep_kernel
+    r3_frame_uniforms uniforms{}; bool uniforms_set = false;
+    float* d_atlas = nullptr; uint32_t atlas_w = 0, atlas_h = 0;
+    r3_camera cams[R3_MAX_CAMERAS];
+    // render targets
+    uint32_t width = 0, height = 0, samples = 1; float clear_color[4] = {0, 0, 0, 0};
+    uint32_t row_begin = 0, row_end = 0;
+    unsigned long long* d_vis = nullptr;      // (depth bits << 32) | (pass << 31) | record
+    float* d_hdr32 = nullptr; uint16_t* d_hdr16 = nullptr; float* d_depth = nullptr; uint8_t* d_ldr = nullptr;
+    std::vector<float*> d_hiz; std::vector<uint32_t> hiz_w, hiz_h;
+    float** d_hiz_ptrs = nullptr; uint32_t* d_hiz_dims = nullptr;
+    r3_tri_record* d_tris[2] = {nullptr, nullptr}; uint64_t tris_cap[2] = {0, 0}; uint64_t n_tris[2] = {0, 0};
+    unsigned long long* d_stats = nullptr;    // [4]
+    void* d_scratch = nullptr; uint64_t scratch_cap = 0;
+};
+
+// ---- error plumbing (nothing throws across the C boundary)
+int r3_fail(r3_ctx* c, int code, const char* msg);
+int r3_cuda_fail(r3_ctx* c, cudaError_t e, const char* where);
+#define R3_CUDA(c, call)                                                  \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) return r3_cuda_fail((c), e__, #call);     \
+    } while (0)
+#define R3_CHECK_LAUNCH(c, name)                                          \
+    do {                                                                  \
+        (c)->launches++;                                                  \
+        cudaError_t e__ = cudaGetLastError();                             \
+        if (e__ != cudaSuccess) return r3_cuda_fail((c), e__, name);      \
+    } while (0)
+#define R3_TRY(expr)                                                      \
+    do {                                                                  \
+        int rc__ = (expr);                                                \
+        if (rc__ != R3_OK) return rc__;                                   \
+    } while (0)
+
+static inline int r3_cam_slot(uint32_t camera) { return camera == R3_CAMERA_VIEWPORT ? 0 : (int)camera + 1; }
+#define R3_CAM_OR_FAIL(ctx, camera)                                                                              \
+    if (!(ctx)) return R3_E_INVALID;                                                                             \
+    if ((camera) != R3_CAMERA_VIEWPORT && (camera) >= R3_MAX_SHADOWS) return r3_fail((ctx), R3_E_INVALID, "bad camera"); \
+    r3_camera* cam = &(ctx)->cams[r3_cam_slot(camera)]
+
+// grow-only device allocation helper: keeps contents when `keep` is set
+int r3_reserve(r3_ctx* c, void** ptr, uint64_t* cap_elems, uint64_t need_elems, size_t elem_size, bool keep, bool zero_new);
+template <typename T, typename C>
+int r3_reserve_t(r3_ctx* c, T** ptr, C* cap, uint64_t need, bool keep = false, bool zero_new = false) {
+    uint64_t cap64 = *cap;
+    int rc = r3_reserve(c, (void**)ptr, &cap64, need, sizeof(T), keep, zero_new);
+    *cap = (C)cap64;
+    return rc;
+}
+
+// stages implemented in the other translation units
+int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode);
+int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam);
+int r3_host_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], uint32_t max_dispatch_count);
+int r3_upload_jobs(r3_ctx* c, r3_camera* cam);
+int r3_iobuf_new(r3_ctx* c, r3_iobuf* b, uint64_t elems, uint64_t elem_size, bool clear_on_swap);
+int r3_iobuf_swap(r3_ctx* c, r3_iobuf* b, uint64_t new_elems);
+
+#ifdef __CUDACC__
+// IEEE, never-contracted arithmetic for the bit-exact stages
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+// M * (x, y, z, w): column-major, accumulated x,y,z,w like WGSL's mat4x4*vec4
+__device__ __forceinline__ float4 mat_vec_rn(const float* __restrict__ m, float x, float y, float z, float w) {
+    float4 r;
+    r.x = mul_rn(m[0], x); r.y = mul_rn(m[1], x); r.z = mul_rn(m[2], x); r.w = mul_rn(m[3], x);
+    r.x = add_rn(r.x, mul_rn(m[4], y)); r.y = add_rn(r.y, mul_rn(m[5], y)); r.z = add_rn(r.z, mul_rn(m[6], y)); r.w = add_rn(r.w, mul_rn(m[7], y));
+    r.x = add_rn(r.x, mul_rn(m[8], z)); r.y = add_rn(r.y, mul_rn(m[9], z)); r.z = add_rn(r.z, mul_rn(m[10], z)); r.w = add_rn(r.w, mul_rn(m[11], z));
+    r.x = add_rn(r.x, mul_rn(m[12], w)); r.y = add_rn(r.y, mul_rn(m[13], w)); r.z = add_rn(r.z, mul_rn(m[14], w)); r.w = add_rn(r.w, mul_rn(m[15], w));
+    return r;
+}
+// M * (x, y, z, 1)
+__device__ __forceinline__ float4 mat_point_rn(const float* __restrict__ m, float x, float y, float z) {
+    float4 r;
+    r.x = mul_rn(m[0], x); r.y = mul_rn(m[1], x); r.z = mul_rn(m[2], x); r.w = mul_rn(m[3], x);
+    r.x = add_rn(r.x, mul_rn(m[4], y)); r.y = add_rn(r.y, mul_rn(m[5], y)); r.z = add_rn(r.z, mul_rn(m[6], y)); r.w = add_rn(r.w, mul_rn(m[7], y));
+    r.x = add_rn(r.x, mul_rn(m[8], z)); r.y = add_rn(r.y, mul_rn(m[9], z)); r.z = add_rn(r.z, mul_rn(m[10], z)); r.w = add_rn(r.w, mul_rn(m[11], z));
+    r.x = add_rn(r.x, m[12]); r.y = add_rn(r.y, m[13]); r.z = add_rn(r.z, m[14]); r.w = add_rn(r.w, m[15]);
+    return r;
+}
+#endif

@@ -1,0 +1,459 @@
+// r3_raster.cu — software rasteriser for the opaque forward pass and the shadow-map passes.
+//
+// Replaces the fixed-function half of ForwardRoutine::add_forward_to_graph
+// (rend3-routine/src/forward.rs:192-315, pipeline state :331-365): vertex pulling of the packed index lists
+// produced by the triangle cull (opaque.wgsl::vs_main :91-135 / depth.wgsl::vs_main :51-87 up to clip space),
+// clipping, triangle setup, coverage and the reverse-Z GreaterEqual depth test.
+//
+// B200 design: a visibility buffer instead of immediate shading.  Every covered sample performs ONE 64-bit
+// atomicMax on  (depth bits << 32) | (pass << 31) | triangle-record  — reverse-Z depth in [0,1] orders like its
+// bit pattern, so the depth test, the "later draw wins ties" rule and the predicted/residual pass order collapse
+// into one integer max in L2.  fs_main then runs once per pixel (r3_shade.cu) instead of once per fragment.
+// Shadow maps are the same kernels with a 32-bit atomicMax on the depth bits of the atlas.
+//   * setup kernel: persistent grid (148 x 8 CTAs), one thread per listed triangle; small triangles (bounding box
+//     <= 16x16 pixels, the common case at 500k+ triangles / frame) are rasterised inline by the thread with
+//     incremental 64-bit edge functions;
+//   * larger ones are split into 16-row bands and queued; the band kernel gives each band to one warp, lanes
+//     span 32 consecutive pixels so the visibility-buffer atomics of a warp hit one or two 128-byte lines,
+//     and 32x16 blocks entirely outside an edge are skipped with one corner evaluation per edge.
+// All setup / coverage / depth arithmetic is __f*_rn in the order of the oracle's RASTER RULES R1-R5
+// (oracle/r3_oracle_forward.inc), integer edge functions with the top-left rule — bit-exact by construction.
+#include "r3_common.cuh"
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr float GUARD = 64.0f;
+constexpr int SMALL_MAX = 16;            // inline raster when the pixel bounding box is at most 16 x 16
+constexpr int BAND_ROWS = 16;
+constexpr uint32_t LARGE_CAP = 1u << 20; // queued large sub-triangles
+constexpr uint32_t BAND_CAP = 1u << 22;  // queued (sub-triangle, band) items
+
+struct SubTri { int32_t x[3], y[3]; float z[3]; uint32_t rec; };   // oriented (area > 0), snapped 24.8
+static_assert(sizeof(SubTri) == 40, "SubTri");
+
+struct RasterParams {
+    // draw source
+    const r3_batch_data* batches; const r3_region* regions; uint32_t n_regions;
+    const r3_indirect_call* calls; const uint32_t* indices; uint64_t index_elems;
+    const unsigned long long* tri_prefix;      // [n_regions + 1] exclusive prefix of listed triangles (opaque + cutout)
+    const r3_object* objects; uint32_t n_slots;
+    const r3_object_matrices* matrices; uint32_t matrices_cap;
+    const uint32_t* mesh; uint64_t mesh_words;
+    // target
+    float ox, oy, vw, vh; int32_t x0, y0, x1, y1; uint32_t pitch; int positive_visible;
+    unsigned long long* vis; uint32_t pass_bit;   // colour passes
+    uint32_t* depth_bits;                          // depth-only passes (shadow atlas)
+    r3_tri_record* records;
+    // queues
+    SubTri* large; uint2* bands; uint32_t* counters;   // [0] n_large, [1] n_bands, [2] band ticket
+    unsigned long long* stats;
+};
+
+__device__ __forceinline__ uint32_t mesh_word(const RasterParams& p, uint64_t i) { return i < p.mesh_words ? __ldg(&p.mesh[i]) : 0u; }
+
+__device__ __forceinline__ float plane_dist(int plane, const float4 v) {
+    switch (plane) {
+        case 0: return v.z;
+        case 1: return sub_rn(v.w, v.z);
+        case 2: return add_rn(v.x, mul_rn(GUARD, v.w));
+        case 3: return sub_rn(mul_rn(GUARD, v.w), v.x);
+        case 4: return add_rn(v.y, mul_rn(GUARD, v.w));
+        default: return sub_rn(mul_rn(GUARD, v.w), v.y);
+    }
+}
+__device__ __forceinline__ float4 clip_lerp(const float4 in, const float4 out, float din, float dout) {
+    const float t = div_rn(din, sub_rn(din, dout));
+    return make_float4(add_rn(in.x, mul_rn(t, sub_rn(out.x, in.x))), add_rn(in.y, mul_rn(t, sub_rn(out.y, in.y))),
+                       add_rn(in.z, mul_rn(t, sub_rn(out.z, in.z))), add_rn(in.w, mul_rn(t, sub_rn(out.w, in.w))));
+}
+// R1 — Sutherland-Hodgman against every violated plane; returns the polygon size (0 = clipped away)
+__device__ __noinline__ int clip_polygon(float4* poly, int n) {
+    for (int plane = 0; plane < 6 && n >= 3; ++plane) {
+        bool any_out = false;
+        for (int i = 0; i < n; ++i) any_out |= plane_dist(plane, poly[i]) < 0.0f;
+        if (!any_out) continue;
+        float4 outp[12];
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const float4 a = poly[i], b = poly[(i + 1) % n];
+            const float da = plane_dist(plane, a), db = plane_dist(plane, b);
+            if (da >= 0.0f) {
+                outp[m++] = a;
+                if (db < 0.0f) outp[m++] = clip_lerp(a, b, da, db);
+            } else if (db >= 0.0f) {
+                outp[m++] = clip_lerp(b, a, db, da);
+            }
+        }
+        n = m;
+        for (int i = 0; i < n; ++i) poly[i] = outp[i];
+    }
+    return n >= 3 ? n : 0;
+}
+
+struct EdgeSetup {
+    long long e0, e1, e2;          // biased edge values at the first pixel centre: >= 0 means inside
+    long long sx0, sx1, sx2;       // step for +1 pixel in x
+    long long sy0, sy1, sy2;       // step for +1 pixel in y
+    int b0, b1, b2;                // top-left biases folded into e* (0 for top/left edges, 1 otherwise)
+    float inv_area;
+};
+__device__ __forceinline__ long long edge_fn(int ax, int ay, int bx, int by, long long px, long long py) {
+    return (long long)(bx - ax) * (py - ay) - (long long)(by - ay) * (px - ax);
+}
+__device__ __forceinline__ int not_top_left(int ax, int ay, int bx, int by) {
+    const int dx = bx - ax, dy = by - ay;
+    return ((dy < 0) || (dy == 0 && dx > 0)) ? 0 : 1;
+}
+// edge functions E_ab, E_bc, E_ca at pixel (px, py): e0 = E_bc (weight of a), e1 = E_ca (weight of b), e2 = E_ab (weight of c)
+__device__ __forceinline__ EdgeSetup make_edges(const SubTri& s, int px, int py) {
+    EdgeSetup e;
+    const long long cx = (long long)px * 256 + 128, cy = (long long)py * 256 + 128;
+    e.b0 = not_top_left(s.x[1], s.y[1], s.x[2], s.y[2]);
+    e.b1 = not_top_left(s.x[2], s.y[2], s.x[0], s.y[0]);
+    e.b2 = not_top_left(s.x[0], s.y[0], s.x[1], s.y[1]);
+    e.e0 = edge_fn(s.x[1], s.y[1], s.x[2], s.y[2], cx, cy) - e.b0;
+    e.e1 = edge_fn(s.x[2], s.y[2], s.x[0], s.y[0], cx, cy) - e.b1;
+    e.e2 = edge_fn(s.x[0], s.y[0], s.x[1], s.y[1], cx, cy) - e.b2;
+    e.sx0 = -(long long)(s.y[2] - s.y[1]) * 256; e.sy0 = (long long)(s.x[2] - s.x[1]) * 256;
+    e.sx1 = -(long long)(s.y[0] - s.y[2]) * 256; e.sy1 = (long long)(s.x[0] - s.x[2]) * 256;
+    e.sx2 = -(long long)(s.y[1] - s.y[0]) * 256; e.sy2 = (long long)(s.x[1] - s.x[0]) * 256;
+    const long long area = edge_fn(s.x[0], s.y[0], s.x[1], s.y[1], s.x[2], s.y[2]);
+    e.inv_area = div_rn(1.0f, __ll2float_rn(area));
+    return e;
+}
+// R5 depth of a covered sample from the (biased) edge values
+__device__ __forceinline__ float sample_depth(const SubTri& s, const EdgeSetup& e, long long e0, long long e1, long long e2) {
+    const float la = mul_rn(__ll2float_rn(e0 + e.b0), e.inv_area), lb = mul_rn(__ll2float_rn(e1 + e.b1), e.inv_area),
+                lc = mul_rn(__ll2float_rn(e2 + e.b2), e.inv_area);
+    const float z = add_rn(add_rn(mul_rn(la, s.z[0]), mul_rn(lb, s.z[1])), mul_rn(lc, s.z[2]));
+    return fminf(fmaxf(z, 0.0f), 1.0f);
+}
+template <bool DEPTH_ONLY>
+__device__ __forceinline__ uint32_t write_sample(const RasterParams& p, int px, int py, float z, uint32_t rec) {
+    const size_t pi = (size_t)py * p.pitch + px;
+    if (DEPTH_ONLY) {
+        const uint32_t zb = __float_as_uint(z);
+        const uint32_t old = atomicMax(&p.depth_bits[pi], zb);
+        return zb >= old ? 1u : 0u;
+    } else {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | ((unsigned long long)p.pass_bit << 31) | rec;
+        const unsigned long long old = atomicMax(&p.vis[pi], key);
+        return key > old ? 1u : 0u;
+    }
+}
+
+__device__ __forceinline__ void pixel_bounds(const RasterParams& p, const SubTri& s, int& px0, int& py0, int& px1, int& py1) {
+    const int minx = min(s.x[0], min(s.x[1], s.x[2])), maxx = max(s.x[0], max(s.x[1], s.x[2]));
+    const int miny = min(s.y[0], min(s.y[1], s.y[2])), maxy = max(s.y[0], max(s.y[1], s.y[2]));
+    px0 = max((minx - 128 + 255) >> 8, p.x0); px1 = min((maxx - 128) >> 8, p.x1 - 1);
+    py0 = max((miny - 128 + 255) >> 8, p.y0); py1 = min((maxy - 128) >> 8, p.y1 - 1);
+}
+
+// R2-R4 for one sub-triangle: snap, orient, then rasterise inline or queue
+template <bool DEPTH_ONLY>
+__device__ bool process_subtriangle(const RasterParams& p, const float4 a, const float4 b, const float4 c, uint32_t rec, uint32_t& frags) {
+    const float4 v[3] = {a, b, c};
+    int sx[3], sy[3];
+    float sz[3];
+    const float hw = mul_rn(p.vw, 0.5f), hh = mul_rn(p.vh, 0.5f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (!(v[k].w > 0.0f)) return false;
+        const float nx = div_rn(v[k].x, v[k].w), ny = div_rn(v[k].y, v[k].w), nz = div_rn(v[k].z, v[k].w);
+        const float fx = add_rn(p.ox, mul_rn(add_rn(nx, 1.0f), hw)), fy = add_rn(p.oy, mul_rn(sub_rn(1.0f, ny), hh));
+        const float qx = rintf(mul_rn(fx, 256.0f)), qy = rintf(mul_rn(fy, 256.0f));
+        if (!(fabsf(qx) < 1.0e9f) || !(fabsf(qy) < 1.0e9f)) return false;
+        sx[k] = (int)qx; sy[k] = (int)qy; sz[k] = nz;
+    }
+    const long long area = (long long)(sx[1] - sx[0]) * (sy[2] - sy[0]) - (long long)(sx[2] - sx[0]) * (sy[1] - sy[0]);
+    if (area == 0) return false;
+    const bool visible = p.positive_visible ? (area < 0) : (area > 0);   // y-down area has the opposite sign of the NDC area
+    if (!visible) return false;
+    SubTri s;
+    if (area > 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { s.x[k] = sx[k]; s.y[k] = sy[k]; s.z[k] = sz[k]; }
+    } else {
+        s.x[0] = sx[0]; s.y[0] = sy[0]; s.z[0] = sz[0]; s.x[1] = sx[2]; s.y[1] = sy[2]; s.z[1] = sz[2]; s.x[2] = sx[1]; s.y[2] = sy[1]; s.z[2] = sz[1];
+    }
+    s.rec = rec;
+    int px0, py0, px1, py1;
+    pixel_bounds(p, s, px0, py0, px1, py1);
+    if (px0 > px1 || py0 > py1) return true;   // set up, but no sample inside the target rectangle
+    const int w = px1 - px0 + 1, h = py1 - py0 + 1;
+    bool inline_raster = (w <= SMALL_MAX && h <= SMALL_MAX);
+    if (!inline_raster) {
+        const uint32_t nb = (uint32_t)((py1 / BAND_ROWS) - (py0 / BAND_ROWS) + 1);
+        const uint32_t li = atomicAdd(&p.counters[0], 1u);
+        uint32_t bi = 0;
+        bool queued = li < LARGE_CAP;
+        if (queued) {
+            bi = atomicAdd(&p.counters[1], nb);
+            queued = bi + nb <= BAND_CAP;
+        }
+        if (queued) {
+            p.large[li] = s;
+            for (uint32_t k = 0; k < nb; ++k) p.bands[bi + k] = make_uint2(li, (uint32_t)(py0 / BAND_ROWS) + k);
+            return true;
+        }
+        inline_raster = true;   // queue full: stay correct, rasterise here
+    }
+    const EdgeSetup e = make_edges(s, px0, py0);
+    long long r0 = e.e0, r1 = e.e1, r2 = e.e2;
+    for (int py = py0; py <= py1; ++py) {
+        long long c0 = r0, c1 = r1, c2 = r2;
+        for (int px = px0; px <= px1; ++px) {
+            if ((c0 | c1 | c2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, sample_depth(s, e, c0, c1, c2), rec);
+            c0 += e.sx0; c1 += e.sx1; c2 += e.sx2;
+        }
+        r0 += e.sy0; r1 += e.sy1; r2 += e.sy2;
+    }
+    return true;
+}
+
+template <bool DEPTH_ONLY>
+__global__ void __launch_bounds__(RS_THREADS) raster_setup_kernel(const __grid_constant__ RasterParams p) {
+    const unsigned long long total = p.tri_prefix[p.n_regions];
+    uint32_t frags = 0, set_up = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * RS_THREADS + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * RS_THREADS) {
+        // region of listed triangle i: last r with tri_prefix[r] <= i
+        uint32_t lo = 0, hi = p.n_regions;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.tri_prefix[mid] <= i) lo = mid; else hi = mid;
+        }
+        const uint32_t r = lo;
+        const uint32_t t = (uint32_t)(i - p.tri_prefix[r]);
+        const uint64_t e = (uint64_t)p.calls[r].base_index + (uint64_t)t * 3u;
+        if (e + 2 >= p.index_elems) continue;
+        const uint32_t k0 = p.indices[e], k1 = p.indices[e + 1], k2 = p.indices[e + 2];
+        if (k0 == R3_INVALID_VERTEX || k1 == R3_INVALID_VERTEX || k2 == R3_INVALID_VERTEX) continue;   // opaque.wgsl:97-101
+        const r3_batch_data* batch = &p.batches[p.regions[r].job_index];
+        const uint32_t oid = batch->object_culling_information[k0 >> 24].object_id;                  // unpack_vertex_index (shader.rs:249-316)
+        if (oid >= p.n_slots || oid >= p.matrices_cap) continue;
+        const r3_object* obj = &p.objects[oid];
+        if (obj->enabled == 0u) continue;                                                             // opaque.wgsl:108-112
+        const uint32_t pos_off = obj->attr_offset[0] >> 2;
+        const float* mvp = p.matrices[oid].model_view_proj;
+        const uint32_t vid[3] = {k0 & 0xFFFFFFu, k1 & 0xFFFFFFu, k2 & 0xFFFFFFu};
+        float4 clip[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint64_t f = (uint64_t)pos_off + (uint64_t)vid[k] * 3u;
+            clip[k] = mat_point_rn(mvp, __uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));
+        }
+        // trivial reject + clip need (R1)
+        bool ox0 = true, ox1 = true, oy0 = true, oy1 = true, oz0 = true, oz1 = true, need_clip = false, nan = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 v = clip[k];
+            ox0 &= v.x < -v.w; ox1 &= v.x > v.w; oy0 &= v.y < -v.w; oy1 &= v.y > v.w; oz0 &= v.z < 0.0f; oz1 &= v.z > v.w;
+#pragma unroll
+            for (int pl = 0; pl < 6; ++pl) need_clip |= plane_dist(pl, v) < 0.0f;
+            nan |= !(v.w == v.w);
+        }
+        if (nan || ox0 || ox1 || oy0 || oy1 || oz0 || oz1) continue;
+        const uint32_t rec = (uint32_t)(i + 1);
+        bool any = false;
+        if (!need_clip) {
+            any = process_subtriangle<DEPTH_ONLY>(p, clip[0], clip[1], clip[2], rec, frags);
+        } else {
+            float4 poly[12];
+            poly[0] = clip[0]; poly[1] = clip[1]; poly[2] = clip[2];
+            const int n = clip_polygon(poly, 3);
+            for (int q = 1; q + 1 < n; ++q) any |= process_subtriangle<DEPTH_ONLY>(p, poly[0], poly[q], poly[q + 1], rec, frags);
+        }
+        if (any) {
+            set_up++;
+            if (!DEPTH_ONLY) {
+                r3_tri_record tr;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { tr.xyw[k][0] = clip[k].x; tr.xyw[k][1] = clip[k].y; tr.xyw[k][2] = clip[k].w; tr.vid[k] = vid[k]; }
+                tr.object_id = oid; tr._pad[0] = tr._pad[1] = tr._pad[2] = 0u;
+                float4* dst = reinterpret_cast<float4*>(&p.records[i]);
+                const float4* src = reinterpret_cast<const float4*>(&tr);
+                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+            }
+        }
+    }
+    // statistics: one atomic per warp
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) { frags += __shfl_xor_sync(0xFFFFFFFFu, frags, s); set_up += __shfl_xor_sync(0xFFFFFFFFu, set_up, s); }
+    if ((threadIdx.x & 31) == 0 && p.stats) {
+        if (set_up) atomicAdd(&p.stats[0], (unsigned long long)set_up);
+        if (frags) atomicAdd(&p.stats[1], (unsigned long long)frags);
+    }
+}
+
+// one warp per (large sub-triangle, 16-row band); lanes = 32 consecutive pixels
+template <bool DEPTH_ONLY>
+__global__ void __launch_bounds__(RS_THREADS) raster_band_kernel(const __grid_constant__ RasterParams p) {
+    const int lane = threadIdx.x & 31;
+    uint32_t n_bands = p.counters[1];
+    if (n_bands > BAND_CAP) n_bands = BAND_CAP;
+    uint32_t frags = 0;
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(&p.counters[2], 1u);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= n_bands) break;
+        const uint2 it = p.bands[item];
+        const SubTri s = p.large[it.x];
+        int px0, py0, px1, py1;
+        pixel_bounds(p, s, px0, py0, px1, py1);
+        const int by0 = max(py0, (int)it.y * BAND_ROWS), by1 = min(py1, (int)it.y * BAND_ROWS + BAND_ROWS - 1);
+        if (by0 > by1) continue;
+        const EdgeSetup e = make_edges(s, px0, by0);
+        const int rows = by1 - by0 + 1;
+        for (int bx = px0; bx <= px1; bx += 32) {
+            // skip the 32 x rows block when it lies entirely outside one edge: evaluate the corner that maximises E
+            const long long dx = bx - px0, wx = min(31, px1 - bx), hy = rows - 1;
+            const long long m0 = e.e0 + dx * e.sx0 + (e.sx0 > 0 ? wx * e.sx0 : 0) + (e.sy0 > 0 ? hy * e.sy0 : 0);
+            const long long m1 = e.e1 + dx * e.sx1 + (e.sx1 > 0 ? wx * e.sx1 : 0) + (e.sy1 > 0 ? hy * e.sy1 : 0);
+            const long long m2 = e.e2 + dx * e.sx2 + (e.sx2 > 0 ? wx * e.sx2 : 0) + (e.sy2 > 0 ? hy * e.sy2 : 0);
+            if ((m0 | m1 | m2) < 0) continue;
+            const int px = bx + lane;
+            long long c0 = e.e0 + (dx + lane) * e.sx0, c1 = e.e1 + (dx + lane) * e.sx1, c2 = e.e2 + (dx + lane) * e.sx2;
+            for (int py = by0; py <= by1; ++py) {
+                if (px <= px1 && (c0 | c1 | c2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, sample_depth(s, e, c0, c1, c2), s.rec);
+                c0 += e.sy0; c1 += e.sy1; c2 += e.sy2;
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) frags += __shfl_xor_sync(0xFFFFFFFFu, frags, s);
+    if (lane == 0 && frags && p.stats) atomicAdd(&p.stats[1], (unsigned long long)frags);
+}
+
+// exclusive prefix over the regions the opaque (key 0) and cutout (key 1) routines draw (forward.rs:286-313)
+__global__ void region_prefix_kernel(const r3_region* __restrict__ regions, const r3_indirect_call* __restrict__ calls, uint32_t n_regions,
+                                     unsigned long long* __restrict__ prefix) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_regions; base += blockDim.x) {
+        const uint32_t r = base + threadIdx.x;
+        unsigned long long v = 0ull;
+        if (r < n_regions && regions[r].material_key <= 1ull) v = calls[r].vertex_count / 3u;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += n;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0ull, wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long n = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                if (lane >= d) wi += n;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const unsigned long long excl = s_carry + s_warp[warp] + incl - v;
+        if (r < n_regions) prefix[r] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) prefix[n_regions] = s_carry;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side
+struct DrawSource { const r3_jobs* jobs; const r3_indirect_call* calls; const uint32_t* indices; uint64_t index_elems; };
+
+static bool draw_source_for(r3_camera* cam, int jobs_idx, int partition, DrawSource* ds) {
+    if (!cam->index_buffer.created || jobs_idx < 0) return false;
+    const r3_jobs* j = &cam->jobs[jobs_idx];
+    if (!j->valid || j->n_regions == 0) return false;
+    const r3_iobuf& ib = cam->index_buffer; const r3_iobuf& db = cam->draw_call_buffer;
+    if (j->n_regions > db.capacity_elements / 2) return false;
+    ds->jobs = j;
+    ds->indices = (const uint32_t*)ib.d + (partition ? ib.in_off() : ib.out_off());
+    ds->index_elems = ib.capacity_elements / 2;
+    ds->calls = (const r3_indirect_call*)db.d + (partition ? db.in_off() : db.out_off());
+    return true;
+}
+
+static int ensure_raster_scratch(r3_ctx* c) {
+    // layout: counters[4] | tri_prefix[...] handled separately | large[LARGE_CAP] | bands[BAND_CAP]
+    const uint64_t need = 64 + (uint64_t)LARGE_CAP * sizeof(SubTri) + (uint64_t)BAND_CAP * sizeof(uint2);
+    return r3_reserve(c, &c->d_scratch, &c->scratch_cap, need, 1, false, false);
+}
+
+static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, bool depth_only, int pass, float ox, float oy, float vw, float vh,
+                      int x0, int y0, int x1, int y1, uint32_t pitch) {
+    const r3_jobs* j = ds.jobs;
+    R3_TRY(ensure_raster_scratch(c));
+    uint32_t* counters = (uint32_t*)c->d_scratch;
+    SubTri* large = (SubTri*)((uint8_t*)c->d_scratch + 64);
+    uint2* bands = (uint2*)((uint8_t*)large + (size_t)LARGE_CAP * sizeof(SubTri));
+    R3_CUDA(c, cudaMemsetAsync(counters, 0, 64, c->stream));
+    R3_TRY(r3_reserve_t(c, &cam->d_block_sums, &cam->block_sums_cap, (uint64_t)j->n_regions + 2));
+    region_prefix_kernel<<<1, 1024, 0, c->stream>>>(j->d_regions, ds.calls, j->n_regions, cam->d_block_sums);
+    R3_CHECK_LAUNCH(c, "region_prefix_kernel");
+
+    RasterParams p;
+    p.batches = j->d_batches; p.regions = j->d_regions; p.n_regions = j->n_regions;
+    p.calls = ds.calls; p.indices = ds.indices; p.index_elems = ds.index_elems; p.tri_prefix = cam->d_block_sums;
+    p.objects = c->d_objects; p.n_slots = c->n_slots; p.matrices = cam->d_matrices; p.matrices_cap = cam->matrices_cap;
+    p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;
+    p.ox = ox; p.oy = oy; p.vw = vw; p.vh = vh; p.x0 = x0; p.y0 = y0; p.x1 = x1; p.y1 = y1; p.pitch = pitch;
+    p.positive_visible = (cam->header.flags & R3_PCU_POSITIVE_AREA_VISIBLE) ? 1 : 0;
+    p.vis = c->d_vis; p.pass_bit = (uint32_t)pass; p.depth_bits = (uint32_t*)c->d_atlas;
+    p.large = large; p.bands = bands; p.counters = counters; p.stats = depth_only ? nullptr : c->d_stats;
+    p.records = nullptr;
+    if (!depth_only) {
+        // one record slot per listed triangle; the listed total is bounded by the partition size
+        const uint64_t max_tris = (uint64_t)j->total_invocations;
+        if (max_tris >= (1ull << 31)) return r3_fail(c, R3_E_INVALID, "more than 2^31 triangles in one pass");
+        R3_TRY(r3_reserve_t(c, &c->d_tris[pass], &c->tris_cap[pass], max_tris + 1));
+        c->n_tris[pass] = max_tris;
+        p.records = c->d_tris[pass];
+    }
+    const int grid = R3_SM_COUNT * 8;
+    if (depth_only) raster_setup_kernel<true><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    else raster_setup_kernel<false><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    R3_CHECK_LAUNCH(c, "raster_setup_kernel");
+    if (depth_only) raster_band_kernel<true><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    else raster_band_kernel<false><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    R3_CHECK_LAUNCH(c, "raster_band_kernel");
+    return R3_OK;
+}
+
+R3_EXPORT int r3_forward_pass(r3_ctx* c, int source) {
+    if (!c || !c->d_vis) return r3_fail(c, R3_E_STATE, "forward_pass before set_render_target");
+    cudaSetDevice(c->device);
+    r3_camera* cam = &c->cams[0];
+    DrawSource ds;
+    if (source == 0) {
+        if (cam->cache_idx < 0) return R3_OK;                                   // forward.rs:224-231
+        if (!draw_source_for(cam, cam->cache_idx, 0, &ds)) return R3_OK;        // Output partition, pre-swap (forward.rs:251)
+    } else {
+        if (!cam->has_draw_call_set) return R3_OK;                              // forward.rs:212-216
+        if (!draw_source_for(cam, cam->cur, 1, &ds)) return R3_OK;              // Input partition, post-swap
+    }
+    R3_TRY(run_raster(c, cam, ds, false, source ? 1 : 0, 0.0f, 0.0f, (float)c->width, (float)c->height, 0, (int)c->row_begin, (int)c->width,
+                      (int)c->row_end, c->width));
+    if (source == 1) cam->cache_idx = cam->cur;                                 // draw_call_set_cache.insert (forward.rs:219)
+    return R3_OK;
+}
+
+R3_EXPORT int r3_shadow_pass(r3_ctx* c, uint32_t shadow_index, uint32_t ox, uint32_t oy, uint32_t size) {
+    if (!c || !c->d_atlas) return r3_fail(c, R3_E_STATE, "shadow_pass before set_directional_lights");
+    if (shadow_index >= R3_MAX_SHADOWS) return r3_fail(c, R3_E_INVALID, "bad shadow index");
+    if ((uint64_t)ox + size > c->atlas_w || (uint64_t)oy + size > c->atlas_h) return r3_fail(c, R3_E_INVALID, "shadow viewport outside the atlas");
+    cudaSetDevice(c->device);
+    r3_camera* cam = &c->cams[shadow_index + 1];
+    DrawSource ds;
+    if (!cam->has_draw_call_set || !draw_source_for(cam, cam->cur, 0, &ds)) return R3_OK;
+    return run_raster(c, cam, ds, true, 0, (float)ox, (float)oy, (float)size, (float)size, (int)ox, (int)oy, (int)(ox + size), (int)(oy + size), c->atlas_w);
+}

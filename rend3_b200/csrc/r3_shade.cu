@@ -1,0 +1,466 @@
+// r3_shade.cu — deferred fs_main over the visibility buffer, hi-Z pyramid, HDR->LDR blit, render targets.
+//
+// Replaces (reference paths):
+//   * opaque.wgsl::vs_main outputs + fs_main + surface_shading   rend3-routine/shaders/src/opaque.wgsl:91-135,203-551
+//     BRDF terms math/brdf.wgsl:3-33, PCF5 shadow/pcf.wgsl:1-9, sRGB decode math/color.wgsl:3-9
+//   * hi_z.wgsl::fs_main min-downsample chain                    rend3-routine/src/hi_z.rs:161-234, hi_z.wgsl:18-33
+//   * blit.wgsl fs_main_scene / fs_main_monitor                  rend3-routine/src/tonemapping.rs:108-147, blit.wgsl:21-31
+//
+// The resolve kernel runs fs_main ONCE per covered pixel: it reads the 64-bit visibility key, fetches the
+// winning triangle's 64-byte record, re-runs the vertex stage for its three vertices (vertex pulling from the
+// mesh megabuffer), interpolates with perspective-correct weights (raster rule R6) and shades.  Lights are
+// staged in shared memory per CTA after a one-block "light prep" kernel has moved them to view space
+// (view_mat3 * -direction, view * position, light.view_proj * inv_view) — work the WGSL repeats per fragment.
+// This translation unit is compiled WITH fused multiply-add: shaded pixels are checked to 1e-4, not bit-exact.
+#include <cuda_fp16.h>
+
+#include "r3_common.cuh"
+
+namespace {
+
+constexpr float R3_PI = 3.14159265359f;   // math/consts.wgsl:1
+constexpr int MAX_SMEM_DIR = 8, MAX_SMEM_POINT = 128;
+
+struct DirPrep { float lm[16]; float l[3]; float color[3]; float inv_res[2]; float offset[2]; float size[2]; float _pad[4]; };   // 32 floats
+struct PointPrep { float pos[3]; float radius; float color[3]; float _pad; };                                                     // 8 floats
+static_assert(sizeof(DirPrep) == 128 && sizeof(PointPrep) == 32, "prep layouts");
+
+struct ShadeParams {
+    const unsigned long long* vis;
+    const r3_tri_record* tris0; const r3_tri_record* tris1; unsigned long long n_tris0, n_tris1;
+    const r3_object* objects; const r3_object_matrices* matrices;
+    const uint32_t* mesh; uint64_t mesh_words;
+    const r3_material* materials; uint32_t n_materials;
+    const DirPrep* dir; uint32_t n_dir; const PointPrep* point; uint32_t n_point;
+    const float* atlas; uint32_t atlas_w, atlas_h;
+    float ambient[4]; float clear[4];
+    uint32_t width, height, row_begin, row_end;
+    float4* hdr32; uint2* hdr16; float* depth;
+    unsigned long long* stats;
+};
+
+__device__ __forceinline__ uint32_t mesh_word(const ShadeParams& p, uint64_t i) { return i < p.mesh_words ? __ldg(&p.mesh[i]) : 0u; }
+__device__ __forceinline__ float3 fetch3(const ShadeParams& p, uint32_t byte_off, uint32_t vid) {
+    const uint64_t f = (uint64_t)(byte_off >> 2) + (uint64_t)vid * 3u;
+    return make_float3(__uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));
+}
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 normalize3(float3 a) { const float r = rsqrtf(dot3(a, a)); return make_float3(a.x * r, a.y * r, a.z * r); }
+__device__ __forceinline__ float saturate(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+__device__ __forceinline__ float srgb_to_linear(float e) { return e > 0.04045f ? powf((e + 0.055f) / 1.055f, 2.4f) : e / 12.92f; }
+
+struct Pixel { float3 diffuse, f0, normal; float roughness; };
+
+// surface_shading (opaque.wgsl:440-468) with brdf_d_ggx / brdf_f_schlick / brdf_v_smith_ggx_correlated / brdf_fd_lambert
+__device__ __forceinline__ float3 surface_shading(const float3 l, const float3 intensity, const Pixel& px, const float3 v, float occlusion) {
+    const float3 h = normalize3(make_float3(v.x + l.x, v.y + l.y, v.z + l.z));
+    const float nov = fabsf(dot3(px.normal, v)) + 0.00001f;
+    const float nol = saturate(dot3(px.normal, l));
+    const float noh = saturate(dot3(px.normal, h));
+    const float loh = saturate(dot3(l, h));
+    const float f90 = saturate((px.f0.x + px.f0.y + px.f0.z) * 16.5f);
+    const float a = px.roughness, a2 = a * a;
+    const float fd = (noh * a2 - noh) * noh + 1.0f;
+    const float d = a2 / (R3_PI * fd * fd);
+    const float om = 1.0f - loh, om2 = om * om, pw = om2 * om2 * om;   // pow(1 - loh, 5)
+    const float3 f = make_float3(px.f0.x + (f90 - px.f0.x) * pw, px.f0.y + (f90 - px.f0.y) * pw, px.f0.z + (f90 - px.f0.z) * pw);
+    const float ggxl = nov * sqrtf((-nol * a2 + nol) * nol + a2);
+    const float ggxv = nol * sqrtf((-nov * a2 + nov) * nov + a2);
+    const float vis = 0.5f / (ggxl + ggxv);
+    const float dv = d * vis;
+    const float inv_pi = 1.0f / R3_PI, s = nol * occlusion;
+    return make_float3((px.diffuse.x * inv_pi + dv * f.x) * intensity.x * s, (px.diffuse.y * inv_pi + dv * f.y) * intensity.y * s,
+                       (px.diffuse.z * inv_pi + dv * f.z) * intensity.z * s);
+}
+
+// textureSampleCompareLevel: linear, GreaterEqual, Repeat-addressed comparison sampler (common/samplers.rs:24,42-56)
+__device__ __forceinline__ float sample_compare(const ShadeParams& p, float u, float v, float ref, int ox, int oy) {
+    const float x = u * (float)p.atlas_w + (float)ox - 0.5f, y = v * (float)p.atlas_h + (float)oy - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y), fx = x - fx0, fy = y - fy0;
+    const long long W = p.atlas_w, H = p.atlas_h, ix = (long long)fx0, iy = (long long)fy0;
+    const long long x0 = ((ix % W) + W) % W, x1 = (((ix + 1) % W) + W) % W, y0 = ((iy % H) + H) % H, y1 = (((iy + 1) % H) + H) % H;
+    const float c00 = ref >= __ldg(&p.atlas[y0 * W + x0]) ? 1.0f : 0.0f, c10 = ref >= __ldg(&p.atlas[y0 * W + x1]) ? 1.0f : 0.0f;
+    const float c01 = ref >= __ldg(&p.atlas[y1 * W + x0]) ? 1.0f : 0.0f, c11 = ref >= __ldg(&p.atlas[y1 * W + x1]) ? 1.0f : 0.0f;
+    const float top = c00 * (1.0f - fx) + c10 * fx, bot = c01 * (1.0f - fx) + c11 * fx;
+    return top * (1.0f - fy) + bot * fy;
+}
+__device__ __forceinline__ float shadow_pcf5(const ShadeParams& p, float u, float v, float depth) {   // shadow/pcf.wgsl:1-9
+    float r = sample_compare(p, u, v, depth, 0, 0);
+    r += sample_compare(p, u, v, depth, 0, 1);
+    r += sample_compare(p, u, v, depth, 0, -1);
+    r += sample_compare(p, u, v, depth, 1, 0);
+    r += sample_compare(p, u, v, depth, -1, 0);
+    return r * 0.2f;
+}
+
+struct VsOut { float4 view_position; float3 normal; float4 color; };
+// vs_main for one vertex (opaque.wgsl:114-134) + get_vertices defaults (rend3/src/shader.rs:249-316)
+__device__ __forceinline__ VsOut vertex_stage(const ShadeParams& p, const uint32_t* attr_offset, const float* __restrict__ mv, const float3 iss, uint32_t vid) {
+    VsOut o;
+    const float3 pos = fetch3(p, attr_offset[0], vid);
+    float3 n = make_float3(0.f, 0.f, 0.f);
+    if (attr_offset[1] != R3_ATTR_ABSENT) n = fetch3(p, attr_offset[1], vid);
+    o.color = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (attr_offset[5] != R3_ATTR_ABSENT) {   // unpack4x8unorm
+        const uint32_t w = mesh_word(p, (uint64_t)(attr_offset[5] >> 2) + vid);
+        o.color = make_float4((float)(w & 0xFFu) / 255.0f, (float)((w >> 8) & 0xFFu) / 255.0f, (float)((w >> 16) & 0xFFu) / 255.0f, (float)(w >> 24) / 255.0f);
+    }
+    o.view_position = make_float4(mv[0] * pos.x + mv[4] * pos.y + mv[8] * pos.z + mv[12], mv[1] * pos.x + mv[5] * pos.y + mv[9] * pos.z + mv[13],
+                                  mv[2] * pos.x + mv[6] * pos.y + mv[10] * pos.z + mv[14], mv[3] * pos.x + mv[7] * pos.y + mv[11] * pos.z + mv[15]);
+    const float3 sn = make_float3(iss.x * n.x, iss.y * n.y, iss.z * n.z);
+    o.normal = normalize3(make_float3(mv[0] * sn.x + mv[4] * sn.y + mv[8] * sn.z, mv[1] * sn.x + mv[5] * sn.y + mv[9] * sn.z, mv[2] * sn.x + mv[6] * sn.y + mv[10] * sn.z));
+    return o;
+}
+
+__global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ ShadeParams p) {
+    __shared__ DirPrep s_dir[MAX_SMEM_DIR];
+    __shared__ PointPrep s_point[MAX_SMEM_POINT];
+    {
+        const uint32_t nd = min(p.n_dir, (uint32_t)MAX_SMEM_DIR) * 32u, np = min(p.n_point, (uint32_t)MAX_SMEM_POINT) * 8u;
+        const float* gd = reinterpret_cast<const float*>(p.dir); const float* gp = reinterpret_cast<const float*>(p.point);
+        float* sd = reinterpret_cast<float*>(s_dir); float* sp = reinterpret_cast<float*>(s_point);
+        for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) sd[i] = gd[i];
+        for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) sp[i] = gp[i];
+        __syncthreads();
+    }
+    // CTA = 32 x 8 pixels: a warp is 32 consecutive pixels of one row (coalesced key reads / colour writes)
+    const uint32_t px = blockIdx.x * 32u + (threadIdx.x & 31u), py = p.row_begin + blockIdx.y * 8u + (threadIdx.x >> 5);
+    if (px >= p.width || py >= p.row_end) return;
+    const size_t pi = (size_t)py * p.width + px;
+    const unsigned long long key = p.vis[pi];
+    const uint32_t rec = (uint32_t)(key & 0x7FFFFFFFull), pass = (uint32_t)((key >> 31) & 1ull);
+    float4 out = make_float4(p.clear[0], p.clear[1], p.clear[2], p.clear[3]);
+    const unsigned long long n_tris = pass ? p.n_tris1 : p.n_tris0;
+    bool shaded = false;
+    if (rec != 0u && rec <= n_tris) {
+        shaded = true;
+        const r3_tri_record* tp = (pass ? p.tris1 : p.tris0) + (rec - 1u);
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp)), q1 = __ldg(reinterpret_cast<const float4*>(tp) + 1),
+                     q2 = __ldg(reinterpret_cast<const float4*>(tp) + 2);
+        const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(tp) + 3);
+        // xyw[3][3] = q0.xyz | q0.w q1.xy | q1.zw q2.x ; object_id = q2.y ; vid = q2.z q2.w q3.x
+        const float3 p0 = make_float3(q0.x, q0.y, q0.z), p1 = make_float3(q0.w, q1.x, q1.y), p2 = make_float3(q1.z, q1.w, q2.x);
+        const uint32_t oid = __float_as_uint(q2.y), vid0 = __float_as_uint(q2.z), vid1 = __float_as_uint(q2.w), vid2 = q3.x;
+        // R6: perspective-correct weights b_i ~ cross(p_j, p_k) . (ndc_x, ndc_y, 1)
+        const float nx = ((float)px + 0.5f) / ((float)p.width * 0.5f) - 1.0f, ny = 1.0f - ((float)py + 0.5f) / ((float)p.height * 0.5f);
+        float b0 = (p1.y * p2.z - p1.z * p2.y) * nx + (p1.z * p2.x - p1.x * p2.z) * ny + (p1.x * p2.y - p1.y * p2.x);
+        float b1 = (p2.y * p0.z - p2.z * p0.y) * nx + (p2.z * p0.x - p2.x * p0.z) * ny + (p2.x * p0.y - p2.y * p0.x);
+        float b2 = (p0.y * p1.z - p0.z * p1.y) * nx + (p0.z * p1.x - p0.x * p1.z) * ny + (p0.x * p1.y - p0.y * p1.x);
+        const float inv_sum = 1.0f / (b0 + b1 + b2);
+        b0 *= inv_sum; b1 *= inv_sum; b2 *= inv_sum;
+
+        const r3_object* obj = &p.objects[oid];
+        const uint4 oa = __ldg(reinterpret_cast<const uint4*>(obj) + 5);   // bytes 80..95 : first_index, index_count, material_index, attr[0]
+        const uint4 ob = __ldg(reinterpret_cast<const uint4*>(obj) + 6);   // bytes 96..111: attr[1..4]
+        const uint4 oc = __ldg(reinterpret_cast<const uint4*>(obj) + 7);   // bytes 112..127: attr[5], enabled
+        const uint32_t attr[6] = {oa.w, ob.x, ob.y, ob.z, ob.w, oc.x};
+        const uint32_t material_index = oa.z;
+        float mv[16];
+        {
+            const float4* m4 = reinterpret_cast<const float4*>(p.matrices[oid].model_view);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float4 c4 = __ldg(&m4[k]); mv[4 * k] = c4.x; mv[4 * k + 1] = c4.y; mv[4 * k + 2] = c4.z; mv[4 * k + 3] = c4.w; }
+        }
+        const float3 iss = make_float3(1.0f / (mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]), 1.0f / (mv[4] * mv[4] + mv[5] * mv[5] + mv[6] * mv[6]),
+                                       1.0f / (mv[8] * mv[8] + mv[9] * mv[9] + mv[10] * mv[10]));   // math/matrix.wgsl:1-7
+        const VsOut v0 = vertex_stage(p, attr, mv, iss, vid0), v1 = vertex_stage(p, attr, mv, iss, vid1), v2 = vertex_stage(p, attr, mv, iss, vid2);
+        const float4 vp = make_float4(b0 * v0.view_position.x + b1 * v1.view_position.x + b2 * v2.view_position.x,
+                                      b0 * v0.view_position.y + b1 * v1.view_position.y + b2 * v2.view_position.y,
+                                      b0 * v0.view_position.z + b1 * v1.view_position.z + b2 * v2.view_position.z,
+                                      b0 * v0.view_position.w + b1 * v1.view_position.w + b2 * v2.view_position.w);
+        const float3 vnormal = make_float3(b0 * v0.normal.x + b1 * v1.normal.x + b2 * v2.normal.x, b0 * v0.normal.y + b1 * v1.normal.y + b2 * v2.normal.y,
+                                           b0 * v0.normal.z + b1 * v1.normal.z + b2 * v2.normal.z);
+        const float4 vcolor = make_float4(b0 * v0.color.x + b1 * v1.color.x + b2 * v2.color.x, b0 * v0.color.y + b1 * v1.color.y + b2 * v2.color.y,
+                                          b0 * v0.color.z + b1 * v1.color.z + b2 * v2.color.z, b0 * v0.color.w + b1 * v1.color.w + b2 * v2.color.w);
+
+        // get_pixel_data_inner for untextured materials (opaque.wgsl:203-424)
+        const r3_material* m = &p.materials[material_index < p.n_materials ? material_index : 0u];
+        const float4 malbedo = __ldg(reinterpret_cast<const float4*>(m->albedo));
+        const float4 mA = __ldg(reinterpret_cast<const float4*>(m->emissive));        // emissive.xyz, roughness
+        const float4 mB = __ldg(reinterpret_cast<const float4*>(&m->metallic));       // metallic, reflectance, clear_coat, clear_coat_roughness
+        const float4 mC = __ldg(reinterpret_cast<const float4*>(&m->anisotropy));     // anisotropy, ambient_occlusion, alpha_cutout, flags
+        const uint32_t flags = __float_as_uint(mC.w);
+        float4 albedo = make_float4(0.f, 0.f, 0.f, 1.f);
+        if (flags & R3_MAT_ALBEDO_ACTIVE) {
+            albedo = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (flags & R3_MAT_ALBEDO_BLEND) {
+                if (flags & R3_MAT_ALBEDO_VERTEX_SRGB) albedo = make_float4(srgb_to_linear(vcolor.x), srgb_to_linear(vcolor.y), srgb_to_linear(vcolor.z), vcolor.w);
+                else albedo = vcolor;
+            }
+        }
+        albedo = make_float4(albedo.x * malbedo.x, albedo.y * malbedo.y, albedo.z * malbedo.z, albedo.w * malbedo.w);
+        if (flags & R3_MAT_UNLIT) {
+            out = albedo;                                                             // opaque.wgsl:476-478
+        } else {
+            Pixel pxl;
+            pxl.normal = normalize3(vnormal);
+            const float ao = mC.y, metallic = mB.x, reflectance = mB.y, clear_coat = mB.z, cc_rough = mB.w;
+            float perceptual = mA.w;
+            const float om = 1.0f - metallic;
+            pxl.diffuse = make_float3(albedo.x * om, albedo.y * om, albedo.z * om);
+            const float rterm = (0.16f * reflectance * reflectance) * om;
+            pxl.f0 = make_float3(albedo.x * metallic + rterm, albedo.y * metallic + rterm, albedo.z * metallic + rterm);
+            if (clear_coat != 0.0f) {
+                const float base = fmaxf(perceptual, cc_rough);
+                perceptual = perceptual * (1.0f - clear_coat) + base * clear_coat;
+            }
+            pxl.roughness = perceptual * perceptual;
+            const float3 nvp = normalize3(make_float3(vp.x, vp.y, vp.z));
+            const float3 v = make_float3(-nvp.x, -nvp.y, -nvp.z);
+            float3 color = make_float3(mA.x, mA.y, mA.z);
+            for (uint32_t i = 0; i < p.n_dir; ++i) {                                   // opaque.wgsl:487-522
+                const DirPrep& L = i < MAX_SMEM_DIR ? s_dir[i] : p.dir[i];
+                const float snx = L.lm[0] * vp.x + L.lm[4] * vp.y + L.lm[8] * vp.z + L.lm[12] * vp.w;
+                const float sny = L.lm[1] * vp.x + L.lm[5] * vp.y + L.lm[9] * vp.z + L.lm[13] * vp.w;
+                const float snz = L.lm[2] * vp.x + L.lm[6] * vp.y + L.lm[10] * vp.z + L.lm[14] * vp.w;
+                const float flx = snx * 0.5f + 0.5f, fly = sny * 0.5f + 0.5f, locy = 1.0f - fly;
+                float tlx = L.offset[0], tly = L.offset[1], trx = tlx + L.size[0], try_ = tly + L.size[1];
+                const float cu = tlx * (1.0f - flx) + trx * flx, cv = tly * (1.0f - locy) + try_ * locy;
+                const float bx = L.inv_res[0] * 1.5f, by = L.inv_res[1] * 1.5f;
+                tlx += bx; tly += by; trx -= bx; try_ -= by;
+                float shadow = 1.0f;
+                if ((flx >= tlx || fly >= tly) && (flx <= trx || fly <= try_) && snz >= 0.0f && snz <= 1.0f)   // literal any() quirk (opaque.wgsl:509-514)
+                    shadow = shadow_pcf5(p, cu, cv, snz);
+                const float3 s = surface_shading(make_float3(L.l[0], L.l[1], L.l[2]), make_float3(L.color[0], L.color[1], L.color[2]), pxl, v, shadow * ao);
+                color.x += s.x; color.y += s.y; color.z += s.z;
+            }
+            for (uint32_t i = 0; i < p.n_point; ++i) {                                 // opaque.wgsl:524-546
+                const PointPrep& L = i < MAX_SMEM_POINT ? s_point[i] : p.point[i];
+                const float3 delta = make_float3(L.pos[0] - vp.x, L.pos[1] - vp.y, L.pos[2] - vp.z);
+                const float d2 = dot3(delta, delta), d = sqrtf(d2);
+                const float sdist = saturate(d / L.radius), s2 = sdist * sdist, inv_s2 = 1.0f - s2;
+                const float att = inv_s2 * inv_s2 / (1.0f + s2);
+                const float inv_d = 1.0f / d;
+                const float3 s = surface_shading(make_float3(delta.x * inv_d, delta.y * inv_d, delta.z * inv_d),
+                                                 make_float3(L.color[0] * att, L.color[1] * att, L.color[2] * att), pxl, v, ao);
+                color.x += fmaxf(s.x, 0.0f); color.y += fmaxf(s.y, 0.0f); color.z += fmaxf(s.z, 0.0f);
+            }
+            out = make_float4(fmaxf(p.ambient[0] * albedo.x, color.x), fmaxf(p.ambient[1] * albedo.y, color.y), fmaxf(p.ambient[2] * albedo.z, color.z),
+                              fmaxf(p.ambient[3] * albedo.w, albedo.w));
+        }
+    }
+    p.hdr32[pi] = out;
+    const __half2 h01 = __floats2half2_rn(out.x, out.y), h23 = __floats2half2_rn(out.z, out.w);
+    p.hdr16[pi] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    p.depth[pi] = __uint_as_float((uint32_t)(key >> 32));
+    const uint32_t cnt = __popc(__ballot_sync(__activemask(), shaded));
+    if ((threadIdx.x & 31u) == 0u && cnt) atomicAdd(&p.stats[2], (unsigned long long)cnt);
+}
+
+// light prep: one thread per light (opaque.wgsl:491,519,528 hoisted out of the fragment loop)
+__global__ void light_prep_kernel(const r3_directional_light* dir, uint32_t n_dir, const r3_point_light* point, uint32_t n_point,
+                                  const __grid_constant__ r3_frame_uniforms u, DirPrep* out_dir, PointPrep* out_point) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_dir) {
+        const r3_directional_light L = dir[i];
+        DirPrep o;
+        for (int j = 0; j < 4; ++j) {   // light.view_proj * uniforms.inv_view, column j
+            const float4 c4 = mat_vec_rn(L.view_proj, u.inv_view[4 * j], u.inv_view[4 * j + 1], u.inv_view[4 * j + 2], u.inv_view[4 * j + 3]);
+            o.lm[4 * j] = c4.x; o.lm[4 * j + 1] = c4.y; o.lm[4 * j + 2] = c4.z; o.lm[4 * j + 3] = c4.w;
+        }
+        const float nx = -L.direction[0], ny = -L.direction[1], nz = -L.direction[2];
+        const float lx = u.view[0] * nx + u.view[4] * ny + u.view[8] * nz, ly = u.view[1] * nx + u.view[5] * ny + u.view[9] * nz,
+                    lz = u.view[2] * nx + u.view[6] * ny + u.view[10] * nz;
+        const float len = sqrtf(lx * lx + ly * ly + lz * lz);
+        o.l[0] = lx / len; o.l[1] = ly / len; o.l[2] = lz / len;
+        for (int k = 0; k < 3; ++k) o.color[k] = L.color[k];
+        for (int k = 0; k < 2; ++k) { o.inv_res[k] = L.inv_resolution[k]; o.offset[k] = L.atlas_offset[k]; o.size[k] = L.atlas_size[k]; }
+        o._pad[0] = o._pad[1] = o._pad[2] = o._pad[3] = 0.f;
+        out_dir[i] = o;
+    }
+    if (i < n_point) {
+        const r3_point_light L = point[i];
+        const float4 v = mat_vec_rn(u.view, L.position[0], L.position[1], L.position[2], L.position[3]);
+        PointPrep o;
+        o.pos[0] = v.x; o.pos[1] = v.y; o.pos[2] = v.z; o.radius = L.radius;
+        o.color[0] = L.color[0]; o.color[1] = L.color[1]; o.color[2] = L.color[2]; o._pad = 0.f;
+        out_point[i] = o;
+    }
+}
+
+// hi-Z: mip 0 = depth bits of the visibility buffer
+__global__ void hiz_mip0_kernel(const unsigned long long* __restrict__ vis, float* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __uint_as_float((uint32_t)(vis[i] >> 32));
+}
+// hi_z.wgsl::fs_main (:18-33): MIN over a 2x2 (+1 on odd source sizes) footprint; texels outside the source are skipped
+__global__ void hiz_downsample_kernel(const float* __restrict__ src, uint32_t sw, uint32_t sh, float* __restrict__ dst, uint32_t dw, uint32_t dh) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const uint32_t oddx = sw & 1u, oddy = sh & 1u;
+    float nearest = 1.0f;
+    for (uint32_t dx = 0; dx < 2u + oddx; ++dx)
+        for (uint32_t dy = 0; dy < 2u + oddy; ++dy) {
+            const uint32_t sx = 2u * x + dx, sy = 2u * y + dy;
+            if (sx < sw && sy < sh) nearest = fminf(nearest, src[(size_t)sy * sw + sx]);
+        }
+    dst[(size_t)y * dw + x] = nearest;
+}
+
+// blit.wgsl: fs_main_scene into an *Srgb target (exact OETF) or fs_main_monitor (x^0.4166 approximation)
+__global__ void tonemap_kernel(const uint2* __restrict__ hdr16, uchar4* __restrict__ ldr, size_t n, int srgb_target) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 h = hdr16[i];
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+    const float in[4] = {a.x, a.y, b.x, b.y};
+    uint8_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float x = in[k];
+        float e;
+        if (k == 3) e = x;
+        else if (srgb_target) e = x <= 0.0031308f ? x * 12.92f : 1.055f * powf(x, 1.0f / 2.4f) - 0.055f;
+        else e = x > 0.0031308f ? 1.055f * powf(x, 0.4166f) - 0.055f : x * 12.92f;
+        e = fminf(fmaxf(e, 0.0f), 1.0f);
+        o[k] = (uint8_t)floorf(e * 255.0f + 0.5f);
+    }
+    ldr[i] = make_uchar4(o[0], o[1], o[2], o[3]);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host side
+R3_EXPORT int r3_set_render_target(r3_ctx* c, uint32_t w, uint32_t h, uint32_t samples, const float clear[4]) {
+    if (!c || !w || !h || !clear) return r3_fail(c, R3_E_INVALID, "set_render_target: bad arguments");
+    if (samples != 1) return r3_fail(c, R3_E_INVALID, "only SampleCount::One is implemented");
+    cudaSetDevice(c->device);
+    if (w != c->width || h != c->height || !c->d_vis) {
+        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_vis); cudaFree(c->d_hdr32); cudaFree(c->d_hdr16); cudaFree(c->d_depth); cudaFree(c->d_ldr);
+        for (float* p : c->d_hiz) cudaFree(p);
+        c->d_hiz.clear(); c->hiz_w.clear(); c->hiz_h.clear();
+        cudaFree(c->d_hiz_ptrs); cudaFree(c->d_hiz_dims);
+        c->d_vis = nullptr; c->d_hdr32 = nullptr; c->d_hdr16 = nullptr; c->d_depth = nullptr; c->d_ldr = nullptr; c->d_hiz_ptrs = nullptr; c->d_hiz_dims = nullptr;
+        const size_t n = (size_t)w * h;
+        R3_CUDA(c, cudaMalloc((void**)&c->d_vis, n * 8));
+        R3_CUDA(c, cudaMalloc((void**)&c->d_hdr32, n * 16));
+        R3_CUDA(c, cudaMalloc((void**)&c->d_hdr16, n * 8));
+        R3_CUDA(c, cudaMalloc((void**)&c->d_depth, n * 4));
+        R3_CUDA(c, cudaMalloc((void**)&c->d_ldr, n * 4));
+        R3_CUDA(c, cudaMemsetAsync(c->d_vis, 0, n * 8, c->stream));
+        // single_sample_mipped depth, cleared to 0.0 (base.rs:256-263, hi_z.rs:170-171)
+        uint32_t m = w > h ? w : h, mips = 0;
+        while (m) { mips++; m >>= 1; }
+        std::vector<uint32_t> dims;
+        for (uint32_t i = 0; i < mips; ++i) {
+            const uint32_t mw = (w >> i) ? (w >> i) : 1u, mh = (h >> i) ? (h >> i) : 1u;
+            float* p = nullptr;
+            R3_CUDA(c, cudaMalloc((void**)&p, (size_t)mw * mh * 4));
+            R3_CUDA(c, cudaMemsetAsync(p, 0, (size_t)mw * mh * 4, c->stream));
+            c->d_hiz.push_back(p); c->hiz_w.push_back(mw); c->hiz_h.push_back(mh);
+            dims.push_back(mw); dims.push_back(mh);
+        }
+        R3_CUDA(c, cudaMalloc((void**)&c->d_hiz_ptrs, mips * sizeof(float*)));
+        R3_CUDA(c, cudaMalloc((void**)&c->d_hiz_dims, mips * 8));
+        R3_CUDA(c, cudaMemcpyAsync(c->d_hiz_ptrs, c->d_hiz.data(), mips * sizeof(float*), cudaMemcpyHostToDevice, c->stream));
+        R3_CUDA(c, cudaMemcpyAsync(c->d_hiz_dims, dims.data(), mips * 8, cudaMemcpyHostToDevice, c->stream));
+        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    c->width = w; c->height = h; c->samples = samples;
+    memcpy(c->clear_color, clear, 16);
+    c->row_begin = 0; c->row_end = h;
+    return R3_OK;
+}
+R3_EXPORT int r3_set_scissor_rows(r3_ctx* c, uint32_t a, uint32_t b) {
+    if (!c || a > b || b > c->height) return r3_fail(c, R3_E_INVALID, "set_scissor_rows: bad range");
+    c->row_begin = a; c->row_end = b;
+    return R3_OK;
+}
+R3_EXPORT int r3_clear_shadow_atlas(r3_ctx* c) {
+    if (!c) return R3_E_INVALID;
+    cudaSetDevice(c->device);
+    if (c->d_atlas) R3_CUDA(c, cudaMemsetAsync(c->d_atlas, 0, (size_t)c->atlas_w * c->atlas_h * 4, c->stream));
+    return R3_OK;
+}
+R3_EXPORT int r3_forward_begin(r3_ctx* c) {
+    if (!c || !c->d_vis) return r3_fail(c, R3_E_STATE, "forward_begin before set_render_target");
+    cudaSetDevice(c->device);
+    R3_CUDA(c, cudaMemsetAsync(c->d_vis, 0, (size_t)c->width * c->height * 8, c->stream));
+    R3_CUDA(c, cudaMemsetAsync(c->d_stats, 0, 32, c->stream));
+    c->n_tris[0] = c->n_tris[1] = 0;
+    return R3_OK;
+}
+R3_EXPORT int r3_hiz_build(r3_ctx* c) {
+    if (!c || !c->d_vis || c->d_hiz.empty()) return r3_fail(c, R3_E_STATE, "hiz_build before set_render_target");
+    cudaSetDevice(c->device);
+    const size_t n = (size_t)c->width * c->height;
+    hiz_mip0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vis, c->d_hiz[0], n);
+    R3_CHECK_LAUNCH(c, "hiz_mip0_kernel");
+    for (size_t m = 1; m < c->d_hiz.size(); ++m) {
+        const dim3 block(32, 8), grid((c->hiz_w[m] + 31) / 32, (c->hiz_h[m] + 7) / 8);
+        hiz_downsample_kernel<<<grid, block, 0, c->stream>>>(c->d_hiz[m - 1], c->hiz_w[m - 1], c->hiz_h[m - 1], c->d_hiz[m], c->hiz_w[m], c->hiz_h[m]);
+        R3_CHECK_LAUNCH(c, "hiz_downsample_kernel");
+    }
+    return R3_OK;
+}
+R3_EXPORT int r3_forward_resolve(r3_ctx* c) {
+    if (!c || !c->d_vis) return r3_fail(c, R3_E_STATE, "forward_resolve before set_render_target");
+    if (!c->uniforms_set) return r3_fail(c, R3_E_STATE, "forward_resolve before set_frame_uniforms");
+    cudaSetDevice(c->device);
+    r3_camera* cam = &c->cams[0];
+    const uint64_t need_floats = (uint64_t)c->n_dir * 32 + (uint64_t)c->n_point * 8 + 64;
+    static_assert(sizeof(DirPrep) == 32 * 4 && sizeof(PointPrep) == 8 * 4, "prep sizes");
+    R3_TRY(r3_reserve_t(c, &c->d_light_mats, &c->light_mats_cap, need_floats));
+    float* prep = c->d_light_mats;
+    DirPrep* d_dir = reinterpret_cast<DirPrep*>(prep);
+    PointPrep* d_point = reinterpret_cast<PointPrep*>(prep + (size_t)c->n_dir * 32);
+    const uint32_t nl = c->n_dir > c->n_point ? c->n_dir : c->n_point;
+    if (nl) {
+        light_prep_kernel<<<(nl + 127) / 128, 128, 0, c->stream>>>(c->d_dir, c->n_dir, c->d_point, c->n_point, c->uniforms, d_dir, d_point);
+        R3_CHECK_LAUNCH(c, "light_prep_kernel");
+    }
+    ShadeParams p;
+    p.vis = c->d_vis;
+    p.tris0 = c->d_tris[0]; p.tris1 = c->d_tris[1]; p.n_tris0 = c->n_tris[0]; p.n_tris1 = c->n_tris[1];
+    p.objects = c->d_objects; p.matrices = cam->d_matrices; p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;
+    p.materials = c->d_materials; p.n_materials = c->n_materials;
+    p.dir = d_dir; p.n_dir = c->n_dir; p.point = d_point; p.n_point = c->n_point;
+    p.atlas = c->d_atlas; p.atlas_w = c->atlas_w; p.atlas_h = c->atlas_h;
+    memcpy(p.ambient, c->uniforms.ambient, 16); memcpy(p.clear, c->clear_color, 16);
+    p.width = c->width; p.height = c->height; p.row_begin = c->row_begin; p.row_end = c->row_end;
+    p.hdr32 = reinterpret_cast<float4*>(c->d_hdr32); p.hdr16 = reinterpret_cast<uint2*>(c->d_hdr16); p.depth = c->d_depth; p.stats = c->d_stats;
+    const uint32_t rows = c->row_end - c->row_begin;
+    if (rows) {
+        const dim3 grid((c->width + 31) / 32, (rows + 7) / 8);
+        resolve_kernel<<<grid, 256, 0, c->stream>>>(p);
+        R3_CHECK_LAUNCH(c, "resolve_kernel");
+    }
+    return R3_OK;
+}
+R3_EXPORT int r3_tonemap(r3_ctx* c, int srgb_target) {
+    if (!c || !c->d_hdr16) return r3_fail(c, R3_E_STATE, "tonemap before set_render_target");
+    cudaSetDevice(c->device);
+    const size_t n = (size_t)c->width * c->height;
+    tonemap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint2*>(c->d_hdr16), reinterpret_cast<uchar4*>(c->d_ldr), n, srgb_target);
+    R3_CHECK_LAUNCH(c, "tonemap_kernel");
+    return R3_OK;
+}
+
+static int copy_out(r3_ctx* c, const void* src, void* out, uint64_t cap, uint64_t count, size_t elem) {
+    if (!src) return r3_fail(c, R3_E_STATE, "readback before the stage ran");
+    if (!out || cap < count) return r3_fail(c, R3_E_INVALID, "readback: capacity too small");
+    cudaSetDevice(c->device);
+    R3_CUDA(c, cudaMemcpyAsync(out, src, count * elem, cudaMemcpyDeviceToHost, c->stream));
+    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    return R3_OK;
+}
+R3_EXPORT int r3_readback_hdr_f32(r3_ctx* c, float* out, uint64_t cap) { return c ? copy_out(c, c->d_hdr32, out, cap, (uint64_t)c->width * c->height * 4, 4) : R3_E_INVALID; }
+R3_EXPORT int r3_readback_hdr_f16(r3_ctx* c, uint16_t* out, uint64_t cap) { return c ? copy_out(c, c->d_hdr16, out, cap, (uint64_t)c->width * c->height * 4, 2) : R3_E_INVALID; }
+R3_EXPORT int r3_readback_depth(r3_ctx* c, float* out, uint64_t cap) { return c ? copy_out(c, c->d_depth, out, cap, (uint64_t)c->width * c->height, 4) : R3_E_INVALID; }
+R3_EXPORT int r3_readback_ldr(r3_ctx* c, uint8_t* out, uint64_t cap) { return c ? copy_out(c, c->d_ldr, out, cap, (uint64_t)c->width * c->height * 4, 1) : R3_E_INVALID; }
+R3_EXPORT int r3_readback_shadow_atlas(r3_ctx* c, float* out, uint64_t cap) { return c ? copy_out(c, c->d_atlas, out, cap, (uint64_t)c->atlas_w * c->atlas_h, 4) : R3_E_INVALID; }
+R3_EXPORT int r3_readback_hiz(r3_ctx* c, uint32_t mip, float* out, uint64_t cap, uint32_t* w, uint32_t* h) {
+    if (!c || mip >= c->d_hiz.size()) return r3_fail(c, R3_E_INVALID, "readback_hiz: mip");
+    if (w) *w = c->hiz_w[mip];
+    if (h) *h = c->hiz_h[mip];
+    if (!out) return R3_OK;
+    return copy_out(c, c->d_hiz[mip], out, cap, (uint64_t)c->hiz_w[mip] * c->hiz_h[mip], 4);
+}
+R3_EXPORT int r3_forward_stats(r3_ctx* c, uint64_t stats[4]) {
+    if (!c || !stats) return R3_E_INVALID;
+    cudaSetDevice(c->device);
+    R3_CUDA(c, cudaMemcpyAsync(stats, c->d_stats, 32, cudaMemcpyDeviceToHost, c->stream));
+    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    return R3_OK;
+}

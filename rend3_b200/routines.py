@@ -121,14 +121,17 @@ class BaseRenderGraph:
 
     def add_to_graph(self, ev: EvalOutput, resolution: Tuple[int, int], samples: int = 1,
                      settings: BaseRenderGraphSettings = BaseRenderGraphSettings(), srgb_target: bool = True,
-                     upload: bool = True):
-        """One frame in the node order of base.rs:135-185."""
+                     upload: bool = True, scissor_rows: Optional[Tuple[int, int]] = None):
+        """One frame in the node order of base.rs:135-185.  `scissor_rows` restricts rasterisation and shading
+        to a band of pixel rows (the screen-tile split of the multi-GPU forward pass)."""
         b, culler = self.backend, self.gpu_culler
         if upload:
             self.upload_world(ev)
         if self._resolution != (resolution, samples, tuple(settings.clear_color)):
             b.set_render_target(resolution[0], resolution[1], samples, settings.clear_color)
             self._resolution = (resolution, samples, tuple(settings.clear_color))
+        if scissor_rows is not None:
+            b.set_scissor_rows(scissor_rows[0], scissor_rows[1])
         b.clear_shadow_atlas()                                                    # base.rs:139
         b.set_frame_uniforms(frame_uniforms(ev.camera, settings.ambient_color, resolution))  # :142
         # skinning (:145) — no animated meshes on this path

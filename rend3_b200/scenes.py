@@ -1,0 +1,184 @@
+"""Seeded synthetic scenes for the BASELINE.json configurations, built vectorised.
+
+Everything here produces the same `EvalOutput` the manager stand-in (world.py) produces, only in bulk:
+object records for 10^4..10^7 objects cannot go through per-object Python calls.  Meshes, materials,
+lights and cameras still go through `world.Renderer` so their bytes follow the same code as the tests.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import glam
+from .layouts import ATTR_ABSENT, OBJECT_DTYPE
+from .runner import cube_mesh
+from .world import LEFT, Camera, DirectionalLight, EvalOutput, MeshBuilder, PbrMaterial, PointLight, Renderer
+
+f32 = np.float32
+
+
+def random_unit_quaternions(rng: np.random.Generator, n: int) -> np.ndarray:
+    q = rng.standard_normal((n, 4)).astype(f32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True).astype(f32)
+    return q.astype(f32)
+
+
+def trs_matrices(translation: np.ndarray, quat: np.ndarray, scale: np.ndarray) -> np.ndarray:
+    """Mat4::from_scale_rotation_translation, vectorised; returns (n, 4, 4) f32 as [col][row]."""
+    x, y, z, w = (quat[:, i].astype(f32) for i in range(4))
+    x2, y2, z2 = x + x, y + y, z + z
+    xx, xy, xz = x * x2, x * y2, x * z2
+    yy, yz, zz = y * y2, y * z2, z * z2
+    wx, wy, wz = w * x2, w * y2, w * z2
+    one = f32(1.0)
+    n = len(x)
+    m = np.zeros((n, 4, 4), dtype=f32)
+    s = scale.astype(f32).reshape(n, scale.shape[1] if scale.ndim > 1 else 1)
+    if s.shape[1] == 1:
+        s = np.repeat(s, 3, axis=1)
+    m[:, 0, 0] = (one - (yy + zz)) * s[:, 0]; m[:, 0, 1] = (xy + wz) * s[:, 0]; m[:, 0, 2] = (xz - wy) * s[:, 0]
+    m[:, 1, 0] = (xy - wz) * s[:, 1]; m[:, 1, 1] = (one - (xx + zz)) * s[:, 1]; m[:, 1, 2] = (yz + wx) * s[:, 1]
+    m[:, 2, 0] = (xz + wy) * s[:, 2]; m[:, 2, 1] = (yz - wx) * s[:, 2]; m[:, 2, 2] = (one - (xx + yy)) * s[:, 2]
+    m[:, 3, :3] = translation.astype(f32)
+    m[:, 3, 3] = one
+    return m
+
+
+def bulk_object_records(renderer: Renderer, transforms: np.ndarray, mesh_ids: np.ndarray, material_ids: np.ndarray,
+                        enabled: Optional[np.ndarray] = None, capacity: Optional[int] = None):
+    """Vectorised object_add_callback (rend3/src/managers/object.rs:230-293) for n objects in slots 0..n-1.
+    Returns (records[capacity], location[capacity,3])."""
+    n = len(transforms)
+    cap = capacity or max(Renderer.STARTING_SIZE, 1 << max(n - 1, 0).bit_length())
+    rec = np.zeros(cap, dtype=OBJECT_DTYPE)
+    t = transforms.astype(f32)
+    rec["transform"][:n] = t.reshape(n, 16)
+    centers = np.array([m["center"] for m in renderer.meshes], dtype=f32)[mesh_ids]
+    radii = np.array([m["radius"] for m in renderer.meshes], dtype=f32)[mesh_ids]
+    # BoundingSphere::apply_transform (util/frustum.rs:22-32) in glam's accumulation order
+    c = t[:, 0, :3] * centers[:, 0:1]
+    c = c + t[:, 1, :3] * centers[:, 1:2]
+    c = c + t[:, 2, :3] * centers[:, 2:3]
+    c = (c + t[:, 3, :3]).astype(f32)
+    ls = [((t[:, k, 0] * t[:, k, 0] + t[:, k, 1] * t[:, k, 1]).astype(f32) + t[:, k, 2] * t[:, k, 2]).astype(f32) for k in range(3)]
+    max_scale = np.sqrt(np.maximum(ls[0], np.maximum(ls[1], ls[2]))).astype(f32)
+    rec["sphere_center"][:n] = c
+    rec["sphere_radius"][:n] = (max_scale * radii).astype(f32)
+    rec["first_index"][:n] = np.array([m["index_start"] // 4 for m in renderer.meshes], dtype=np.uint32)[mesh_ids]
+    rec["index_count"][:n] = np.array([m["index_count"] for m in renderer.meshes], dtype=np.uint32)[mesh_ids]
+    rec["material_index"][:n] = material_ids
+    offs = np.array([[m["ranges"].get(s, ATTR_ABSENT) for s in range(6)] for m in renderer.meshes], dtype=np.uint32)
+    rec["attr_offset"][:n] = offs[mesh_ids]
+    rec["enabled"][:n] = 1 if enabled is None else enabled.astype(np.uint32)
+    loc = np.zeros((cap, 3), dtype=f32)
+    loc[:n] = c
+    return rec, loc
+
+
+def eval_with_bulk_objects(renderer: Renderer, rec: np.ndarray, loc: np.ndarray, n_live: int) -> EvalOutput:
+    ev = renderer.evaluate()
+    cap = len(rec)
+    mats = renderer.materials
+    mi = rec["material_index"][:n_live]
+    key_of = np.array([m.key() for m in mats], dtype=np.uint64)
+    atomic_of = np.array([m.atomic_capable() for m in mats], dtype=np.uint8)
+    b2f_of = np.array([m.back_to_front() for m in mats], dtype=np.uint8)
+    ev.object_buffer = rec
+    ev.object_material_key = np.zeros(cap, dtype=np.uint64); ev.object_material_key[:n_live] = key_of[mi]
+    ev.object_atomic = np.zeros(cap, dtype=np.uint8); ev.object_atomic[:n_live] = atomic_of[mi]
+    ev.object_back_to_front = np.zeros(cap, dtype=np.uint8); ev.object_back_to_front[:n_live] = b2f_of[mi]
+    ev.object_live = np.zeros(cap, dtype=np.uint8); ev.object_live[:n_live] = 1
+    ev.object_location = loc
+    return ev
+
+
+def cube_example_camera(pull_back: float = 1.0) -> Camera:
+    """examples/src/cube/mod.rs:99-107: view = euler XYZ(-0.55, 0.5, 0) * translate(-(3, 3, -5) * pull_back)."""
+    loc = np.array([3.0, 3.0, -5.0], dtype=f32) * f32(pull_back)
+    view = glam.mul(glam.from_euler_xyz(-0.55, 0.5, 0.0), glam.from_translation(-loc))
+    return Camera(("perspective", 60.0, 0.1), view)
+
+
+def subdivided_cube_mesh(k: int):
+    """Cube [-1,1]^3 whose faces are k x k quads (12 k^2 triangles), same winding as rend3-test's cube."""
+    if k == 1:
+        return cube_mesh()
+    faces = [  # origin corner, u edge, v edge chosen so (o, o+u, o+u+v, o+v) matches helpers.rs:78-109
+        ((-1, -1, 1), (2, 0, 0), (0, 2, 0)), ((-1, 1, -1), (2, 0, 0), (0, -2, 0)), ((1, -1, -1), (0, 2, 0), (0, 0, 2)),
+        ((-1, -1, 1), (0, 2, 0), (0, 0, -2)), ((1, 1, -1), (-2, 0, 0), (0, 0, 2)), ((1, -1, 1), (-2, 0, 0), (0, 0, -2)),
+    ]
+    pos, idx = [], []
+    for o, u, v in faces:
+        o, u, v = (np.array(a, dtype=np.float64) for a in (o, u, v))
+        base = len(pos)
+        for j in range(k + 1):
+            for i in range(k + 1):
+                pos.append(o + u * (i / k) + v * (j / k))
+        for j in range(k):
+            for i in range(k):
+                a = base + j * (k + 1) + i
+                b, c, d = a + 1, a + 1 + (k + 1), a + (k + 1)
+                idx += [a, b, c, c, d, a]
+    return MeshBuilder.new(np.array(pos, dtype=f32), LEFT).with_indices(idx).build()
+
+
+def cube_field_scene(n_objects: int = 10_000, seed: int = 1, resolution: Tuple[int, int] = (1920, 1080), extent: float = 50.0,
+                     pull_back: float = 20.0, n_point_lights: int = 0, n_dir_lights: int = 1, shadow_resolution: int = 2048,
+                     shadow_distance: float = 400.0, roughness: float = 0.5, subdivisions=(1,), material_count: int = 1,
+                     scale_range: Tuple[float, float] = (0.2, 1.0)) -> EvalOutput:
+    """BASELINE config C1 family: n cubes, centres U([-extent, extent]^3), uniform scale U(0.2, 1),
+    random rotation, PBR material albedo 0.5, directional light(s) like examples/src/cube, camera pulled back."""
+    rng = np.random.default_rng(seed)
+    r = Renderer(LEFT, aspect_ratio=resolution[0] / resolution[1])
+    mesh_ids_avail = [r.add_mesh(subdivided_cube_mesh(k)) for k in subdivisions]
+    for m in range(material_count):
+        g = 0.5 if material_count == 1 else 0.25 + 0.5 * (m / max(material_count - 1, 1))
+        r.add_material(PbrMaterial(albedo_value=(0.5, g, 0.5 if material_count == 1 else 1.0 - g, 1.0), roughness_factor=roughness))
+    r.set_camera_data(cube_example_camera(pull_back))
+    dirs = [(-1.0, -4.0, 2.0), (2.0, -3.0, -1.0), (-2.0, -5.0, -3.0), (1.0, -2.0, 3.0)]
+    for i in range(n_dir_lights):
+        r.add_directional_light(DirectionalLight(color=(1, 1, 1), intensity=1.0 / max(n_dir_lights, 1), direction=dirs[i % 4],
+                                                 distance=shadow_distance, resolution=shadow_resolution))
+    for i in range(n_point_lights):
+        p = rng.uniform(-extent, extent, 3)
+        col = rng.uniform(0.2, 1.0, 3)
+        r.add_point_light(PointLight(position=tuple(p), color=tuple(col), radius=float(rng.uniform(5.0, 20.0)), intensity=4.0))
+    centers = rng.uniform(-extent, extent, (n_objects, 3)).astype(f32)
+    scale = rng.uniform(scale_range[0], scale_range[1], (n_objects, 1)).astype(f32)
+    quat = random_unit_quaternions(rng, n_objects)
+    transforms = trs_matrices(centers, quat, scale)
+    mesh_ids = np.asarray(mesh_ids_avail, dtype=np.int64)[rng.integers(0, len(mesh_ids_avail), n_objects)]
+    material_ids = rng.integers(0, material_count, n_objects).astype(np.uint32)
+    rec, loc = bulk_object_records(r, transforms, mesh_ids, material_ids)
+    return eval_with_bulk_objects(r, rec, loc, n_objects)
+
+
+def object_cloud_records(n: int, seed: int = 2, extent: float = 1000.0, disabled_fraction: float = 0.01) -> np.ndarray:
+    """BASELINE configs C2 / C4: object records only (no mesh work).  Centres U([-extent, extent]^3), uniform scale
+    log-U(0.1, 10), random rotation, bounding radius sqrt(3) * scale (unit cube mesh), 1% disabled."""
+    rng = np.random.default_rng(seed)
+    rec = np.zeros(n, dtype=OBJECT_DTYPE)
+    chunk = 1 << 20
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        m = e - s
+        centers = rng.uniform(-extent, extent, (m, 3)).astype(f32)
+        scale = np.exp(rng.uniform(np.log(0.1), np.log(10.0), (m, 1))).astype(f32)
+        t = trs_matrices(centers, random_unit_quaternions(rng, m), scale)
+        rec["transform"][s:e] = t.reshape(m, 16)
+        rec["sphere_center"][s:e] = centers
+        ls = [((t[:, k, 0] * t[:, k, 0] + t[:, k, 1] * t[:, k, 1]).astype(f32) + t[:, k, 2] * t[:, k, 2]).astype(f32) for k in range(3)]
+        rec["sphere_radius"][s:e] = (np.sqrt(np.maximum(ls[0], np.maximum(ls[1], ls[2]))).astype(f32) * f32(np.sqrt(f32(3.0)))).astype(f32)
+        rec["index_count"][s:e] = 36
+        rec["attr_offset"][s:e] = [0, 288, ATTR_ABSENT, ATTR_ABSENT, ATTR_ABSENT, ATTR_ABSENT]
+        rec["first_index"][s:e] = 144
+        rec["enabled"][s:e] = (rng.random(m) >= disabled_fraction).astype(np.uint32)
+    return rec
+
+
+def cloud_camera(resolution: Tuple[int, int] = (1920, 1080), pull_back: float = 150.0):
+    """Camera family of the cull-only configs: the cube-example view pulled back into the cloud."""
+    from .world import CameraState
+
+    return CameraState(cube_example_camera(pull_back), LEFT, resolution[0] / resolution[1])

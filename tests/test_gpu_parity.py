@@ -1,0 +1,227 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs, plus the reference's golden scenes rendered by the CUDA path.
+
+Bars (BASELINE.json north_star): visible-object indices, MV/MVP, batches, packed index lists, draw records,
+visibility bits, depth, shadow atlas and hi-Z are integer / bit-pattern artefacts and must be IDENTICAL;
+shaded HDR pixels must agree within 1e-4 (absolute below 1.0, relative above — the target is HDR) on the f32
+shading result, and the rgba16f store within one f16 ulp of that.
+"""
+import numpy as np
+import pytest
+
+from rend3_b200 import glam
+from rend3_b200.backend import CAMERA_VIEWPORT, CB_BAKE, CB_CULL, load_cuda_backend
+from rend3_b200.layouts import OBJECT_DTYPE
+from rend3_b200.routines import BaseRenderGraph, BaseRenderGraphSettings, per_camera_header
+from rend3_b200.scenes import cloud_camera, cube_field_scene, object_cloud_records
+from rend3_b200.world import Camera
+
+from oracle import load_oracle_backend
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture()
+def cuda():
+    """A fresh context per test: contexts carry cross-frame state (previous invocations, culling buffers)."""
+    b = load_cuda_backend(0)
+    yield b
+    b.close()
+
+
+def hdr_close(a, b, what=""):
+    err = np.abs(a.astype(np.float64) - b.astype(np.float64)) / np.maximum(1.0, np.abs(b.astype(np.float64)))
+    bad = np.nan_to_num(err, nan=np.inf) > TOL
+    both_nan = np.isnan(a) & np.isnan(b)
+    bad &= ~both_nan
+    assert not bad.any(), f"{what}: {bad.sum()} channel values differ by more than {TOL} (max {np.nanmax(err):.3e})"
+
+
+# ------------------------------------------------------------------ object cull + uniform bake
+@pytest.mark.parametrize("n", [1, 31, 2048, 2049, 200_000])
+def test_cull_bake_matches_oracle(cuda, n):
+    rec = object_cloud_records(n, seed=2 + n)
+    cam = cloud_camera()
+    header = per_camera_header(cam, CAMERA_VIEWPORT, (1920, 1080), 1, n)
+    out = {}
+    for name, b in (("cuda", cuda), ("oracle", load_oracle_backend())):
+        b.set_objects(rec)
+        b.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+        out[name] = (b.readback_visible(CAMERA_VIEWPORT).copy(), b.readback_object_matrices(CAMERA_VIEWPORT, 0, n).copy())
+    vis_c, mat_c = out["cuda"]
+    vis_o, mat_o = out["oracle"]
+    assert np.array_equal(vis_c, vis_o)
+    assert np.all(np.diff(vis_c.astype(np.int64)) > 0), "visible list must be ascending"
+    en = rec["enabled"] != 0
+    assert np.array_equal(mat_c.view(np.uint32).reshape(n, 32)[en], mat_o.view(np.uint32).reshape(n, 32)[en]), "MV/MVP not bit-identical"
+    if n >= 2048:
+        assert 0 < len(vis_c) < n
+
+
+def test_cull_only_and_bake_only_modes(cuda):
+    n = 50_000
+    rec = object_cloud_records(n, seed=11)
+    header = per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (1920, 1080), 1, n)
+    orc = load_oracle_backend()
+    for b in (cuda, orc):
+        b.set_objects(rec)
+        b.object_uniform_upload(CAMERA_VIEWPORT, header, CB_CULL)
+    assert np.array_equal(cuda.readback_visible(CAMERA_VIEWPORT), orc.readback_visible(CAMERA_VIEWPORT))
+    for b in (cuda, orc):
+        b.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE)
+    en = rec["enabled"] != 0
+    a = cuda.readback_object_matrices(CAMERA_VIEWPORT, 0, n).view(np.uint32).reshape(n, 32)
+    o = orc.readback_object_matrices(CAMERA_VIEWPORT, 0, n).view(np.uint32).reshape(n, 32)
+    assert np.array_equal(a[en], o[en])
+
+
+def test_live_mask_and_update_objects(cuda):
+    """Slots that are live but disabled stay in the visible set (batching.rs:144 iterates enumerated objects),
+    and r3_update_objects scatters like ScatterCopy."""
+    n = 5000
+    rec = object_cloud_records(n, seed=5, extent=100.0, disabled_fraction=0.2)
+    header = per_camera_header(cloud_camera(pull_back=30.0), CAMERA_VIEWPORT, (640, 480), 1, n)
+    live = (np.arange(n) % 7 != 0).astype(np.uint8)
+    key = np.zeros(n, dtype=np.uint64)
+    loc = rec["sphere_center"].copy()
+    orc = load_oracle_backend()
+    slots = np.array([3, 77, 4096, 4999, 10_000], dtype=np.uint32)   # last one is out of range -> dropped
+    new = object_cloud_records(len(slots), seed=99, extent=100.0, disabled_fraction=0.0)
+    for b in (cuda, orc):
+        b.set_objects(rec)
+        b.set_object_sort_info(key, live | 2, loc)
+        b.update_objects(slots, new)
+        b.object_uniform_upload(CAMERA_VIEWPORT, header)
+    vc, vo = cuda.readback_visible(CAMERA_VIEWPORT), orc.readback_visible(CAMERA_VIEWPORT)
+    assert np.array_equal(vc, vo)
+    assert not np.any(vc % 7 == 0)
+    mc = cuda.readback_object_matrices(CAMERA_VIEWPORT, 0, n).view(np.uint32).reshape(n, 32)
+    mo = orc.readback_object_matrices(CAMERA_VIEWPORT, 0, n).view(np.uint32).reshape(n, 32)
+    assert np.array_equal(mc[[3, 77, 4096, 4999]], mo[[3, 77, 4096, 4999]])
+
+
+# ------------------------------------------------------------------ whole frames
+def compare_frame_state(cuda, orc, ev, cameras, check_pixels=True, what=""):
+    for cam in cameras:
+        bc, rc = cuda.readback_batches(cam)
+        bo, ro = orc.readback_batches(cam)
+        assert bc.tobytes() == bo.tobytes() and rc.tobytes() == ro.tobytes(), f"{what} camera {cam}: batches differ"
+        for part in (0, 1):
+            dc, do = cuda.readback_draw_calls(cam, part), orc.readback_draw_calls(cam, part)
+            assert dc.tobytes() == do.tobytes(), f"{what} camera {cam}: draw calls (partition {part}) differ"
+            ic, io = cuda.readback_indices(cam, part), orc.readback_indices(cam, part)
+            for r in range(len(dc)):   # only the listed part of each region is defined
+                b0, cnt = int(dc[r]["base_index"]), int(dc[r]["vertex_count"])
+                if part == 1 and cam != CAMERA_VIEWPORT:
+                    continue
+                assert np.array_equal(ic[b0:b0 + cnt], io[b0:b0 + cnt]), f"{what} camera {cam}: index list of region {r} differs"
+        assert np.array_equal(cuda.readback_culling_results(cam, 0), orc.readback_culling_results(cam, 0)), f"{what}: visibility bits differ"
+    if check_pixels:
+        assert np.array_equal(cuda.readback_depth().view(np.uint32), orc.readback_depth().view(np.uint32)), f"{what}: depth differs"
+        hdr_close(cuda.readback_hdr_f32(), orc.readback_hdr_f32(), what + " hdr f32")
+        h16c, h16o = cuda.readback_hdr_f16().astype(np.float32), orc.readback_hdr_f16().astype(np.float32)
+        ulp = np.maximum(np.abs(h16o) * 2.0 ** -10, 2.0 ** -24)
+        assert np.all(np.abs(h16c - h16o) <= ulp + TOL * np.maximum(1.0, np.abs(h16o))), f"{what}: rgba16f target differs by more than 1 ulp"
+        lc, lo = cuda.readback_ldr().astype(int), orc.readback_ldr().astype(int)
+        assert np.abs(lc - lo).max() <= 1, f"{what}: 8-bit output differs by more than 1 LSB"
+        assert np.count_nonzero(lc != lo) <= 1e-3 * lc.size
+        if ev.shadows:
+            w, h = ev.shadow_target_size
+            assert np.array_equal(cuda.readback_shadow_atlas(w, h).view(np.uint32), orc.readback_shadow_atlas(w, h).view(np.uint32)), f"{what}: shadow atlas differs"
+
+
+def test_cube_field_frame_matches_oracle(cuda):
+    """C1-shaped scene at reduced size: 2000 cubes, directional light with shadow map, 3 point lights."""
+    res = (480, 270)
+    ev = cube_field_scene(n_objects=2000, seed=1, resolution=res, n_point_lights=3, shadow_resolution=512, pull_back=12.0, extent=30.0)
+    orc = load_oracle_backend()
+    settings = BaseRenderGraphSettings(clear_color=(0.1, 0.05, 0.1, 1.0), ambient_color=(0.02, 0.02, 0.02, 1.0))
+    for b in (cuda, orc):
+        BaseRenderGraph(b).add_to_graph(ev, res, 1, settings)
+    compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], what="cube field")
+    st = cuda.forward_stats()
+    assert st[0] > 0 and st[1] >= st[2] > 0
+    for mip in range(0, 9, 2):
+        assert np.array_equal(cuda.readback_hiz(mip).view(np.uint32), orc.readback_hiz(mip).view(np.uint32))
+
+
+def test_multi_frame_predicted_residual(cuda):
+    """Three frames with a 0.5 degree yaw step: predicted pass + hi-Z occlusion + residual pass (base.rs:158-172)."""
+    res = (320, 200)
+    ev = cube_field_scene(n_objects=1500, seed=3, resolution=res, n_dir_lights=0, pull_back=8.0, extent=20.0, subdivisions=(1, 2))
+    orc = load_oracle_backend()
+    graphs = {id(b): BaseRenderGraph(b) for b in (cuda, orc)}
+    from rend3_b200.world import CameraState, LEFT
+    base_view = ev.camera.view.copy()
+    for frame in range(3):
+        view = glam.mul(glam.from_rotation_y(np.float32(np.radians(0.5 * frame))), base_view)
+        ev.camera = CameraState(Camera(("perspective", 60.0, 0.1), view), LEFT, res[0] / res[1])
+        for b in (cuda, orc):
+            graphs[id(b)].add_to_graph(ev, res, 1, BaseRenderGraphSettings(), upload=(frame == 0))
+        compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT], what=f"frame {frame}")
+    # in steady state most triangles are predicted: the residual list is (much) shorter than the predicted one
+    pred = cuda.readback_draw_calls(CAMERA_VIEWPORT, 0)["vertex_count"].sum()
+    resid = cuda.readback_draw_calls(CAMERA_VIEWPORT, 1)["vertex_count"].sum()
+    assert resid < pred
+
+
+def test_near_plane_clipping_and_large_triangles(cuda):
+    """Camera inside the field: triangles cross the near plane (clipper) and cover many bands (large path)."""
+    res = (384, 216)
+    ev = cube_field_scene(n_objects=400, seed=9, resolution=res, n_dir_lights=1, shadow_resolution=256, shadow_distance=60.0,
+                          pull_back=0.6, extent=6.0)
+    orc = load_oracle_backend()
+    for b in (cuda, orc):
+        BaseRenderGraph(b).add_to_graph(ev, res, 1, BaseRenderGraphSettings(clear_color=(0, 0, 0, 1)))
+    compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], what="near-plane")
+    assert cuda.forward_stats()[2] > 0.3 * res[0] * res[1]
+
+
+def test_empty_and_ragged_inputs(cuda):
+    res = (64, 64)
+    # empty world: nothing visible, clear colour everywhere
+    ev = cube_field_scene(n_objects=0, seed=1, resolution=res, n_dir_lights=0)
+    BaseRenderGraph(cuda).add_to_graph(ev, res, 1, BaseRenderGraphSettings(clear_color=(0.25, 0.5, 0.75, 1.0)))
+    assert cuda.visible_count(CAMERA_VIEWPORT) == 0
+    assert np.allclose(cuda.readback_hdr_f32(), np.array([0.25, 0.5, 0.75, 1.0], dtype=np.float32))
+    # every object disabled
+    ev = cube_field_scene(n_objects=100, seed=1, resolution=res, n_dir_lights=0)
+    ev.object_buffer["enabled"][:] = 0
+    ev.object_live[:] = 0
+    orc = load_oracle_backend()
+    for b in (cuda, orc):
+        BaseRenderGraph(b).add_to_graph(ev, res, 1, BaseRenderGraphSettings())
+    assert cuda.visible_count(CAMERA_VIEWPORT) == 0
+    assert np.array_equal(cuda.readback_ldr(), orc.readback_ldr())
+
+
+# ------------------------------------------------------------------ the reference's golden scenes through the CUDA path
+def test_reference_goldens_on_cuda(cuda, monkeypatch):
+    import test_oracle_golden as g
+
+    monkeypatch.setattr(g, "load_oracle_backend", lambda: load_cuda_backend(0))
+    g.test_empty()
+    for args in [("Left", "Cw", True), ("Left", "Ccw", False), ("Right", "Cw", False), ("Right", "Ccw", True)]:
+        g.test_triangle(*args)
+    g.test_coordinate_space()
+    g.test_sample_coverage_1()
+    g.test_multi_frame_add()
+    g.test_duplicate_object_retain()
+    g.test_shadow_plane()
+    g.test_shadow_cube()
+    g.test_cube_example_screenshot()
+
+
+def test_error_paths(cuda):
+    from rend3_b200.backend import R3Error
+
+    with pytest.raises(R3Error):
+        cuda.set_render_target(64, 64, 4)           # MSAA x4 is a "next" row
+    with pytest.raises(R3Error):
+        cuda.readback_hiz(99)
+    rec = np.zeros(4, dtype=OBJECT_DTYPE)
+    cuda.set_objects(rec)
+    hdr = per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (64, 64), 1, 9)   # object_count > buffer
+    with pytest.raises(R3Error):
+        cuda.object_uniform_upload(CAMERA_VIEWPORT, hdr)
