@@ -255,8 +255,8 @@ def main():
     forward = None
     if not args.no_forward:
         res = (3840, 2160)
-        ev = cube_field_scene(n_objects=4400, seed=5, resolution=res, extent=30.0, pull_back=14.0, n_point_lights=64, n_dir_lights=4,
-                              shadow_resolution=2048, shadow_distance=200.0, subdivisions=(2, 3, 3, 4), scale_range=(0.6, 2.4))
+        ev = cube_field_scene(n_objects=4400, seed=5, resolution=res, extent=30.0, pull_back=7.0, n_point_lights=64, n_dir_lights=4,
+                              shadow_resolution=2048, shadow_distance=200.0, subdivisions=(2, 3, 3, 4), scale_range=(0.6, 2.4), slabs=True)
         fb = load_cuda_backend(local)
         fstream = torch.cuda.ExternalStream(fb.stream(), device=torch.device("cuda", local))
         graph = BaseRenderGraph(fb)

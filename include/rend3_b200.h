@@ -133,8 +133,8 @@ int r3_readback_depth(r3_ctx*, float* depth, uint64_t capacity);
 int r3_readback_ldr(r3_ctx*, uint8_t* rgba8, uint64_t capacity);
 int r3_readback_shadow_atlas(r3_ctx*, float* depth, uint64_t capacity);
 int r3_readback_hiz(r3_ctx*, uint32_t mip, float* depth, uint64_t capacity, uint32_t* width, uint32_t* height);
-/* forward statistics of the last frame: [0] triangles set up, [1] fragments that passed the depth
- * test when rasterised, [2] pixels shaded by r3_forward_resolve */
+/* forward statistics of the last frame: [0] triangles set up, [1] fragments rasterised (covered samples sent
+ * to the depth test), [2] fragments shaded by r3_forward_resolve (fs_main invocations) */
 int r3_forward_stats(r3_ctx*, uint64_t stats[4]);
 
 /* ------------------------------------------------------------------ multi-GPU plumbing

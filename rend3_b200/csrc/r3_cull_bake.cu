@@ -8,26 +8,27 @@
 // and emits the visible slots as one ASCENDING u32 list (the canonical, bit-exact artefact).
 //
 // Design (HBM-bound: 128 B read + 128 B written per object, 224 flop):
-//   * one persistent CTA (256 threads) per SM slot pulls 2048-object tiles from an atomic ticket;
+//   * persistent CTAs (256 threads, 4 per SM) pull 512-object tiles from an atomic ticket;
 //   * 8 lanes own one 128-byte object record: lane k loads float4 k, so a warp load instruction covers
 //     512 contiguous bytes (4 records) and each lane keeps 8 independent 16-byte loads in flight;
 //   * lanes 0-3 multiply `view` by transform column k, lanes 4-7 multiply `view_proj` by column k-4
 //     (fetched by shuffle); lane k then stores float4 k of the 128-byte MV|MVP record: stores are as
 //     coalesced as the loads.  All arithmetic is __fmul_rn/__fadd_rn in WGSL's accumulation order,
 //     never contracted, so MV/MVP are bit-identical to the CPU oracle;
-//   * visibility is a warp ballot -> one 32-bit word per 32 objects, kept in shared memory; the CTA's
-//     64 words are scanned by warp 0 and the tile's base offset comes from a decoupled look-back over
+//   * the sphere test runs one object per lane (spheres parked in shared memory by the lane that loaded
+//     them), so its ballot is directly the 32-bit visibility word of 32 objects; the CTA's
+//     16 words are scanned by warp 0 and the tile's base offset comes from a decoupled look-back over
 //     the preceding tiles' descriptors (single pass, no second kernel), after which every warp writes
 //     its surviving slot ids in ascending order.
+#include <cstdlib>
+
 #include "r3_common.cuh"
 
 namespace {
 
 constexpr int CB_THREADS = 256;
 constexpr int CB_WARPS = CB_THREADS / 32;
-constexpr int CB_WTILES_PER_WARP = 8;                       // 32-object warp tiles per warp per CTA tile
-constexpr int CB_WORDS = CB_WARPS * CB_WTILES_PER_WARP;     // 64 visibility words per CTA tile
-constexpr int CB_TILE_OBJECTS = CB_WORDS * 32;              // 2048
+// WT = 32-object warp tiles per warp per CTA tile (template parameter): a CTA tile is 8 * WT * 32 objects
 
 struct CullBakeParams {
     float view[16];
@@ -46,16 +47,20 @@ __device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long lon
     *reinterpret_cast<volatile unsigned long long*>(p) = v;
 }
 
-template <bool BAKE, bool CULL, bool LIVE>
-__global__ void __launch_bounds__(CB_THREADS)
+template <bool BAKE, bool CULL, bool LIVE, int WT, int MINB>
+__global__ void __launch_bounds__(CB_THREADS, MINB)
 cull_bake_kernel(const float4* __restrict__ objects, float4* __restrict__ matrices, const uint32_t* __restrict__ live_bits,
                  uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count, unsigned long long* tile_state,
                  const __grid_constant__ CullBakeParams p) {
+    constexpr int CB_WTILES_PER_WARP = WT, CB_WORDS = CB_WARPS * WT, CB_TILE_OBJECTS = CB_WORDS * 32;
+    static_assert(CB_WORDS <= 64, "the word scan handles at most two words per lane");
     __shared__ float s_mat[32];
     __shared__ float s_frustum[20];
     __shared__ uint32_t s_words[CB_WORDS];
     __shared__ uint32_t s_excl[CB_WORDS];
     __shared__ uint32_t s_tile, s_base;
+    __shared__ float4 s_sphere[CB_WARPS][32];
+    __shared__ uint32_t s_enabled[CB_WARPS][32];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = lane & 7, g = lane >> 3;
@@ -80,56 +85,56 @@ cull_bake_kernel(const float4* __restrict__ objects, float4* __restrict__ matric
                 const bool want = BAKE ? true : (k == 4 || k == 7);
                 r[it] = (obj < p.object_count && want) ? __ldcs(&objects[(size_t)obj * 8 + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            uint32_t live_word = 0xFFFFFFFFu;
-            if (LIVE && CULL) live_word = (base < p.object_count) ? __ldg(&live_bits[base >> 5]) : 0u;
-            uint32_t word = 0;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const uint32_t obj = base + it * 4 + g;
-                const uint32_t enabled = __float_as_uint(__shfl_sync(0xFFFFFFFFu, r[it].y, (lane & 24) | 7));
+                // float4 #4 is the bounding sphere, float4 #7 carries `enabled` in .y: park them for the per-lane cull below
+                if (CULL && k == 4) s_sphere[warp][it * 4 + g] = r[it];
+                if (CULL && !LIVE && k == 7) s_enabled[warp][it * 4 + g] = __float_as_uint(r[it].y);
                 if (BAKE) {
+                    const uint32_t enabled = __float_as_uint(__shfl_sync(0xFFFFFFFFu, r[it].y, (lane & 24) | 7));
                     const int src = (k < 4) ? lane : lane - 4;
                     const float cx = __shfl_sync(0xFFFFFFFFu, r[it].x, src), cy = __shfl_sync(0xFFFFFFFFu, r[it].y, src);
                     const float cz = __shfl_sync(0xFFFFFFFFu, r[it].z, src), cw = __shfl_sync(0xFFFFFFFFu, r[it].w, src);
                     const float4 o = mat_vec_rn(&s_mat[(k >> 2) * 16], cx, cy, cz, cw);
                     if (obj < p.object_count && enabled != 0u) __stcs(&matrices[(size_t)obj * 8 + k], o);
                 }
-                if (CULL) {
-                    bool vis = false;
-                    if (k == 4 && obj < p.object_count) {
-                        const bool live = LIVE ? ((live_word >> (it * 4 + g)) & 1u) : (enabled != 0u);
-                        // Plane::distance = abc.dot(center) + d with glam's scalar dot order (util/frustum.rs:79-81)
-                        const float neg_radius = -r[it].w;
-                        bool inside = true;
-#pragma unroll
-                        for (int pl = 0; pl < 5; ++pl) {
-                            const float d = add_rn(add_rn(add_rn(mul_rn(s_frustum[pl * 4 + 0], r[it].x), mul_rn(s_frustum[pl * 4 + 1], r[it].y)),
-                                                          mul_rn(s_frustum[pl * 4 + 2], r[it].z)), s_frustum[pl * 4 + 3]);
-                            inside = inside && (d >= neg_radius);
-                        }
-                        vis = live && inside;
-                    }
-                    const uint32_t b = __ballot_sync(0xFFFFFFFFu, vis);     // bits 4,12,20,28
-                    word |= (((b >> 4) & 1u) | ((b >> 11) & 2u) | ((b >> 18) & 4u) | ((b >> 25) & 8u)) << (it * 4);
-                }
             }
-            if (CULL && lane == 0) s_words[word_idx] = word;
+            if (CULL) {
+                __syncwarp();
+                // one object per lane: Plane::distance = abc.dot(center) + d with glam's scalar dot order (util/frustum.rs:79-81,148-161)
+                const uint32_t obj = base + lane;
+                const float4 sp = s_sphere[warp][lane];
+                bool live;
+                if (LIVE) live = (((base < p.object_count) ? __ldg(&live_bits[base >> 5]) : 0u) >> lane) & 1u;
+                else live = s_enabled[warp][lane] != 0u;
+                const float neg_radius = -sp.w;
+                bool inside = true;
+#pragma unroll
+                for (int pl = 0; pl < 5; ++pl) {
+                    const float d = add_rn(add_rn(add_rn(mul_rn(s_frustum[pl * 4 + 0], sp.x), mul_rn(s_frustum[pl * 4 + 1], sp.y)),
+                                                  mul_rn(s_frustum[pl * 4 + 2], sp.z)), s_frustum[pl * 4 + 3]);
+                    inside = inside && (d >= neg_radius);
+                }
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, obj < p.object_count && live && inside);
+                if (lane == 0) s_words[word_idx] = word;
+                __syncwarp();
+            }
         }
         if (!CULL) continue;
         __syncthreads();
 
         if (warp == 0) {
-            // exclusive scan of the 64 word popcounts (2 per lane)
-            const uint32_t c0 = __popc(s_words[2 * lane]), c1 = __popc(s_words[2 * lane + 1]);
+            // exclusive scan of the CB_WORDS word popcounts (up to two per lane)
+            const uint32_t c0 = (2 * lane < CB_WORDS) ? __popc(s_words[2 * lane]) : 0u, c1 = (2 * lane + 1 < CB_WORDS) ? __popc(s_words[2 * lane + 1]) : 0u;
             uint32_t incl = c0 + c1;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d);
                 if (lane >= d) incl += n;
             }
-            const uint32_t excl = incl - (c0 + c1);
-            s_excl[2 * lane] = excl;
-            s_excl[2 * lane + 1] = excl + c0;
+            if (2 * lane < CB_WORDS) s_excl[2 * lane] = incl - (c0 + c1);
+            if (2 * lane + 1 < CB_WORDS) s_excl[2 * lane + 1] = incl - c1;
             const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
             // decoupled look-back for the tile's base offset
             uint32_t running = 0;
@@ -174,29 +179,41 @@ cull_bake_kernel(const float4* __restrict__ objects, float4* __restrict__ matric
 
 }  // namespace
 
+template <int WT, int MINB>
+static void launch_variant(r3_ctx* c, r3_camera* cam, const CullBakeParams& p, uint32_t grid, bool bake, bool cull, bool live) {
+    const float4* obj = reinterpret_cast<const float4*>(c->d_objects);
+    float4* mats = reinterpret_cast<float4*>(cam->d_matrices);
+#define R3_CB_LAUNCH(B, C, L) \
+    cull_bake_kernel<B, C, L, WT, MINB><<<grid, CB_THREADS, 0, c->stream>>>(obj, mats, c->d_live_bits, cam->d_visible, cam->d_visible_count, cam->d_tile_state, p)
+    if (bake && cull) { if (live) R3_CB_LAUNCH(true, true, true); else R3_CB_LAUNCH(true, true, false); }
+    else if (bake) R3_CB_LAUNCH(true, false, false);
+    else { if (live) R3_CB_LAUNCH(false, true, true); else R3_CB_LAUNCH(false, true, false); }
+#undef R3_CB_LAUNCH
+}
+
 int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode) {
     const uint32_t n = cam->header.object_count;
     const bool bake = mode & R3_CB_BAKE, cull = mode & R3_CB_CULL;
     if (cull) R3_CUDA(c, cudaMemsetAsync(cam->d_visible_count, 0, 4, c->stream));
     if (n == 0 || (!bake && !cull)) return R3_OK;
+    // tuning knobs (profiles/README.md): R3_CB_WT = warp tiles per warp (tile = 256*WT objects), R3_CB_MINB = CTAs per SM
+    static const int wt = getenv("R3_CB_WT") ? atoi(getenv("R3_CB_WT")) : 8;
+    static const int minb = getenv("R3_CB_MINB") ? atoi(getenv("R3_CB_MINB")) : 3;
+    const uint32_t tile_objects = CB_WARPS * 32u * (uint32_t)(wt == 2 ? 2 : wt == 4 ? 4 : 8);
     CullBakeParams p;
     memcpy(p.view, cam->header.view, 64);
     memcpy(p.view_proj, cam->header.view_proj, 64);
     memcpy(p.frustum, cam->header.frustum, 80);
     p.object_count = n;
-    p.n_tiles = (n + CB_TILE_OBJECTS - 1) / CB_TILE_OBJECTS;
+    p.n_tiles = (n + tile_objects - 1) / tile_objects;
     R3_TRY(r3_reserve_t(c, &cam->d_tile_state, &cam->tile_state_cap, (uint64_t)p.n_tiles + 1));
     R3_CUDA(c, cudaMemsetAsync(cam->d_tile_state, 0, ((size_t)p.n_tiles + 1) * 8, c->stream));
-    const uint32_t grid = p.n_tiles < (uint32_t)(R3_SM_COUNT * 8) ? p.n_tiles : (uint32_t)(R3_SM_COUNT * 8);
-    const float4* obj = reinterpret_cast<const float4*>(c->d_objects);
-    float4* mats = reinterpret_cast<float4*>(cam->d_matrices);
+    const uint32_t resident = (uint32_t)(R3_SM_COUNT * (minb == 4 ? 4 : 3));
+    const uint32_t grid = p.n_tiles < resident ? p.n_tiles : resident;
     const bool live = c->have_live && cull;
-#define R3_CB_LAUNCH(B, C, L) \
-    cull_bake_kernel<B, C, L><<<grid, CB_THREADS, 0, c->stream>>>(obj, mats, c->d_live_bits, cam->d_visible, cam->d_visible_count, cam->d_tile_state, p)
-    if (bake && cull) { if (live) R3_CB_LAUNCH(true, true, true); else R3_CB_LAUNCH(true, true, false); }
-    else if (bake) R3_CB_LAUNCH(true, false, false);
-    else { if (live) R3_CB_LAUNCH(false, true, true); else R3_CB_LAUNCH(false, true, false); }
-#undef R3_CB_LAUNCH
+    if (wt == 2) { if (minb == 4) launch_variant<2, 4>(c, cam, p, grid, bake, cull, live); else launch_variant<2, 3>(c, cam, p, grid, bake, cull, live); }
+    else if (wt == 4) { if (minb == 4) launch_variant<4, 4>(c, cam, p, grid, bake, cull, live); else launch_variant<4, 3>(c, cam, p, grid, bake, cull, live); }
+    else { if (minb == 4) launch_variant<8, 4>(c, cam, p, grid, bake, cull, live); else launch_variant<8, 3>(c, cam, p, grid, bake, cull, live); }
     R3_CHECK_LAUNCH(c, "cull_bake_kernel");
     return R3_OK;
 }

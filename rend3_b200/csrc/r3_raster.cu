@@ -131,16 +131,16 @@ __device__ __forceinline__ float sample_depth(const SubTri& s, const EdgeSetup& 
 }
 template <bool DEPTH_ONLY>
 __device__ __forceinline__ uint32_t write_sample(const RasterParams& p, int px, int py, float z, uint32_t rec) {
+    // the result of the atomic is never read, so it compiles to a fire-and-forget RED.MAX: a thread can have
+    // hundreds of samples in flight instead of one L2 round trip per sample
     const size_t pi = (size_t)py * p.pitch + px;
     if (DEPTH_ONLY) {
-        const uint32_t zb = __float_as_uint(z);
-        const uint32_t old = atomicMax(&p.depth_bits[pi], zb);
-        return zb >= old ? 1u : 0u;
+        atomicMax(&p.depth_bits[pi], __float_as_uint(z));
     } else {
         const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | ((unsigned long long)p.pass_bit << 31) | rec;
-        const unsigned long long old = atomicMax(&p.vis[pi], key);
-        return key > old ? 1u : 0u;
+        atomicMax(&p.vis[pi], key);
     }
+    return 1u;   // statistics count rasterised (covered) samples
 }
 
 __device__ __forceinline__ void pixel_bounds(const RasterParams& p, const SubTri& s, int& px0, int& py0, int& px1, int& py1) {

@@ -49,28 +49,32 @@ __device__ __forceinline__ float3 normalize3(float3 a) { const float r = rsqrtf(
 __device__ __forceinline__ float saturate(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 __device__ __forceinline__ float srgb_to_linear(float e) { return e > 0.04045f ? powf((e + 0.055f) / 1.055f, 2.4f) : e / 12.92f; }
 
-struct Pixel { float3 diffuse, f0, normal; float roughness; };
+struct Pixel { float3 diffuse_pi, f0, normal; float roughness, f90; };   // diffuse_pi = diffuse_color * (1/pi)
 
-// surface_shading (opaque.wgsl:440-468) with brdf_d_ggx / brdf_f_schlick / brdf_v_smith_ggx_correlated / brdf_fd_lambert
-__device__ __forceinline__ float3 surface_shading(const float3 l, const float3 intensity, const Pixel& px, const float3 v, float occlusion) {
-    const float3 h = normalize3(make_float3(v.x + l.x, v.y + l.y, v.z + l.z));
-    const float nov = fabsf(dot3(px.normal, v)) + 0.00001f;
+// MUFU-based approximations (<= 2 ulp): the shaded result is checked to 1e-4, not bit-exact
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// surface_shading (opaque.wgsl:440-468) with brdf_d_ggx / brdf_f_schlick / brdf_v_smith_ggx_correlated / brdf_fd_lambert.
+// When roughness > 0 every term is finite, so a light with n.l <= 0 contributes exactly 0 and is skipped; with
+// roughness == 0 the reference's 0 * inf = NaN must survive to the caller's max(), so the full path runs.
+__device__ __forceinline__ float3 surface_shading(const float3 l, const float3 intensity, const Pixel& px, const float3 v, float nov, float occlusion) {
     const float nol = saturate(dot3(px.normal, l));
+    const float a = px.roughness, a2 = a * a;
+    if (nol <= 0.0f && a2 > 0.0f) return make_float3(0.f, 0.f, 0.f);
+    const float3 h = normalize3(make_float3(v.x + l.x, v.y + l.y, v.z + l.z));
     const float noh = saturate(dot3(px.normal, h));
     const float loh = saturate(dot3(l, h));
-    const float f90 = saturate((px.f0.x + px.f0.y + px.f0.z) * 16.5f);
-    const float a = px.roughness, a2 = a * a;
     const float fd = (noh * a2 - noh) * noh + 1.0f;
-    const float d = a2 / (R3_PI * fd * fd);
+    const float d = a2 * rcp_approx(R3_PI * fd * fd);
     const float om = 1.0f - loh, om2 = om * om, pw = om2 * om2 * om;   // pow(1 - loh, 5)
-    const float3 f = make_float3(px.f0.x + (f90 - px.f0.x) * pw, px.f0.y + (f90 - px.f0.y) * pw, px.f0.z + (f90 - px.f0.z) * pw);
-    const float ggxl = nov * sqrtf((-nol * a2 + nol) * nol + a2);
-    const float ggxv = nol * sqrtf((-nov * a2 + nov) * nov + a2);
-    const float vis = 0.5f / (ggxl + ggxv);
-    const float dv = d * vis;
-    const float inv_pi = 1.0f / R3_PI, s = nol * occlusion;
-    return make_float3((px.diffuse.x * inv_pi + dv * f.x) * intensity.x * s, (px.diffuse.y * inv_pi + dv * f.y) * intensity.y * s,
-                       (px.diffuse.z * inv_pi + dv * f.z) * intensity.z * s);
+    const float3 f = make_float3(px.f0.x + (px.f90 - px.f0.x) * pw, px.f0.y + (px.f90 - px.f0.y) * pw, px.f0.z + (px.f90 - px.f0.z) * pw);
+    const float ggxl = nov * sqrt_approx((-nol * a2 + nol) * nol + a2);
+    const float ggxv = nol * sqrt_approx((-nov * a2 + nov) * nov + a2);
+    const float dv = d * (0.5f * rcp_approx(ggxl + ggxv));
+    const float s = nol * occlusion;
+    return make_float3((px.diffuse_pi.x + dv * f.x) * intensity.x * s, (px.diffuse_pi.y + dv * f.y) * intensity.y * s,
+                       (px.diffuse_pi.z + dv * f.z) * intensity.z * s);
 }
 
 // textureSampleCompareLevel: linear, GreaterEqual, Repeat-addressed comparison sampler (common/samplers.rs:24,42-56)
@@ -197,7 +201,8 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
             const float ao = mC.y, metallic = mB.x, reflectance = mB.y, clear_coat = mB.z, cc_rough = mB.w;
             float perceptual = mA.w;
             const float om = 1.0f - metallic;
-            pxl.diffuse = make_float3(albedo.x * om, albedo.y * om, albedo.z * om);
+            const float inv_pi = 1.0f / R3_PI;
+            pxl.diffuse_pi = make_float3(albedo.x * om * inv_pi, albedo.y * om * inv_pi, albedo.z * om * inv_pi);
             const float rterm = (0.16f * reflectance * reflectance) * om;
             pxl.f0 = make_float3(albedo.x * metallic + rterm, albedo.y * metallic + rterm, albedo.z * metallic + rterm);
             if (clear_coat != 0.0f) {
@@ -205,8 +210,10 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
                 perceptual = perceptual * (1.0f - clear_coat) + base * clear_coat;
             }
             pxl.roughness = perceptual * perceptual;
+            pxl.f90 = saturate((pxl.f0.x + pxl.f0.y + pxl.f0.z) * 16.5f);
             const float3 nvp = normalize3(make_float3(vp.x, vp.y, vp.z));
             const float3 v = make_float3(-nvp.x, -nvp.y, -nvp.z);
+            const float nov = fabsf(dot3(pxl.normal, v)) + 0.00001f;
             float3 color = make_float3(mA.x, mA.y, mA.z);
             for (uint32_t i = 0; i < p.n_dir; ++i) {                                   // opaque.wgsl:487-522
                 const DirPrep& L = i < MAX_SMEM_DIR ? s_dir[i] : p.dir[i];
@@ -221,18 +228,20 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
                 float shadow = 1.0f;
                 if ((flx >= tlx || fly >= tly) && (flx <= trx || fly <= try_) && snz >= 0.0f && snz <= 1.0f)   // literal any() quirk (opaque.wgsl:509-514)
                     shadow = shadow_pcf5(p, cu, cv, snz);
-                const float3 s = surface_shading(make_float3(L.l[0], L.l[1], L.l[2]), make_float3(L.color[0], L.color[1], L.color[2]), pxl, v, shadow * ao);
+                const float3 s = surface_shading(make_float3(L.l[0], L.l[1], L.l[2]), make_float3(L.color[0], L.color[1], L.color[2]), pxl, v, nov, shadow * ao);
                 color.x += s.x; color.y += s.y; color.z += s.z;
             }
             for (uint32_t i = 0; i < p.n_point; ++i) {                                 // opaque.wgsl:524-546
                 const PointPrep& L = i < MAX_SMEM_POINT ? s_point[i] : p.point[i];
                 const float3 delta = make_float3(L.pos[0] - vp.x, L.pos[1] - vp.y, L.pos[2] - vp.z);
-                const float d2 = dot3(delta, delta), d = sqrtf(d2);
-                const float sdist = saturate(d / L.radius), s2 = sdist * sdist, inv_s2 = 1.0f - s2;
-                const float att = inv_s2 * inv_s2 / (1.0f + s2);
-                const float inv_d = 1.0f / d;
+                const float d2 = dot3(delta, delta);
+                // att = (1 - s^2)^2 / (1 + s^2) with s = saturate(d / radius) is exactly 0 at and beyond the radius
+                if (d2 >= L.radius * L.radius && pxl.roughness > 0.0f) continue;
+                const float inv_d = rsqrtf(d2), d = d2 * inv_d;
+                const float sdist = saturate(d * rcp_approx(L.radius)), s2 = sdist * sdist, inv_s2 = 1.0f - s2;
+                const float att = inv_s2 * inv_s2 * rcp_approx(1.0f + s2);
                 const float3 s = surface_shading(make_float3(delta.x * inv_d, delta.y * inv_d, delta.z * inv_d),
-                                                 make_float3(L.color[0] * att, L.color[1] * att, L.color[2] * att), pxl, v, ao);
+                                                 make_float3(L.color[0] * att, L.color[1] * att, L.color[2] * att), pxl, v, nov, ao);
                 color.x += fmaxf(s.x, 0.0f); color.y += fmaxf(s.y, 0.0f); color.z += fmaxf(s.z, 0.0f);
             }
             out = make_float4(fmaxf(p.ambient[0] * albedo.x, color.x), fmaxf(p.ambient[1] * albedo.y, color.y), fmaxf(p.ambient[2] * albedo.z, color.z),

@@ -126,7 +126,7 @@ def subdivided_cube_mesh(k: int):
 def cube_field_scene(n_objects: int = 10_000, seed: int = 1, resolution: Tuple[int, int] = (1920, 1080), extent: float = 50.0,
                      pull_back: float = 20.0, n_point_lights: int = 0, n_dir_lights: int = 1, shadow_resolution: int = 2048,
                      shadow_distance: float = 400.0, roughness: float = 0.5, subdivisions=(1,), material_count: int = 1,
-                     scale_range: Tuple[float, float] = (0.2, 1.0)) -> EvalOutput:
+                     scale_range: Tuple[float, float] = (0.2, 1.0), slabs: bool = False) -> EvalOutput:
     """BASELINE config C1 family: n cubes, centres U([-extent, extent]^3), uniform scale U(0.2, 1),
     random rotation, PBR material albedo 0.5, directional light(s) like examples/src/cube, camera pulled back."""
     rng = np.random.default_rng(seed)
@@ -150,6 +150,18 @@ def cube_field_scene(n_objects: int = 10_000, seed: int = 1, resolution: Tuple[i
     transforms = trs_matrices(centers, quat, scale)
     mesh_ids = np.asarray(mesh_ids_avail, dtype=np.int64)[rng.integers(0, len(mesh_ids_avail), n_objects)]
     material_ids = rng.integers(0, material_count, n_objects).astype(np.uint32)
+    if slabs:
+        # a floor and two back walls (one 12-triangle box each) so that the frame is fully covered, as in an interior scene;
+        # their screen-filling triangles exercise the banded large-triangle path
+        slab_mesh = r.add_mesh(cube_mesh())
+        e, t = f32(extent * 1.25), f32(0.5)
+        sc = np.array([[e, t, e], [t, e, e], [e, e, t]], dtype=f32)
+        tr = np.array([[0, -e, 0], [-e, 0, 0], [0, 0, e]], dtype=f32)
+        ident = np.tile(np.array([[0, 0, 0, 1]], dtype=f32), (3, 1))
+        transforms = np.concatenate([transforms, trs_matrices(tr, ident, sc)])
+        mesh_ids = np.concatenate([mesh_ids, np.full(3, slab_mesh, dtype=np.int64)])
+        material_ids = np.concatenate([material_ids, np.zeros(3, dtype=np.uint32)])
+        n_objects += 3
     rec, loc = bulk_object_records(r, transforms, mesh_ids, material_ids)
     return eval_with_bulk_objects(r, rec, loc, n_objects)
 
