@@ -77,24 +77,44 @@ __device__ __forceinline__ float3 surface_shading(const float3 l, const float3 i
                        (px.diffuse_pi.z + dv * f.z) * intensity.z * s);
 }
 
-// textureSampleCompareLevel: linear, GreaterEqual, Repeat-addressed comparison sampler (common/samplers.rs:24,42-56)
-__device__ __forceinline__ float sample_compare(const ShadeParams& p, float u, float v, float ref, int ox, int oy) {
-    const float x = u * (float)p.atlas_w + (float)ox - 0.5f, y = v * (float)p.atlas_h + (float)oy - 0.5f;
-    const float fx0 = floorf(x), fy0 = floorf(y), fx = x - fx0, fy = y - fy0;
-    const long long W = p.atlas_w, H = p.atlas_h, ix = (long long)fx0, iy = (long long)fy0;
-    const long long x0 = ((ix % W) + W) % W, x1 = (((ix + 1) % W) + W) % W, y0 = ((iy % H) + H) % H, y1 = (((iy + 1) % H) + H) % H;
-    const float c00 = ref >= __ldg(&p.atlas[y0 * W + x0]) ? 1.0f : 0.0f, c10 = ref >= __ldg(&p.atlas[y0 * W + x1]) ? 1.0f : 0.0f;
-    const float c01 = ref >= __ldg(&p.atlas[y1 * W + x0]) ? 1.0f : 0.0f, c11 = ref >= __ldg(&p.atlas[y1 * W + x1]) ? 1.0f : 0.0f;
-    const float top = c00 * (1.0f - fx) + c10 * fx, bot = c01 * (1.0f - fx) + c11 * fx;
-    return top * (1.0f - fy) + bot * fy;
+// shadow_sample_pcf5 (shadow/pcf.wgsl:1-9): five textureSampleCompareLevel taps (centre, +-1 texel in x and y) with the
+// linear, GreaterEqual, Repeat-addressed comparison sampler (common/samplers.rs:24,42-56).  All taps share the same
+// bilinear fractions, so the 20 texel compares collapse to the 12 distinct texels of a 4x4 neighbourhood without corners.
+__device__ __forceinline__ int wrap_texel(int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;   // common case: no division
+    const int m = i % n;
+    return m < 0 ? m + n : m;
 }
-__device__ __forceinline__ float shadow_pcf5(const ShadeParams& p, float u, float v, float depth) {   // shadow/pcf.wgsl:1-9
-    float r = sample_compare(p, u, v, depth, 0, 0);
-    r += sample_compare(p, u, v, depth, 0, 1);
-    r += sample_compare(p, u, v, depth, 0, -1);
-    r += sample_compare(p, u, v, depth, 1, 0);
-    r += sample_compare(p, u, v, depth, -1, 0);
-    return r * 0.2f;
+__device__ __forceinline__ float shadow_pcf5(const ShadeParams& p, float u, float v, float ref) {
+    const float x = u * (float)p.atlas_w - 0.5f, y = v * (float)p.atlas_h - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y), fx = x - fx0, fy = y - fy0;
+    // clamp before the int conversion: coordinates far outside the atlas only arise for fragments outside the light volume
+    const int ix = (int)fminf(fmaxf(fx0, -1.0e9f), 1.0e9f), iy = (int)fminf(fmaxf(fy0, -1.0e9f), 1.0e9f);
+    const int W = (int)p.atlas_w, H = (int)p.atlas_h;
+    int xs[4], ys[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { xs[k] = wrap_texel(ix - 1 + k, W); ys[k] = wrap_texel(iy - 1 + k, H); }
+    float c[4][4];   // c[row][col] = ref >= texel ? 1 : 0
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool corner = (r == 0 || r == 3) && (q == 0 || q == 3);
+            c[r][q] = (!corner && ref >= __ldg(&p.atlas[(size_t)ys[r] * W + xs[q]])) ? 1.0f : 0.0f;
+        }
+    const float gx = 1.0f - fx, gy = 1.0f - fy;
+    // bilinear(tap at texel offset (a, b)) = (c[b][a]*gx + c[b][a+1]*fx)*gy + (c[b+1][a]*gx + c[b+1][a+1]*fx)*fy, offsets re-based by +1
+    float h[4][3];   // horizontal lerps h[row][a] = c[row][a]*gx + c[row][a+1]*fx
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) h[r][a] = c[r][a] * gx + c[r][a + 1] * fx;
+    const float centre = h[1][1] * gy + h[2][1] * fy;
+    const float up = h[2][1] * gy + h[3][1] * fy;      // offset (0, +1)
+    const float down = h[0][1] * gy + h[1][1] * fy;    // offset (0, -1)
+    const float right = h[1][2] * gy + h[2][2] * fy;   // offset (+1, 0)
+    const float left = h[1][0] * gy + h[2][0] * fy;    // offset (-1, 0)
+    return ((((centre + up) + down) + right) + left) * 0.2f;
 }
 
 struct VsOut { float4 view_position; float3 normal; float4 color; };
