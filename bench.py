@@ -7,7 +7,7 @@
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic input:
   * headline workload (BASELINE config 4, the one the target metric is quoted on): fused per-object frustum cull +
     object-uniform bake over 10 M object records PER GPU (weak scaling), 1% disabled, visible list ascending;
-    at N > 1 the visible lists are all-gathered with NCCL (counts, then padded lists) as north_star asks;
+    at N > 1 the visible sets are all-gathered with NCCL (as 1-bit-per-object words) as north_star asks;
   * `value` = objects culled+baked per second, inputs resident in HBM, CUDA events on the library's stream;
   * `e2e`   = the same through the C ABI with HOST buffers: r3_set_objects (pinned H2D of every record) +
     r3_object_uniform_upload + r3_readback_visible (D2H) inside the timed region;
@@ -103,7 +103,7 @@ def reference_arm(args):
     if rank != 0:
         return
     n = min(args.objects, 2_000_000)   # bounded sample: 2 M of the 10 M records per step
-    cores = os.cpu_count() or 1
+    cores = oracle.set_threads(os.cpu_count() or 1)
     rec = object_cloud_records(n, seed=4)
     header = per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (1920, 1080), 1, n)
     b = oracle.load_oracle_backend()
@@ -129,6 +129,7 @@ def reference_arm(args):
 def cpu_baseline(n_total):
     import oracle
 
+    oracle.set_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1
     n = min(n_total, 2_000_000)
     rec = object_cloud_records(n, seed=4)
     header = per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (1920, 1080), 1, n)
@@ -140,7 +141,7 @@ def cpu_baseline(n_total):
         b.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
         reps += 1
     dt = (time.perf_counter() - t0) / reps
-    return {"value": n / dt, "unit": "objects/s", "cores": os.cpu_count() or 1, "kind": "port",
+    return {"value": n / dt, "unit": "objects/s", "cores": oracle.set_threads(os.cpu_count() or 1), "kind": "port",
             "sample": f"{n} of {n_total} records, {reps} repetitions, OpenMP over all host cores (oracle/r3_oracle.c)"}
 
 
@@ -157,6 +158,9 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return reference_arm(args)
+    # keep stdout clean for the single JSON line: anything libraries print (e.g. NCCL's version banner) goes to stderr
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -180,20 +184,18 @@ def main():
     header = per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (1920, 1080), 1, n)
     backend.set_objects(host_rec)
     vis_host = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    gathered_words = torch.empty(world * ((n + 31) // 32), dtype=torch.int32, device=f"cuda:{local}")
 
     def gather_visible():
+        """North-star exchange: every rank ends up with the visible set of all shards.  The set travels in its
+        1-bit-per-object form (the stream kernel's visibility words, n/8 bytes per shard instead of 4 B per visible
+        object): fixed size, so no count exchange and no host synchronisation."""
         if world == 1:
             return
-        cptr, _ = backend.device_ptr(CAMERA_VIEWPORT, 3)
-        vptr, vbytes = backend.device_ptr(CAMERA_VIEWPORT, 0)
+        wptr, wbytes = backend.device_ptr(CAMERA_VIEWPORT, 4)
         with torch.cuda.stream(stream):
-            cnt = torch.as_tensor(DeviceView(cptr, 4, "<i4", 4), device=f"cuda:{local}")
-            counts = torch.empty(world, dtype=torch.int32, device=f"cuda:{local}")
-            dist.all_gather_into_tensor(counts, cnt)
-            m = int(counts.max().item())
-            mine = torch.as_tensor(DeviceView(vptr, vbytes, "<i4", 4), device=f"cuda:{local}")[:max(m, 1)]
-            out = torch.empty(world * max(m, 1), dtype=torch.int32, device=f"cuda:{local}")
-            dist.all_gather_into_tensor(out, mine)
+            mine = torch.as_tensor(DeviceView(wptr, wbytes, "<i4", 4), device=f"cuda:{local}")
+            dist.all_gather_into_tensor(gathered_words, mine)
 
     def step_resident():
         backend.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
@@ -304,7 +306,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE config 4: fused frustum cull + uniform bake, 10 M object records per GPU (128 B std430 records, 1% disabled)",
-                       "objects_per_gpu": n, "visible_fraction": n_vis / n, "parallelism": f"object-range shards x{world}, NCCL all-gather of the visible lists" if world > 1 else "single GPU",
+                       "objects_per_gpu": n, "visible_fraction": n_vis / n, "parallelism": f"object-range shards x{world}, NCCL all-gather of the visibility words (1 bit/object)" if world > 1 else "single GPU",
                        "l2": "inputs (1.28 GB) + outputs (1.28 GB) per step exceed the 126 MB L2; no explicit flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "cull_bake_kernel<bake,cull>", "kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_launch": BYTES_PER_OBJECT * n + BYTES_PER_VISIBLE * n_vis,
@@ -312,6 +314,8 @@ def main():
             "cpu_baseline": cpu_baseline(n),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "forward": forward,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -139,7 +139,8 @@ int r3_forward_stats(r3_ctx*, uint64_t stats[4]);
 
 /* ------------------------------------------------------------------ multi-GPU plumbing
  * raw device views so torch.distributed / NCCL can move the visible list and tile rows without a
- * host bounce.  which: 0 visible list (u32), 1 hdr f16 colour, 2 object matrices */
+ * host bounce.  which: 0 visible list (u32), 1 hdr f16 colour, 2 object matrices, 3 visible count (u32),
+ * 4 visibility words (1 bit per object slot, bit i of word w = slot 32*w + i) */
 int r3_device_ptr(r3_ctx*, uint32_t camera, int which, void** device_ptr, uint64_t* nbytes);
 /* restrict rasterisation + shading to pixel rows [row_begin, row_end) (screen-tile split) */
 int r3_set_scissor_rows(r3_ctx*, uint32_t row_begin, uint32_t row_end);

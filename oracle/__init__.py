@@ -28,3 +28,10 @@ def load_oracle_backend():
     from rend3_b200.backend import Backend
 
     return Backend(ctypes.CDLL(build()), "r3o_", 0)
+
+
+def set_threads(n: int) -> int:
+    """Pin the oracle's OpenMP thread count (torchrun exports OMP_NUM_THREADS=1); returns the count in effect."""
+    lib = ctypes.CDLL(build())
+    lib.r3o_set_threads(int(n))
+    return int(lib.r3o_get_threads())
