@@ -71,7 +71,7 @@ int r3_host_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], uint
     const int w = (cam->cache_idx == 0) ? 1 : 0;   // never overwrite the DrawCallSet cached for the predicted pass
     cam->cur = w;
     r3_jobs& jobs = cam->jobs[w];
-    jobs.batches.clear(); jobs.regions.clear(); jobs.total_invocations = 0; jobs.valid = false;
+    jobs.batches.clear(); jobs.regions.clear(); jobs.total_invocations = 0; jobs.valid = false; jobs.device_built = false;
 
     std::vector<uint32_t> cur_map(cap, R3_NO_PREVIOUS);          // get_and_reset_camera / set_camera (batching.rs:111-117)
     const std::vector<uint32_t>& prev_map = cam->prev_invocation;
@@ -145,6 +145,9 @@ int r3_upload_jobs(r3_ctx* c, r3_camera* cam) {
     R3_CUDA(c, cudaMemcpyAsync(j.d_batches, j.batches.data(), (size_t)nb * sizeof(r3_batch_data), cudaMemcpyHostToDevice, c->stream));
     R3_CUDA(c, cudaMemcpyAsync(j.d_regions, j.regions.data(), (size_t)nr * sizeof(r3_region), cudaMemcpyHostToDevice, c->stream));
     R3_CUDA(c, cudaMemcpyAsync(j.d_region_first_inv, first.data(), ((size_t)nr + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    if (!j.d_header) R3_CUDA(c, cudaMalloc((void**)&j.d_header, 32));
+    const uint32_t hdr[8] = {(uint32_t)(cam->visible_count_host < 0 ? 0 : cam->visible_count_host), nb, nr, j.total_invocations, 0, 0, 0, 0};
+    R3_CUDA(c, cudaMemcpyAsync(j.d_header, hdr, 32, cudaMemcpyHostToDevice, c->stream));
     R3_CUDA(c, cudaStreamSynchronize(c->stream));   // `first` and the vectors are pageable host memory
     j.n_batches = nb; j.n_regions = nr; j.valid = true;
     return R3_OK;

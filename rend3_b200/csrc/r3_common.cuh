@@ -26,7 +26,11 @@ struct r3_jobs {
     r3_batch_data* d_batches = nullptr; uint32_t batches_cap = 0, n_batches = 0;
     r3_region* d_regions = nullptr; uint32_t regions_cap = 0, n_regions = 0;
     uint32_t* d_region_first_inv = nullptr;   // [n_regions+1] first global invocation of each region
-    uint32_t total_invocations = 0;
+    // device-side job header the downstream kernels read their counts from (so a frame needs no host sync):
+    // [0] n_visible  [1] n_batches  [2] n_regions  [3] total_invocations  [4] overflow flag
+    uint32_t* d_header = nullptr;
+    uint32_t total_invocations = 0;           // exact (host batching) or an upper bound (device batching)
+    bool device_built = false;                // host vectors are filled lazily by readbacks
     std::vector<r3_batch_data> batches;      // host copies (batch_objects builds these on the CPU)
     std::vector<r3_region> regions;
     bool valid = false;
@@ -42,7 +46,11 @@ struct r3_camera {
     int visible_count_host = -1;              // cached after a readback, -1 = unknown
     r3_jobs jobs[2]; int cur = 0;             // jobs[cur] = this frame, jobs[cur^1] = cached DrawCallSet (forward.rs:219)
     bool has_draw_call_set = false; int cache_idx = -1;   // cache_idx: which jobs[] the forward routine cached, -1 = none
-    std::vector<uint32_t> prev_invocation;    // PerCameraPreviousInvocationsMap (batching.rs:102-118)
+    std::vector<uint32_t> prev_invocation;    // PerCameraPreviousInvocationsMap (batching.rs:102-118), host batching
+    uint32_t* d_prev_inv[2] = {nullptr, nullptr}; uint32_t prev_inv_cap = 0; int prev_inv_cur = 0;   // same map, device batching
+    unsigned long long* d_sort_keys[2] = {nullptr, nullptr}; uint64_t sort_keys_cap = 0, sort_keys_cap2 = 0;
+    uint32_t* d_sort_hist = nullptr; uint64_t sort_hist_cap = 0;
+    uint32_t* d_batch_tmp = nullptr; uint64_t batch_tmp_cap = 0;
     r3_iobuf index_buffer, draw_call_buffer, results_buffer;   // CullingBuffers (culler.rs:88-125)
     // scratch of the ordered triangle compaction
     uint32_t* d_resid_bits = nullptr; uint64_t resid_bits_cap = 0;
@@ -62,6 +70,8 @@ struct r3_ctx {
     r3_object* d_objects = nullptr; uint32_t n_slots = 0, objects_cap = 0; bool objects_borrowed = false;
     std::vector<uint64_t> sort_key; std::vector<uint8_t> sort_flags; std::vector<float> sort_loc;
     uint32_t* d_live_bits = nullptr; uint32_t live_bits_cap = 0; bool have_live = false;
+    uint8_t* d_sort_key8 = nullptr; float* d_sort_loc = nullptr; uint32_t sort_dev_cap = 0; bool gpu_batching_ok = false;
+    uint64_t max_total_invocations = 0; bool max_invocations_valid = false;   // sum over all slots of round_up(tris, 256)
     uint32_t* d_mesh = nullptr; uint64_t mesh_words = 0, mesh_cap = 0;
     r3_material* d_materials = nullptr; uint32_t n_materials = 0, materials_cap = 0;
     r3_directional_light* d_dir = nullptr; uint32_t n_dir = 0, dir_cap = 0;
@@ -123,6 +133,9 @@ int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode);
 int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam);
 int r3_host_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], uint32_t max_dispatch_count);
 int r3_upload_jobs(r3_ctx* c, r3_camera* cam);
+int r3_device_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], uint32_t max_dispatch_count);
+int r3_download_jobs(r3_ctx* c, r3_camera* cam);          // device-built jobs -> host vectors (readbacks / tests)
+int r3_compute_max_invocations(r3_ctx* c);
 int r3_iobuf_new(r3_ctx* c, r3_iobuf* b, uint64_t elems, uint64_t elem_size, bool clear_on_swap);
 int r3_iobuf_swap(r3_ctx* c, r3_iobuf* b, uint64_t new_elems);
 

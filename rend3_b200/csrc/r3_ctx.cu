@@ -1,6 +1,7 @@
 // r3_ctx.cu — context, uploads, readbacks and the C ABI glue of librend3_b200.so (include/rend3_b200.h).
 // Host logic only; the kernels live in r3_cull_bake.cu, r3_tri_cull.cu, r3_raster.cu, r3_shade.cu.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -60,13 +61,14 @@ R3_EXPORT int r3_ctx_create(int device, r3_ctx** out) {
     return R3_OK;
 }
 
-static void free_jobs(r3_jobs& j) { cudaFree(j.d_batches); cudaFree(j.d_regions); cudaFree(j.d_region_first_inv); }
+static void free_jobs(r3_jobs& j) { cudaFree(j.d_batches); cudaFree(j.d_regions); cudaFree(j.d_region_first_inv); cudaFree(j.d_header); }
 
 R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     if (!c) return R3_E_INVALID;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (!c->objects_borrowed) cudaFree(c->d_objects);
+    cudaFree(c->d_sort_key8); cudaFree(c->d_sort_loc);
     cudaFree(c->d_live_bits); cudaFree(c->d_mesh); cudaFree(c->d_materials); cudaFree(c->d_dir); cudaFree(c->d_point);
     cudaFree(c->d_light_mats); cudaFree(c->d_atlas);
     for (auto& k : c->cams) {
@@ -74,6 +76,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
         free_jobs(k.jobs[0]); free_jobs(k.jobs[1]);
         cudaFree(k.index_buffer.d); cudaFree(k.draw_call_buffer.d); cudaFree(k.results_buffer.d);
         cudaFree(k.d_resid_bits); cudaFree(k.d_word_scan); cudaFree(k.d_block_sums);
+        cudaFree(k.d_prev_inv[0]); cudaFree(k.d_prev_inv[1]); cudaFree(k.d_sort_keys[0]); cudaFree(k.d_sort_keys[1]); cudaFree(k.d_sort_hist); cudaFree(k.d_batch_tmp);
     }
     cudaFree(c->d_vis); cudaFree(c->d_hdr32); cudaFree(c->d_hdr16); cudaFree(c->d_depth); cudaFree(c->d_ldr);
     for (float* p : c->d_hiz) cudaFree(p);
@@ -108,6 +111,7 @@ R3_EXPORT int r3_set_objects(r3_ctx* c, const r3_object* recs, uint32_t n) {
     R3_TRY(r3_reserve_t(c, &c->d_objects, &c->objects_cap, n));
     if (n) R3_CUDA(c, cudaMemcpyAsync(c->d_objects, recs, (size_t)n * sizeof(r3_object), cudaMemcpyHostToDevice, c->stream));
     c->n_slots = n;
+    c->max_invocations_valid = false;
     R3_CUDA(c, cudaStreamSynchronize(c->stream));   // host pointer is only borrowed for the call
     return R3_OK;
 }
@@ -116,6 +120,7 @@ R3_EXPORT int r3_set_objects_device(r3_ctx* c, const void* dptr, uint32_t n) {
     if (!c->objects_borrowed) { cudaFree(c->d_objects); }
     c->d_objects = (r3_object*)dptr;
     c->objects_cap = n; c->n_slots = n; c->objects_borrowed = true;
+    c->max_invocations_valid = false;
     return R3_OK;
 }
 
@@ -139,6 +144,7 @@ R3_EXPORT int r3_update_objects(r3_ctx* c, const uint32_t* slots, const r3_objec
     R3_CUDA(c, cudaMemcpyAsync(d_slots, slots, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
     scatter_objects_kernel<<<(n * 8 + 255) / 256, 256, 0, c->stream>>>(c->d_objects, d_recs, d_slots, n, c->n_slots);
     R3_CHECK_LAUNCH(c, "scatter_objects_kernel");
+    c->max_invocations_valid = false;
     R3_CUDA(c, cudaStreamSynchronize(c->stream));
     return R3_OK;
 }
@@ -154,8 +160,28 @@ R3_EXPORT int r3_set_object_sort_info(r3_ctx* c, const uint64_t* key, const uint
         if (flags[i] & 1) bits[i >> 5] |= 1u << (i & 31);
     R3_TRY(r3_reserve_t(c, &c->d_live_bits, &c->live_bits_cap, words));
     R3_CUDA(c, cudaMemcpyAsync(c->d_live_bits, bits.data(), (size_t)words * 4, cudaMemcpyHostToDevice, c->stream));
+    // device copies for the on-device batch_objects: key8 = ((material_key << 1 | reason) << 1) | back_to_front
+    bool ok = true;
+    std::vector<uint8_t> key8(n ? n : 1, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (key[i] >= 64) ok = false;
+        const uint32_t reason = (flags[i] & 2) ? 0u : 1u;
+        key8[i] = (uint8_t)(((((uint32_t)key[i] & 63u) << 1 | reason) << 1) | ((flags[i] & 4) ? 1u : 0u));
+    }
+    uint32_t cap2 = c->sort_dev_cap;
+    R3_TRY(r3_reserve_t(c, &c->d_sort_key8, &c->sort_dev_cap, n));
+    if (!c->d_sort_loc || cap2 != c->sort_dev_cap) {
+        cudaFree(c->d_sort_loc);
+        c->d_sort_loc = nullptr;
+        R3_CUDA(c, cudaMalloc((void**)&c->d_sort_loc, ((size_t)c->sort_dev_cap * 3 + 4) * 4));
+    }
+    if (n) {
+        R3_CUDA(c, cudaMemcpyAsync(c->d_sort_key8, key8.data(), n, cudaMemcpyHostToDevice, c->stream));
+        R3_CUDA(c, cudaMemcpyAsync(c->d_sort_loc, loc, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+    }
     R3_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_live = true;
+    c->gpu_batching_ok = ok && n < (1u << 24) && !getenv("R3_HOST_BATCHING");
     return R3_OK;
 }
 R3_EXPORT int r3_set_mesh_buffer(r3_ctx* c, const void* bytes, uint64_t nbytes) {
@@ -348,18 +374,27 @@ R3_EXPORT int r3_batch_objects(r3_ctx* c, uint32_t camera, const float vp_loc[3]
     R3_CAM_OR_FAIL(c, camera);
     if (!vp_loc) return r3_fail(c, R3_E_INVALID, "batch_objects: null location");
     cudaSetDevice(c->device);
+    if (c->gpu_batching_ok && c->sort_key.size() >= cam->header.object_count) return r3_device_batch_objects(c, cam, vp_loc, max_dispatch_count);
     return r3_host_batch_objects(c, cam, vp_loc, max_dispatch_count);
 }
 R3_EXPORT int r3_batch_counts(r3_ctx* c, uint32_t camera, uint32_t* nb, uint32_t* nr, uint32_t* tot) {
     R3_CAM_OR_FAIL(c, camera);
+    cudaSetDevice(c->device);
+    R3_TRY(r3_download_jobs(c, cam));
     const r3_jobs& j = cam->jobs[cam->cur];
     if (nb) *nb = (uint32_t)j.batches.size();
     if (nr) *nr = (uint32_t)j.regions.size();
-    if (tot) *tot = j.total_invocations;
+    if (tot) {
+        uint64_t t = 0;
+        for (const auto& b : j.batches) t += b.total_invocations;
+        *tot = (uint32_t)t;
+    }
     return R3_OK;
 }
 R3_EXPORT int r3_readback_batches(r3_ctx* c, uint32_t camera, r3_batch_data* b, r3_region* r) {
     R3_CAM_OR_FAIL(c, camera);
+    cudaSetDevice(c->device);
+    R3_TRY(r3_download_jobs(c, cam));
     const r3_jobs& j = cam->jobs[cam->cur];
     if (b && !j.batches.empty()) memcpy(b, j.batches.data(), j.batches.size() * sizeof *b);
     if (r && !j.regions.empty()) memcpy(r, j.regions.data(), j.regions.size() * sizeof *r);
@@ -380,9 +415,12 @@ R3_EXPORT int r3_cull(r3_ctx* c, uint32_t camera, const r3_batch_data* batches, 
         uint64_t tot = 0;
         for (const auto& b : j.batches) tot += b.total_invocations;
         j.total_invocations = (uint32_t)tot;
+        j.device_built = false;
     }
-    if (j.batches.empty()) { cam->has_draw_call_set = false; return R3_OK; }   // culler.rs:705-707
-    R3_TRY(r3_upload_jobs(c, cam));
+    if (!j.device_built) {
+        if (j.batches.empty()) { cam->has_draw_call_set = false; return R3_OK; }   // culler.rs:705-707
+        R3_TRY(r3_upload_jobs(c, cam));
+    }
     return r3_launch_triangle_cull(c, cam);
 }
 

@@ -34,7 +34,7 @@ static_assert(sizeof(SubTri) == 40, "SubTri");
 
 struct RasterParams {
     // draw source
-    const r3_batch_data* batches; const r3_region* regions; uint32_t n_regions;
+    const r3_batch_data* batches; const r3_region* regions; const uint32_t* header;   // header[2] = n_regions (device-side count)
     const r3_indirect_call* calls; const uint32_t* indices; uint64_t index_elems;
     const unsigned long long* tri_prefix;      // [n_regions + 1] exclusive prefix of listed triangles (opaque + cutout)
     const r3_object* objects; uint32_t n_slots;
@@ -214,11 +214,12 @@ __device__ bool process_subtriangle(const RasterParams& p, const float4 a, const
 
 template <bool DEPTH_ONLY>
 __global__ void __launch_bounds__(RS_THREADS) raster_setup_kernel(const __grid_constant__ RasterParams p) {
-    const unsigned long long total = p.tri_prefix[p.n_regions];
+    const uint32_t n_regions = p.header[2];
+    const unsigned long long total = p.tri_prefix[n_regions];
     uint32_t frags = 0, set_up = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * RS_THREADS + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * RS_THREADS) {
         // region of listed triangle i: last r with tri_prefix[r] <= i
-        uint32_t lo = 0, hi = p.n_regions;
+        uint32_t lo = 0, hi = n_regions;
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
             if (p.tri_prefix[mid] <= i) lo = mid; else hi = mid;
@@ -327,10 +328,11 @@ __global__ void __launch_bounds__(RS_THREADS) raster_band_kernel(const __grid_co
 }
 
 // exclusive prefix over the regions the opaque (key 0) and cutout (key 1) routines draw (forward.rs:286-313)
-__global__ void region_prefix_kernel(const r3_region* __restrict__ regions, const r3_indirect_call* __restrict__ calls, uint32_t n_regions,
+__global__ void region_prefix_kernel(const r3_region* __restrict__ regions, const r3_indirect_call* __restrict__ calls, const uint32_t* __restrict__ header,
                                      unsigned long long* __restrict__ prefix) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry;
+    const uint32_t n_regions = header[2];
     if (threadIdx.x == 0) s_carry = 0ull;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -373,7 +375,7 @@ struct DrawSource { const r3_jobs* jobs; const r3_indirect_call* calls; const ui
 static bool draw_source_for(r3_camera* cam, int jobs_idx, int partition, DrawSource* ds) {
     if (!cam->index_buffer.created || jobs_idx < 0) return false;
     const r3_jobs* j = &cam->jobs[jobs_idx];
-    if (!j->valid || j->n_regions == 0) return false;
+    if (!j->valid || (!j->device_built && j->n_regions == 0)) return false;
     const r3_iobuf& ib = cam->index_buffer; const r3_iobuf& db = cam->draw_call_buffer;
     if (j->n_regions > db.capacity_elements / 2) return false;
     ds->jobs = j;
@@ -398,11 +400,11 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, bool dept
     uint2* bands = (uint2*)((uint8_t*)large + (size_t)LARGE_CAP * sizeof(SubTri));
     R3_CUDA(c, cudaMemsetAsync(counters, 0, 64, c->stream));
     R3_TRY(r3_reserve_t(c, &cam->d_block_sums, &cam->block_sums_cap, (uint64_t)j->n_regions + 2));
-    region_prefix_kernel<<<1, 1024, 0, c->stream>>>(j->d_regions, ds.calls, j->n_regions, cam->d_block_sums);
+    region_prefix_kernel<<<1, 1024, 0, c->stream>>>(j->d_regions, ds.calls, j->d_header, cam->d_block_sums);
     R3_CHECK_LAUNCH(c, "region_prefix_kernel");
 
     RasterParams p;
-    p.batches = j->d_batches; p.regions = j->d_regions; p.n_regions = j->n_regions;
+    p.batches = j->d_batches; p.regions = j->d_regions; p.header = j->d_header;
     p.calls = ds.calls; p.indices = ds.indices; p.index_elems = ds.index_elems; p.tri_prefix = cam->d_block_sums;
     p.objects = c->d_objects; p.n_slots = c->n_slots; p.matrices = cam->d_matrices; p.matrices_cap = cam->matrices_cap;
     p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;

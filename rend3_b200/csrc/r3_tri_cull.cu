@@ -28,7 +28,7 @@ struct TriCullParams {
     const r3_batch_data* batches;
     const uint32_t* wg_info;             // per workgroup: (batch << 8) | batch-local object
     const uint32_t* region_first_inv;    // [n_regions + 1]
-    uint32_t n_workgroups;
+    const uint32_t* header;              // job header: [1] n_batches, [3] total_invocations (device-side counts)
     uint32_t* idx_pred; uint32_t* idx_resid;
     r3_indirect_call* dc_pred; r3_indirect_call* dc_resid;
     uint32_t* res_out; const uint32_t* res_in; uint64_t res_in_words;
@@ -106,8 +106,9 @@ __device__ bool execute_culling(const TriCullParams& p, const float* __restrict_
     return !(depth < occl);
 }
 
-__global__ void expand_wg_info_kernel(const r3_batch_data* __restrict__ batches, uint32_t* __restrict__ wg_info) {
+__global__ void expand_wg_info_kernel(const r3_batch_data* __restrict__ batches, const uint32_t* __restrict__ header, uint32_t* __restrict__ wg_info) {
     const uint32_t b = blockIdx.x, o = threadIdx.x;
+    if (b >= header[1]) return;
     const r3_batch_data* job = &batches[b];
     if (o >= job->total_objects) return;
     const r3_object_culling_info info = job->object_culling_information[o];
@@ -122,13 +123,14 @@ __global__ void __launch_bounds__(TC_THREADS) triangle_cull_kernel(const __grid_
     __shared__ uint32_t s_base_pred, s_base_resid;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool shadow = p.cam.shadow_index != R3_CAMERA_VIEWPORT;
+    const uint32_t n_workgroups = p.header[3] / TC_THREADS;
 
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_wg = (uint32_t)atomicAdd(&p.state[0], 1ull);
         __syncthreads();
         const uint32_t wg = s_wg;
-        if (wg >= p.n_workgroups) return;
+        if (wg >= n_workgroups) return;
 
         const uint32_t wi = __ldg(&p.wg_info[wg]);
         const r3_batch_data* job = &p.batches[wi >> 8];
@@ -267,14 +269,14 @@ int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam) {
     R3_TRY(r3_reserve_t(c, &cam->d_resid_bits, &cam->resid_bits_cap, n_wg));
     R3_TRY(r3_reserve_t(c, &cam->d_word_scan, &cam->word_scan_cap, (uint64_t)n_wg + 1));
     R3_CUDA(c, cudaMemsetAsync(cam->d_word_scan, 0, ((size_t)n_wg + 1) * 8, c->stream));
-    expand_wg_info_kernel<<<j.n_batches, 256, 0, c->stream>>>(j.d_batches, cam->d_resid_bits);
+    expand_wg_info_kernel<<<j.n_batches, 256, 0, c->stream>>>(j.d_batches, j.d_header, cam->d_resid_bits);
     R3_CHECK_LAUNCH(c, "expand_wg_info_kernel");
 
     TriCullParams p;
     p.cam = cam->header;
     p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;
     p.objects = c->d_objects; p.matrices = cam->d_matrices; p.batches = j.d_batches;
-    p.wg_info = cam->d_resid_bits; p.region_first_inv = j.d_region_first_inv; p.n_workgroups = n_wg;
+    p.wg_info = cam->d_resid_bits; p.region_first_inv = j.d_region_first_inv; p.header = j.d_header;
     p.idx_pred = (uint32_t*)cam->index_buffer.d + cam->index_buffer.out_off();
     p.idx_resid = (uint32_t*)cam->index_buffer.d + cam->index_buffer.in_off();
     p.dc_pred = (r3_indirect_call*)cam->draw_call_buffer.d + cam->draw_call_buffer.out_off();

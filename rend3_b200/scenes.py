@@ -126,7 +126,7 @@ def subdivided_cube_mesh(k: int):
 def cube_field_scene(n_objects: int = 10_000, seed: int = 1, resolution: Tuple[int, int] = (1920, 1080), extent: float = 50.0,
                      pull_back: float = 20.0, n_point_lights: int = 0, n_dir_lights: int = 1, shadow_resolution: int = 2048,
                      shadow_distance: float = 400.0, roughness: float = 0.5, subdivisions=(1,), material_count: int = 1,
-                     scale_range: Tuple[float, float] = (0.2, 1.0), slabs: bool = False) -> EvalOutput:
+                     scale_range: Tuple[float, float] = (0.2, 1.0), slabs: bool = False, mixed_transparency: bool = False) -> EvalOutput:
     """BASELINE config C1 family: n cubes, centres U([-extent, extent]^3), uniform scale U(0.2, 1),
     random rotation, PBR material albedo 0.5, directional light(s) like examples/src/cube, camera pulled back."""
     rng = np.random.default_rng(seed)
@@ -134,7 +134,10 @@ def cube_field_scene(n_objects: int = 10_000, seed: int = 1, resolution: Tuple[i
     mesh_ids_avail = [r.add_mesh(subdivided_cube_mesh(k)) for k in subdivisions]
     for m in range(material_count):
         g = 0.5 if material_count == 1 else 0.25 + 0.5 * (m / max(material_count - 1, 1))
-        r.add_material(PbrMaterial(albedo_value=(0.5, g, 0.5 if material_count == 1 else 1.0 - g, 1.0), roughness_factor=roughness))
+        # mixed_transparency: materials cycle opaque / cutout / blend, i.e. material keys 0 / 1 / 2 (pbr/material.rs:497-503)
+        transparency = (m % 3) if mixed_transparency else 0
+        r.add_material(PbrMaterial(albedo_value=(0.5, g, 0.5 if material_count == 1 else 1.0 - g, 1.0), roughness_factor=roughness,
+                                   transparency=transparency))
     r.set_camera_data(cube_example_camera(pull_back))
     dirs = [(-1.0, -4.0, 2.0), (2.0, -3.0, -1.0), (-2.0, -5.0, -3.0), (1.0, -2.0, 3.0)]
     for i in range(n_dir_lights):

@@ -106,17 +106,26 @@ def compare_frame_state(cuda, orc, ev, cameras, check_pixels=True, what=""):
     for cam in cameras:
         bc, rc = cuda.readback_batches(cam)
         bo, ro = orc.readback_batches(cam)
-        assert bc.tobytes() == bo.tobytes() and rc.tobytes() == ro.tobytes(), f"{what} camera {cam}: batches differ"
+        assert len(bc) == len(bo) and rc.tobytes() == ro.tobytes(), f"{what} camera {cam}: batch / region tables differ"
+        for k in range(len(bo)):   # slots past total_objects are unspecified (the reference reuses its scratch array, batching.rs:186)
+            n_obj = int(bo[k]["total_objects"])
+            for f in ("total_objects", "total_invocations", "batch_base_invocation"):
+                assert bc[k][f] == bo[k][f], f"{what} camera {cam}: batch {k} {f}"
+            assert bc[k]["object_culling_information"][:n_obj].tobytes() == bo[k]["object_culling_information"][:n_obj].tobytes(), \
+                f"{what} camera {cam}: batch {k} object table differs"
         for part in (0, 1):
+            # the CUDA path sizes its buffers with device-side upper bounds: compare what the oracle defines, the rest stays cleared
             dc, do = cuda.readback_draw_calls(cam, part), orc.readback_draw_calls(cam, part)
-            assert dc.tobytes() == do.tobytes(), f"{what} camera {cam}: draw calls (partition {part}) differ"
+            assert dc[:len(do)].tobytes() == do.tobytes(), f"{what} camera {cam}: draw calls (partition {part}) differ"
+            assert not dc[len(do):].view(np.uint8).any(), f"{what} camera {cam}: stray draw calls"
             ic, io = cuda.readback_indices(cam, part), orc.readback_indices(cam, part)
-            for r in range(len(dc)):   # only the listed part of each region is defined
-                b0, cnt = int(dc[r]["base_index"]), int(dc[r]["vertex_count"])
+            for r in range(len(do)):   # only the listed part of each region is defined
+                b0, cnt = int(do[r]["base_index"]), int(do[r]["vertex_count"])
                 if part == 1 and cam != CAMERA_VIEWPORT:
                     continue
                 assert np.array_equal(ic[b0:b0 + cnt], io[b0:b0 + cnt]), f"{what} camera {cam}: index list of region {r} differs"
-        assert np.array_equal(cuda.readback_culling_results(cam, 0), orc.readback_culling_results(cam, 0)), f"{what}: visibility bits differ"
+        ro_bits = orc.readback_culling_results(cam, 0)
+        assert np.array_equal(cuda.readback_culling_results(cam, 0)[:len(ro_bits)], ro_bits), f"{what}: visibility bits differ"
     if check_pixels:
         assert np.array_equal(cuda.readback_depth().view(np.uint32), orc.readback_depth().view(np.uint32)), f"{what}: depth differs"
         hdr_close(cuda.readback_hdr_f32(), orc.readback_hdr_f32(), what + " hdr f32")
@@ -225,3 +234,23 @@ def test_error_paths(cuda):
     hdr = per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (64, 64), 1, 9)   # object_count > buffer
     with pytest.raises(R3Error):
         cuda.object_uniform_upload(CAMERA_VIEWPORT, hdr)
+
+
+def test_device_batching_equals_host_batching_and_oracle(cuda, monkeypatch):
+    """batch_objects on the device (radix sort + block scans) against the host implementation and the oracle, with
+    three material keys (opaque / cutout / blend: atomic and non-atomic regions, front-to-back and back-to-front)."""
+    res = (320, 180)
+    ev = cube_field_scene(n_objects=3000, seed=12, resolution=res, n_dir_lights=1, shadow_resolution=256, shadow_distance=120.0, pull_back=9.0,
+                          extent=25.0, subdivisions=(1, 2, 5), material_count=6, mixed_transparency=True)
+    orc = load_oracle_backend()
+    BaseRenderGraph(orc).add_to_graph(ev, res, 1, BaseRenderGraphSettings())
+    BaseRenderGraph(cuda).add_to_graph(ev, res, 1, BaseRenderGraphSettings())
+    compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], what="device batching")
+    bo, ro = orc.readback_batches(CAMERA_VIEWPORT)
+    assert len(bo) > 1 and len(ro) > len(bo), "scene must span several batches and split regions on key changes"
+    assert set(int(r["material_key"]) for r in ro) == {0, 1, 2}
+    monkeypatch.setenv("R3_HOST_BATCHING", "1")
+    host = load_cuda_backend(0)
+    BaseRenderGraph(host).add_to_graph(ev, res, 1, BaseRenderGraphSettings())
+    compare_frame_state(host, orc, ev, [CAMERA_VIEWPORT, 0], what="host batching")
+    host.close()
