@@ -11,8 +11,8 @@
 // into one integer max in L2.  fs_main then runs once per pixel (r3_shade.cu) instead of once per fragment.
 // Shadow maps are the same kernels with a 32-bit atomicMax on the depth bits of the atlas.
 //   * setup kernel: persistent grid (148 x 8 CTAs), one thread per listed triangle; small triangles (bounding box
-//     <= 16x16 pixels, the common case at 500k+ triangles / frame) are rasterised inline by the thread with
-//     incremental 64-bit edge functions;
+//     <= 64 pixels) are rasterised inline by the thread with incremental 64-bit edge functions; medium ones
+//     (box <= 32x32) are handed to the whole warp: ballot, broadcast the setup by shuffle, 32 pixels per step;
 //   * larger ones are split into 16-row bands and queued; the band kernel gives each band to one warp, lanes
 //     span 32 consecutive pixels so the visibility-buffer atomics of a warp hit one or two 128-byte lines,
 //     and 32x16 blocks entirely outside an edge are skipped with one corner evaluation per edge.
@@ -24,10 +24,11 @@ namespace {
 
 constexpr int RS_THREADS = 256;
 constexpr float GUARD = 64.0f;
-constexpr int SMALL_MAX = 16;            // inline raster when the pixel bounding box is at most 16 x 16
+constexpr int SMALL_AREA = 64;           // inline raster when the pixel bounding box covers at most 64 pixels
+constexpr int MEDIUM_MAX = 32;           // warp-cooperative raster up to a 32 x 32 pixel box (<= 32 steps of 32 lanes)
 constexpr int BAND_ROWS = 16;
-constexpr uint32_t LARGE_CAP = 1u << 20; // queued large sub-triangles
-constexpr uint32_t BAND_CAP = 1u << 22;  // queued (sub-triangle, band) items
+constexpr uint32_t LARGE_CAP = 1u << 22; // queued large sub-triangles (160 MB)
+constexpr uint32_t BAND_CAP = 1u << 24;  // queued (sub-triangle, band) items (128 MB)
 
 struct SubTri { int32_t x[3], y[3]; float z[3]; uint32_t rec; };   // oriented (area > 0), snapped 24.8
 static_assert(sizeof(SubTri) == 40, "SubTri");
@@ -150,9 +151,13 @@ __device__ __forceinline__ void pixel_bounds(const RasterParams& p, const SubTri
     py0 = max((miny - 128 + 255) >> 8, p.y0); py1 = min((maxy - 128) >> 8, p.y1 - 1);
 }
 
-// R2-R4 for one sub-triangle: snap, orient, then rasterise inline or queue
+// R2-R4 for one sub-triangle: snap, orient, then pick the raster path by the size of its pixel bounding box:
+//   small  (<= 8x8 .. 64 px)   : inline, by the thread that set it up;
+//   medium (<= 32 x 32)         : handed back through `defer` and rasterised by the whole warp (32 pixels per step);
+//   large                       : split into 16-row bands and queued for raster_band_kernel.
 template <bool DEPTH_ONLY>
-__device__ bool process_subtriangle(const RasterParams& p, const float4 a, const float4 b, const float4 c, uint32_t rec, uint32_t& frags) {
+__device__ bool process_subtriangle(const RasterParams& p, const float4 a, const float4 b, const float4 c, uint32_t rec, uint32_t& frags, SubTri* defer,
+                                    bool* deferred) {
     const float4 v[3] = {a, b, c};
     int sx[3], sy[3];
     float sz[3];
@@ -182,7 +187,12 @@ __device__ bool process_subtriangle(const RasterParams& p, const float4 a, const
     pixel_bounds(p, s, px0, py0, px1, py1);
     if (px0 > px1 || py0 > py1) return true;   // set up, but no sample inside the target rectangle
     const int w = px1 - px0 + 1, h = py1 - py0 + 1;
-    bool inline_raster = (w <= SMALL_MAX && h <= SMALL_MAX);
+    bool inline_raster = (w * h <= SMALL_AREA);
+    if (!inline_raster && defer && w <= MEDIUM_MAX && h <= MEDIUM_MAX) {
+        *defer = s;
+        *deferred = true;
+        return true;
+    }
     if (!inline_raster) {
         const uint32_t nb = (uint32_t)((py1 / BAND_ROWS) - (py0 / BAND_ROWS) + 1);
         const uint32_t li = atomicAdd(&p.counters[0], 1u);
@@ -197,7 +207,12 @@ __device__ bool process_subtriangle(const RasterParams& p, const float4 a, const
             for (uint32_t k = 0; k < nb; ++k) p.bands[bi + k] = make_uint2(li, (uint32_t)(py0 / BAND_ROWS) + k);
             return true;
         }
-        inline_raster = true;   // queue full: stay correct, rasterise here
+        if (defer) {   // queues full: stay correct, let the warp rasterise it
+            *defer = s;
+            *deferred = true;
+            return true;
+        }
+        inline_raster = true;
     }
     const EdgeSetup e = make_edges(s, px0, py0);
     long long r0 = e.e0, r1 = e.e1, r2 = e.e2;
@@ -212,76 +227,117 @@ __device__ bool process_subtriangle(const RasterParams& p, const float4 a, const
     return true;
 }
 
+// medium triangles: all 32 lanes rasterise one sub-triangle; the lane grid is 32x1, 16x2 or 8x4 pixels depending on the box width
+template <bool DEPTH_ONLY>
+__device__ __forceinline__ void raster_cooperative(const RasterParams& p, const SubTri& s, int lane, uint32_t& frags) {
+    int px0, py0, px1, py1;
+    pixel_bounds(p, s, px0, py0, px1, py1);
+    const int w = px1 - px0 + 1;
+    const int lw = w <= 8 ? 8 : (w <= 16 ? 16 : 32), lh = 32 / lw, lx = lane % lw, ly = lane / lw;
+    const EdgeSetup e = make_edges(s, px0, py0);
+    for (int py = py0 + ly; py <= py1; py += lh) {
+        const long long dy = py - py0;
+        long long c0 = e.e0 + dy * e.sy0 + (long long)lx * e.sx0, c1 = e.e1 + dy * e.sy1 + (long long)lx * e.sx1, c2 = e.e2 + dy * e.sy2 + (long long)lx * e.sx2;
+        for (int px = px0 + lx; px <= px1; px += lw) {
+            if ((c0 | c1 | c2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, sample_depth(s, e, c0, c1, c2), s.rec);
+            c0 += lw * e.sx0; c1 += lw * e.sx1; c2 += lw * e.sx2;
+        }
+    }
+}
+
+// vertex stage up to clip space, clipping and setup of listed triangle i; medium sub-triangles come back through `defer`
+template <bool DEPTH_ONLY>
+__device__ void setup_listed_triangle(const RasterParams& p, unsigned long long i, uint32_t n_regions, uint32_t& frags, uint32_t& set_up, SubTri* defer, bool* deferred) {
+    // region of listed triangle i: last r with tri_prefix[r] <= i
+    uint32_t lo = 0, hi = n_regions;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p.tri_prefix[mid] <= i) lo = mid; else hi = mid;
+    }
+    const uint32_t r = lo;
+    const uint32_t t = (uint32_t)(i - p.tri_prefix[r]);
+    const uint64_t e = (uint64_t)p.calls[r].base_index + (uint64_t)t * 3u;
+    if (e + 2 >= p.index_elems) return;
+    const uint32_t k0 = p.indices[e], k1 = p.indices[e + 1], k2 = p.indices[e + 2];
+    if (k0 == R3_INVALID_VERTEX || k1 == R3_INVALID_VERTEX || k2 == R3_INVALID_VERTEX) return;   // opaque.wgsl:97-101
+    const r3_batch_data* batch = &p.batches[p.regions[r].job_index];
+    const uint32_t oid = batch->object_culling_information[k0 >> 24].object_id;                  // unpack_vertex_index (shader.rs:249-316)
+    if (oid >= p.n_slots || oid >= p.matrices_cap) return;
+    const r3_object* obj = &p.objects[oid];
+    if (obj->enabled == 0u) return;                                                               // opaque.wgsl:108-112
+    const uint32_t pos_off = obj->attr_offset[0] >> 2;
+    const float* mvp = p.matrices[oid].model_view_proj;
+    const uint32_t vid[3] = {k0 & 0xFFFFFFu, k1 & 0xFFFFFFu, k2 & 0xFFFFFFu};
+    float4 clip[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint64_t f = (uint64_t)pos_off + (uint64_t)vid[k] * 3u;
+        clip[k] = mat_point_rn(mvp, __uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));
+    }
+    // trivial reject + clip need (R1)
+    bool ox0 = true, ox1 = true, oy0 = true, oy1 = true, oz0 = true, oz1 = true, need_clip = false, nan = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 v = clip[k];
+        ox0 &= v.x < -v.w; ox1 &= v.x > v.w; oy0 &= v.y < -v.w; oy1 &= v.y > v.w; oz0 &= v.z < 0.0f; oz1 &= v.z > v.w;
+#pragma unroll
+        for (int pl = 0; pl < 6; ++pl) need_clip |= plane_dist(pl, v) < 0.0f;
+        nan |= !(v.w == v.w);
+    }
+    if (nan || ox0 || ox1 || oy0 || oy1 || oz0 || oz1) return;
+    const uint32_t rec = (uint32_t)(i + 1);
+    bool any = false;
+    if (!need_clip) {
+        any = process_subtriangle<DEPTH_ONLY>(p, clip[0], clip[1], clip[2], rec, frags, defer, deferred);
+    } else {
+        float4 poly[12];
+        poly[0] = clip[0]; poly[1] = clip[1]; poly[2] = clip[2];
+        const int n = clip_polygon(poly, 3);
+        for (int q = 1; q + 1 < n; ++q) any |= process_subtriangle<DEPTH_ONLY>(p, poly[0], poly[q], poly[q + 1], rec, frags, nullptr, nullptr);
+    }
+    if (any) {
+        set_up++;
+        if (!DEPTH_ONLY) {
+            r3_tri_record tr;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { tr.xyw[k][0] = clip[k].x; tr.xyw[k][1] = clip[k].y; tr.xyw[k][2] = clip[k].w; tr.vid[k] = vid[k]; }
+            tr.object_id = oid; tr._pad[0] = tr._pad[1] = tr._pad[2] = 0u;
+            float4* dst = reinterpret_cast<float4*>(&p.records[i]);
+            const float4* src = reinterpret_cast<const float4*>(&tr);
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        }
+    }
+}
+
 template <bool DEPTH_ONLY>
 __global__ void __launch_bounds__(RS_THREADS) raster_setup_kernel(const __grid_constant__ RasterParams p) {
     const uint32_t n_regions = p.header[2];
     const unsigned long long total = p.tri_prefix[n_regions];
+    const int lane = threadIdx.x & 31;
     uint32_t frags = 0, set_up = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * RS_THREADS + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * RS_THREADS) {
-        // region of listed triangle i: last r with tri_prefix[r] <= i
-        uint32_t lo = 0, hi = n_regions;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (p.tri_prefix[mid] <= i) lo = mid; else hi = mid;
-        }
-        const uint32_t r = lo;
-        const uint32_t t = (uint32_t)(i - p.tri_prefix[r]);
-        const uint64_t e = (uint64_t)p.calls[r].base_index + (uint64_t)t * 3u;
-        if (e + 2 >= p.index_elems) continue;
-        const uint32_t k0 = p.indices[e], k1 = p.indices[e + 1], k2 = p.indices[e + 2];
-        if (k0 == R3_INVALID_VERTEX || k1 == R3_INVALID_VERTEX || k2 == R3_INVALID_VERTEX) continue;   // opaque.wgsl:97-101
-        const r3_batch_data* batch = &p.batches[p.regions[r].job_index];
-        const uint32_t oid = batch->object_culling_information[k0 >> 24].object_id;                  // unpack_vertex_index (shader.rs:249-316)
-        if (oid >= p.n_slots || oid >= p.matrices_cap) continue;
-        const r3_object* obj = &p.objects[oid];
-        if (obj->enabled == 0u) continue;                                                             // opaque.wgsl:108-112
-        const uint32_t pos_off = obj->attr_offset[0] >> 2;
-        const float* mvp = p.matrices[oid].model_view_proj;
-        const uint32_t vid[3] = {k0 & 0xFFFFFFu, k1 & 0xFFFFFFu, k2 & 0xFFFFFFu};
-        float4 clip[3];
+    // warp-uniform trip count: every iteration a warp takes 32 consecutive listed triangles
+    for (unsigned long long base = (unsigned long long)blockIdx.x * RS_THREADS + (threadIdx.x & ~31u); base < total; base += (unsigned long long)gridDim.x * RS_THREADS) {
+        const unsigned long long i = base + lane;
+        SubTri med;
+        bool has_med = false;
+        if (i < total) setup_listed_triangle<DEPTH_ONLY>(p, i, n_regions, frags, set_up, &med, &has_med);
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, has_med);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            SubTri s;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const uint64_t f = (uint64_t)pos_off + (uint64_t)vid[k] * 3u;
-            clip[k] = mat_point_rn(mvp, __uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));
-        }
-        // trivial reject + clip need (R1)
-        bool ox0 = true, ox1 = true, oy0 = true, oy1 = true, oz0 = true, oz1 = true, need_clip = false, nan = false;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float4 v = clip[k];
-            ox0 &= v.x < -v.w; ox1 &= v.x > v.w; oy0 &= v.y < -v.w; oy1 &= v.y > v.w; oz0 &= v.z < 0.0f; oz1 &= v.z > v.w;
-#pragma unroll
-            for (int pl = 0; pl < 6; ++pl) need_clip |= plane_dist(pl, v) < 0.0f;
-            nan |= !(v.w == v.w);
-        }
-        if (nan || ox0 || ox1 || oy0 || oy1 || oz0 || oz1) continue;
-        const uint32_t rec = (uint32_t)(i + 1);
-        bool any = false;
-        if (!need_clip) {
-            any = process_subtriangle<DEPTH_ONLY>(p, clip[0], clip[1], clip[2], rec, frags);
-        } else {
-            float4 poly[12];
-            poly[0] = clip[0]; poly[1] = clip[1]; poly[2] = clip[2];
-            const int n = clip_polygon(poly, 3);
-            for (int q = 1; q + 1 < n; ++q) any |= process_subtriangle<DEPTH_ONLY>(p, poly[0], poly[q], poly[q + 1], rec, frags);
-        }
-        if (any) {
-            set_up++;
-            if (!DEPTH_ONLY) {
-                r3_tri_record tr;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { tr.xyw[k][0] = clip[k].x; tr.xyw[k][1] = clip[k].y; tr.xyw[k][2] = clip[k].w; tr.vid[k] = vid[k]; }
-                tr.object_id = oid; tr._pad[0] = tr._pad[1] = tr._pad[2] = 0u;
-                float4* dst = reinterpret_cast<float4*>(&p.records[i]);
-                const float4* src = reinterpret_cast<const float4*>(&tr);
-                dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+            for (int k = 0; k < 3; ++k) {
+                s.x[k] = __shfl_sync(0xFFFFFFFFu, med.x[k], src); s.y[k] = __shfl_sync(0xFFFFFFFFu, med.y[k], src); s.z[k] = __shfl_sync(0xFFFFFFFFu, med.z[k], src);
             }
+            s.rec = __shfl_sync(0xFFFFFFFFu, med.rec, src);
+            raster_cooperative<DEPTH_ONLY>(p, s, lane, frags);
         }
     }
     // statistics: one atomic per warp
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) { frags += __shfl_xor_sync(0xFFFFFFFFu, frags, s); set_up += __shfl_xor_sync(0xFFFFFFFFu, set_up, s); }
-    if ((threadIdx.x & 31) == 0 && p.stats) {
+    if (lane == 0 && p.stats) {
         if (set_up) atomicAdd(&p.stats[0], (unsigned long long)set_up);
         if (frags) atomicAdd(&p.stats[1], (unsigned long long)frags);
     }

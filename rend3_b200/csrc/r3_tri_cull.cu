@@ -1,4 +1,4 @@
-// r3_tri_cull.cu — per-triangle cull + ORDERED index compaction (single pass).
+// r3_tri_cull.cu — per-triangle cull + ORDERED index compaction.
 //
 // Replaces GpuCuller::cull + cull.wgsl::cs_main (rend3-routine/src/culling/culler.rs:531-659,
 // rend3-routine/shaders/src/cull.wgsl:264-390): back-face determinant, misses-pixel-centre, hi-Z occlusion,
@@ -7,18 +7,23 @@
 //
 // B200 design.  The reference launches one dispatch per 256-object batch and appends survivors with a global
 // atomicAdd per triangle on a handful of contended counters, which also makes the list order nondeterministic.
-// Here ONE launch covers every batch; a CTA is one reference workgroup (256 invocations) taken from an atomic
-// ticket, each warp's ballot is the 32-bit visibility word the reference assembles with workgroup atomics, and
-// the output slot of every surviving triangle comes from a decoupled look-back that is *segmented by region*:
-// the first workgroup of a region publishes its count as a finished prefix, later ones look back only until
-// they meet one.  Survivors therefore land in ascending invocation order (one legal outcome of the reference's
-// atomics), without re-reading anything: the indices are still in registers when the slot is known.  The last
-// workgroup of a region writes its two IndirectCall records.
+// Here every batch is handled by the same launches, all of them plain streaming kernels without inter-CTA waits:
+//   test     one CTA per reference workgroup (256 invocations), one warp per 32: the cull test; the warp ballot IS the
+//            32-bit visibility word the reference assembles with workgroup atomics (1 bit per invocation to HBM), a
+//            second word marks the residual triangles; per-superblock (1024 words) survivor counts by one atomic per CTA;
+//   scan     one block: exclusive prefix of the superblock counts;
+//   regions  one CTA per region: survivors in front of the region -> its two IndirectCall records;
+//   compact  one CTA per superblock: block scan of the word popcounts, then each surviving triangle re-reads its three
+//            indices (12 B) and lands at  region base + (survivors before it in the region): ascending invocation order,
+//            one legal outcome of the reference's atomics, reproducible run to run.
+// (Round-1 history: a single-pass version with a per-workgroup decoupled look-back measured 1.66 ms per camera on the
+//  200k-object config — ticket + look-back latency per 256 invocations; see profiles/README.md.)
 #include "r3_common.cuh"
 
 namespace {
 
 constexpr int TC_THREADS = 256;
+constexpr int SB_WORDS = 1024;                       // words per superblock (32768 invocations, 128 workgroups)
 
 struct TriCullParams {
     r3_camera_header cam;
@@ -28,21 +33,15 @@ struct TriCullParams {
     const r3_batch_data* batches;
     const uint32_t* wg_info;             // per workgroup: (batch << 8) | batch-local object
     const uint32_t* region_first_inv;    // [n_regions + 1]
-    const uint32_t* header;              // job header: [1] n_batches, [3] total_invocations (device-side counts)
+    const uint32_t* header;              // job header: [1] n_batches, [2] n_regions, [3] total_invocations (device-side counts)
     uint32_t* idx_pred; uint32_t* idx_resid;
     r3_indirect_call* dc_pred; r3_indirect_call* dc_resid;
     uint32_t* res_out; const uint32_t* res_in; uint64_t res_in_words;
+    uint32_t* resid_bits;                // [n_words] residual marks (scratch)
+    unsigned long long* sb_counts;       // [n_superblocks + 1] (pred << 32 | resid): counts, then their exclusive prefix
+    unsigned long long* region_prefix;   // [n_regions + 1] survivors in front of each region
     float* const* hiz; const uint32_t* hiz_dims; uint32_t hiz_mips;
-    unsigned long long* state;           // [0] ticket, [1 + wg] descriptors
 };
-
-// descriptor: [63:62] flag (0 invalid, 1 aggregate, 2 prefix) | [61:31] predicted count | [30:0] residual count
-constexpr unsigned long long TD_AGG = 1ull << 62, TD_PREFIX = 2ull << 62, TD_MASK = (1ull << 31) - 1;
-__device__ __forceinline__ unsigned long long td_pack(unsigned long long flag, uint32_t pred, uint32_t resid) {
-    return flag | ((unsigned long long)pred << 31) | (unsigned long long)resid;
-}
-__device__ __forceinline__ unsigned long long ld_vol(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
-__device__ __forceinline__ void st_vol(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
 
 __device__ __forceinline__ uint32_t mesh_word(const TriCullParams& p, uint64_t i) { return i < p.mesh_words ? __ldg(&p.mesh[i]) : 0u; }
 
@@ -117,130 +116,203 @@ __global__ void expand_wg_info_kernel(const r3_batch_data* __restrict__ batches,
     for (uint32_t i = 0; i < count; ++i) wg_info[first + i] = (b << 8) | o;
 }
 
-__global__ void __launch_bounds__(TC_THREADS) triangle_cull_kernel(const __grid_constant__ TriCullParams p) {
-    __shared__ uint32_t s_wg;
+// ---- test: cull.wgsl::cs_main up to the visibility decision
+__global__ void __launch_bounds__(TC_THREADS) triangle_test_kernel(const __grid_constant__ TriCullParams p) {
     __shared__ uint32_t s_pred[8], s_resid[8];
-    __shared__ uint32_t s_base_pred, s_base_resid;
+    const uint32_t wg = blockIdx.x;
+    if (wg >= p.header[3] / TC_THREADS) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool shadow = p.cam.shadow_index != R3_CAMERA_VIEWPORT;
-    const uint32_t n_workgroups = p.header[3] / TC_THREADS;
+    const uint32_t wi = __ldg(&p.wg_info[wg]);
+    const r3_batch_data* job = &p.batches[wi >> 8];
+    const uint32_t local_object = wi & 0xFFu;
+    const r3_object_culling_info info = job->object_culling_information[local_object];   // find_object_info (cull.wgsl:181-207)
+    const uint32_t global_invocation = wg * TC_THREADS + threadIdx.x;
+    const uint32_t gid = global_invocation - job->batch_base_invocation;                 // invocation within the batch
+    const bool real = gid < info.invocation_end;
+    const uint32_t object_invocation = gid - info.invocation_start;
 
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_wg = (uint32_t)atomicAdd(&p.state[0], 1ull);
-        __syncthreads();
-        const uint32_t wg = s_wg;
-        if (wg >= n_workgroups) return;
-
-        const uint32_t wi = __ldg(&p.wg_info[wg]);
-        const r3_batch_data* job = &p.batches[wi >> 8];
-        const uint32_t local_object = wi & 0xFFu;
-        const r3_object_culling_info info = job->object_culling_information[local_object];   // find_object_info (cull.wgsl:181-207)
-        const uint32_t global_invocation = wg * TC_THREADS + threadIdx.x;
-        const uint32_t gid = global_invocation - job->batch_base_invocation;                 // invocation within the batch
-        const bool real = gid < info.invocation_end;
-        const uint32_t object_invocation = gid - info.invocation_start;
-
-        uint32_t pk0 = R3_INVALID_VERTEX, pk1 = R3_INVALID_VERTEX, pk2 = R3_INVALID_VERTEX;
-        bool passes = false, resid = false;
-        if (real) {
-            const r3_object* obj = &p.objects[info.object_id];
-            const uint32_t first_index = obj->first_index, pos_off = obj->attr_offset[0] >> 2;
-            const uint64_t ib = (uint64_t)first_index + (uint64_t)object_invocation * 3u;      // vertex_fetch (cull.wgsl:9-32)
-            const uint32_t i0 = mesh_word(p, ib), i1 = mesh_word(p, ib + 1), i2 = mesh_word(p, ib + 2);
-            float3 v[3];
-            const uint32_t ids[3] = {i0, i1, i2};
+    bool passes = false, resid = false;
+    uint32_t i0 = 0, i1 = 0, i2 = 0;
+    if (real) {
+        const r3_object* obj = &p.objects[info.object_id];
+        const uint32_t first_index = obj->first_index, pos_off = obj->attr_offset[0] >> 2;
+        const uint64_t ib = (uint64_t)first_index + (uint64_t)object_invocation * 3u;      // vertex_fetch (cull.wgsl:9-32)
+        i0 = mesh_word(p, ib); i1 = mesh_word(p, ib + 1); i2 = mesh_word(p, ib + 2);
+        float3 v[3];
+        const uint32_t ids[3] = {i0, i1, i2};
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const uint64_t f = (uint64_t)pos_off + (uint64_t)ids[k] * 3u;                  // extract_attribute_vec3_f32
-                v[k] = make_float3(__uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));
-            }
-            passes = execute_culling(p, p.matrices[info.object_id].model_view_proj, v[0], v[1], v[2]);
-            pk0 = (local_object << 24) | (i0 & 0xFFFFFFu); pk1 = (local_object << 24) | (i1 & 0xFFFFFFu); pk2 = (local_object << 24) | (i2 & 0xFFFFFFu);
-            if (passes && !shadow && info.atomic_capable == 1u) {
-                bool prev = false;                                                            // get_previous_culling_result (cull.wgsl:152-160)
-                if (info.previous_global_invocation != R3_NO_PREVIOUS) {
-                    const uint64_t pgi = (uint64_t)object_invocation + info.previous_global_invocation;
-                    const uint32_t mask = (pgi >> 5) < p.res_in_words ? p.res_in[pgi >> 5] : 0u;
-                    prev = (mask >> (pgi & 31)) & 1u;
-                }
-                resid = !prev;
-            }
+        for (int k = 0; k < 3; ++k) {
+            const uint64_t f = (uint64_t)pos_off + (uint64_t)ids[k] * 3u;                  // extract_attribute_vec3_f32
+            v[k] = make_float3(__uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));
         }
-        const uint32_t word_pred = __ballot_sync(0xFFFFFFFFu, passes);
-        const uint32_t word_resid = __ballot_sync(0xFFFFFFFFu, resid);
-        if (lane == 0) p.res_out[global_invocation >> 5] = word_pred;                        // save_culling_results (cull.wgsl:229-241)
+        passes = execute_culling(p, p.matrices[info.object_id].model_view_proj, v[0], v[1], v[2]);
+        if (passes && !shadow && info.atomic_capable == 1u) {
+            bool prev = false;                                                            // get_previous_culling_result (cull.wgsl:152-160)
+            if (info.previous_global_invocation != R3_NO_PREVIOUS) {
+                const uint64_t pgi = (uint64_t)object_invocation + info.previous_global_invocation;
+                const uint32_t mask = (pgi >> 5) < p.res_in_words ? p.res_in[pgi >> 5] : 0u;
+                prev = (mask >> (pgi & 31)) & 1u;
+            }
+            resid = !prev;
+        }
+    }
+    const uint32_t word_pred = __ballot_sync(0xFFFFFFFFu, passes);
+    const uint32_t word_resid = __ballot_sync(0xFFFFFFFFu, resid);
+    if (lane == 0) {
+        p.res_out[global_invocation >> 5] = word_pred;                                     // save_culling_results (cull.wgsl:229-241)
+        p.resid_bits[global_invocation >> 5] = word_resid;
+    }
+    if (info.atomic_capable == 0u) {
+        // non-atomic (blend) objects keep their slot: survivors in place, everything else INVALID (cull.wgsl:374-380,343-347)
+        const uint64_t o = (uint64_t)global_invocation * 3u;
+        const uint32_t hi = local_object << 24;
+        p.idx_resid[o] = passes ? (hi | (i0 & 0xFFFFFFu)) : R3_INVALID_VERTEX;
+        p.idx_resid[o + 1] = passes ? (hi | (i1 & 0xFFFFFFu)) : R3_INVALID_VERTEX;
+        p.idx_resid[o + 2] = passes ? (hi | (i2 & 0xFFFFFFu)) : R3_INVALID_VERTEX;
+    }
+    // every visibility word is counted (atomic or not) so that the prefix over words is one consistent global scan
+    if (lane == 0) { s_pred[warp] = __popc(word_pred); s_resid[warp] = __popc(word_resid); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += ((unsigned long long)s_pred[w] << 32) | s_resid[w];
+        if (t) atomicAdd(&p.sb_counts[wg / (SB_WORDS / 8)], t);
+    }
+}
 
-        if (info.atomic_capable == 0u) {
-            // non-atomic (blend) objects keep their slot: survivors in place, everything else INVALID (cull.wgsl:374-380,343-347)
-            const uint64_t o = (uint64_t)global_invocation * 3u;
-            p.idx_resid[o] = passes ? pk0 : R3_INVALID_VERTEX; p.idx_resid[o + 1] = passes ? pk1 : R3_INVALID_VERTEX;
-            p.idx_resid[o + 2] = passes ? pk2 : R3_INVALID_VERTEX;
-        }
-        if (lane == 0) { s_pred[warp] = __popc(word_pred); s_resid[warp] = __popc(word_resid); }
+// ---- scan: exclusive prefix of the superblock counts (packed pair), one block
+__global__ void __launch_bounds__(1024) superblock_scan_kernel(unsigned long long* __restrict__ counts, const uint32_t* __restrict__ header) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const uint32_t n = (header[3] / 32u + SB_WORDS - 1) / SB_WORDS;
+    if (threadIdx.x == 0) s_carry = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base <= n; base += 1024) {   // <= n: entry n receives the grand total
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long v = i < n ? counts[i] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-
-        const uint32_t region = info.region_id;
-        const uint32_t region_first = __ldg(&p.region_first_inv[region]), region_end = __ldg(&p.region_first_inv[region + 1]);
-        const bool first_of_region = (region_first >> 8) == wg, last_of_region = (region_end >> 8) == wg + 1;
         if (warp == 0) {
-            uint32_t cp = lane < 8 ? s_pred[lane] : 0u, cr = lane < 8 ? s_resid[lane] : 0u;
-            uint32_t ip = cp, ir = cr;
+            const unsigned long long w = s_warp[lane];
+            unsigned long long wi = w;
 #pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-                const uint32_t np = __shfl_up_sync(0xFFFFFFFFu, ip, d), nr = __shfl_up_sync(0xFFFFFFFFu, ir, d);
-                if (lane >= d) { ip += np; ir += nr; }
-            }
-            const uint32_t tot_p = __shfl_sync(0xFFFFFFFFu, ip, 7), tot_r = __shfl_sync(0xFFFFFFFFu, ir, 7);
-            if (lane < 8) { s_pred[lane] = ip - cp; s_resid[lane] = ir - cr; }                // exclusive offsets of the 8 warps
-            uint32_t run_p = 0, run_r = 0;
-            if (!first_of_region) {
-                if (lane == 0) st_vol(&p.state[1 + wg], td_pack(TD_AGG, tot_p, tot_r));
-                int pred = (int)wg - 1;
-                for (;;) {
-                    const int idx = pred - lane;
-                    unsigned long long d = (idx >= 0) ? ld_vol(&p.state[1 + idx]) : TD_PREFIX;
-                    while (__any_sync(0xFFFFFFFFu, (d >> 62) == 0ull)) {
-                        if ((d >> 62) == 0ull) d = ld_vol(&p.state[1 + idx]);
-                    }
-                    const uint32_t pmask = __ballot_sync(0xFFFFFFFFu, (d >> 62) == 2ull);
-                    const int first = pmask ? (__ffs(pmask) - 1) : 31;
-                    uint32_t vp = (lane <= first) ? (uint32_t)((d >> 31) & TD_MASK) : 0u, vr = (lane <= first) ? (uint32_t)(d & TD_MASK) : 0u;
-#pragma unroll
-                    for (int s = 16; s > 0; s >>= 1) { vp += __shfl_xor_sync(0xFFFFFFFFu, vp, s); vr += __shfl_xor_sync(0xFFFFFFFFu, vr, s); }
-                    run_p += vp; run_r += vr;
-                    if (pmask) break;
-                    pred -= 32;
-                }
-            }
-            if (lane == 0) {
-                st_vol(&p.state[1 + wg], td_pack(TD_PREFIX, run_p + tot_p, run_r + tot_r));
-                s_base_pred = run_p; s_base_resid = run_r;
-                if (last_of_region) {
-                    // init_draw_calls + the final vertex_count the atomics would have reached (cull.wgsl:47-73)
-                    const bool atomic_region = info.atomic_capable == 1u;
-                    r3_indirect_call pc, rc;
-                    pc.vertex_count = atomic_region ? 3u * (run_p + tot_p) : 0u;
-                    rc.vertex_count = atomic_region ? 3u * (run_r + tot_r) : 3u * (region_end - region_first);
-                    pc.instance_count = rc.instance_count = 1u;
-                    pc.base_index = rc.base_index = region_first * 3u;
-                    pc.vertex_offset = rc.vertex_offset = 0;
-                    pc.base_instance = rc.base_instance = 0u;
-                    p.dc_pred[region] = pc;
-                    p.dc_resid[region] = rc;
-                }
-            }
+            for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += t; }
+            s_warp[lane] = wi - w;
         }
         __syncthreads();
-        if (info.atomic_capable == 1u) {
+        const unsigned long long excl = s_carry + s_warp[warp] + incl - v;
+        if (i <= n) counts[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+}
+
+// survivors (pred << 32 | resid) in front of word `w`: superblock prefix + the words of the superblock before it
+__device__ unsigned long long prefix_before_word(const TriCullParams& p, uint32_t w, unsigned long long* s_red) {
+    const uint32_t sb = w / SB_WORDS, first = sb * SB_WORDS;
+    unsigned long long acc = 0;
+    for (uint32_t i = first + threadIdx.x; i < w; i += blockDim.x) acc += ((unsigned long long)__popc(p.res_out[i]) << 32) | __popc(p.resid_bits[i]);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    unsigned long long tot = 0;
+    for (uint32_t k = 0; k < blockDim.x / 32; ++k) tot += s_red[k];
+    return p.sb_counts[sb] + tot;
+}
+
+// ---- regions: survivors in front of every region, and the IndirectCall records (init_draw_calls + final vertex_count)
+__global__ void __launch_bounds__(256) region_finish_kernel(const __grid_constant__ TriCullParams p) {
+    __shared__ unsigned long long s_red[8];
+    const uint32_t r = blockIdx.x, n_regions = p.header[2];
+    if (r >= n_regions) return;
+    const uint32_t first_inv = p.region_first_inv[r], end_inv = p.region_first_inv[r + 1];
+    const unsigned long long before = prefix_before_word(p, first_inv >> 5, s_red);
+    const unsigned long long after = prefix_before_word(p, end_inv >> 5, s_red);
+    if (threadIdx.x == 0) {
+        p.region_prefix[r] = before;
+        if (end_inv > first_inv) {
+            // the region's first object decides atomic / non-atomic for the whole region (one material key per region)
+            const uint32_t wi = p.wg_info[first_inv >> 8];
+            const bool atomic_region = p.batches[wi >> 8].object_culling_information[wi & 0xFFu].atomic_capable == 1u;
+            const unsigned long long cnt = after - before;
+            r3_indirect_call pc, rc;
+            pc.vertex_count = atomic_region ? 3u * (uint32_t)(cnt >> 32) : 0u;
+            rc.vertex_count = atomic_region ? 3u * (uint32_t)(cnt & 0xFFFFFFFFull) : 3u * (end_inv - first_inv);
+            pc.instance_count = rc.instance_count = 1u;
+            pc.base_index = rc.base_index = first_inv * 3u;
+            pc.vertex_offset = rc.vertex_offset = 0;
+            pc.base_instance = rc.base_instance = 0u;
+            p.dc_pred[r] = pc;
+            p.dc_resid[r] = rc;
+        }
+    }
+}
+
+// ---- compact: ordered expansion of the surviving triangles (write_predicted/residual_atomic_triangle, cull.wgsl:84-116)
+__global__ void __launch_bounds__(SB_WORDS) triangle_compact_kernel(const __grid_constant__ TriCullParams p) {
+    __shared__ unsigned long long s_warp[32];
+    const uint32_t n_words = p.header[3] / 32u;
+    const uint32_t w = blockIdx.x * SB_WORDS + threadIdx.x;
+    if (blockIdx.x * SB_WORDS >= n_words) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wp = w < n_words ? p.res_out[w] : 0u, wr = w < n_words ? p.resid_bits[w] : 0u;
+    const unsigned long long c = ((unsigned long long)__popc(wp) << 32) | __popc(wr);
+    unsigned long long incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long v = s_warp[lane];
+        unsigned long long vi = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, vi, d); if (lane >= d) vi += t; }
+        s_warp[lane] = vi - v;
+    }
+    __syncthreads();
+    const unsigned long long excl = p.sb_counts[blockIdx.x] + s_warp[warp] + incl - c;   // survivors in front of word w (global)
+    // per-word facts needed to re-read the indices and place them
+    uint32_t base_pred = 0, base_resid = 0, idx_base = 0, hi = 0;
+    bool atomic_word = false;
+    if (wp | wr) {
+        const uint32_t wi = __ldg(&p.wg_info[w >> 3]);
+        const r3_batch_data* job = &p.batches[wi >> 8];
+        const r3_object_culling_info info = job->object_culling_information[wi & 0xFFu];
+        atomic_word = info.atomic_capable == 1u;
+        const unsigned long long rp = p.region_prefix[info.region_id];
+        const uint32_t region_first = p.region_first_inv[info.region_id];
+        base_pred = region_first + (uint32_t)((excl - rp) >> 32);
+        base_resid = region_first + (uint32_t)((excl & 0xFFFFFFFFull) - (rp & 0xFFFFFFFFull));
+        // index of the first invocation of this word inside the mesh buffer
+        idx_base = p.objects[info.object_id].first_index + (w * 32u - job->batch_base_invocation - info.invocation_start) * 3u;
+        hi = (wi & 0xFFu) << 24;
+    }
+    // the 32 words of a warp are expanded one after the other, one triangle per lane
+    const uint32_t any = __ballot_sync(0xFFFFFFFFu, atomic_word && (wp | wr));
+#pragma unroll 1
+    for (uint32_t m = any; m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        const uint32_t jp = __shfl_sync(0xFFFFFFFFu, wp, j), jr = __shfl_sync(0xFFFFFFFFu, wr, j);
+        const uint32_t jbp = __shfl_sync(0xFFFFFFFFu, base_pred, j), jbr = __shfl_sync(0xFFFFFFFFu, base_resid, j);
+        const uint32_t jib = __shfl_sync(0xFFFFFFFFu, idx_base, j), jhi = __shfl_sync(0xFFFFFFFFu, hi, j);
+        if ((jp >> lane) & 1u) {   // residual bits are a subset of the predicted bits
+            const uint64_t ib = (uint64_t)jib + (uint64_t)lane * 3u;
+            const uint32_t k0 = jhi | (mesh_word(p, ib) & 0xFFFFFFu), k1 = jhi | (mesh_word(p, ib + 1) & 0xFFFFFFu), k2 = jhi | (mesh_word(p, ib + 2) & 0xFFFFFFu);
             const uint32_t lt = (1u << lane) - 1u;
-            if (passes) {                                                                     // write_predicted_atomic_triangle (cull.wgsl:84-99)
-                const uint64_t slot = (uint64_t)region_first + s_base_pred + s_pred[warp] + __popc(word_pred & lt);
-                p.idx_pred[slot * 3] = pk0; p.idx_pred[slot * 3 + 1] = pk1; p.idx_pred[slot * 3 + 2] = pk2;
-            }
-            if (resid) {                                                                      // write_residual_atomic_triangle (cull.wgsl:101-116)
-                const uint64_t slot = (uint64_t)region_first + s_base_resid + s_resid[warp] + __popc(word_resid & lt);
-                p.idx_resid[slot * 3] = pk0; p.idx_resid[slot * 3 + 1] = pk1; p.idx_resid[slot * 3 + 2] = pk2;
+            const uint64_t sp = ((uint64_t)jbp + __popc(jp & lt)) * 3u;
+            p.idx_pred[sp] = k0; p.idx_pred[sp + 1] = k1; p.idx_pred[sp + 2] = k2;
+            if ((jr >> lane) & 1u) {
+                const uint64_t sr = ((uint64_t)jbr + __popc(jr & lt)) * 3u;
+                p.idx_resid[sr] = k0; p.idx_resid[sr + 1] = k1; p.idx_resid[sr + 2] = k2;
             }
         }
     }
@@ -250,7 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS) triangle_cull_kernel(const __grid_
 
 int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam) {
     r3_jobs& j = cam->jobs[cam->cur];
-    const uint64_t inv = j.total_invocations, words = (inv + 31) / 32;
+    const uint64_t inv = j.total_invocations, words = (inv + 31) / 32;   // exact (host batching) or an upper bound (device batching)
     if (!cam->index_buffer.created) {                      // CullingBuffers::new (culler.rs:96-112)
         R3_TRY(r3_iobuf_new(c, &cam->index_buffer, inv * 3, 4, false));
         R3_TRY(r3_iobuf_new(c, &cam->draw_call_buffer, j.n_regions, 20, true));
@@ -263,20 +335,25 @@ int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam) {
     R3_CUDA(c, cudaMemsetAsync(cam->draw_call_buffer.d, 0, cam->draw_call_buffer.capacity_elements * 20, c->stream));   // culler.rs:642
     const uint32_t n_wg = (uint32_t)(inv / TC_THREADS);
     cam->has_draw_call_set = true;
-    if (n_wg == 0) return R3_OK;
+    if (n_wg == 0 || j.n_batches == 0 || j.n_regions == 0) return R3_OK;
 
-    // scratch: wg_info [n_wg] + look-back state [1 + n_wg]
-    R3_TRY(r3_reserve_t(c, &cam->d_resid_bits, &cam->resid_bits_cap, n_wg));
-    R3_TRY(r3_reserve_t(c, &cam->d_word_scan, &cam->word_scan_cap, (uint64_t)n_wg + 1));
-    R3_CUDA(c, cudaMemsetAsync(cam->d_word_scan, 0, ((size_t)n_wg + 1) * 8, c->stream));
-    expand_wg_info_kernel<<<j.n_batches, 256, 0, c->stream>>>(j.d_batches, j.d_header, cam->d_resid_bits);
+    const uint32_t n_sb = (uint32_t)((words + SB_WORDS - 1) / SB_WORDS);
+    // scratch: wg_info [n_wg] | resid_bits [words]   and   sb_counts [n_sb + 1] | region_prefix [n_regions + 1]
+    R3_TRY(r3_reserve_t(c, &cam->d_resid_bits, &cam->resid_bits_cap, (uint64_t)n_wg + words + 2));
+    R3_TRY(r3_reserve_t(c, &cam->d_word_scan, &cam->word_scan_cap, (uint64_t)n_sb + j.n_regions + 4));
+    uint32_t* wg_info = cam->d_resid_bits;
+    uint32_t* resid_bits = wg_info + n_wg;
+    unsigned long long* sb_counts = cam->d_word_scan;
+    unsigned long long* region_prefix = sb_counts + n_sb + 1;
+    R3_CUDA(c, cudaMemsetAsync(sb_counts, 0, ((size_t)n_sb + 1) * 8, c->stream));
+    expand_wg_info_kernel<<<j.n_batches, 256, 0, c->stream>>>(j.d_batches, j.d_header, wg_info);
     R3_CHECK_LAUNCH(c, "expand_wg_info_kernel");
 
     TriCullParams p;
     p.cam = cam->header;
     p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;
     p.objects = c->d_objects; p.matrices = cam->d_matrices; p.batches = j.d_batches;
-    p.wg_info = cam->d_resid_bits; p.region_first_inv = j.d_region_first_inv; p.header = j.d_header;
+    p.wg_info = wg_info; p.region_first_inv = j.d_region_first_inv; p.header = j.d_header;
     p.idx_pred = (uint32_t*)cam->index_buffer.d + cam->index_buffer.out_off();
     p.idx_resid = (uint32_t*)cam->index_buffer.d + cam->index_buffer.in_off();
     p.dc_pred = (r3_indirect_call*)cam->draw_call_buffer.d + cam->draw_call_buffer.out_off();
@@ -284,11 +361,17 @@ int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam) {
     p.res_out = (uint32_t*)cam->results_buffer.d + cam->results_buffer.out_off();
     p.res_in = (const uint32_t*)cam->results_buffer.d + cam->results_buffer.in_off();
     p.res_in_words = cam->results_buffer.capacity_elements / 2;
+    p.resid_bits = resid_bits; p.sb_counts = sb_counts; p.region_prefix = region_prefix;
     const bool viewport = cam->header.shadow_index == R3_CAMERA_VIEWPORT;
     p.hiz = c->d_hiz_ptrs; p.hiz_dims = c->d_hiz_dims; p.hiz_mips = viewport ? (uint32_t)c->d_hiz.size() : 0u;
-    p.state = cam->d_word_scan;
-    const uint32_t grid = n_wg < (uint32_t)(R3_SM_COUNT * 8) ? n_wg : (uint32_t)(R3_SM_COUNT * 8);
-    triangle_cull_kernel<<<grid, TC_THREADS, 0, c->stream>>>(p);
-    R3_CHECK_LAUNCH(c, "triangle_cull_kernel");
+
+    triangle_test_kernel<<<n_wg, TC_THREADS, 0, c->stream>>>(p);
+    R3_CHECK_LAUNCH(c, "triangle_test_kernel");
+    superblock_scan_kernel<<<1, 1024, 0, c->stream>>>(sb_counts, j.d_header);
+    R3_CHECK_LAUNCH(c, "superblock_scan_kernel");
+    region_finish_kernel<<<j.n_regions, 256, 0, c->stream>>>(p);
+    R3_CHECK_LAUNCH(c, "region_finish_kernel");
+    triangle_compact_kernel<<<n_sb, SB_WORDS, 0, c->stream>>>(p);
+    R3_CHECK_LAUNCH(c, "triangle_compact_kernel");
     return R3_OK;
 }

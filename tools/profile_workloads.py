@@ -30,6 +30,9 @@ def main():
             res = (3840, 2160)
             ev = cube_field_scene(n_objects=4400, seed=5, resolution=res, extent=30.0, pull_back=7.0, n_point_lights=64, n_dir_lights=4,
                                   shadow_resolution=2048, shadow_distance=200.0, subdivisions=(2, 3, 3, 4), scale_range=(0.6, 2.4), slabs=True)
+        elif mode == "c3":
+            from rend3_b200 import configs
+            ev, res = configs.config3()
         else:
             res = (1920, 1080)
             ev = cube_field_scene(n_objects=10_000, seed=1, resolution=res)
