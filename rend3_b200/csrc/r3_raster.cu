@@ -26,6 +26,7 @@ constexpr int RS_THREADS = 256;
 constexpr float GUARD = 64.0f;
 constexpr int SMALL_AREA = 64;           // inline raster when the pixel bounding box covers at most 64 pixels
 constexpr int MEDIUM_MAX = 32;           // warp-cooperative raster up to a 32 x 32 pixel box (<= 32 steps of 32 lanes)
+constexpr int COOP_MAX_LANES = 33;       // >32 = never: measured on C3/C5, the cooperative walk wins even when every lane holds a medium triangle
 constexpr int BAND_ROWS = 16;
 constexpr uint32_t LARGE_CAP = 1u << 22; // queued large sub-triangles (160 MB)
 constexpr uint32_t BAND_CAP = 1u << 24;  // queued (sub-triangle, band) items (128 MB)
@@ -151,6 +152,21 @@ __device__ __forceinline__ void pixel_bounds(const RasterParams& p, const SubTri
     py0 = max((miny - 128 + 255) >> 8, p.y0); py1 = min((maxy - 128) >> 8, p.y1 - 1);
 }
 
+// one thread walks the pixel box of its own sub-triangle with incremental edge functions
+template <bool DEPTH_ONLY>
+__device__ __forceinline__ void raster_inline(const RasterParams& p, const SubTri& s, int px0, int py0, int px1, int py1, uint32_t& frags) {
+    const EdgeSetup e = make_edges(s, px0, py0);
+    long long r0 = e.e0, r1 = e.e1, r2 = e.e2;
+    for (int py = py0; py <= py1; ++py) {
+        long long c0 = r0, c1 = r1, c2 = r2;
+        for (int px = px0; px <= px1; ++px) {
+            if ((c0 | c1 | c2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, sample_depth(s, e, c0, c1, c2), s.rec);
+            c0 += e.sx0; c1 += e.sx1; c2 += e.sx2;
+        }
+        r0 += e.sy0; r1 += e.sy1; r2 += e.sy2;
+    }
+}
+
 // R2-R4 for one sub-triangle: snap, orient, then pick the raster path by the size of its pixel bounding box:
 //   small  (<= 8x8 .. 64 px)   : inline, by the thread that set it up;
 //   medium (<= 32 x 32)         : handed back through `defer` and rasterised by the whole warp (32 pixels per step);
@@ -214,16 +230,7 @@ __device__ bool process_subtriangle(const RasterParams& p, const float4 a, const
         }
         inline_raster = true;
     }
-    const EdgeSetup e = make_edges(s, px0, py0);
-    long long r0 = e.e0, r1 = e.e1, r2 = e.e2;
-    for (int py = py0; py <= py1; ++py) {
-        long long c0 = r0, c1 = r1, c2 = r2;
-        for (int px = px0; px <= px1; ++px) {
-            if ((c0 | c1 | c2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, sample_depth(s, e, c0, c1, c2), rec);
-            c0 += e.sx0; c1 += e.sx1; c2 += e.sx2;
-        }
-        r0 += e.sy0; r1 += e.sy1; r2 += e.sy2;
-    }
+    raster_inline<DEPTH_ONLY>(p, s, px0, py0, px1, py1, frags);
     return true;
 }
 
@@ -322,6 +329,15 @@ __global__ void __launch_bounds__(RS_THREADS) raster_setup_kernel(const __grid_c
         bool has_med = false;
         if (i < total) setup_listed_triangle<DEPTH_ONLY>(p, i, n_regions, frags, set_up, &med, &has_med);
         uint32_t m = __ballot_sync(0xFFFFFFFFu, has_med);
+        if (__popc(m) >= COOP_MAX_LANES) {
+            // most lanes hold a medium triangle: 32 boxes walked in parallel beat 32 boxes walked one after the other
+            if (has_med) {
+                int px0, py0, px1, py1;
+                pixel_bounds(p, med, px0, py0, px1, py1);
+                raster_inline<DEPTH_ONLY>(p, med, px0, py0, px1, py1, frags);
+            }
+            m = 0;
+        }
         while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;
