@@ -188,4 +188,20 @@ R3_STATIC_ASSERT(sizeof(r3_material) == 208, "GpuMaterialData");
 R3_STATIC_ASSERT(offsetof(r3_material, albedo) == 144, "albedo");
 R3_STATIC_ASSERT(offsetof(r3_material, flags) == 204, "flags");
 
+/* GpuSkinningInput — rend3-routine/src/skinning.rs:20-45, skinning.wgsl:3-26 (40 bytes, byte offsets into the mesh buffer,
+ * R3_ATTR_ABSENT when an attribute is missing) */
+typedef struct r3_skinning_input {
+    uint32_t base_position_offset;
+    uint32_t base_normal_offset;
+    uint32_t base_tangent_offset;
+    uint32_t joint_indices_offset;    /* [u16; 4] per vertex */
+    uint32_t joint_weight_offset;     /* vec4<f32> per vertex */
+    uint32_t updated_position_offset;
+    uint32_t updated_normal_offset;
+    uint32_t updated_tangent_offset;
+    uint32_t joint_matrix_base_offset;
+    uint32_t vertex_count;
+} r3_skinning_input;
+R3_STATIC_ASSERT(sizeof(r3_skinning_input) == 40, "GpuSkinningInput");
+
 #endif /* R3_LAYOUTS_H */

@@ -79,6 +79,13 @@ int r3_set_directional_lights(r3_ctx*, const void* bytes, uint64_t nbytes,
 int r3_set_point_lights(r3_ctx*, const void* bytes, uint64_t nbytes);              /* point.rs:58-74 */
 int r3_set_frame_uniforms(r3_ctx*, const r3_frame_uniforms* uniforms);             /* uniforms.rs:94-106 */
 
+/* ------------------------------------------------------------------ GPU skinning
+ * add_skinning_to_graph / GpuSkinner::execute_pass (rend3-routine/src/skinning.rs:54-199) + skinning.wgsl:37-94:
+ * 4-joint linear blend of position / normal / tangent from the unskinned attribute ranges into the skeleton's
+ * overridden ranges of the mesh buffer, one launch for all skeletons.  joint_matrices = global_joint_count mat4. */
+int r3_skin(r3_ctx*, const r3_skinning_input* inputs, uint32_t n_skeletons, const float* joint_matrices, uint32_t n_joints);
+int r3_readback_mesh_buffer(r3_ctx*, void* bytes, uint64_t capacity_bytes);
+
 /* ------------------------------------------------------------------ per-object cull + uniform bake
  * GpuCuller::object_uniform_upload (culler.rs:427-529) fused with the sphere-frustum test of
  * batch_objects (batching.rs:144-148, util/frustum.rs:148-161): for every slot < object_count

@@ -37,7 +37,7 @@ ENTRY_POINTS = [
     "readback_draw_calls", "readback_culling_results", "set_render_target", "clear_shadow_atlas",
     "shadow_pass", "forward_begin", "forward_pass", "hiz_build", "forward_resolve", "tonemap",
     "readback_hdr_f32", "readback_hdr_f16", "readback_depth", "readback_ldr", "readback_shadow_atlas",
-    "readback_hiz", "forward_stats", "device_ptr", "set_scissor_rows",
+    "readback_hiz", "forward_stats", "device_ptr", "set_scissor_rows", "skin", "readback_mesh_buffer",
 ]
 
 
@@ -136,6 +136,18 @@ class Backend:
         b = record.tobytes()
         assert len(b) == 496
         self._call("set_frame_uniforms", C.c_char_p(b))
+
+    # ---- skinning
+    def skin(self, inputs: np.ndarray, joint_matrices: np.ndarray):
+        inputs = np.ascontiguousarray(inputs)
+        assert inputs.dtype.itemsize == 40
+        jm = np.ascontiguousarray(joint_matrices, dtype=np.float32).reshape(-1, 16)
+        self._call("skin", _ptr(inputs), C.c_uint32(len(inputs)), _ptr(jm), C.c_uint32(len(jm)))
+
+    def readback_mesh_buffer(self, n_words: int) -> np.ndarray:
+        out = np.empty(n_words, dtype=np.uint32)
+        self._call("readback_mesh_buffer", _ptr(out), C.c_uint64(out.nbytes))
+        return out
 
     # ---- object cull + bake
     def object_uniform_upload(self, camera: int, header: np.ndarray, mode: int = CB_BAKE | CB_CULL):

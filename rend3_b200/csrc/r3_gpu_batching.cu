@@ -32,18 +32,50 @@ __device__ __forceinline__ uint32_t sortable_f32(float f) {   // order-preservin
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+__device__ __forceinline__ unsigned long long make_sort_key(const uint32_t* __restrict__ visible, const uint8_t* __restrict__ key8, const float* __restrict__ loc,
+                                                            float vx, float vy, float vz, uint32_t j) {
+    const uint32_t h = visible[j];
+    const uint8_t k = key8[h];                                   // (material_key << 1 | reason) << 1 | back_to_front
+    const float dx = sub_rn(vx, loc[3 * (size_t)h]), dy = sub_rn(vy, loc[3 * (size_t)h + 1]), dz = sub_rn(vz, loc[3 * (size_t)h + 2]);
+    float d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));   // Vec3A::distance_squared (batching.rs:156-157)
+    if (k & 1u) d2 = -d2;                                                        // SortingOrder::BackToFront (batching.rs:158-160)
+    return ((unsigned long long)(k >> 1) << 56) | ((unsigned long long)sortable_f32(d2) << 24) | (unsigned long long)j;
+}
+
+// cap <= SMALL_SORT_MAX: keys are unique (the low 24 bits are the position in the visible list), so an unstable
+// bitonic network yields the same order as the stable radix sort
+constexpr uint32_t SMALL_SORT_MAX = 2048;   // measured: the one-CTA network costs 170 us at 16384 keys, the multi-block radix ~50 us
+__global__ void __launch_bounds__(1024) small_sort_kernel(const uint32_t* __restrict__ visible, const uint32_t* __restrict__ visible_count,
+                                                          const uint8_t* __restrict__ key8, const float* __restrict__ loc, float vx, float vy, float vz,
+                                                          unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ header) {
+    extern __shared__ unsigned long long s_keys[];
+    const uint32_t nv = *visible_count;
+    if (threadIdx.x == 0) { header[0] = nv; header[4] = 0u; }
+    uint32_t n_pad = 1;
+    while (n_pad < nv) n_pad <<= 1;
+    for (uint32_t j = threadIdx.x; j < n_pad; j += blockDim.x) s_keys[j] = j < nv ? make_sort_key(visible, key8, loc, vx, vy, vz, j) : ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= n_pad; k <<= 1) {
+        for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+                const uint32_t i = ((t & ~(jj - 1u)) << 1) | (t & (jj - 1u)), l = i | jj;
+                const unsigned long long a = s_keys[i], b = s_keys[l];
+                const bool ascending = (i & k) == 0u;
+                if ((a > b) == ascending) { s_keys[i] = b; s_keys[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t j = threadIdx.x; j < nv; j += blockDim.x) keys_out[j] = s_keys[j];
+}
+
 __global__ void keygen_kernel(const uint32_t* __restrict__ visible, const uint32_t* __restrict__ visible_count, const uint8_t* __restrict__ key8,
                               const float* __restrict__ loc, float vx, float vy, float vz, unsigned long long* __restrict__ keys, uint32_t* __restrict__ header) {
     const uint32_t nv = *visible_count;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == 0) { header[0] = nv; header[4] = (nv >= (1u << 24)) ? 1u : 0u; }
     if (j >= nv) return;
-    const uint32_t h = visible[j];
-    const uint8_t k = key8[h];                                   // (material_key << 1 | reason) << 1 | back_to_front
-    const float dx = sub_rn(vx, loc[3 * (size_t)h]), dy = sub_rn(vy, loc[3 * (size_t)h + 1]), dz = sub_rn(vz, loc[3 * (size_t)h + 2]);
-    float d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));   // Vec3A::distance_squared (batching.rs:156-157)
-    if (k & 1u) d2 = -d2;                                                        // SortingOrder::BackToFront (batching.rs:158-160)
-    keys[j] = ((unsigned long long)(k >> 1) << 56) | ((unsigned long long)sortable_f32(d2) << 24) | (unsigned long long)j;
+    keys[j] = make_sort_key(visible, key8, loc, vx, vy, vz, j);
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) radix_hist_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ header,
@@ -348,19 +380,31 @@ int r3_device_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], ui
     R3_CUDA(c, cudaMemsetAsync(j.d_header, 0, 32, c->stream));
 
     if (cap) {
-        keygen_kernel<<<(cap + 255) / 256, 256, 0, c->stream>>>(cam->d_visible, cam->d_visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2],
-                                                                 cam->d_sort_keys[0], j.d_header);
-        R3_CHECK_LAUNCH(c, "keygen_kernel");
         int src = 0;
-        for (int pass = 0; pass < SORT_PASSES; ++pass) {
-            const int shift = KEY_SHIFT0 + 8 * pass;
-            radix_hist_kernel<<<sort_blocks, SORT_THREADS, 0, c->stream>>>(cam->d_sort_keys[src], j.d_header, shift, cam->d_sort_hist);
-            R3_CHECK_LAUNCH(c, "radix_hist_kernel");
-            scan_u32_kernel<<<1, 1024, 0, c->stream>>>(cam->d_sort_hist, sort_blocks * 256u);
-            R3_CHECK_LAUNCH(c, "scan_u32_kernel");
-            radix_scatter_kernel<<<sort_blocks, SORT_THREADS, 0, c->stream>>>(cam->d_sort_keys[src], cam->d_sort_keys[src ^ 1], j.d_header, shift, cam->d_sort_hist);
-            R3_CHECK_LAUNCH(c, "radix_scatter_kernel");
-            src ^= 1;
+        if (cap <= SMALL_SORT_MAX) {
+            // small worlds: key generation + a bitonic sort of the (unique) keys in shared memory, one CTA, one launch
+            uint32_t pad = 1;
+            while (pad < cap) pad <<= 1;
+            const size_t smem = (size_t)pad * 8;
+            static bool attr_set = false;
+            if (!attr_set) { cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SORT_MAX * 8); attr_set = true; }
+            small_sort_kernel<<<1, 1024, smem, c->stream>>>(cam->d_visible, cam->d_visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2],
+                                                            cam->d_sort_keys[0], j.d_header);
+            R3_CHECK_LAUNCH(c, "small_sort_kernel");
+        } else {
+            keygen_kernel<<<(cap + 255) / 256, 256, 0, c->stream>>>(cam->d_visible, cam->d_visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2],
+                                                                     cam->d_sort_keys[0], j.d_header);
+            R3_CHECK_LAUNCH(c, "keygen_kernel");
+            for (int pass = 0; pass < SORT_PASSES; ++pass) {
+                const int shift = KEY_SHIFT0 + 8 * pass;
+                radix_hist_kernel<<<sort_blocks, SORT_THREADS, 0, c->stream>>>(cam->d_sort_keys[src], j.d_header, shift, cam->d_sort_hist);
+                R3_CHECK_LAUNCH(c, "radix_hist_kernel");
+                scan_u32_kernel<<<1, 1024, 0, c->stream>>>(cam->d_sort_hist, sort_blocks * 256u);
+                R3_CHECK_LAUNCH(c, "scan_u32_kernel");
+                radix_scatter_kernel<<<sort_blocks, SORT_THREADS, 0, c->stream>>>(cam->d_sort_keys[src], cam->d_sort_keys[src ^ 1], j.d_header, shift, cam->d_sort_hist);
+                R3_CHECK_LAUNCH(c, "radix_scatter_kernel");
+                src ^= 1;
+            }
         }
         BuildParams p;
         p.keys = cam->d_sort_keys[src]; p.visible = cam->d_visible; p.objects = c->d_objects;

@@ -42,6 +42,7 @@ struct RasterParams {
     const r3_object* objects; uint32_t n_slots;
     const r3_object_matrices* matrices; uint32_t matrices_cap;
     const uint32_t* mesh; uint64_t mesh_words;
+    const r3_material* materials; uint32_t n_materials;
     // target
     float ox, oy, vw, vh; int32_t x0, y0, x1, y1; uint32_t pitch; int positive_visible;
     unsigned long long* vis; uint32_t pass_bit;   // colour passes
@@ -272,6 +273,12 @@ __device__ void setup_listed_triangle(const RasterParams& p, unsigned long long 
     if (oid >= p.n_slots || oid >= p.matrices_cap) return;
     const r3_object* obj = &p.objects[oid];
     if (obj->enabled == 0u) return;                                                               // opaque.wgsl:108-112
+    if (p.regions[r].material_key == 1ull) {
+        // cutout routine (pbr/routine.rs:97-133, `discard` variant): untextured alpha = material.albedo.a, constant over the
+        // object unless the vertex colour is blended in, so the discard (opaque.wgsl:231-235, depth.wgsl:186-207) is per triangle
+        const r3_material* m = &p.materials[obj->material_index < p.n_materials ? obj->material_index : 0u];
+        if (!(m->flags & R3_MAT_ALBEDO_BLEND) && m->albedo[3] < m->alpha_cutout) return;
+    }
     const uint32_t pos_off = obj->attr_offset[0] >> 2;
     const float* mvp = p.matrices[oid].model_view_proj;
     const uint32_t vid[3] = {k0 & 0xFFFFFFu, k1 & 0xFFFFFFu, k2 & 0xFFFFFFu};
@@ -479,7 +486,7 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, bool dept
     p.batches = j->d_batches; p.regions = j->d_regions; p.header = j->d_header;
     p.calls = ds.calls; p.indices = ds.indices; p.index_elems = ds.index_elems; p.tri_prefix = cam->d_block_sums;
     p.objects = c->d_objects; p.n_slots = c->n_slots; p.matrices = cam->d_matrices; p.matrices_cap = cam->matrices_cap;
-    p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;
+    p.mesh = c->d_mesh; p.mesh_words = c->mesh_words; p.materials = c->d_materials; p.n_materials = c->n_materials;
     p.ox = ox; p.oy = oy; p.vw = vw; p.vh = vh; p.x0 = x0; p.y0 = y0; p.x1 = x1; p.y1 = y1; p.pitch = pitch;
     p.positive_visible = (cam->header.flags & R3_PCU_POSITIVE_AREA_VISIBLE) ? 1 : 0;
     p.vis = c->d_vis; p.pass_bit = (uint32_t)pass; p.depth_bits = (uint32_t*)c->d_atlas;

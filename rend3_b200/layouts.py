@@ -146,3 +146,12 @@ MATERIAL_DTYPE = _dt(
     ],
     208,
 )
+
+SKINNING_INPUT_DTYPE = _dt(
+    [
+        ("base_position_offset", u4, 0), ("base_normal_offset", u4, 4), ("base_tangent_offset", u4, 8), ("joint_indices_offset", u4, 12),
+        ("joint_weight_offset", u4, 16), ("updated_position_offset", u4, 20), ("updated_normal_offset", u4, 24), ("updated_tangent_offset", u4, 28),
+        ("joint_matrix_base_offset", u4, 32), ("vertex_count", u4, 36),
+    ],
+    40,
+)

@@ -136,8 +136,10 @@ def cube_field_scene(n_objects: int = 10_000, seed: int = 1, resolution: Tuple[i
         g = 0.5 if material_count == 1 else 0.25 + 0.5 * (m / max(material_count - 1, 1))
         # mixed_transparency: materials cycle opaque / cutout / blend, i.e. material keys 0 / 1 / 2 (pbr/material.rs:497-503)
         transparency = (m % 3) if mixed_transparency else 0
-        r.add_material(PbrMaterial(albedo_value=(0.5, g, 0.5 if material_count == 1 else 1.0 - g, 1.0), roughness_factor=roughness,
-                                   transparency=transparency))
+        # every other cutout material has alpha below its cutout threshold: its objects are discarded in the forward and shadow passes
+        alpha = 0.3 if (mixed_transparency and m % 6 == 1) else 1.0
+        r.add_material(PbrMaterial(albedo_value=(0.5, g, 0.5 if material_count == 1 else 1.0 - g, alpha), roughness_factor=roughness,
+                                   transparency=transparency, alpha_cutout=0.5))
     r.set_camera_data(cube_example_camera(pull_back))
     dirs = [(-1.0, -4.0, 2.0), (2.0, -3.0, -1.0), (-2.0, -5.0, -3.0), (1.0, -2.0, 3.0)]
     for i in range(n_dir_lights):

@@ -101,6 +101,21 @@ def test_live_mask_and_update_objects(cuda):
     assert np.array_equal(mc[[3, 77, 4096, 4999]], mo[[3, 77, 4096, 4999]])
 
 
+def test_gpu_skinning_is_bit_exact(cuda):
+    """skinning.wgsl on the GPU against the oracle: the whole mesh buffer (skinned positions + normals written into the
+    overridden ranges) must be bit-identical — the positions feed the bit-exact cull and raster stages."""
+    import skinning_case
+
+    words, inputs, joints, _ = skinning_case.build(seed=2, vertex_counts=(257, 5000, 1), joints_per_skeleton=(3, 16, 1))
+    orc = load_oracle_backend()
+    for b in (cuda, orc):
+        b.set_mesh_buffer(words)
+        b.skin(inputs, joints)
+    a, o = cuda.readback_mesh_buffer(len(words)), orc.readback_mesh_buffer(len(words))
+    assert np.array_equal(a, o)
+    assert not np.array_equal(a, words), "skinning must have written the overridden ranges"
+
+
 # ------------------------------------------------------------------ whole frames
 def compare_frame_state(cuda, orc, ev, cameras, check_pixels=True, what=""):
     for cam in cameras:

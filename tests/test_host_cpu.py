@@ -191,6 +191,33 @@ def test_culling_buffers_ping_pong_like_suballoc():
     assert np.array_equal(img1, b.readback_ldr()), "a static scene renders identically through the predicted pass"
 
 
+def test_oracle_skinning_matches_float64_blend():
+    """skinning.wgsl:37-94 restated: skinned positions equal the float64 4-joint blend, normals are unit length, and
+    identity joints leave the mesh untouched."""
+    import skinning_case
+
+    words, inputs, joints, expect = skinning_case.build(seed=1)
+    b = load_oracle_backend()
+    b.set_mesh_buffer(words)
+    b.skin(inputs, joints)
+    out = b.readback_mesh_buffer(len(words))
+    for rec, exp in zip(inputs, expect):
+        nv = int(rec["vertex_count"])
+        p = out[rec["updated_position_offset"] // 4:][: nv * 3].view(np.float32).reshape(nv, 3)
+        n = out[rec["updated_normal_offset"] // 4:][: nv * 3].view(np.float32).reshape(nv, 3)
+        assert np.allclose(p, exp, rtol=1e-5, atol=1e-5)
+        assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-5)
+    ident = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (len(joints), 1))
+    b.set_mesh_buffer(words)
+    b.skin(inputs, ident)
+    out = b.readback_mesh_buffer(len(words))
+    for rec in inputs:
+        nv = int(rec["vertex_count"])
+        src = words[rec["base_position_offset"] // 4:][: nv * 3].view(np.float32)
+        dst = out[rec["updated_position_offset"] // 4:][: nv * 3].view(np.float32)
+        assert np.allclose(dst, src, rtol=1e-6, atol=1e-6)
+
+
 # ------------------------------------------------------------------ multi-GPU sharding logic over gloo (world_size 2, CPU)
 SHARD_SCRIPT = r'''
 import os, sys
