@@ -45,6 +45,7 @@ struct RasterParams {
     const r3_material* materials; uint32_t n_materials;
     // target
     float ox, oy, vw, vh; int32_t x0, y0, x1, y1; uint32_t pitch; int positive_visible;
+    uint32_t samples;                              // 1 or 4 (R7: standard 4x pattern); shadow passes are always single-sampled
     unsigned long long* vis; uint32_t pass_bit;   // colour passes
     uint32_t* depth_bits;                          // depth-only passes (shadow atlas)
     r3_tri_record* records;
@@ -133,7 +134,7 @@ __device__ __forceinline__ float sample_depth(const SubTri& s, const EdgeSetup& 
     return fminf(fmaxf(z, 0.0f), 1.0f);
 }
 template <bool DEPTH_ONLY>
-__device__ __forceinline__ uint32_t write_sample(const RasterParams& p, int px, int py, float z, uint32_t rec) {
+__device__ __forceinline__ uint32_t write_sample(const RasterParams& p, int px, int py, uint32_t k, float z, uint32_t rec) {
     // the result of the atomic is never read, so it compiles to a fire-and-forget RED.MAX: a thread can have
     // hundreds of samples in flight instead of one L2 round trip per sample
     const size_t pi = (size_t)py * p.pitch + px;
@@ -141,16 +142,43 @@ __device__ __forceinline__ uint32_t write_sample(const RasterParams& p, int px, 
         atomicMax(&p.depth_bits[pi], __float_as_uint(z));
     } else {
         const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | ((unsigned long long)p.pass_bit << 31) | rec;
-        atomicMax(&p.vis[pi], key);
+        atomicMax(&p.vis[pi * p.samples + k], key);
     }
     return 1u;   // statistics count rasterised (covered) samples
+}
+
+// R7: sample offsets from the pixel centre in 1/256 pixel (standard 4x pattern)
+__device__ __constant__ int c_sample_dx[4] = {-32, 96, -96, 32};
+__device__ __constant__ int c_sample_dy[4] = {-96, -32, 32, 96};
+
+// coverage + depth of one pixel given the biased edge values at its centre
+template <bool DEPTH_ONLY>
+__device__ __forceinline__ void emit_pixel(const RasterParams& p, const SubTri& s, const EdgeSetup& e, int px, int py, long long c0, long long c1, long long c2,
+                                           uint32_t& frags) {
+    if (DEPTH_ONLY || p.samples == 1u) {
+        if ((c0 | c1 | c2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, 0u, sample_depth(s, e, c0, c1, c2), s.rec);
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // E(centre + o) = E(centre) + (step_x * o.x + step_y * o.y) / 256 (the steps are exact multiples of 256)
+        const long long a0 = c0 + (e.sx0 >> 8) * c_sample_dx[k] + (e.sy0 >> 8) * c_sample_dy[k];
+        const long long a1 = c1 + (e.sx1 >> 8) * c_sample_dx[k] + (e.sy1 >> 8) * c_sample_dy[k];
+        const long long a2 = c2 + (e.sx2 >> 8) * c_sample_dx[k] + (e.sy2 >> 8) * c_sample_dy[k];
+        if ((a0 | a1 | a2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, (uint32_t)k, sample_depth(s, e, a0, a1, a2), s.rec);
+    }
 }
 
 __device__ __forceinline__ void pixel_bounds(const RasterParams& p, const SubTri& s, int& px0, int& py0, int& px1, int& py1) {
     const int minx = min(s.x[0], min(s.x[1], s.x[2])), maxx = max(s.x[0], max(s.x[1], s.x[2]));
     const int miny = min(s.y[0], min(s.y[1], s.y[2])), maxy = max(s.y[0], max(s.y[1], s.y[2]));
-    px0 = max((minx - 128 + 255) >> 8, p.x0); px1 = min((maxx - 128) >> 8, p.x1 - 1);
-    py0 = max((miny - 128 + 255) >> 8, p.y0); py1 = min((maxy - 128) >> 8, p.y1 - 1);
+    if (p.samples == 1u) {
+        px0 = max((minx - 128 + 255) >> 8, p.x0); px1 = min((maxx - 128) >> 8, p.x1 - 1);
+        py0 = max((miny - 128 + 255) >> 8, p.y0); py1 = min((maxy - 128) >> 8, p.y1 - 1);
+    } else {   // any sample of a touched pixel may be covered
+        px0 = max(minx >> 8, p.x0); px1 = min(maxx >> 8, p.x1 - 1);
+        py0 = max(miny >> 8, p.y0); py1 = min(maxy >> 8, p.y1 - 1);
+    }
 }
 
 // one thread walks the pixel box of its own sub-triangle with incremental edge functions
@@ -161,7 +189,7 @@ __device__ __forceinline__ void raster_inline(const RasterParams& p, const SubTr
     for (int py = py0; py <= py1; ++py) {
         long long c0 = r0, c1 = r1, c2 = r2;
         for (int px = px0; px <= px1; ++px) {
-            if ((c0 | c1 | c2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, sample_depth(s, e, c0, c1, c2), s.rec);
+            emit_pixel<DEPTH_ONLY>(p, s, e, px, py, c0, c1, c2, frags);
             c0 += e.sx0; c1 += e.sx1; c2 += e.sx2;
         }
         r0 += e.sy0; r1 += e.sy1; r2 += e.sy2;
@@ -247,7 +275,7 @@ __device__ __forceinline__ void raster_cooperative(const RasterParams& p, const 
         const long long dy = py - py0;
         long long c0 = e.e0 + dy * e.sy0 + (long long)lx * e.sx0, c1 = e.e1 + dy * e.sy1 + (long long)lx * e.sx1, c2 = e.e2 + dy * e.sy2 + (long long)lx * e.sx2;
         for (int px = px0 + lx; px <= px1; px += lw) {
-            if ((c0 | c1 | c2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, sample_depth(s, e, c0, c1, c2), s.rec);
+            emit_pixel<DEPTH_ONLY>(p, s, e, px, py, c0, c1, c2, frags);
             c0 += lw * e.sx0; c1 += lw * e.sx1; c2 += lw * e.sx2;
         }
     }
@@ -389,14 +417,17 @@ __global__ void __launch_bounds__(RS_THREADS) raster_band_kernel(const __grid_co
         for (int bx = px0; bx <= px1; bx += 32) {
             // skip the 32 x rows block when it lies entirely outside one edge: evaluate the corner that maximises E
             const long long dx = bx - px0, wx = min(31, px1 - bx), hy = rows - 1;
-            const long long m0 = e.e0 + dx * e.sx0 + (e.sx0 > 0 ? wx * e.sx0 : 0) + (e.sy0 > 0 ? hy * e.sy0 : 0);
-            const long long m1 = e.e1 + dx * e.sx1 + (e.sx1 > 0 ? wx * e.sx1 : 0) + (e.sy1 > 0 ? hy * e.sy1 : 0);
-            const long long m2 = e.e2 + dx * e.sx2 + (e.sx2 > 0 ? wx * e.sx2 : 0) + (e.sy2 > 0 ? hy * e.sy2 : 0);
+            // multisampling: a sample sits up to 96/256 pixel from the centre, widen the block by half a pixel per axis
+            const long long k0 = p.samples == 1u ? 0 : (llabs(e.sx0) + llabs(e.sy0)) / 2, k1 = p.samples == 1u ? 0 : (llabs(e.sx1) + llabs(e.sy1)) / 2,
+                            k2 = p.samples == 1u ? 0 : (llabs(e.sx2) + llabs(e.sy2)) / 2;
+            const long long m0 = k0 + e.e0 + dx * e.sx0 + (e.sx0 > 0 ? wx * e.sx0 : 0) + (e.sy0 > 0 ? hy * e.sy0 : 0);
+            const long long m1 = k1 + e.e1 + dx * e.sx1 + (e.sx1 > 0 ? wx * e.sx1 : 0) + (e.sy1 > 0 ? hy * e.sy1 : 0);
+            const long long m2 = k2 + e.e2 + dx * e.sx2 + (e.sx2 > 0 ? wx * e.sx2 : 0) + (e.sy2 > 0 ? hy * e.sy2 : 0);
             if ((m0 | m1 | m2) < 0) continue;
             const int px = bx + lane;
             long long c0 = e.e0 + (dx + lane) * e.sx0, c1 = e.e1 + (dx + lane) * e.sx1, c2 = e.e2 + (dx + lane) * e.sx2;
             for (int py = by0; py <= by1; ++py) {
-                if (px <= px1 && (c0 | c1 | c2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, sample_depth(s, e, c0, c1, c2), s.rec);
+                if (px <= px1) emit_pixel<DEPTH_ONLY>(p, s, e, px, py, c0, c1, c2, frags);
                 c0 += e.sy0; c1 += e.sy1; c2 += e.sy2;
             }
         }
@@ -489,6 +520,7 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, bool dept
     p.mesh = c->d_mesh; p.mesh_words = c->mesh_words; p.materials = c->d_materials; p.n_materials = c->n_materials;
     p.ox = ox; p.oy = oy; p.vw = vw; p.vh = vh; p.x0 = x0; p.y0 = y0; p.x1 = x1; p.y1 = y1; p.pitch = pitch;
     p.positive_visible = (cam->header.flags & R3_PCU_POSITIVE_AREA_VISIBLE) ? 1 : 0;
+    p.samples = depth_only ? 1u : c->samples;
     p.vis = c->d_vis; p.pass_bit = (uint32_t)pass; p.depth_bits = (uint32_t*)c->d_atlas;
     p.large = large; p.bands = bands; p.counters = counters; p.stats = depth_only ? nullptr : c->d_stats;
     p.records = nullptr;

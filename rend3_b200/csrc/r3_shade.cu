@@ -34,7 +34,7 @@ struct ShadeParams {
     const DirPrep* dir; uint32_t n_dir; const PointPrep* point; uint32_t n_point;
     const float* atlas; uint32_t atlas_w, atlas_h;
     float ambient[4]; float clear[4];
-    uint32_t width, height, row_begin, row_end;
+    uint32_t width, height, row_begin, row_end, samples;
     float4* hdr32; uint2* hdr16; float* depth;
     unsigned long long* stats;
 };
@@ -136,6 +136,121 @@ __device__ __forceinline__ VsOut vertex_stage(const ShadeParams& p, const uint32
     return o;
 }
 
+// vs_main outputs interpolated at the centre of pixel (px, py) + fs_main for triangle record `rec` of pass `pass`
+__device__ __forceinline__ float4 shade_fragment(const ShadeParams& p, const DirPrep* __restrict__ s_dir, const PointPrep* __restrict__ s_point, uint32_t pass,
+                                                 uint32_t rec, uint32_t px, uint32_t py) {
+    const r3_tri_record* tp = (pass ? p.tris1 : p.tris0) + (rec - 1u);
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp)), q1 = __ldg(reinterpret_cast<const float4*>(tp) + 1),
+                 q2 = __ldg(reinterpret_cast<const float4*>(tp) + 2);
+    const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(tp) + 3);
+    // xyw[3][3] = q0.xyz | q0.w q1.xy | q1.zw q2.x ; object_id = q2.y ; vid = q2.z q2.w q3.x
+    const float3 p0 = make_float3(q0.x, q0.y, q0.z), p1 = make_float3(q0.w, q1.x, q1.y), p2 = make_float3(q1.z, q1.w, q2.x);
+    const uint32_t oid = __float_as_uint(q2.y), vid0 = __float_as_uint(q2.z), vid1 = __float_as_uint(q2.w), vid2 = q3.x;
+    // R6: perspective-correct weights b_i ~ cross(p_j, p_k) . (ndc_x, ndc_y, 1)
+    const float nx = ((float)px + 0.5f) / ((float)p.width * 0.5f) - 1.0f, ny = 1.0f - ((float)py + 0.5f) / ((float)p.height * 0.5f);
+    float b0 = (p1.y * p2.z - p1.z * p2.y) * nx + (p1.z * p2.x - p1.x * p2.z) * ny + (p1.x * p2.y - p1.y * p2.x);
+    float b1 = (p2.y * p0.z - p2.z * p0.y) * nx + (p2.z * p0.x - p2.x * p0.z) * ny + (p2.x * p0.y - p2.y * p0.x);
+    float b2 = (p0.y * p1.z - p0.z * p1.y) * nx + (p0.z * p1.x - p0.x * p1.z) * ny + (p0.x * p1.y - p0.y * p1.x);
+    const float inv_sum = 1.0f / (b0 + b1 + b2);
+    b0 *= inv_sum; b1 *= inv_sum; b2 *= inv_sum;
+
+    const r3_object* obj = &p.objects[oid];
+    const uint4 oa = __ldg(reinterpret_cast<const uint4*>(obj) + 5);   // bytes 80..95 : first_index, index_count, material_index, attr[0]
+    const uint4 ob = __ldg(reinterpret_cast<const uint4*>(obj) + 6);   // bytes 96..111: attr[1..4]
+    const uint4 oc = __ldg(reinterpret_cast<const uint4*>(obj) + 7);   // bytes 112..127: attr[5], enabled
+    const uint32_t attr[6] = {oa.w, ob.x, ob.y, ob.z, ob.w, oc.x};
+    const uint32_t material_index = oa.z;
+    float mv[16];
+    {
+        const float4* m4 = reinterpret_cast<const float4*>(p.matrices[oid].model_view);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float4 c4 = __ldg(&m4[k]); mv[4 * k] = c4.x; mv[4 * k + 1] = c4.y; mv[4 * k + 2] = c4.z; mv[4 * k + 3] = c4.w; }
+    }
+    const float3 iss = make_float3(1.0f / (mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]), 1.0f / (mv[4] * mv[4] + mv[5] * mv[5] + mv[6] * mv[6]),
+                                   1.0f / (mv[8] * mv[8] + mv[9] * mv[9] + mv[10] * mv[10]));   // math/matrix.wgsl:1-7
+    const VsOut v0 = vertex_stage(p, attr, mv, iss, vid0), v1 = vertex_stage(p, attr, mv, iss, vid1), v2 = vertex_stage(p, attr, mv, iss, vid2);
+    const float4 vp = make_float4(b0 * v0.view_position.x + b1 * v1.view_position.x + b2 * v2.view_position.x,
+                                  b0 * v0.view_position.y + b1 * v1.view_position.y + b2 * v2.view_position.y,
+                                  b0 * v0.view_position.z + b1 * v1.view_position.z + b2 * v2.view_position.z,
+                                  b0 * v0.view_position.w + b1 * v1.view_position.w + b2 * v2.view_position.w);
+    const float3 vnormal = make_float3(b0 * v0.normal.x + b1 * v1.normal.x + b2 * v2.normal.x, b0 * v0.normal.y + b1 * v1.normal.y + b2 * v2.normal.y,
+                                       b0 * v0.normal.z + b1 * v1.normal.z + b2 * v2.normal.z);
+    const float4 vcolor = make_float4(b0 * v0.color.x + b1 * v1.color.x + b2 * v2.color.x, b0 * v0.color.y + b1 * v1.color.y + b2 * v2.color.y,
+                                      b0 * v0.color.z + b1 * v1.color.z + b2 * v2.color.z, b0 * v0.color.w + b1 * v1.color.w + b2 * v2.color.w);
+
+    // get_pixel_data_inner for untextured materials (opaque.wgsl:203-424)
+    const r3_material* m = &p.materials[material_index < p.n_materials ? material_index : 0u];
+    const float4 malbedo = __ldg(reinterpret_cast<const float4*>(m->albedo));
+    const float4 mA = __ldg(reinterpret_cast<const float4*>(m->emissive));        // emissive.xyz, roughness
+    const float4 mB = __ldg(reinterpret_cast<const float4*>(&m->metallic));       // metallic, reflectance, clear_coat, clear_coat_roughness
+    const float4 mC = __ldg(reinterpret_cast<const float4*>(&m->anisotropy));     // anisotropy, ambient_occlusion, alpha_cutout, flags
+    const uint32_t flags = __float_as_uint(mC.w);
+    float4 albedo = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (flags & R3_MAT_ALBEDO_ACTIVE) {
+        albedo = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (flags & R3_MAT_ALBEDO_BLEND) {
+            if (flags & R3_MAT_ALBEDO_VERTEX_SRGB) albedo = make_float4(srgb_to_linear(vcolor.x), srgb_to_linear(vcolor.y), srgb_to_linear(vcolor.z), vcolor.w);
+            else albedo = vcolor;
+        }
+    }
+    albedo = make_float4(albedo.x * malbedo.x, albedo.y * malbedo.y, albedo.z * malbedo.z, albedo.w * malbedo.w);
+    if (flags & R3_MAT_UNLIT) {
+        return albedo;                                                             // opaque.wgsl:476-478
+    } else {
+        Pixel pxl;
+        pxl.normal = normalize3(vnormal);
+        const float ao = mC.y, metallic = mB.x, reflectance = mB.y, clear_coat = mB.z, cc_rough = mB.w;
+        float perceptual = mA.w;
+        const float om = 1.0f - metallic;
+        const float inv_pi = 1.0f / R3_PI;
+        pxl.diffuse_pi = make_float3(albedo.x * om * inv_pi, albedo.y * om * inv_pi, albedo.z * om * inv_pi);
+        const float rterm = (0.16f * reflectance * reflectance) * om;
+        pxl.f0 = make_float3(albedo.x * metallic + rterm, albedo.y * metallic + rterm, albedo.z * metallic + rterm);
+        if (clear_coat != 0.0f) {
+            const float base = fmaxf(perceptual, cc_rough);
+            perceptual = perceptual * (1.0f - clear_coat) + base * clear_coat;
+        }
+        pxl.roughness = perceptual * perceptual;
+        pxl.f90 = saturate((pxl.f0.x + pxl.f0.y + pxl.f0.z) * 16.5f);
+        const float3 nvp = normalize3(make_float3(vp.x, vp.y, vp.z));
+        const float3 v = make_float3(-nvp.x, -nvp.y, -nvp.z);
+        const float nov = fabsf(dot3(pxl.normal, v)) + 0.00001f;
+        float3 color = make_float3(mA.x, mA.y, mA.z);
+        for (uint32_t i = 0; i < p.n_dir; ++i) {                                   // opaque.wgsl:487-522
+            const DirPrep& L = i < MAX_SMEM_DIR ? s_dir[i] : p.dir[i];
+            const float snx = L.lm[0] * vp.x + L.lm[4] * vp.y + L.lm[8] * vp.z + L.lm[12] * vp.w;
+            const float sny = L.lm[1] * vp.x + L.lm[5] * vp.y + L.lm[9] * vp.z + L.lm[13] * vp.w;
+            const float snz = L.lm[2] * vp.x + L.lm[6] * vp.y + L.lm[10] * vp.z + L.lm[14] * vp.w;
+            const float flx = snx * 0.5f + 0.5f, fly = sny * 0.5f + 0.5f, locy = 1.0f - fly;
+            float tlx = L.offset[0], tly = L.offset[1], trx = tlx + L.size[0], try_ = tly + L.size[1];
+            const float cu = tlx * (1.0f - flx) + trx * flx, cv = tly * (1.0f - locy) + try_ * locy;
+            const float bx = L.inv_res[0] * 1.5f, by = L.inv_res[1] * 1.5f;
+            tlx += bx; tly += by; trx -= bx; try_ -= by;
+            float shadow = 1.0f;
+            if ((flx >= tlx || fly >= tly) && (flx <= trx || fly <= try_) && snz >= 0.0f && snz <= 1.0f)   // literal any() quirk (opaque.wgsl:509-514)
+                shadow = shadow_pcf5(p, cu, cv, snz);
+            const float3 s = surface_shading(make_float3(L.l[0], L.l[1], L.l[2]), make_float3(L.color[0], L.color[1], L.color[2]), pxl, v, nov, shadow * ao);
+            color.x += s.x; color.y += s.y; color.z += s.z;
+        }
+        for (uint32_t i = 0; i < p.n_point; ++i) {                                 // opaque.wgsl:524-546
+            const PointPrep& L = i < MAX_SMEM_POINT ? s_point[i] : p.point[i];
+            const float3 delta = make_float3(L.pos[0] - vp.x, L.pos[1] - vp.y, L.pos[2] - vp.z);
+            const float d2 = dot3(delta, delta);
+            // att = (1 - s^2)^2 / (1 + s^2) with s = saturate(d / radius) is exactly 0 at and beyond the radius
+            if (d2 >= L.radius * L.radius && pxl.roughness > 0.0f) continue;
+            const float inv_d = rsqrtf(d2), d = d2 * inv_d;
+            const float sdist = saturate(d * rcp_approx(L.radius)), s2 = sdist * sdist, inv_s2 = 1.0f - s2;
+            const float att = inv_s2 * inv_s2 * rcp_approx(1.0f + s2);
+            const float3 s = surface_shading(make_float3(delta.x * inv_d, delta.y * inv_d, delta.z * inv_d),
+                                             make_float3(L.color[0] * att, L.color[1] * att, L.color[2] * att), pxl, v, nov, ao);
+            color.x += fmaxf(s.x, 0.0f); color.y += fmaxf(s.y, 0.0f); color.z += fmaxf(s.z, 0.0f);
+        }
+        return make_float4(fmaxf(p.ambient[0] * albedo.x, color.x), fmaxf(p.ambient[1] * albedo.y, color.y), fmaxf(p.ambient[2] * albedo.z, color.z),
+                          fmaxf(p.ambient[3] * albedo.w, albedo.w));
+    }
+}
+
+template <int SAMPLES>
 __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ ShadeParams p) {
     __shared__ DirPrep s_dir[MAX_SMEM_DIR];
     __shared__ PointPrep s_point[MAX_SMEM_POINT];
@@ -151,129 +266,50 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
     const uint32_t px = blockIdx.x * 32u + (threadIdx.x & 31u), py = p.row_begin + blockIdx.y * 8u + (threadIdx.x >> 5);
     if (px >= p.width || py >= p.row_end) return;
     const size_t pi = (size_t)py * p.width + px;
-    const unsigned long long key = p.vis[pi];
-    const uint32_t rec = (uint32_t)(key & 0x7FFFFFFFull), pass = (uint32_t)((key >> 31) & 1ull);
-    float4 out = make_float4(p.clear[0], p.clear[1], p.clear[2], p.clear[3]);
-    const unsigned long long n_tris = pass ? p.n_tris1 : p.n_tris0;
-    bool shaded = false;
-    if (rec != 0u && rec <= n_tris) {
-        shaded = true;
-        const r3_tri_record* tp = (pass ? p.tris1 : p.tris0) + (rec - 1u);
-        const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp)), q1 = __ldg(reinterpret_cast<const float4*>(tp) + 1),
-                     q2 = __ldg(reinterpret_cast<const float4*>(tp) + 2);
-        const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(tp) + 3);
-        // xyw[3][3] = q0.xyz | q0.w q1.xy | q1.zw q2.x ; object_id = q2.y ; vid = q2.z q2.w q3.x
-        const float3 p0 = make_float3(q0.x, q0.y, q0.z), p1 = make_float3(q0.w, q1.x, q1.y), p2 = make_float3(q1.z, q1.w, q2.x);
-        const uint32_t oid = __float_as_uint(q2.y), vid0 = __float_as_uint(q2.z), vid1 = __float_as_uint(q2.w), vid2 = q3.x;
-        // R6: perspective-correct weights b_i ~ cross(p_j, p_k) . (ndc_x, ndc_y, 1)
-        const float nx = ((float)px + 0.5f) / ((float)p.width * 0.5f) - 1.0f, ny = 1.0f - ((float)py + 0.5f) / ((float)p.height * 0.5f);
-        float b0 = (p1.y * p2.z - p1.z * p2.y) * nx + (p1.z * p2.x - p1.x * p2.z) * ny + (p1.x * p2.y - p1.y * p2.x);
-        float b1 = (p2.y * p0.z - p2.z * p0.y) * nx + (p2.z * p0.x - p2.x * p0.z) * ny + (p2.x * p0.y - p2.y * p0.x);
-        float b2 = (p0.y * p1.z - p0.z * p1.y) * nx + (p0.z * p1.x - p0.x * p1.z) * ny + (p0.x * p1.y - p0.y * p1.x);
-        const float inv_sum = 1.0f / (b0 + b1 + b2);
-        b0 *= inv_sum; b1 *= inv_sum; b2 *= inv_sum;
-
-        const r3_object* obj = &p.objects[oid];
-        const uint4 oa = __ldg(reinterpret_cast<const uint4*>(obj) + 5);   // bytes 80..95 : first_index, index_count, material_index, attr[0]
-        const uint4 ob = __ldg(reinterpret_cast<const uint4*>(obj) + 6);   // bytes 96..111: attr[1..4]
-        const uint4 oc = __ldg(reinterpret_cast<const uint4*>(obj) + 7);   // bytes 112..127: attr[5], enabled
-        const uint32_t attr[6] = {oa.w, ob.x, ob.y, ob.z, ob.w, oc.x};
-        const uint32_t material_index = oa.z;
-        float mv[16];
-        {
-            const float4* m4 = reinterpret_cast<const float4*>(p.matrices[oid].model_view);
+    float4 out;
+    float depth;
+    uint32_t n_shaded = 0;
+    if (SAMPLES == 1) {
+        const unsigned long long key = p.vis[pi];
+        const uint32_t rec = (uint32_t)(key & 0x7FFFFFFFull), pass = (uint32_t)((key >> 31) & 1ull);
+        out = make_float4(p.clear[0], p.clear[1], p.clear[2], p.clear[3]);
+        if (rec != 0u && rec <= (pass ? p.n_tris1 : p.n_tris0)) { out = shade_fragment(p, s_dir, s_point, pass, rec, px, py); n_shaded = 1; }
+        depth = __uint_as_float((uint32_t)(key >> 32));
+    } else {
+        // SampleCount::Four: a primitive is shaded once per pixel for all the samples it owns; the rgba16f samples are box-filtered
+        // ((s0 + s1) + (s2 + s3)) * 0.25 like the resolve attachment (base.rs:245-255); depth resolves to the MIN over the samples
+        unsigned long long keys[4];
+        float4 col[4];
+        depth = 1.0f;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { const float4 c4 = __ldg(&m4[k]); mv[4 * k] = c4.x; mv[4 * k + 1] = c4.y; mv[4 * k + 2] = c4.z; mv[4 * k + 3] = c4.w; }
+        for (int k = 0; k < 4; ++k) {
+            keys[k] = p.vis[pi * 4u + k];
+            depth = fminf(depth, __uint_as_float((uint32_t)(keys[k] >> 32)));
         }
-        const float3 iss = make_float3(1.0f / (mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]), 1.0f / (mv[4] * mv[4] + mv[5] * mv[5] + mv[6] * mv[6]),
-                                       1.0f / (mv[8] * mv[8] + mv[9] * mv[9] + mv[10] * mv[10]));   // math/matrix.wgsl:1-7
-        const VsOut v0 = vertex_stage(p, attr, mv, iss, vid0), v1 = vertex_stage(p, attr, mv, iss, vid1), v2 = vertex_stage(p, attr, mv, iss, vid2);
-        const float4 vp = make_float4(b0 * v0.view_position.x + b1 * v1.view_position.x + b2 * v2.view_position.x,
-                                      b0 * v0.view_position.y + b1 * v1.view_position.y + b2 * v2.view_position.y,
-                                      b0 * v0.view_position.z + b1 * v1.view_position.z + b2 * v2.view_position.z,
-                                      b0 * v0.view_position.w + b1 * v1.view_position.w + b2 * v2.view_position.w);
-        const float3 vnormal = make_float3(b0 * v0.normal.x + b1 * v1.normal.x + b2 * v2.normal.x, b0 * v0.normal.y + b1 * v1.normal.y + b2 * v2.normal.y,
-                                           b0 * v0.normal.z + b1 * v1.normal.z + b2 * v2.normal.z);
-        const float4 vcolor = make_float4(b0 * v0.color.x + b1 * v1.color.x + b2 * v2.color.x, b0 * v0.color.y + b1 * v1.color.y + b2 * v2.color.y,
-                                          b0 * v0.color.z + b1 * v1.color.z + b2 * v2.color.z, b0 * v0.color.w + b1 * v1.color.w + b2 * v2.color.w);
-
-        // get_pixel_data_inner for untextured materials (opaque.wgsl:203-424)
-        const r3_material* m = &p.materials[material_index < p.n_materials ? material_index : 0u];
-        const float4 malbedo = __ldg(reinterpret_cast<const float4*>(m->albedo));
-        const float4 mA = __ldg(reinterpret_cast<const float4*>(m->emissive));        // emissive.xyz, roughness
-        const float4 mB = __ldg(reinterpret_cast<const float4*>(&m->metallic));       // metallic, reflectance, clear_coat, clear_coat_roughness
-        const float4 mC = __ldg(reinterpret_cast<const float4*>(&m->anisotropy));     // anisotropy, ambient_occlusion, alpha_cutout, flags
-        const uint32_t flags = __float_as_uint(mC.w);
-        float4 albedo = make_float4(0.f, 0.f, 0.f, 1.f);
-        if (flags & R3_MAT_ALBEDO_ACTIVE) {
-            albedo = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (flags & R3_MAT_ALBEDO_BLEND) {
-                if (flags & R3_MAT_ALBEDO_VERTEX_SRGB) albedo = make_float4(srgb_to_linear(vcolor.x), srgb_to_linear(vcolor.y), srgb_to_linear(vcolor.z), vcolor.w);
-                else albedo = vcolor;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t id = (uint32_t)keys[k], rec = id & 0x7FFFFFFFu, pass = id >> 31;
+            col[k] = make_float4(p.clear[0], p.clear[1], p.clear[2], p.clear[3]);
+            if (rec != 0u && rec <= (pass ? p.n_tris1 : p.n_tris0)) {
+                int reuse = -1;
+                for (int q = 0; q < k; ++q) if ((uint32_t)keys[q] == id && reuse < 0) reuse = q;
+                if (reuse >= 0) col[k] = col[reuse];
+                else { col[k] = shade_fragment(p, s_dir, s_point, pass, rec, px, py); n_shaded++; }
             }
+            // each sample lives in the rgba16f multisampled target
+            col[k] = make_float4(__half2float(__float2half_rn(col[k].x)), __half2float(__float2half_rn(col[k].y)), __half2float(__float2half_rn(col[k].z)),
+                                 __half2float(__float2half_rn(col[k].w)));
         }
-        albedo = make_float4(albedo.x * malbedo.x, albedo.y * malbedo.y, albedo.z * malbedo.z, albedo.w * malbedo.w);
-        if (flags & R3_MAT_UNLIT) {
-            out = albedo;                                                             // opaque.wgsl:476-478
-        } else {
-            Pixel pxl;
-            pxl.normal = normalize3(vnormal);
-            const float ao = mC.y, metallic = mB.x, reflectance = mB.y, clear_coat = mB.z, cc_rough = mB.w;
-            float perceptual = mA.w;
-            const float om = 1.0f - metallic;
-            const float inv_pi = 1.0f / R3_PI;
-            pxl.diffuse_pi = make_float3(albedo.x * om * inv_pi, albedo.y * om * inv_pi, albedo.z * om * inv_pi);
-            const float rterm = (0.16f * reflectance * reflectance) * om;
-            pxl.f0 = make_float3(albedo.x * metallic + rterm, albedo.y * metallic + rterm, albedo.z * metallic + rterm);
-            if (clear_coat != 0.0f) {
-                const float base = fmaxf(perceptual, cc_rough);
-                perceptual = perceptual * (1.0f - clear_coat) + base * clear_coat;
-            }
-            pxl.roughness = perceptual * perceptual;
-            pxl.f90 = saturate((pxl.f0.x + pxl.f0.y + pxl.f0.z) * 16.5f);
-            const float3 nvp = normalize3(make_float3(vp.x, vp.y, vp.z));
-            const float3 v = make_float3(-nvp.x, -nvp.y, -nvp.z);
-            const float nov = fabsf(dot3(pxl.normal, v)) + 0.00001f;
-            float3 color = make_float3(mA.x, mA.y, mA.z);
-            for (uint32_t i = 0; i < p.n_dir; ++i) {                                   // opaque.wgsl:487-522
-                const DirPrep& L = i < MAX_SMEM_DIR ? s_dir[i] : p.dir[i];
-                const float snx = L.lm[0] * vp.x + L.lm[4] * vp.y + L.lm[8] * vp.z + L.lm[12] * vp.w;
-                const float sny = L.lm[1] * vp.x + L.lm[5] * vp.y + L.lm[9] * vp.z + L.lm[13] * vp.w;
-                const float snz = L.lm[2] * vp.x + L.lm[6] * vp.y + L.lm[10] * vp.z + L.lm[14] * vp.w;
-                const float flx = snx * 0.5f + 0.5f, fly = sny * 0.5f + 0.5f, locy = 1.0f - fly;
-                float tlx = L.offset[0], tly = L.offset[1], trx = tlx + L.size[0], try_ = tly + L.size[1];
-                const float cu = tlx * (1.0f - flx) + trx * flx, cv = tly * (1.0f - locy) + try_ * locy;
-                const float bx = L.inv_res[0] * 1.5f, by = L.inv_res[1] * 1.5f;
-                tlx += bx; tly += by; trx -= bx; try_ -= by;
-                float shadow = 1.0f;
-                if ((flx >= tlx || fly >= tly) && (flx <= trx || fly <= try_) && snz >= 0.0f && snz <= 1.0f)   // literal any() quirk (opaque.wgsl:509-514)
-                    shadow = shadow_pcf5(p, cu, cv, snz);
-                const float3 s = surface_shading(make_float3(L.l[0], L.l[1], L.l[2]), make_float3(L.color[0], L.color[1], L.color[2]), pxl, v, nov, shadow * ao);
-                color.x += s.x; color.y += s.y; color.z += s.z;
-            }
-            for (uint32_t i = 0; i < p.n_point; ++i) {                                 // opaque.wgsl:524-546
-                const PointPrep& L = i < MAX_SMEM_POINT ? s_point[i] : p.point[i];
-                const float3 delta = make_float3(L.pos[0] - vp.x, L.pos[1] - vp.y, L.pos[2] - vp.z);
-                const float d2 = dot3(delta, delta);
-                // att = (1 - s^2)^2 / (1 + s^2) with s = saturate(d / radius) is exactly 0 at and beyond the radius
-                if (d2 >= L.radius * L.radius && pxl.roughness > 0.0f) continue;
-                const float inv_d = rsqrtf(d2), d = d2 * inv_d;
-                const float sdist = saturate(d * rcp_approx(L.radius)), s2 = sdist * sdist, inv_s2 = 1.0f - s2;
-                const float att = inv_s2 * inv_s2 * rcp_approx(1.0f + s2);
-                const float3 s = surface_shading(make_float3(delta.x * inv_d, delta.y * inv_d, delta.z * inv_d),
-                                                 make_float3(L.color[0] * att, L.color[1] * att, L.color[2] * att), pxl, v, nov, ao);
-                color.x += fmaxf(s.x, 0.0f); color.y += fmaxf(s.y, 0.0f); color.z += fmaxf(s.z, 0.0f);
-            }
-            out = make_float4(fmaxf(p.ambient[0] * albedo.x, color.x), fmaxf(p.ambient[1] * albedo.y, color.y), fmaxf(p.ambient[2] * albedo.z, color.z),
-                              fmaxf(p.ambient[3] * albedo.w, albedo.w));
-        }
+        out = make_float4(((col[0].x + col[1].x) + (col[2].x + col[3].x)) * 0.25f, ((col[0].y + col[1].y) + (col[2].y + col[3].y)) * 0.25f,
+                          ((col[0].z + col[1].z) + (col[2].z + col[3].z)) * 0.25f, ((col[0].w + col[1].w) + (col[2].w + col[3].w)) * 0.25f);
     }
     p.hdr32[pi] = out;
     const __half2 h01 = __floats2half2_rn(out.x, out.y), h23 = __floats2half2_rn(out.z, out.w);
     p.hdr16[pi] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-    p.depth[pi] = __uint_as_float((uint32_t)(key >> 32));
-    const uint32_t cnt = __popc(__ballot_sync(__activemask(), shaded));
-    if ((threadIdx.x & 31u) == 0u && cnt) atomicAdd(&p.stats[2], (unsigned long long)cnt);
+    p.depth[pi] = depth;
+    const uint32_t active = __activemask();
+    const uint32_t total = __reduce_add_sync(active, n_shaded);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(active) - 1) && total) atomicAdd(&p.stats[2], (unsigned long long)total);
 }
 
 // light prep: one thread per light (opaque.wgsl:491,519,528 hoisted out of the fragment loop)
@@ -308,9 +344,13 @@ __global__ void light_prep_kernel(const r3_directional_light* dir, uint32_t n_di
 }
 
 // hi-Z: mip 0 = depth bits of the visibility buffer
-__global__ void hiz_mip0_kernel(const unsigned long long* __restrict__ vis, float* __restrict__ out, size_t n) {
+// (multisampled: resolve_depth_min.wgsl:18-27 keeps the MIN over the samples)
+__global__ void hiz_mip0_kernel(const unsigned long long* __restrict__ vis, float* __restrict__ out, size_t n, uint32_t samples) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __uint_as_float((uint32_t)(vis[i] >> 32));
+    if (i >= n) return;
+    float d = 1.0f;
+    for (uint32_t k = 0; k < samples; ++k) d = fminf(d, __uint_as_float((uint32_t)(vis[i * samples + k] >> 32)));
+    out[i] = d;
 }
 // hi_z.wgsl::fs_main (:18-33): MIN over a 2x2 (+1 on odd source sizes) footprint; texels outside the source are skipped
 __global__ void hiz_downsample_kernel(const float* __restrict__ src, uint32_t sw, uint32_t sh, float* __restrict__ dst, uint32_t dw, uint32_t dh) {
@@ -352,9 +392,9 @@ __global__ void tonemap_kernel(const uint2* __restrict__ hdr16, uchar4* __restri
 // ------------------------------------------------------------------ host side
 R3_EXPORT int r3_set_render_target(r3_ctx* c, uint32_t w, uint32_t h, uint32_t samples, const float clear[4]) {
     if (!c || !w || !h || !clear) return r3_fail(c, R3_E_INVALID, "set_render_target: bad arguments");
-    if (samples != 1) return r3_fail(c, R3_E_INVALID, "only SampleCount::One is implemented");
+    if (samples != 1 && samples != 4) return r3_fail(c, R3_E_INVALID, "SampleCount must be One or Four");
     cudaSetDevice(c->device);
-    if (w != c->width || h != c->height || !c->d_vis) {
+    if (w != c->width || h != c->height || samples != c->samples || !c->d_vis) {
         R3_CUDA(c, cudaStreamSynchronize(c->stream));
         cudaFree(c->d_vis); cudaFree(c->d_hdr32); cudaFree(c->d_hdr16); cudaFree(c->d_depth); cudaFree(c->d_ldr);
         for (float* p : c->d_hiz) cudaFree(p);
@@ -362,12 +402,12 @@ R3_EXPORT int r3_set_render_target(r3_ctx* c, uint32_t w, uint32_t h, uint32_t s
         cudaFree(c->d_hiz_ptrs); cudaFree(c->d_hiz_dims);
         c->d_vis = nullptr; c->d_hdr32 = nullptr; c->d_hdr16 = nullptr; c->d_depth = nullptr; c->d_ldr = nullptr; c->d_hiz_ptrs = nullptr; c->d_hiz_dims = nullptr;
         const size_t n = (size_t)w * h;
-        R3_CUDA(c, cudaMalloc((void**)&c->d_vis, n * 8));
+        R3_CUDA(c, cudaMalloc((void**)&c->d_vis, n * 8 * samples));
         R3_CUDA(c, cudaMalloc((void**)&c->d_hdr32, n * 16));
         R3_CUDA(c, cudaMalloc((void**)&c->d_hdr16, n * 8));
         R3_CUDA(c, cudaMalloc((void**)&c->d_depth, n * 4));
         R3_CUDA(c, cudaMalloc((void**)&c->d_ldr, n * 4));
-        R3_CUDA(c, cudaMemsetAsync(c->d_vis, 0, n * 8, c->stream));
+        R3_CUDA(c, cudaMemsetAsync(c->d_vis, 0, n * 8 * samples, c->stream));
         // single_sample_mipped depth, cleared to 0.0 (base.rs:256-263, hi_z.rs:170-171)
         uint32_t m = w > h ? w : h, mips = 0;
         while (m) { mips++; m >>= 1; }
@@ -405,7 +445,7 @@ R3_EXPORT int r3_clear_shadow_atlas(r3_ctx* c) {
 R3_EXPORT int r3_forward_begin(r3_ctx* c) {
     if (!c || !c->d_vis) return r3_fail(c, R3_E_STATE, "forward_begin before set_render_target");
     cudaSetDevice(c->device);
-    R3_CUDA(c, cudaMemsetAsync(c->d_vis, 0, (size_t)c->width * c->height * 8, c->stream));
+    R3_CUDA(c, cudaMemsetAsync(c->d_vis, 0, (size_t)c->width * c->height * 8 * c->samples, c->stream));
     R3_CUDA(c, cudaMemsetAsync(c->d_stats, 0, 32, c->stream));
     c->n_tris[0] = c->n_tris[1] = 0;
     return R3_OK;
@@ -414,7 +454,7 @@ R3_EXPORT int r3_hiz_build(r3_ctx* c) {
     if (!c || !c->d_vis || c->d_hiz.empty()) return r3_fail(c, R3_E_STATE, "hiz_build before set_render_target");
     cudaSetDevice(c->device);
     const size_t n = (size_t)c->width * c->height;
-    hiz_mip0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vis, c->d_hiz[0], n);
+    hiz_mip0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vis, c->d_hiz[0], n, c->samples);
     R3_CHECK_LAUNCH(c, "hiz_mip0_kernel");
     for (size_t m = 1; m < c->d_hiz.size(); ++m) {
         const dim3 block(32, 8), grid((c->hiz_w[m] + 31) / 32, (c->hiz_h[m] + 7) / 8);
@@ -447,12 +487,13 @@ R3_EXPORT int r3_forward_resolve(r3_ctx* c) {
     p.dir = d_dir; p.n_dir = c->n_dir; p.point = d_point; p.n_point = c->n_point;
     p.atlas = c->d_atlas; p.atlas_w = c->atlas_w; p.atlas_h = c->atlas_h;
     memcpy(p.ambient, c->uniforms.ambient, 16); memcpy(p.clear, c->clear_color, 16);
-    p.width = c->width; p.height = c->height; p.row_begin = c->row_begin; p.row_end = c->row_end;
+    p.width = c->width; p.height = c->height; p.row_begin = c->row_begin; p.row_end = c->row_end; p.samples = c->samples;
     p.hdr32 = reinterpret_cast<float4*>(c->d_hdr32); p.hdr16 = reinterpret_cast<uint2*>(c->d_hdr16); p.depth = c->d_depth; p.stats = c->d_stats;
     const uint32_t rows = c->row_end - c->row_begin;
     if (rows) {
         const dim3 grid((c->width + 31) / 32, (rows + 7) / 8);
-        resolve_kernel<<<grid, 256, 0, c->stream>>>(p);
+        if (c->samples == 1) resolve_kernel<1><<<grid, 256, 0, c->stream>>>(p);
+        else resolve_kernel<4><<<grid, 256, 0, c->stream>>>(p);
         R3_CHECK_LAUNCH(c, "resolve_kernel");
     }
     return R3_OK;

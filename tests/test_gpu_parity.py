@@ -190,6 +190,21 @@ def test_multi_frame_predicted_residual(cuda):
     assert resid < pred
 
 
+def test_msaa_four_frame_matches_oracle(cuda):
+    """SampleCount::Four: per-sample coverage / depth, one shade per pixel and primitive, box resolve, min-depth hi-Z;
+    two frames so that the multisampled predicted + residual passes and the MULTISAMPLED cull flag are exercised."""
+    res = (256, 160)
+    ev = cube_field_scene(n_objects=800, seed=21, resolution=res, n_point_lights=2, shadow_resolution=256, shadow_distance=100.0, pull_back=6.0, extent=12.0,
+                          subdivisions=(1, 2))
+    orc = load_oracle_backend()
+    graphs = {id(b): BaseRenderGraph(b) for b in (cuda, orc)}
+    for frame in range(2):
+        for b in (cuda, orc):
+            graphs[id(b)].add_to_graph(ev, res, 4, BaseRenderGraphSettings(clear_color=(0.2, 0.1, 0.3, 1.0)), upload=(frame == 0))
+        compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], what=f"msaa frame {frame}")
+    assert cuda.forward_stats()[1] > cuda.forward_stats()[2] > 0
+
+
 def test_near_plane_clipping_and_large_triangles(cuda):
     """Camera inside the field: triangles cross the near plane (clipper) and cover many bands (large path)."""
     res = (384, 216)
@@ -229,7 +244,9 @@ def test_reference_goldens_on_cuda(cuda, monkeypatch):
     for args in [("Left", "Cw", True), ("Left", "Ccw", False), ("Right", "Cw", False), ("Right", "Ccw", True)]:
         g.test_triangle(*args)
     g.test_coordinate_space()
-    g.test_sample_coverage_1()
+    g.test_sample_coverage(1)
+    g.test_sample_coverage(4)
+    g.test_msaa_four()
     g.test_multi_frame_add()
     g.test_duplicate_object_retain()
     g.test_shadow_plane()
@@ -241,7 +258,7 @@ def test_error_paths(cuda):
     from rend3_b200.backend import R3Error
 
     with pytest.raises(R3Error):
-        cuda.set_render_target(64, 64, 4)           # MSAA x4 is a "next" row
+        cuda.set_render_target(64, 64, 2)           # SampleCount is One or Four (rend3-types SampleCount)
     with pytest.raises(R3Error):
         cuda.readback_hiz(99)
     rec = np.zeros(4, dtype=OBJECT_DTYPE)
