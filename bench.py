@@ -49,24 +49,54 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  The timed region of this
+    workload is a few milliseconds, far shorter than one `nvidia-smi` invocation, so the sampler polls NVML directly
+    (nvidia_ml_py: the library nvidia-smi itself reads) every ~0.5 ms and only falls back to nvidia-smi without it."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
+    def __init__(self, index, uuid=None):
+        self.index, self.rows, self.stop, self.nvml, self.handle, self.source = index, [], False, None, None, "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if str(uuid).startswith("GPU-") else f"GPU-{uuid}") if uuid else None
+            except Exception:
+                self.handle = None
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self.run, daemon=True)
+
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.rows.append((sm, self.max_mhz, mask))
+            return
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            c = [x.strip() for x in out.split(",")]
+            mask = sum(bit for k, bit in zip(range(2, 6), (0x8, 0x40, 0x20, 0x4)) if len(c) > k and c[k].lower().startswith("active"))
+            self.rows.append((float(c[0]), float(c[1]), mask))
 
     def run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self.sample()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.0005 if self.nvml is not None else 0.1)
 
     def __enter__(self):
         self.t.start()
@@ -78,12 +108,13 @@ class ClockSampler:
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0, "source": self.source}
+        sm = sorted(r[0] for r in self.rows)
+        mask = 0
+        for r in self.rows:
+            mask |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": [k for k, bit in self.BITS.items() if mask & bit],
+                "samples": len(self.rows), "source": self.source}
 
 
 class DeviceView:
@@ -213,7 +244,7 @@ def main():
     launches0 = backend.launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) as clocks:
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
             starts[i].record(stream)

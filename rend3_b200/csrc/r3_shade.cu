@@ -117,6 +117,15 @@ __device__ __forceinline__ float shadow_pcf5(const ShadeParams& p, float u, floa
     return ((((centre + up) + down) + right) + left) * 0.2f;
 }
 
+// one perspective weight numerator of raster rule R6, oracle order: ((c.x * nx + c.y * ny) + c.z) with c = cross(a, b) over (x, y, w)
+__device__ __forceinline__ float cross_term_rn(const float3 a, const float3 b, float nx, float ny) {
+    const float cx = sub_rn(mul_rn(a.y, b.z), mul_rn(a.z, b.y)), cy = sub_rn(mul_rn(a.z, b.x), mul_rn(a.x, b.z)), cz = sub_rn(mul_rn(a.x, b.y), mul_rn(a.y, b.x));
+    return add_rn(add_rn(mul_rn(cx, nx), mul_rn(cy, ny)), cz);
+}
+__device__ __forceinline__ float lerp3_rn(float b0, float b1, float b2, float a0, float a1, float a2) {
+    return add_rn(add_rn(mul_rn(b0, a0), mul_rn(b1, a1)), mul_rn(b2, a2));
+}
+
 struct VsOut { float4 view_position; float3 normal; float4 color; };
 // vs_main for one vertex (opaque.wgsl:114-134) + get_vertices defaults (rend3/src/shader.rs:249-316)
 __device__ __forceinline__ VsOut vertex_stage(const ShadeParams& p, const uint32_t* attr_offset, const float* __restrict__ mv, const float3 iss, uint32_t vid) {
@@ -129,8 +138,7 @@ __device__ __forceinline__ VsOut vertex_stage(const ShadeParams& p, const uint32
         const uint32_t w = mesh_word(p, (uint64_t)(attr_offset[5] >> 2) + vid);
         o.color = make_float4((float)(w & 0xFFu) / 255.0f, (float)((w >> 8) & 0xFFu) / 255.0f, (float)((w >> 16) & 0xFFu) / 255.0f, (float)(w >> 24) / 255.0f);
     }
-    o.view_position = make_float4(mv[0] * pos.x + mv[4] * pos.y + mv[8] * pos.z + mv[12], mv[1] * pos.x + mv[5] * pos.y + mv[9] * pos.z + mv[13],
-                                  mv[2] * pos.x + mv[6] * pos.y + mv[10] * pos.z + mv[14], mv[3] * pos.x + mv[7] * pos.y + mv[11] * pos.z + mv[15]);
+    o.view_position = mat_point_rn(mv, pos.x, pos.y, pos.z);
     const float3 sn = make_float3(iss.x * n.x, iss.y * n.y, iss.z * n.z);
     o.normal = normalize3(make_float3(mv[0] * sn.x + mv[4] * sn.y + mv[8] * sn.z, mv[1] * sn.x + mv[5] * sn.y + mv[9] * sn.z, mv[2] * sn.x + mv[6] * sn.y + mv[10] * sn.z));
     return o;
@@ -147,12 +155,12 @@ __device__ __forceinline__ float4 shade_fragment(const ShadeParams& p, const Dir
     const float3 p0 = make_float3(q0.x, q0.y, q0.z), p1 = make_float3(q0.w, q1.x, q1.y), p2 = make_float3(q1.z, q1.w, q2.x);
     const uint32_t oid = __float_as_uint(q2.y), vid0 = __float_as_uint(q2.z), vid1 = __float_as_uint(q2.w), vid2 = q3.x;
     // R6: perspective-correct weights b_i ~ cross(p_j, p_k) . (ndc_x, ndc_y, 1)
-    const float nx = ((float)px + 0.5f) / ((float)p.width * 0.5f) - 1.0f, ny = 1.0f - ((float)py + 0.5f) / ((float)p.height * 0.5f);
-    float b0 = (p1.y * p2.z - p1.z * p2.y) * nx + (p1.z * p2.x - p1.x * p2.z) * ny + (p1.x * p2.y - p1.y * p2.x);
-    float b1 = (p2.y * p0.z - p2.z * p0.y) * nx + (p2.z * p0.x - p2.x * p0.z) * ny + (p2.x * p0.y - p2.y * p0.x);
-    float b2 = (p0.y * p1.z - p0.z * p1.y) * nx + (p0.z * p1.x - p0.x * p1.z) * ny + (p0.x * p1.y - p0.y * p1.x);
-    const float inv_sum = 1.0f / (b0 + b1 + b2);
-    b0 *= inv_sum; b1 *= inv_sum; b2 *= inv_sum;
+    const float nx = sub_rn(div_rn((float)px + 0.5f, (float)p.width * 0.5f), 1.0f), ny = sub_rn(1.0f, div_rn((float)py + 0.5f, (float)p.height * 0.5f));
+    // The chain b_i -> view_position -> shadow-space depth feeds the (discontinuous) shadow compare, so it is evaluated in
+    // source order without contraction, exactly like the oracle; everything downstream of the compare is continuous.
+    float b0 = cross_term_rn(p1, p2, nx, ny), b1 = cross_term_rn(p2, p0, nx, ny), b2 = cross_term_rn(p0, p1, nx, ny);
+    const float bsum = add_rn(add_rn(b0, b1), b2);
+    b0 = div_rn(b0, bsum); b1 = div_rn(b1, bsum); b2 = div_rn(b2, bsum);
 
     const r3_object* obj = &p.objects[oid];
     const uint4 oa = __ldg(reinterpret_cast<const uint4*>(obj) + 5);   // bytes 80..95 : first_index, index_count, material_index, attr[0]
@@ -169,10 +177,10 @@ __device__ __forceinline__ float4 shade_fragment(const ShadeParams& p, const Dir
     const float3 iss = make_float3(1.0f / (mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]), 1.0f / (mv[4] * mv[4] + mv[5] * mv[5] + mv[6] * mv[6]),
                                    1.0f / (mv[8] * mv[8] + mv[9] * mv[9] + mv[10] * mv[10]));   // math/matrix.wgsl:1-7
     const VsOut v0 = vertex_stage(p, attr, mv, iss, vid0), v1 = vertex_stage(p, attr, mv, iss, vid1), v2 = vertex_stage(p, attr, mv, iss, vid2);
-    const float4 vp = make_float4(b0 * v0.view_position.x + b1 * v1.view_position.x + b2 * v2.view_position.x,
-                                  b0 * v0.view_position.y + b1 * v1.view_position.y + b2 * v2.view_position.y,
-                                  b0 * v0.view_position.z + b1 * v1.view_position.z + b2 * v2.view_position.z,
-                                  b0 * v0.view_position.w + b1 * v1.view_position.w + b2 * v2.view_position.w);
+    const float4 vp = make_float4(lerp3_rn(b0, b1, b2, v0.view_position.x, v1.view_position.x, v2.view_position.x),
+                                  lerp3_rn(b0, b1, b2, v0.view_position.y, v1.view_position.y, v2.view_position.y),
+                                  lerp3_rn(b0, b1, b2, v0.view_position.z, v1.view_position.z, v2.view_position.z),
+                                  lerp3_rn(b0, b1, b2, v0.view_position.w, v1.view_position.w, v2.view_position.w));
     const float3 vnormal = make_float3(b0 * v0.normal.x + b1 * v1.normal.x + b2 * v2.normal.x, b0 * v0.normal.y + b1 * v1.normal.y + b2 * v2.normal.y,
                                        b0 * v0.normal.z + b1 * v1.normal.z + b2 * v2.normal.z);
     const float4 vcolor = make_float4(b0 * v0.color.x + b1 * v1.color.x + b2 * v2.color.x, b0 * v0.color.y + b1 * v1.color.y + b2 * v2.color.y,
@@ -218,10 +226,9 @@ __device__ __forceinline__ float4 shade_fragment(const ShadeParams& p, const Dir
         float3 color = make_float3(mA.x, mA.y, mA.z);
         for (uint32_t i = 0; i < p.n_dir; ++i) {                                   // opaque.wgsl:487-522
             const DirPrep& L = i < MAX_SMEM_DIR ? s_dir[i] : p.dir[i];
-            const float snx = L.lm[0] * vp.x + L.lm[4] * vp.y + L.lm[8] * vp.z + L.lm[12] * vp.w;
-            const float sny = L.lm[1] * vp.x + L.lm[5] * vp.y + L.lm[9] * vp.z + L.lm[13] * vp.w;
-            const float snz = L.lm[2] * vp.x + L.lm[6] * vp.y + L.lm[10] * vp.z + L.lm[14] * vp.w;
-            const float flx = snx * 0.5f + 0.5f, fly = sny * 0.5f + 0.5f, locy = 1.0f - fly;
+            const float4 sn = mat_vec_rn(L.lm, vp.x, vp.y, vp.z, vp.w);
+            const float snx = sn.x, sny = sn.y, snz = sn.z;
+            const float flx = add_rn(mul_rn(snx, 0.5f), 0.5f), fly = add_rn(mul_rn(sny, 0.5f), 0.5f), locy = 1.0f - fly;
             float tlx = L.offset[0], tly = L.offset[1], trx = tlx + L.size[0], try_ = tly + L.size[1];
             const float cu = tlx * (1.0f - flx) + trx * flx, cv = tly * (1.0f - locy) + try_ * locy;
             const float bx = L.inv_res[0] * 1.5f, by = L.inv_res[1] * 1.5f;

@@ -30,9 +30,14 @@ def cuda():
     b.close()
 
 
-def hdr_close(a, b, what=""):
-    err = np.abs(a.astype(np.float64) - b.astype(np.float64)) / np.maximum(1.0, np.abs(b.astype(np.float64)))
-    bad = np.nan_to_num(err, nan=np.inf) > TOL
+def hdr_close(a, b, what="", f16_samples=False):
+    """TOL = 1e-4 (north_star), relative above 1.0.  With SampleCount::Four the samples live in an rgba16f target BEFORE the
+    box filter (base.rs:245-255), so a 1e-6 difference in a shaded colour can land on the other side of a half-precision
+    rounding boundary: there the bound is TOL plus one f16 ulp of the value."""
+    ref = np.abs(b.astype(np.float64))
+    err = np.abs(a.astype(np.float64) - b.astype(np.float64)) / np.maximum(1.0, ref)
+    bound = TOL + (np.maximum(ref * 2.0 ** -10, 2.0 ** -24) / np.maximum(1.0, ref) if f16_samples else 0.0)
+    bad = np.nan_to_num(err, nan=np.inf) > bound
     both_nan = np.isnan(a) & np.isnan(b)
     bad &= ~both_nan
     assert not bad.any(), f"{what}: {bad.sum()} channel values differ by more than {TOL} (max {np.nanmax(err):.3e})"
@@ -117,7 +122,7 @@ def test_gpu_skinning_is_bit_exact(cuda):
 
 
 # ------------------------------------------------------------------ whole frames
-def compare_frame_state(cuda, orc, ev, cameras, check_pixels=True, what=""):
+def compare_frame_state(cuda, orc, ev, cameras, check_pixels=True, what="", f16_samples=False):
     for cam in cameras:
         bc, rc = cuda.readback_batches(cam)
         bo, ro = orc.readback_batches(cam)
@@ -143,7 +148,7 @@ def compare_frame_state(cuda, orc, ev, cameras, check_pixels=True, what=""):
         assert np.array_equal(cuda.readback_culling_results(cam, 0)[:len(ro_bits)], ro_bits), f"{what}: visibility bits differ"
     if check_pixels:
         assert np.array_equal(cuda.readback_depth().view(np.uint32), orc.readback_depth().view(np.uint32)), f"{what}: depth differs"
-        hdr_close(cuda.readback_hdr_f32(), orc.readback_hdr_f32(), what + " hdr f32")
+        hdr_close(cuda.readback_hdr_f32(), orc.readback_hdr_f32(), what + " hdr f32", f16_samples)
         h16c, h16o = cuda.readback_hdr_f16().astype(np.float32), orc.readback_hdr_f16().astype(np.float32)
         ulp = np.maximum(np.abs(h16o) * 2.0 ** -10, 2.0 ** -24)
         assert np.all(np.abs(h16c - h16o) <= ulp + TOL * np.maximum(1.0, np.abs(h16o))), f"{what}: rgba16f target differs by more than 1 ulp"
@@ -190,6 +195,53 @@ def test_multi_frame_predicted_residual(cuda):
     assert resid < pred
 
 
+def test_config1_full_size_matches_oracle(cuda):
+    """BASELINE config 1 at its full size: 10k untextured cubes, 1 directional light (2048^2 shadow map), 1920x1080 —
+    the case the reference itself runs on a CPU/software adapter.  Every integer artefact identical, pixels within 1e-4."""
+    from rend3_b200 import configs
+
+    ev, res = configs.config1()
+    orc = load_oracle_backend()
+    settings = BaseRenderGraphSettings(clear_color=(0.10, 0.05, 0.10, 1.0))
+    for b in (cuda, orc):
+        BaseRenderGraph(b).add_to_graph(ev, res, 1, settings)
+    compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], what="config 1")
+    assert cuda.visible_count(CAMERA_VIEWPORT) > 5000
+
+
+def test_full_size_cull_bake_properties(cuda):
+    """BASELINE configs 2 / 4 at full size (10 M object records on one GPU), checked through size-independent properties:
+    sortedness, agreement with an independent float64 classification away from the plane boundaries, idempotence,
+    cull-only == cull+bake, and linearity of the baked matrices on a sample."""
+    n = 10_000_000
+    rec = object_cloud_records(n, seed=4)
+    cam = cloud_camera()
+    header = per_camera_header(cam, CAMERA_VIEWPORT, (1920, 1080), 1, n)
+    cuda.set_objects(rec)
+    cuda.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+    vis = cuda.readback_visible(CAMERA_VIEWPORT).copy()
+    assert np.all(np.diff(vis.astype(np.int64)) > 0), "ascending, no duplicates"
+    fr = cam.world_frustum.astype(np.float64)
+    margin = rec["sphere_center"].astype(np.float64) @ fr[:, :3].T + fr[:, 3] + rec["sphere_radius"].astype(np.float64)[:, None]
+    enabled = rec["enabled"] != 0
+    mask = np.zeros(n, dtype=bool)
+    mask[vis] = True
+    eps = 1e-2 * (1.0 + np.abs(margin))   # f32 evaluation error of a 2000-unit world
+    assert mask[(margin > eps).all(axis=1) & enabled].all(), "objects clearly inside must be listed"
+    assert not mask[(margin < -eps).any(axis=1) | ~enabled].any(), "objects clearly outside / disabled must not be listed"
+    cuda.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+    assert np.array_equal(cuda.readback_visible(CAMERA_VIEWPORT), vis), "idempotent"
+    cuda.object_uniform_upload(CAMERA_VIEWPORT, header, CB_CULL)
+    assert np.array_equal(cuda.readback_visible(CAMERA_VIEWPORT), vis), "cull-only lists the same set"
+    sample = np.linspace(0, n - 1, 257).astype(np.int64)
+    vp = cam.view_proj.astype(np.float64).T
+    for i in sample:
+        if enabled[i]:
+            m = cuda.readback_object_matrices(CAMERA_VIEWPORT, int(i), 1)[0]
+            t = rec["transform"][i].reshape(4, 4).astype(np.float64).T
+            assert np.allclose(m["model_view_proj"].reshape(4, 4).T, vp @ t, rtol=2e-5, atol=2e-2)
+
+
 def test_msaa_four_frame_matches_oracle(cuda):
     """SampleCount::Four: per-sample coverage / depth, one shade per pixel and primitive, box resolve, min-depth hi-Z;
     two frames so that the multisampled predicted + residual passes and the MULTISAMPLED cull flag are exercised."""
@@ -201,7 +253,7 @@ def test_msaa_four_frame_matches_oracle(cuda):
     for frame in range(2):
         for b in (cuda, orc):
             graphs[id(b)].add_to_graph(ev, res, 4, BaseRenderGraphSettings(clear_color=(0.2, 0.1, 0.3, 1.0)), upload=(frame == 0))
-        compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], what=f"msaa frame {frame}")
+        compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], what=f"msaa frame {frame}", f16_samples=True)
     assert cuda.forward_stats()[1] > cuda.forward_stats()[2] > 0
 
 
