@@ -132,6 +132,11 @@ int r3_forward_pass(r3_ctx*, int source);
 int r3_hiz_build(r3_ctx*);                                                          /* hi_z.rs:161-234 */
 /* run opaque.wgsl::fs_main for the winning fragment of every covered pixel */
 int r3_forward_resolve(r3_ctx*);
+/* pbr_forward_rendering_transparent (base.rs:181,450-466): the blend routine (pbr/routine.rs:129; material key 2,
+ * BlendState::ALPHA_BLENDING, depth test + write) over this frame's residual list, whose non-atomic regions keep the
+ * back-to-front object order of batch_objects (cull.wgsl:374-380).  Call after r3_forward_resolve: it blends into the
+ * shaded rgba16f target.  A no-op when no object carries material key 2. */
+int r3_forward_blend(r3_ctx*);
 int r3_tonemap(r3_ctx*, int srgb_target);                                           /* tonemapping.rs:108-147 */
 
 int r3_readback_hdr_f32(r3_ctx*, float* rgba, uint64_t capacity_floats);            /* pre-f16 shading result (parity) */
@@ -141,7 +146,8 @@ int r3_readback_ldr(r3_ctx*, uint8_t* rgba8, uint64_t capacity);
 int r3_readback_shadow_atlas(r3_ctx*, float* depth, uint64_t capacity);
 int r3_readback_hiz(r3_ctx*, uint32_t mip, float* depth, uint64_t capacity, uint32_t* width, uint32_t* height);
 /* forward statistics of the last frame: [0] triangles set up, [1] fragments rasterised (covered samples sent
- * to the depth test), [2] fragments shaded by r3_forward_resolve (fs_main invocations) */
+ * to the depth test), [2] fragments shaded by r3_forward_resolve (fs_main invocations), [3] sample fragments blended by
+ * r3_forward_blend (depth-test survivors of the blend routine) */
 int r3_forward_stats(r3_ctx*, uint64_t stats[4]);
 
 /* ------------------------------------------------------------------ multi-GPU plumbing

@@ -35,7 +35,7 @@ ENTRY_POINTS = [
     "object_uniform_upload", "visible_count", "readback_visible", "readback_object_matrices",
     "batch_objects", "batch_counts", "readback_batches", "cull", "readback_indices",
     "readback_draw_calls", "readback_culling_results", "set_render_target", "clear_shadow_atlas",
-    "shadow_pass", "forward_begin", "forward_pass", "hiz_build", "forward_resolve", "tonemap",
+    "shadow_pass", "forward_begin", "forward_pass", "hiz_build", "forward_resolve", "forward_blend", "tonemap",
     "readback_hdr_f32", "readback_hdr_f16", "readback_depth", "readback_ldr", "readback_shadow_atlas",
     "readback_hiz", "forward_stats", "device_ptr", "set_scissor_rows", "skin", "readback_mesh_buffer",
 ]
@@ -238,6 +238,9 @@ class Backend:
 
     def forward_resolve(self):
         self._call("forward_resolve")
+
+    def forward_blend(self):
+        self._call("forward_blend")
 
     def tonemap(self, srgb_target: bool = True):
         self._call("tonemap", C.c_int(1 if srgb_target else 0))

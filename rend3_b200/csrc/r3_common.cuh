@@ -87,8 +87,12 @@ struct r3_ctx {
     float* d_hdr32 = nullptr; uint16_t* d_hdr16 = nullptr; float* d_depth = nullptr; uint8_t* d_ldr = nullptr;
     std::vector<float*> d_hiz; std::vector<uint32_t> hiz_w, hiz_h;
     float** d_hiz_ptrs = nullptr; uint32_t* d_hiz_dims = nullptr;
-    r3_tri_record* d_tris[2] = {nullptr, nullptr}; uint64_t tris_cap[2] = {0, 0}; uint64_t n_tris[2] = {0, 0};
-    unsigned long long* d_stats = nullptr;    // [4]
+    r3_tri_record* d_tris[3] = {nullptr, nullptr, nullptr}; uint64_t tris_cap[3] = {0, 0, 0}; uint64_t n_tris[3] = {0, 0, 0};   // predicted, residual, blend
+    unsigned long long* d_stats = nullptr;    // [8]: [0..3] forward statistics, [4] scratch of r3_compute_max_invocations
+    // blend routine: per-sample fragment lists (head = node index + 1, 0 = empty; node = {record, depth bits, next, 0})
+    bool any_blend = false;                   // some live object carries material key 2 (TransparencyType::Blend)
+    uint32_t* d_frag_heads = nullptr; uint64_t frag_heads_cap = 0;
+    uint4* d_frag_nodes = nullptr; uint64_t frag_nodes_cap = 0;
     void* d_scratch = nullptr; uint64_t scratch_cap = 0;
 };
 
@@ -136,6 +140,7 @@ int r3_upload_jobs(r3_ctx* c, r3_camera* cam);
 int r3_device_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], uint32_t max_dispatch_count);
 int r3_download_jobs(r3_ctx* c, r3_camera* cam);          // device-built jobs -> host vectors (readbacks / tests)
 int r3_compute_max_invocations(r3_ctx* c);
+int r3_blend_collect(r3_ctx* c, bool* ran);   // r3_raster.cu: per-sample fragment lists of the blend routine
 int r3_iobuf_new(r3_ctx* c, r3_iobuf* b, uint64_t elems, uint64_t elem_size, bool clear_on_swap);
 int r3_iobuf_swap(r3_ctx* c, r3_iobuf* b, uint64_t new_elems);
 

@@ -55,8 +55,8 @@ R3_EXPORT int r3_ctx_create(int device, r3_ctx** out) {
         cudaGetLastError();
         return R3_E_CUDA;
     }
-    if (cudaMalloc((void**)&c->d_stats, 4 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return R3_E_OOM; }
-    cudaMemsetAsync(c->d_stats, 0, 32, c->stream);
+    if (cudaMalloc((void**)&c->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return R3_E_OOM; }
+    cudaMemsetAsync(c->d_stats, 0, 64, c->stream);
     *out = c;
     return R3_OK;
 }
@@ -81,7 +81,8 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     cudaFree(c->d_vis); cudaFree(c->d_hdr32); cudaFree(c->d_hdr16); cudaFree(c->d_depth); cudaFree(c->d_ldr);
     for (float* p : c->d_hiz) cudaFree(p);
     cudaFree(c->d_hiz_ptrs); cudaFree(c->d_hiz_dims);
-    cudaFree(c->d_tris[0]); cudaFree(c->d_tris[1]); cudaFree(c->d_stats); cudaFree(c->d_scratch);
+    cudaFree(c->d_tris[0]); cudaFree(c->d_tris[1]); cudaFree(c->d_tris[2]); cudaFree(c->d_stats); cudaFree(c->d_scratch);
+    cudaFree(c->d_frag_heads); cudaFree(c->d_frag_nodes);
     cudaStreamDestroy(c->stream);
     delete c;
     return R3_OK;
@@ -163,8 +164,10 @@ R3_EXPORT int r3_set_object_sort_info(r3_ctx* c, const uint64_t* key, const uint
     // device copies for the on-device batch_objects: key8 = ((material_key << 1 | reason) << 1) | back_to_front
     bool ok = true;
     std::vector<uint8_t> key8(n ? n : 1, 0);
+    c->any_blend = false;
     for (uint32_t i = 0; i < n; ++i) {
         if (key[i] >= 64) ok = false;
+        if (key[i] == 2 && (flags[i] & 1)) c->any_blend = true;   // TransparencyType::Blend as u64 (pbr/material.rs:497-503)
         const uint32_t reason = (flags[i] & 2) ? 0u : 1u;
         key8[i] = (uint8_t)(((((uint32_t)key[i] & 63u) << 1 | reason) << 1) | ((flags[i] & 4) ? 1u : 0u));
     }

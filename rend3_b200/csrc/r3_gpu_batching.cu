@@ -325,11 +325,11 @@ int r3_compute_max_invocations(r3_ctx* c) {
     if (c->max_invocations_valid) return R3_OK;
     c->max_total_invocations = 0;
     if (c->n_slots) {
-        R3_CUDA(c, cudaMemsetAsync(c->d_stats + 3, 0, 8, c->stream));
-        max_invocations_kernel<<<R3_SM_COUNT * 4, 256, 0, c->stream>>>(c->d_objects, c->n_slots, c->d_stats + 3);
+        R3_CUDA(c, cudaMemsetAsync(c->d_stats + 4, 0, 8, c->stream));
+        max_invocations_kernel<<<R3_SM_COUNT * 4, 256, 0, c->stream>>>(c->d_objects, c->n_slots, c->d_stats + 4);
         R3_CHECK_LAUNCH(c, "max_invocations_kernel");
         unsigned long long v = 0;
-        R3_CUDA(c, cudaMemcpyAsync(&v, c->d_stats + 3, 8, cudaMemcpyDeviceToHost, c->stream));
+        R3_CUDA(c, cudaMemcpyAsync(&v, c->d_stats + 4, 8, cudaMemcpyDeviceToHost, c->stream));
         R3_CUDA(c, cudaStreamSynchronize(c->stream));
         c->max_total_invocations = v;
     }

@@ -30,6 +30,9 @@ constexpr int COOP_MAX_LANES = 33;       // >32 = never: measured on C3/C5, the 
 constexpr int BAND_ROWS = 16;
 constexpr uint32_t LARGE_CAP = 1u << 22; // queued large sub-triangles (160 MB)
 constexpr uint32_t BAND_CAP = 1u << 24;  // queued (sub-triangle, band) items (128 MB)
+constexpr int MODE_COLOUR = 0;           // opaque + cutout forward routines into the visibility buffer
+constexpr int MODE_DEPTH = 1;            // shadow passes into the atlas
+constexpr int MODE_BLEND = 2;            // blend routine: collect per-sample fragment lists
 
 struct SubTri { int32_t x[3], y[3]; float z[3]; uint32_t rec; };   // oriented (area > 0), snapped 24.8
 static_assert(sizeof(SubTri) == 40, "SubTri");
@@ -38,7 +41,7 @@ struct RasterParams {
     // draw source
     const r3_batch_data* batches; const r3_region* regions; const uint32_t* header;   // header[2] = n_regions (device-side count)
     const r3_indirect_call* calls; const uint32_t* indices; uint64_t index_elems;
-    const unsigned long long* tri_prefix;      // [n_regions + 1] exclusive prefix of listed triangles (opaque + cutout)
+    const unsigned long long* tri_prefix;      // [n_regions + 1] exclusive prefix of the listed triangles of the regions in [key_lo, key_hi]
     const r3_object* objects; uint32_t n_slots;
     const r3_object_matrices* matrices; uint32_t matrices_cap;
     const uint32_t* mesh; uint64_t mesh_words;
@@ -50,7 +53,9 @@ struct RasterParams {
     uint32_t* depth_bits;                          // depth-only passes (shadow atlas)
     r3_tri_record* records;
     // queues
-    SubTri* large; uint2* bands; uint32_t* counters;   // [0] n_large, [1] n_bands, [2] band ticket
+    SubTri* large; uint2* bands; uint32_t* counters;   // [0] n_large, [1] n_bands, [2] band ticket, [3] blend fragment nodes
+    uint32_t* frag_heads; uint4* frag_nodes; uint32_t frag_cap;   // blend routine
+    unsigned long long key_lo, key_hi;                 // material keys of the routine(s) drawing (forward.rs:286-313)
     unsigned long long* stats;
 };
 
@@ -133,16 +138,28 @@ __device__ __forceinline__ float sample_depth(const SubTri& s, const EdgeSetup& 
     const float z = add_rn(add_rn(mul_rn(la, s.z[0]), mul_rn(lb, s.z[1])), mul_rn(lc, s.z[2]));
     return fminf(fmaxf(z, 0.0f), 1.0f);
 }
-template <bool DEPTH_ONLY>
+template <int MODE>
 __device__ __forceinline__ uint32_t write_sample(const RasterParams& p, int px, int py, uint32_t k, float z, uint32_t rec) {
     // the result of the atomic is never read, so it compiles to a fire-and-forget RED.MAX: a thread can have
     // hundreds of samples in flight instead of one L2 round trip per sample
     const size_t pi = (size_t)py * p.pitch + px;
-    if (DEPTH_ONLY) {
+    if (MODE == MODE_DEPTH) {
         atomicMax(&p.depth_bits[pi], __float_as_uint(z));
-    } else {
+    } else if (MODE == MODE_COLOUR) {
         const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | ((unsigned long long)p.pass_bit << 31) | rec;
         atomicMax(&p.vis[pi * p.samples + k], key);
+    } else {
+        // blend routine: fragments must be applied in draw order, so they are only collected here (one list per sample).
+        // The depth buffer of a sample never decreases, so a fragment behind the opaque depth can never pass.
+        const size_t si = pi * p.samples + k;
+        if (__float_as_uint(z) >= (uint32_t)(p.vis[si] >> 32)) {
+            const uint32_t node = atomicAdd(&p.counters[3], 1u);
+            if (node < p.frag_cap) {
+                const uint32_t next = atomicExch(&p.frag_heads[si], node + 1u);
+                p.frag_nodes[node] = make_uint4(rec, __float_as_uint(z), next, 0u);
+            }
+        }
+        return 0u;
     }
     return 1u;   // statistics count rasterised (covered) samples
 }
@@ -152,11 +169,11 @@ __device__ __constant__ int c_sample_dx[4] = {-32, 96, -96, 32};
 __device__ __constant__ int c_sample_dy[4] = {-96, -32, 32, 96};
 
 // coverage + depth of one pixel given the biased edge values at its centre
-template <bool DEPTH_ONLY>
+template <int MODE>
 __device__ __forceinline__ void emit_pixel(const RasterParams& p, const SubTri& s, const EdgeSetup& e, int px, int py, long long c0, long long c1, long long c2,
                                            uint32_t& frags) {
-    if (DEPTH_ONLY || p.samples == 1u) {
-        if ((c0 | c1 | c2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, 0u, sample_depth(s, e, c0, c1, c2), s.rec);
+    if (MODE == MODE_DEPTH || p.samples == 1u) {
+        if ((c0 | c1 | c2) >= 0) frags += write_sample<MODE>(p, px, py, 0u, sample_depth(s, e, c0, c1, c2), s.rec);
         return;
     }
 #pragma unroll
@@ -165,7 +182,7 @@ __device__ __forceinline__ void emit_pixel(const RasterParams& p, const SubTri& 
         const long long a0 = c0 + (e.sx0 >> 8) * c_sample_dx[k] + (e.sy0 >> 8) * c_sample_dy[k];
         const long long a1 = c1 + (e.sx1 >> 8) * c_sample_dx[k] + (e.sy1 >> 8) * c_sample_dy[k];
         const long long a2 = c2 + (e.sx2 >> 8) * c_sample_dx[k] + (e.sy2 >> 8) * c_sample_dy[k];
-        if ((a0 | a1 | a2) >= 0) frags += write_sample<DEPTH_ONLY>(p, px, py, (uint32_t)k, sample_depth(s, e, a0, a1, a2), s.rec);
+        if ((a0 | a1 | a2) >= 0) frags += write_sample<MODE>(p, px, py, (uint32_t)k, sample_depth(s, e, a0, a1, a2), s.rec);
     }
 }
 
@@ -182,14 +199,14 @@ __device__ __forceinline__ void pixel_bounds(const RasterParams& p, const SubTri
 }
 
 // one thread walks the pixel box of its own sub-triangle with incremental edge functions
-template <bool DEPTH_ONLY>
+template <int MODE>
 __device__ __forceinline__ void raster_inline(const RasterParams& p, const SubTri& s, int px0, int py0, int px1, int py1, uint32_t& frags) {
     const EdgeSetup e = make_edges(s, px0, py0);
     long long r0 = e.e0, r1 = e.e1, r2 = e.e2;
     for (int py = py0; py <= py1; ++py) {
         long long c0 = r0, c1 = r1, c2 = r2;
         for (int px = px0; px <= px1; ++px) {
-            emit_pixel<DEPTH_ONLY>(p, s, e, px, py, c0, c1, c2, frags);
+            emit_pixel<MODE>(p, s, e, px, py, c0, c1, c2, frags);
             c0 += e.sx0; c1 += e.sx1; c2 += e.sx2;
         }
         r0 += e.sy0; r1 += e.sy1; r2 += e.sy2;
@@ -200,7 +217,7 @@ __device__ __forceinline__ void raster_inline(const RasterParams& p, const SubTr
 //   small  (<= 8x8 .. 64 px)   : inline, by the thread that set it up;
 //   medium (<= 32 x 32)         : handed back through `defer` and rasterised by the whole warp (32 pixels per step);
 //   large                       : split into 16-row bands and queued for raster_band_kernel.
-template <bool DEPTH_ONLY>
+template <int MODE>
 __device__ bool process_subtriangle(const RasterParams& p, const float4 a, const float4 b, const float4 c, uint32_t rec, uint32_t& frags, SubTri* defer,
                                     bool* deferred) {
     const float4 v[3] = {a, b, c};
@@ -259,12 +276,12 @@ __device__ bool process_subtriangle(const RasterParams& p, const float4 a, const
         }
         inline_raster = true;
     }
-    raster_inline<DEPTH_ONLY>(p, s, px0, py0, px1, py1, frags);
+    raster_inline<MODE>(p, s, px0, py0, px1, py1, frags);
     return true;
 }
 
 // medium triangles: all 32 lanes rasterise one sub-triangle; the lane grid is 32x1, 16x2 or 8x4 pixels depending on the box width
-template <bool DEPTH_ONLY>
+template <int MODE>
 __device__ __forceinline__ void raster_cooperative(const RasterParams& p, const SubTri& s, int lane, uint32_t& frags) {
     int px0, py0, px1, py1;
     pixel_bounds(p, s, px0, py0, px1, py1);
@@ -275,14 +292,14 @@ __device__ __forceinline__ void raster_cooperative(const RasterParams& p, const 
         const long long dy = py - py0;
         long long c0 = e.e0 + dy * e.sy0 + (long long)lx * e.sx0, c1 = e.e1 + dy * e.sy1 + (long long)lx * e.sx1, c2 = e.e2 + dy * e.sy2 + (long long)lx * e.sx2;
         for (int px = px0 + lx; px <= px1; px += lw) {
-            emit_pixel<DEPTH_ONLY>(p, s, e, px, py, c0, c1, c2, frags);
+            emit_pixel<MODE>(p, s, e, px, py, c0, c1, c2, frags);
             c0 += lw * e.sx0; c1 += lw * e.sx1; c2 += lw * e.sx2;
         }
     }
 }
 
 // vertex stage up to clip space, clipping and setup of listed triangle i; medium sub-triangles come back through `defer`
-template <bool DEPTH_ONLY>
+template <int MODE>
 __device__ void setup_listed_triangle(const RasterParams& p, unsigned long long i, uint32_t n_regions, uint32_t& frags, uint32_t& set_up, SubTri* defer, bool* deferred) {
     // region of listed triangle i: last r with tri_prefix[r] <= i
     uint32_t lo = 0, hi = n_regions;
@@ -330,16 +347,16 @@ __device__ void setup_listed_triangle(const RasterParams& p, unsigned long long 
     const uint32_t rec = (uint32_t)(i + 1);
     bool any = false;
     if (!need_clip) {
-        any = process_subtriangle<DEPTH_ONLY>(p, clip[0], clip[1], clip[2], rec, frags, defer, deferred);
+        any = process_subtriangle<MODE>(p, clip[0], clip[1], clip[2], rec, frags, defer, deferred);
     } else {
         float4 poly[12];
         poly[0] = clip[0]; poly[1] = clip[1]; poly[2] = clip[2];
         const int n = clip_polygon(poly, 3);
-        for (int q = 1; q + 1 < n; ++q) any |= process_subtriangle<DEPTH_ONLY>(p, poly[0], poly[q], poly[q + 1], rec, frags, nullptr, nullptr);
+        for (int q = 1; q + 1 < n; ++q) any |= process_subtriangle<MODE>(p, poly[0], poly[q], poly[q + 1], rec, frags, nullptr, nullptr);
     }
     if (any) {
         set_up++;
-        if (!DEPTH_ONLY) {
+        if (MODE != MODE_DEPTH) {
             r3_tri_record tr;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { tr.xyw[k][0] = clip[k].x; tr.xyw[k][1] = clip[k].y; tr.xyw[k][2] = clip[k].w; tr.vid[k] = vid[k]; }
@@ -351,7 +368,7 @@ __device__ void setup_listed_triangle(const RasterParams& p, unsigned long long 
     }
 }
 
-template <bool DEPTH_ONLY>
+template <int MODE>
 __global__ void __launch_bounds__(RS_THREADS) raster_setup_kernel(const __grid_constant__ RasterParams p) {
     const uint32_t n_regions = p.header[2];
     const unsigned long long total = p.tri_prefix[n_regions];
@@ -362,14 +379,14 @@ __global__ void __launch_bounds__(RS_THREADS) raster_setup_kernel(const __grid_c
         const unsigned long long i = base + lane;
         SubTri med;
         bool has_med = false;
-        if (i < total) setup_listed_triangle<DEPTH_ONLY>(p, i, n_regions, frags, set_up, &med, &has_med);
+        if (i < total) setup_listed_triangle<MODE>(p, i, n_regions, frags, set_up, &med, &has_med);
         uint32_t m = __ballot_sync(0xFFFFFFFFu, has_med);
         if (__popc(m) >= COOP_MAX_LANES) {
             // most lanes hold a medium triangle: 32 boxes walked in parallel beat 32 boxes walked one after the other
             if (has_med) {
                 int px0, py0, px1, py1;
                 pixel_bounds(p, med, px0, py0, px1, py1);
-                raster_inline<DEPTH_ONLY>(p, med, px0, py0, px1, py1, frags);
+                raster_inline<MODE>(p, med, px0, py0, px1, py1, frags);
             }
             m = 0;
         }
@@ -382,7 +399,7 @@ __global__ void __launch_bounds__(RS_THREADS) raster_setup_kernel(const __grid_c
                 s.x[k] = __shfl_sync(0xFFFFFFFFu, med.x[k], src); s.y[k] = __shfl_sync(0xFFFFFFFFu, med.y[k], src); s.z[k] = __shfl_sync(0xFFFFFFFFu, med.z[k], src);
             }
             s.rec = __shfl_sync(0xFFFFFFFFu, med.rec, src);
-            raster_cooperative<DEPTH_ONLY>(p, s, lane, frags);
+            raster_cooperative<MODE>(p, s, lane, frags);
         }
     }
     // statistics: one atomic per warp
@@ -395,7 +412,7 @@ __global__ void __launch_bounds__(RS_THREADS) raster_setup_kernel(const __grid_c
 }
 
 // one warp per (large sub-triangle, 16-row band); lanes = 32 consecutive pixels
-template <bool DEPTH_ONLY>
+template <int MODE>
 __global__ void __launch_bounds__(RS_THREADS) raster_band_kernel(const __grid_constant__ RasterParams p) {
     const int lane = threadIdx.x & 31;
     uint32_t n_bands = p.counters[1];
@@ -427,7 +444,7 @@ __global__ void __launch_bounds__(RS_THREADS) raster_band_kernel(const __grid_co
             const int px = bx + lane;
             long long c0 = e.e0 + (dx + lane) * e.sx0, c1 = e.e1 + (dx + lane) * e.sx1, c2 = e.e2 + (dx + lane) * e.sx2;
             for (int py = by0; py <= by1; ++py) {
-                if (px <= px1) emit_pixel<DEPTH_ONLY>(p, s, e, px, py, c0, c1, c2, frags);
+                if (px <= px1) emit_pixel<MODE>(p, s, e, px, py, c0, c1, c2, frags);
                 c0 += e.sy0; c1 += e.sy1; c2 += e.sy2;
             }
         }
@@ -437,9 +454,9 @@ __global__ void __launch_bounds__(RS_THREADS) raster_band_kernel(const __grid_co
     if (lane == 0 && frags && p.stats) atomicAdd(&p.stats[1], (unsigned long long)frags);
 }
 
-// exclusive prefix over the regions the opaque (key 0) and cutout (key 1) routines draw (forward.rs:286-313)
+// exclusive prefix over the regions the routines with material keys in [key_lo, key_hi] draw (forward.rs:286-313)
 __global__ void region_prefix_kernel(const r3_region* __restrict__ regions, const r3_indirect_call* __restrict__ calls, const uint32_t* __restrict__ header,
-                                     unsigned long long* __restrict__ prefix) {
+                                     unsigned long long* __restrict__ prefix, unsigned long long key_lo, unsigned long long key_hi) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry;
     const uint32_t n_regions = header[2];
@@ -449,7 +466,7 @@ __global__ void region_prefix_kernel(const r3_region* __restrict__ regions, cons
     for (uint32_t base = 0; base < n_regions; base += blockDim.x) {
         const uint32_t r = base + threadIdx.x;
         unsigned long long v = 0ull;
-        if (r < n_regions && regions[r].material_key <= 1ull) v = calls[r].vertex_count / 3u;
+        if (r < n_regions && regions[r].material_key >= key_lo && regions[r].material_key <= key_hi) v = calls[r].vertex_count / 3u;
         unsigned long long incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -501,8 +518,9 @@ static int ensure_raster_scratch(r3_ctx* c) {
     return r3_reserve(c, &c->d_scratch, &c->scratch_cap, need, 1, false, false);
 }
 
-static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, bool depth_only, int pass, float ox, float oy, float vw, float vh,
+static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, int mode, int pass, float ox, float oy, float vw, float vh,
                       int x0, int y0, int x1, int y1, uint32_t pitch) {
+    const bool depth_only = mode == MODE_DEPTH;
     const r3_jobs* j = ds.jobs;
     R3_TRY(ensure_raster_scratch(c));
     uint32_t* counters = (uint32_t*)c->d_scratch;
@@ -510,7 +528,8 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, bool dept
     uint2* bands = (uint2*)((uint8_t*)large + (size_t)LARGE_CAP * sizeof(SubTri));
     R3_CUDA(c, cudaMemsetAsync(counters, 0, 64, c->stream));
     R3_TRY(r3_reserve_t(c, &cam->d_block_sums, &cam->block_sums_cap, (uint64_t)j->n_regions + 2));
-    region_prefix_kernel<<<1, 1024, 0, c->stream>>>(j->d_regions, ds.calls, j->d_header, cam->d_block_sums);
+    const unsigned long long key_lo = mode == MODE_BLEND ? 2ull : 0ull, key_hi = mode == MODE_BLEND ? 2ull : 1ull;
+    region_prefix_kernel<<<1, 1024, 0, c->stream>>>(j->d_regions, ds.calls, j->d_header, cam->d_block_sums, key_lo, key_hi);
     R3_CHECK_LAUNCH(c, "region_prefix_kernel");
 
     RasterParams p;
@@ -521,8 +540,9 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, bool dept
     p.ox = ox; p.oy = oy; p.vw = vw; p.vh = vh; p.x0 = x0; p.y0 = y0; p.x1 = x1; p.y1 = y1; p.pitch = pitch;
     p.positive_visible = (cam->header.flags & R3_PCU_POSITIVE_AREA_VISIBLE) ? 1 : 0;
     p.samples = depth_only ? 1u : c->samples;
-    p.vis = c->d_vis; p.pass_bit = (uint32_t)pass; p.depth_bits = (uint32_t*)c->d_atlas;
-    p.large = large; p.bands = bands; p.counters = counters; p.stats = depth_only ? nullptr : c->d_stats;
+    p.vis = c->d_vis; p.pass_bit = (uint32_t)(pass & 1); p.depth_bits = (uint32_t*)c->d_atlas;
+    p.frag_heads = c->d_frag_heads; p.frag_nodes = c->d_frag_nodes; p.frag_cap = (uint32_t)c->frag_nodes_cap; p.key_lo = key_lo; p.key_hi = key_hi;
+    p.large = large; p.bands = bands; p.counters = counters; p.stats = mode == MODE_COLOUR ? c->d_stats : nullptr;   // statistics describe the opaque + cutout passes
     p.records = nullptr;
     if (!depth_only) {
         // one record slot per listed triangle; the listed total is bounded by the partition size
@@ -533,11 +553,13 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, bool dept
         p.records = c->d_tris[pass];
     }
     const int grid = R3_SM_COUNT * 8;
-    if (depth_only) raster_setup_kernel<true><<<grid, RS_THREADS, 0, c->stream>>>(p);
-    else raster_setup_kernel<false><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    if (mode == MODE_DEPTH) raster_setup_kernel<MODE_DEPTH><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    else if (mode == MODE_COLOUR) raster_setup_kernel<MODE_COLOUR><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    else raster_setup_kernel<MODE_BLEND><<<grid, RS_THREADS, 0, c->stream>>>(p);
     R3_CHECK_LAUNCH(c, "raster_setup_kernel");
-    if (depth_only) raster_band_kernel<true><<<grid, RS_THREADS, 0, c->stream>>>(p);
-    else raster_band_kernel<false><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    if (mode == MODE_DEPTH) raster_band_kernel<MODE_DEPTH><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    else if (mode == MODE_COLOUR) raster_band_kernel<MODE_COLOUR><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    else raster_band_kernel<MODE_BLEND><<<grid, RS_THREADS, 0, c->stream>>>(p);
     R3_CHECK_LAUNCH(c, "raster_band_kernel");
     return R3_OK;
 }
@@ -554,7 +576,7 @@ R3_EXPORT int r3_forward_pass(r3_ctx* c, int source) {
         if (!cam->has_draw_call_set) return R3_OK;                              // forward.rs:212-216
         if (!draw_source_for(cam, cam->cur, 1, &ds)) return R3_OK;              // Input partition, post-swap
     }
-    R3_TRY(run_raster(c, cam, ds, false, source ? 1 : 0, 0.0f, 0.0f, (float)c->width, (float)c->height, 0, (int)c->row_begin, (int)c->width,
+    R3_TRY(run_raster(c, cam, ds, MODE_COLOUR, source ? 1 : 0, 0.0f, 0.0f, (float)c->width, (float)c->height, 0, (int)c->row_begin, (int)c->width,
                       (int)c->row_end, c->width));
     if (source == 1) cam->cache_idx = cam->cur;                                 // draw_call_set_cache.insert (forward.rs:219)
     return R3_OK;
@@ -568,5 +590,30 @@ R3_EXPORT int r3_shadow_pass(r3_ctx* c, uint32_t shadow_index, uint32_t ox, uint
     r3_camera* cam = &c->cams[shadow_index + 1];
     DrawSource ds;
     if (!cam->has_draw_call_set || !draw_source_for(cam, cam->cur, 0, &ds)) return R3_OK;
-    return run_raster(c, cam, ds, true, 0, (float)ox, (float)oy, (float)size, (float)size, (int)ox, (int)oy, (int)(ox + size), (int)(oy + size), c->atlas_w);
+    return run_raster(c, cam, ds, MODE_DEPTH, 0, (float)ox, (float)oy, (float)size, (float)size, (int)ox, (int)oy, (int)(ox + size), (int)(oy + size), c->atlas_w);
+}
+
+// blend routine, first half: rasterise the key-2 regions of this frame's residual list into per-sample fragment lists.
+// The pool holds every fragment that is not behind the opaque depth; when it is too small the pass is repeated with a
+// larger one (the only host round trip of the frame, and only in frames with transparent objects).
+int r3_blend_collect(r3_ctx* c, bool* ran) {
+    *ran = false;
+    r3_camera* cam = &c->cams[0];
+    DrawSource ds;
+    if (!c->any_blend || !cam->has_draw_call_set || !draw_source_for(cam, cam->cur, 1, &ds)) return R3_OK;   // CullingSource::Residual
+    const uint64_t n_samples = (uint64_t)c->width * c->height * c->samples;
+    R3_TRY(r3_reserve_t(c, &c->d_frag_heads, &c->frag_heads_cap, n_samples));
+    if (c->frag_nodes_cap == 0) R3_TRY(r3_reserve_t(c, &c->d_frag_nodes, &c->frag_nodes_cap, n_samples < (1u << 20) ? (1u << 20) : n_samples));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        R3_CUDA(c, cudaMemsetAsync(c->d_frag_heads, 0, n_samples * 4, c->stream));
+        R3_TRY(run_raster(c, cam, ds, MODE_BLEND, 2, 0.0f, 0.0f, (float)c->width, (float)c->height, 0, (int)c->row_begin, (int)c->width, (int)c->row_end,
+                          c->width));
+        uint32_t used = 0;
+        R3_CUDA(c, cudaMemcpyAsync(&used, (const uint32_t*)c->d_scratch + 3, 4, cudaMemcpyDeviceToHost, c->stream));
+        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (used <= c->frag_nodes_cap) { *ran = true; return R3_OK; }
+        if (attempt == 1 || used >= 0xFFFFFFF0u) break;
+        R3_TRY(r3_reserve_t(c, &c->d_frag_nodes, &c->frag_nodes_cap, (uint64_t)used + (used >> 3)));
+    }
+    return r3_fail(c, R3_E_OOM, "forward_blend: fragment pool overflow");
 }

@@ -33,6 +33,8 @@ struct ShadeParams {
     const r3_material* materials; uint32_t n_materials;
     const DirPrep* dir; uint32_t n_dir; const PointPrep* point; uint32_t n_point;
     const float* atlas; uint32_t atlas_w, atlas_h;
+    // blend routine (r3_forward_blend): triangle records of the key-2 regions + the per-sample fragment lists
+    const r3_tri_record* tris2; unsigned long long n_tris2; const uint32_t* frag_heads; const uint4* frag_nodes;
     float ambient[4]; float clear[4];
     uint32_t width, height, row_begin, row_end, samples;
     float4* hdr32; uint2* hdr16; float* depth;
@@ -145,9 +147,8 @@ __device__ __forceinline__ VsOut vertex_stage(const ShadeParams& p, const uint32
 }
 
 // vs_main outputs interpolated at the centre of pixel (px, py) + fs_main for triangle record `rec` of pass `pass`
-__device__ __forceinline__ float4 shade_fragment(const ShadeParams& p, const DirPrep* __restrict__ s_dir, const PointPrep* __restrict__ s_point, uint32_t pass,
-                                                 uint32_t rec, uint32_t px, uint32_t py) {
-    const r3_tri_record* tp = (pass ? p.tris1 : p.tris0) + (rec - 1u);
+__device__ __forceinline__ float4 shade_fragment(const ShadeParams& p, const DirPrep* __restrict__ s_dir, const PointPrep* __restrict__ s_point,
+                                                 const r3_tri_record* tp, uint32_t px, uint32_t py) {
     const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp)), q1 = __ldg(reinterpret_cast<const float4*>(tp) + 1),
                  q2 = __ldg(reinterpret_cast<const float4*>(tp) + 2);
     const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(tp) + 3);
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
         const unsigned long long key = p.vis[pi];
         const uint32_t rec = (uint32_t)(key & 0x7FFFFFFFull), pass = (uint32_t)((key >> 31) & 1ull);
         out = make_float4(p.clear[0], p.clear[1], p.clear[2], p.clear[3]);
-        if (rec != 0u && rec <= (pass ? p.n_tris1 : p.n_tris0)) { out = shade_fragment(p, s_dir, s_point, pass, rec, px, py); n_shaded = 1; }
+        if (rec != 0u && rec <= (pass ? p.n_tris1 : p.n_tris0)) { out = shade_fragment(p, s_dir, s_point, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py); n_shaded = 1; }
         depth = __uint_as_float((uint32_t)(key >> 32));
     } else {
         // SampleCount::Four: a primitive is shaded once per pixel for all the samples it owns; the rgba16f samples are box-filtered
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
                 int reuse = -1;
                 for (int q = 0; q < k; ++q) if ((uint32_t)keys[q] == id && reuse < 0) reuse = q;
                 if (reuse >= 0) col[k] = col[reuse];
-                else { col[k] = shade_fragment(p, s_dir, s_point, pass, rec, px, py); n_shaded++; }
+                else { col[k] = shade_fragment(p, s_dir, s_point, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py); n_shaded++; }
             }
             // each sample lives in the rgba16f multisampled target
             col[k] = make_float4(__half2float(__float2half_rn(col[k].x)), __half2float(__float2half_rn(col[k].y)), __half2float(__float2half_rn(col[k].z)),
@@ -317,6 +318,117 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
     const uint32_t active = __activemask();
     const uint32_t total = __reduce_add_sync(active, n_shaded);
     if ((threadIdx.x & 31u) == (uint32_t)(__ffs(active) - 1) && total) atomicAdd(&p.stats[2], (unsigned long long)total);
+}
+
+
+__device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
+
+// pbr_forward_rendering_transparent (base.rs:181,450-466), second half: apply the collected fragments of a pixel in draw
+// order (= record order: non-atomic regions keep their slots, cull.wgsl:374-380).  Per sample: depth test GreaterEqual with
+// depth write (forward.rs:331-365), then BlendState::ALPHA_BLENDING (pbr/routine.rs:115-118) into the rgba16f target —
+// rule R8 of the oracle: rgb' = (src.rgb * src.a) + (dst.rgb * (1 - src.a)), a' = src.a + dst.a * (1 - src.a), rounded to
+// half precision after every primitive.  A primitive is shaded once per pixel for all the samples it covers (R7).
+template <int SAMPLES>
+__global__ void __launch_bounds__(256) blend_apply_kernel(const __grid_constant__ ShadeParams p) {
+    __shared__ DirPrep s_dir[MAX_SMEM_DIR];
+    __shared__ PointPrep s_point[MAX_SMEM_POINT];
+    {
+        const uint32_t nd = min(p.n_dir, (uint32_t)MAX_SMEM_DIR) * 32u, np = min(p.n_point, (uint32_t)MAX_SMEM_POINT) * 8u;
+        const float* gd = reinterpret_cast<const float*>(p.dir); const float* gp = reinterpret_cast<const float*>(p.point);
+        float* sd = reinterpret_cast<float*>(s_dir); float* sp = reinterpret_cast<float*>(s_point);
+        for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) sd[i] = gd[i];
+        for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) sp[i] = gp[i];
+        __syncthreads();
+    }
+    const uint32_t px = blockIdx.x * 32u + (threadIdx.x & 31u), py = p.row_begin + blockIdx.y * 8u + (threadIdx.x >> 5);
+    if (px >= p.width || py >= p.row_end) return;
+    const size_t pi = (size_t)py * p.width + px;
+    uint32_t head[SAMPLES];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < SAMPLES; ++k) { head[k] = p.frag_heads[pi * SAMPLES + k]; any |= head[k] != 0u; }
+    if (!any) return;
+
+    // destination samples as the colour target holds them (rgba16f) + their depth
+    float4 dst[SAMPLES];
+    uint32_t zdst[SAMPLES];
+    if (SAMPLES == 1) {
+        const uint2 h = p.hdr16[pi];
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+        dst[0] = make_float4(a.x, a.y, b.x, b.y);
+        zdst[0] = (uint32_t)(p.vis[pi] >> 32);
+    } else {
+        // the multisampled target is not kept after the box filter: the opaque samples of the (few) pixels that carry
+        // transparent fragments are shaded again, exactly as resolve_kernel<4> did
+        uint32_t ids[SAMPLES];
+#pragma unroll
+        for (int k = 0; k < SAMPLES; ++k) {
+            const unsigned long long key = p.vis[pi * SAMPLES + k];
+            ids[k] = (uint32_t)key; zdst[k] = (uint32_t)(key >> 32);
+            const uint32_t rec = ids[k] & 0x7FFFFFFFu, pass = ids[k] >> 31;
+            float4 col = make_float4(p.clear[0], p.clear[1], p.clear[2], p.clear[3]);
+            if (rec != 0u && rec <= (pass ? p.n_tris1 : p.n_tris0)) {
+                int reuse = -1;
+                for (int q = 0; q < k; ++q) if (ids[q] == ids[k] && reuse < 0) reuse = q;
+                if (reuse >= 0) col = dst[reuse];
+                else col = shade_fragment(p, s_dir, s_point, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py);
+            }
+            dst[k] = make_float4(f16_round(col.x), f16_round(col.y), f16_round(col.z), f16_round(col.w));
+        }
+    }
+
+    uint32_t last = 0u, n_blended = 0u;
+    for (;;) {
+        // next primitive in draw order over all the samples of the pixel
+        uint32_t next = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < SAMPLES; ++k)
+            for (uint32_t n = head[k]; n != 0u;) {
+                const uint4 node = __ldg(&p.frag_nodes[n - 1u]);
+                if (node.x > last && node.x < next) next = node.x;
+                n = node.z;
+            }
+        if (next == 0xFFFFFFFFu) break;
+        last = next;
+        if (next > p.n_tris2) continue;
+        bool shaded = false;
+        float4 src = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < SAMPLES; ++k) {
+            uint32_t z = 0u; bool found = false;
+            for (uint32_t n = head[k]; n != 0u && !found;) {
+                const uint4 node = __ldg(&p.frag_nodes[n - 1u]);
+                if (node.x == next) { z = node.y; found = true; }
+                n = node.z;
+            }
+            if (!found || z < zdst[k]) continue;   // GreaterEqual (reverse-Z bits order like the floats)
+            zdst[k] = z;                            // depth write
+            if (!shaded) { src = shade_fragment(p, s_dir, s_point, p.tris2 + (next - 1u), px, py); shaded = true; }
+            const float inv_a = sub_rn(1.0f, src.w);
+            dst[k] = make_float4(f16_round(add_rn(mul_rn(src.x, src.w), mul_rn(dst[k].x, inv_a))), f16_round(add_rn(mul_rn(src.y, src.w), mul_rn(dst[k].y, inv_a))),
+                                 f16_round(add_rn(mul_rn(src.z, src.w), mul_rn(dst[k].z, inv_a))), f16_round(add_rn(src.w, mul_rn(dst[k].w, inv_a))));
+            n_blended++;
+        }
+    }
+    if (n_blended) {
+        float4 out;
+        float depth;
+        if (SAMPLES == 1) { out = dst[0]; depth = __uint_as_float(zdst[0]); }
+        else {
+            out = make_float4(((dst[0].x + dst[1 % SAMPLES].x) + (dst[2 % SAMPLES].x + dst[3 % SAMPLES].x)) * 0.25f,
+                              ((dst[0].y + dst[1 % SAMPLES].y) + (dst[2 % SAMPLES].y + dst[3 % SAMPLES].y)) * 0.25f,
+                              ((dst[0].z + dst[1 % SAMPLES].z) + (dst[2 % SAMPLES].z + dst[3 % SAMPLES].z)) * 0.25f,
+                              ((dst[0].w + dst[1 % SAMPLES].w) + (dst[2 % SAMPLES].w + dst[3 % SAMPLES].w)) * 0.25f);
+            depth = 1.0f;
+#pragma unroll
+            for (int k = 0; k < SAMPLES; ++k) depth = fminf(depth, __uint_as_float(zdst[k]));
+        }
+        p.hdr32[pi] = out;
+        const __half2 h01 = __floats2half2_rn(out.x, out.y), h23 = __floats2half2_rn(out.z, out.w);
+        p.hdr16[pi] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        p.depth[pi] = depth;
+        atomicAdd(&p.stats[3], (unsigned long long)n_blended);
+    }
 }
 
 // light prep: one thread per light (opaque.wgsl:491,519,528 hoisted out of the fragment loop)
@@ -454,7 +566,7 @@ R3_EXPORT int r3_forward_begin(r3_ctx* c) {
     cudaSetDevice(c->device);
     R3_CUDA(c, cudaMemsetAsync(c->d_vis, 0, (size_t)c->width * c->height * 8 * c->samples, c->stream));
     R3_CUDA(c, cudaMemsetAsync(c->d_stats, 0, 32, c->stream));
-    c->n_tris[0] = c->n_tris[1] = 0;
+    c->n_tris[0] = c->n_tris[1] = c->n_tris[2] = 0;
     return R3_OK;
 }
 R3_EXPORT int r3_hiz_build(r3_ctx* c) {
@@ -470,11 +582,26 @@ R3_EXPORT int r3_hiz_build(r3_ctx* c) {
     }
     return R3_OK;
 }
+static void fill_shade_params(r3_ctx* c, ShadeParams* out) {
+    r3_camera* cam = &c->cams[0];
+    ShadeParams& p = *out;
+    DirPrep* d_dir = reinterpret_cast<DirPrep*>(c->d_light_mats);
+    PointPrep* d_point = reinterpret_cast<PointPrep*>(c->d_light_mats + (size_t)c->n_dir * 32);
+    p.vis = c->d_vis;
+    p.tris0 = c->d_tris[0]; p.tris1 = c->d_tris[1]; p.n_tris0 = c->n_tris[0]; p.n_tris1 = c->n_tris[1];
+    p.tris2 = c->d_tris[2]; p.n_tris2 = c->n_tris[2]; p.frag_heads = c->d_frag_heads; p.frag_nodes = c->d_frag_nodes;
+    p.objects = c->d_objects; p.matrices = cam->d_matrices; p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;
+    p.materials = c->d_materials; p.n_materials = c->n_materials;
+    p.dir = d_dir; p.n_dir = c->n_dir; p.point = d_point; p.n_point = c->n_point;
+    p.atlas = c->d_atlas; p.atlas_w = c->atlas_w; p.atlas_h = c->atlas_h;
+    memcpy(p.ambient, c->uniforms.ambient, 16); memcpy(p.clear, c->clear_color, 16);
+    p.width = c->width; p.height = c->height; p.row_begin = c->row_begin; p.row_end = c->row_end; p.samples = c->samples;
+    p.hdr32 = reinterpret_cast<float4*>(c->d_hdr32); p.hdr16 = reinterpret_cast<uint2*>(c->d_hdr16); p.depth = c->d_depth; p.stats = c->d_stats;
+}
 R3_EXPORT int r3_forward_resolve(r3_ctx* c) {
     if (!c || !c->d_vis) return r3_fail(c, R3_E_STATE, "forward_resolve before set_render_target");
     if (!c->uniforms_set) return r3_fail(c, R3_E_STATE, "forward_resolve before set_frame_uniforms");
     cudaSetDevice(c->device);
-    r3_camera* cam = &c->cams[0];
     const uint64_t need_floats = (uint64_t)c->n_dir * 32 + (uint64_t)c->n_point * 8 + 64;
     static_assert(sizeof(DirPrep) == 32 * 4 && sizeof(PointPrep) == 8 * 4, "prep sizes");
     R3_TRY(r3_reserve_t(c, &c->d_light_mats, &c->light_mats_cap, need_floats));
@@ -487,15 +614,7 @@ R3_EXPORT int r3_forward_resolve(r3_ctx* c) {
         R3_CHECK_LAUNCH(c, "light_prep_kernel");
     }
     ShadeParams p;
-    p.vis = c->d_vis;
-    p.tris0 = c->d_tris[0]; p.tris1 = c->d_tris[1]; p.n_tris0 = c->n_tris[0]; p.n_tris1 = c->n_tris[1];
-    p.objects = c->d_objects; p.matrices = cam->d_matrices; p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;
-    p.materials = c->d_materials; p.n_materials = c->n_materials;
-    p.dir = d_dir; p.n_dir = c->n_dir; p.point = d_point; p.n_point = c->n_point;
-    p.atlas = c->d_atlas; p.atlas_w = c->atlas_w; p.atlas_h = c->atlas_h;
-    memcpy(p.ambient, c->uniforms.ambient, 16); memcpy(p.clear, c->clear_color, 16);
-    p.width = c->width; p.height = c->height; p.row_begin = c->row_begin; p.row_end = c->row_end; p.samples = c->samples;
-    p.hdr32 = reinterpret_cast<float4*>(c->d_hdr32); p.hdr16 = reinterpret_cast<uint2*>(c->d_hdr16); p.depth = c->d_depth; p.stats = c->d_stats;
+    fill_shade_params(c, &p);
     const uint32_t rows = c->row_end - c->row_begin;
     if (rows) {
         const dim3 grid((c->width + 31) / 32, (rows + 7) / 8);
@@ -503,6 +622,22 @@ R3_EXPORT int r3_forward_resolve(r3_ctx* c) {
         else resolve_kernel<4><<<grid, 256, 0, c->stream>>>(p);
         R3_CHECK_LAUNCH(c, "resolve_kernel");
     }
+    return R3_OK;
+}
+R3_EXPORT int r3_forward_blend(r3_ctx* c) {
+    if (!c || !c->d_vis) return r3_fail(c, R3_E_STATE, "forward_blend before set_render_target");
+    if (!c->uniforms_set) return r3_fail(c, R3_E_STATE, "forward_blend before set_frame_uniforms");
+    cudaSetDevice(c->device);
+    bool ran = false;
+    R3_TRY(r3_blend_collect(c, &ran));
+    const uint32_t rows = c->row_end - c->row_begin;
+    if (!ran || !rows) return R3_OK;
+    ShadeParams p;
+    fill_shade_params(c, &p);   // the lights were prepared by r3_forward_resolve of this frame
+    const dim3 grid((c->width + 31) / 32, (rows + 7) / 8);
+    if (c->samples == 1) blend_apply_kernel<1><<<grid, 256, 0, c->stream>>>(p);
+    else blend_apply_kernel<4><<<grid, 256, 0, c->stream>>>(p);
+    R3_CHECK_LAUNCH(c, "blend_apply_kernel");
     return R3_OK;
 }
 R3_EXPORT int r3_tonemap(r3_ctx* c, int srgb_target) {

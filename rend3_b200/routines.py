@@ -147,6 +147,7 @@ class BaseRenderGraph:
         b.hiz_build()                                                             # :162
         culler.cull(ev, CAMERA_VIEWPORT)                                          # :169
         b.forward_pass(1)                                                         # :172 residual triangles
-        # skybox (:175) and blend (:181) are outside this path
-        b.forward_resolve()
+        b.forward_resolve()                                                       # fs_main of the opaque + cutout fragments
+        # skybox (:175) is outside this path
+        b.forward_blend()                                                         # :181 transparent objects, back to front
         b.tonemap(srgb_target)                                                    # :184

@@ -138,6 +138,8 @@ def cube_field_scene(n_objects: int = 10_000, seed: int = 1, resolution: Tuple[i
         transparency = (m % 3) if mixed_transparency else 0
         # every other cutout material has alpha below its cutout threshold: its objects are discarded in the forward and shadow passes
         alpha = 0.3 if (mixed_transparency and m % 6 == 1) else 1.0
+        if mixed_transparency and m % 3 == 2:
+            alpha = 0.25 + 0.5 * (m / max(material_count - 1, 1))   # blend materials are actually translucent
         r.add_material(PbrMaterial(albedo_value=(0.5, g, 0.5 if material_count == 1 else 1.0 - g, alpha), roughness_factor=roughness,
                                    transparency=transparency, alpha_cutout=0.5))
     r.set_camera_data(cube_example_camera(pull_back))

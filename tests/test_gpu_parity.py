@@ -320,6 +320,44 @@ def test_error_paths(cuda):
         cuda.object_uniform_upload(CAMERA_VIEWPORT, hdr)
 
 
+@pytest.mark.parametrize("far_first", [True, False])
+@pytest.mark.parametrize("samples", [1, 4])
+def test_blend_routine_known_answer(cuda, far_first, samples):
+    """The hand-evaluated ALPHA_BLENDING chain of tests/blend_case.py (depth test + depth write, back-to-front object order)."""
+    import blend_case
+
+    r = blend_case.build(cuda, far_first)
+    r.render_frame(64, samples)
+    want = blend_case.expected(far_first)
+    hdr = cuda.readback_hdr_f32()
+    assert np.array_equal(hdr.reshape(-1, 4), np.broadcast_to(want, (64 * 64, 4))), (hdr[32, 32], want)
+    assert np.allclose(cuda.readback_depth(), 0.6, rtol=0, atol=1e-6)
+    assert cuda.forward_stats()[3] == 64 * 64 * samples * (2 if far_first else 1)
+
+
+@pytest.mark.parametrize("samples", [1, 4])
+def test_blend_routine_matches_oracle(cuda, samples):
+    """Translucent cubes between opaque and cutout ones, two frames (the blend routine always draws the residual list):
+    every artefact of the frame, then the blended rgba16f target within one half-precision ulp per blended layer."""
+    res = (320, 180)
+    ev = cube_field_scene(n_objects=1500, seed=31, resolution=res, n_dir_lights=1, n_point_lights=2, shadow_resolution=256, shadow_distance=120.0,
+                          pull_back=8.0, extent=20.0, subdivisions=(1, 2), material_count=6, mixed_transparency=True, scale_range=(0.5, 2.5))
+    orc = load_oracle_backend()
+    graphs = {id(b): BaseRenderGraph(b) for b in (cuda, orc)}
+    for frame in range(2):
+        for b in (cuda, orc):
+            graphs[id(b)].add_to_graph(ev, res, samples, BaseRenderGraphSettings(clear_color=(0.1, 0.2, 0.3, 1.0)), upload=(frame == 0))
+        compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], check_pixels=False, what=f"blend frame {frame}")
+        sc, so = cuda.forward_stats(), orc.forward_stats()
+        assert so[3] > 1000 and sc[3] == so[3], (sc, so)
+        assert np.array_equal(cuda.readback_depth().view(np.uint32), orc.readback_depth().view(np.uint32)), "depth after the blend routine"
+        a, o = cuda.readback_hdr_f32().astype(np.float64), orc.readback_hdr_f32().astype(np.float64)
+        # every blended layer rounds to half precision: allow one f16 ulp per layer (at most 8 layers deep here) on top of TOL
+        bound = TOL * np.maximum(1.0, np.abs(o)) + 8.0 * np.maximum(np.abs(o) * 2.0 ** -10, 2.0 ** -24)
+        assert np.all(np.abs(a - o) <= bound), f"frame {frame}: {np.count_nonzero(np.abs(a - o) > bound)} channel values off (max {np.abs(a - o).max():.3e})"
+        assert np.mean(np.abs(a - o) > TOL) < 0.02, "half-precision rounding flips must stay rare"
+
+
 def test_device_batching_equals_host_batching_and_oracle(cuda, monkeypatch):
     """batch_objects on the device (radix sort + block scans) against the host implementation and the oracle, with
     three material keys (opaque / cutout / blend: atomic and non-atomic regions, front-to-back and back-to-front)."""
@@ -329,12 +367,12 @@ def test_device_batching_equals_host_batching_and_oracle(cuda, monkeypatch):
     orc = load_oracle_backend()
     BaseRenderGraph(orc).add_to_graph(ev, res, 1, BaseRenderGraphSettings())
     BaseRenderGraph(cuda).add_to_graph(ev, res, 1, BaseRenderGraphSettings())
-    compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], what="device batching")
+    compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], what="device batching", f16_samples=True)
     bo, ro = orc.readback_batches(CAMERA_VIEWPORT)
     assert len(bo) > 1 and len(ro) > len(bo), "scene must span several batches and split regions on key changes"
     assert set(int(r["material_key"]) for r in ro) == {0, 1, 2}
     monkeypatch.setenv("R3_HOST_BATCHING", "1")
     host = load_cuda_backend(0)
     BaseRenderGraph(host).add_to_graph(ev, res, 1, BaseRenderGraphSettings())
-    compare_frame_state(host, orc, ev, [CAMERA_VIEWPORT, 0], what="host batching")
+    compare_frame_state(host, orc, ev, [CAMERA_VIEWPORT, 0], what="host batching", f16_samples=True)
     host.close()

@@ -191,6 +191,26 @@ def test_culling_buffers_ping_pong_like_suballoc():
     assert np.array_equal(img1, b.readback_ldr()), "a static scene renders identically through the predicted pass"
 
 
+@pytest.mark.parametrize("far_first", [True, False])
+@pytest.mark.parametrize("samples", [1, 4])
+def test_oracle_blend_routine_known_answer(far_first, samples):
+    """pbr_forward_rendering_transparent (base.rs:181): ALPHA_BLENDING in back-to-front object order with depth test AND
+    depth write; the reference holds no golden for it, so the oracle is pinned to the blend equation evaluated by hand."""
+    import blend_case
+
+    orc = load_oracle_backend()
+    r = blend_case.build(orc, far_first)
+    r.render_frame(64, samples)
+    want = blend_case.expected(far_first)
+    hdr = orc.readback_hdr_f32()
+    assert np.array_equal(hdr.reshape(-1, 4), np.broadcast_to(want, (64 * 64, 4))), (hdr[32, 32], want)
+    assert np.allclose(orc.readback_depth(), 0.6, rtol=0, atol=1e-6)   # the nearest transparent layer wrote depth
+    st = orc.forward_stats()
+    assert st[3] == 64 * 64 * samples * (2 if far_first else 1)
+    _, regions = orc.readback_batches(CAMERA_VIEWPORT)
+    assert sorted(int(k) for k in regions["material_key"]) == [0, 2]
+
+
 def test_oracle_skinning_matches_float64_blend():
     """skinning.wgsl:37-94 restated: skinned positions equal the float64 4-joint blend, normals are unit length, and
     identity joints leave the mesh untouched."""
