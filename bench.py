@@ -14,7 +14,8 @@ One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one
   * `forward` = BASELINE config 5 (4K, ~500k triangles, 64 point lights + 4 shadow-mapped directional lights):
     whole frames through BaseRenderGraph.add_to_graph; Mfrag/s = fs_main invocations / frame time; at N > 1 the
     screen is split in row tiles, one per rank, and the rgba16f rows are all-gathered.
-Inputs (1.28 GB of records + 1.28 GB of matrices per step) exceed the 126 MB L2, so no explicit flush is needed.
+Inputs (0.8 GB of transforms + spheres read, 1.28 GB of matrices written per step) exceed the 126 MB L2, so no explicit
+flush is needed.
 """
 import argparse
 import json
@@ -338,7 +339,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE config 4: fused frustum cull + uniform bake, 10 M object records per GPU (128 B std430 records, 1% disabled)",
                        "objects_per_gpu": n, "visible_fraction": n_vis / n, "parallelism": f"object-range shards x{world}, NCCL all-gather of the visibility words (1 bit/object)" if world > 1 else "single GPU",
-                       "l2": "inputs (1.28 GB) + outputs (1.28 GB) per step exceed the 126 MB L2; no explicit flush"},
+                       "l2": "inputs (0.8 GB) + outputs (1.28 GB) per step exceed the 126 MB L2; no explicit flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "cull_bake_kernel<bake,cull>", "kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_launch": BYTES_PER_OBJECT * n + BYTES_PER_VISIBLE * n_vis,
                          "peak_source": peak_src},

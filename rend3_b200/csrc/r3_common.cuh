@@ -68,6 +68,8 @@ struct r3_ctx {
     uint64_t launches = 0;
     // world
     r3_object* d_objects = nullptr; uint32_t n_slots = 0, objects_cap = 0; bool objects_borrowed = false;
+    // dense copies of the fields the cull + bake stream reads (r3_cull_bake.cu): transform columns, bounding spheres, enabled bits
+    float4* d_hot_transform = nullptr; float4* d_hot_sphere = nullptr; uint32_t* d_enabled_bits = nullptr; uint64_t hot_cap = 0; bool hot_valid = false;
     std::vector<uint64_t> sort_key; std::vector<uint8_t> sort_flags; std::vector<float> sort_loc;
     uint32_t* d_live_bits = nullptr; uint32_t live_bits_cap = 0; bool have_live = false;
     uint8_t* d_sort_key8 = nullptr; float* d_sort_loc = nullptr; uint32_t sort_dev_cap = 0; bool gpu_batching_ok = false;
@@ -134,6 +136,8 @@ int r3_reserve_t(r3_ctx* c, T** ptr, C* cap, uint64_t need, bool keep = false, b
 
 // stages implemented in the other translation units
 int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode);
+int r3_split_objects(r3_ctx* c);
+int r3_split_slots(r3_ctx* c, const uint32_t* d_slots, uint32_t n);
 int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam);
 int r3_host_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], uint32_t max_dispatch_count);
 int r3_upload_jobs(r3_ctx* c, r3_camera* cam);

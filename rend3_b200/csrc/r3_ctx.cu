@@ -68,6 +68,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (!c->objects_borrowed) cudaFree(c->d_objects);
+    cudaFree(c->d_hot_transform); cudaFree(c->d_hot_sphere); cudaFree(c->d_enabled_bits);
     cudaFree(c->d_sort_key8); cudaFree(c->d_sort_loc);
     cudaFree(c->d_live_bits); cudaFree(c->d_mesh); cudaFree(c->d_materials); cudaFree(c->d_dir); cudaFree(c->d_point);
     cudaFree(c->d_light_mats); cudaFree(c->d_atlas);
@@ -113,6 +114,7 @@ R3_EXPORT int r3_set_objects(r3_ctx* c, const r3_object* recs, uint32_t n) {
     if (n) R3_CUDA(c, cudaMemcpyAsync(c->d_objects, recs, (size_t)n * sizeof(r3_object), cudaMemcpyHostToDevice, c->stream));
     c->n_slots = n;
     c->max_invocations_valid = false;
+    R3_TRY(r3_split_objects(c));
     R3_CUDA(c, cudaStreamSynchronize(c->stream));   // host pointer is only borrowed for the call
     return R3_OK;
 }
@@ -122,7 +124,8 @@ R3_EXPORT int r3_set_objects_device(r3_ctx* c, const void* dptr, uint32_t n) {
     c->d_objects = (r3_object*)dptr;
     c->objects_cap = n; c->n_slots = n; c->objects_borrowed = true;
     c->max_invocations_valid = false;
-    return R3_OK;
+    cudaSetDevice(c->device);
+    return r3_split_objects(c);   // snapshot of the hot fields: call again after changing the records
 }
 
 __global__ void scatter_objects_kernel(r3_object* dst, const r3_object* src, const uint32_t* slots, uint32_t n, uint32_t n_slots) {
@@ -145,6 +148,7 @@ R3_EXPORT int r3_update_objects(r3_ctx* c, const uint32_t* slots, const r3_objec
     R3_CUDA(c, cudaMemcpyAsync(d_slots, slots, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
     scatter_objects_kernel<<<(n * 8 + 255) / 256, 256, 0, c->stream>>>(c->d_objects, d_recs, d_slots, n, c->n_slots);
     R3_CHECK_LAUNCH(c, "scatter_objects_kernel");
+    R3_TRY(r3_split_slots(c, d_slots, n));
     c->max_invocations_valid = false;
     R3_CUDA(c, cudaStreamSynchronize(c->stream));
     return R3_OK;

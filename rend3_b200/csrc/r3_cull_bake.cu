@@ -7,22 +7,26 @@
 //       Frustum::contains_sphere, 5 planes        rend3/src/util/frustum.rs:148-161
 // and emits the visible slots as one ASCENDING u32 list (the canonical, bit-exact artefact).
 //
-// Design (HBM-bound: 128 B read + 128 B written per object, 224 flop).
-//   stream kernel  — no inter-CTA dependency, so it runs at copy speed:
-//     * 8 lanes own one 128-byte object record: lane k loads float4 k, so a warp load instruction covers 512
-//       contiguous bytes (4 records) and each lane keeps 8 independent 16-byte loads in flight;
-//     * lanes 0-3 multiply `view` by transform column k, lanes 4-7 multiply `view_proj` by column k-4 (fetched
-//       by shuffle); lane k then stores float4 k of the 128-byte MV|MVP record, so stores are as coalesced as
-//       the loads.  Arithmetic is __fmul_rn/__fadd_rn in WGSL's accumulation order, never contracted: MV/MVP
-//       are bit-identical to the CPU oracle;
-//     * the sphere test runs one object per lane (spheres parked in shared memory by the lanes that loaded
-//       them); its ballot IS the 32-bit visibility word of 32 objects (1 bit per object goes to HBM);
-//     * each CTA (1024 objects) also leaves its survivor count.
+// Design (HBM-bound: 224 flop against >= 212 bytes per object).
+//   hot/cold split — the reference's 128-byte Object record (object.rs:23-36) stays the canonical store for the kernels
+//     that need its cold fields (first_index, index_count, material, attribute offsets); the 84 bytes this path reads
+//     (transform, bounding sphere, enabled) are ALSO kept as dense arrays — transforms[4n] float4, spheres[n] float4,
+//     enabled 1 bit per slot — filled by split_objects_kernel whenever records are uploaded (r3_set_objects,
+//     r3_set_objects_device) or scattered (r3_update_objects).  With the AoS records every 32-byte sector of a record is
+//     touched, i.e. 128 B read per object; the dense arrays bring that to 80 B + 1 bit (and to 16 B for cull-only).
+//   stream kernel  — no inter-CTA dependency, no shared memory, no shuffles:
+//     * a warp owns 32 consecutive slots.  Four fully coalesced 512-byte loads fetch their 128 transform columns; the
+//       lane holding column j of slot o multiplies it by `view` and by `view_proj` (operands straight from the constant
+//       bank) and stores column j of MV and of MVP — 64-byte runs, whole sectors.  Arithmetic is __fmul_rn/__fadd_rn in
+//       WGSL's accumulation order, never contracted: MV/MVP are bit-identical to the CPU oracle;
+//     * lane l loads the sphere of slot base+l (one coalesced 512-byte load) and tests it; the ballot IS the 32-bit
+//       visibility word of the 32 slots (1 bit per object goes to HBM);
+//     * each CTA (1024 slots) also leaves its survivor count.
 //   compact kernel — one CTA per 32768 objects: sums the CTA counts in front of it (<= 40 KB, L2 resident),
 //     scans its 1024 visibility words and writes the surviving slot ids in ascending order.  It moves
 //     N/8 + 4*visible bytes, ~1% of the stream kernel's traffic.
-// (A single-pass variant with a decoupled look-back was measured first: the look-back stalls cost 20% at 10 M
-//  objects — profiles/README.md — while the streaming half alone already ran at the measured copy bandwidth.)
+// (History, profiles/README.md: a single-pass kernel with a decoupled look-back lost 20% to look-back stalls; the
+//  two-kernel AoS version ran at the copy bandwidth but moved 256 B per object.)
 #include <cstdlib>
 
 #include "r3_common.cuh"
@@ -44,70 +48,94 @@ struct CullBakeParams {
     uint32_t object_count;
 };
 
+// AoS Object records -> the dense hot arrays.  8 lanes per 128-byte record (coalesced 512-byte loads); float4 #0-3 =
+// transform, #4 = bounding sphere, #7.y = `enabled` (byte 116).
+__global__ void __launch_bounds__(256) split_objects_kernel(const float4* __restrict__ objects, uint32_t n, float4* __restrict__ transforms,
+                                                            float4* __restrict__ spheres, uint32_t* __restrict__ enabled_bits) {
+    const int lane = threadIdx.x & 31, k = lane & 7, g = lane >> 3;
+    const uint32_t wtile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, base = wtile * 32u;
+    if (base >= n) return;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const uint32_t obj = base + it * 4 + g;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (obj < n) {
+            r = __ldcs(&objects[(size_t)obj * 8 + k]);
+            if (k < 4) transforms[(size_t)obj * 4 + k] = r;
+            else if (k == 4) spheres[obj] = r;
+        }
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, k == 7 && obj < n && __float_as_uint(r.y) != 0u);   // lanes 7, 15, 23, 31
+        bits |= (((b >> 7) & 1u) | (((b >> 15) & 1u) << 1) | (((b >> 23) & 1u) << 2) | (((b >> 31) & 1u) << 3)) << (it * 4);
+    }
+    if (lane == 0) enabled_bits[wtile] = bits;
+}
+// the same for the records r3_update_objects has just scattered (ScatterCopy, util/scatter_copy.rs:69-136)
+__global__ void __launch_bounds__(256) split_slots_kernel(const float4* __restrict__ objects, const uint32_t* __restrict__ slots, uint32_t n_updates, uint32_t n_slots,
+                                                          float4* __restrict__ transforms, float4* __restrict__ spheres, uint32_t* __restrict__ enabled_bits) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, k = threadIdx.x & 7;
+    if (i >= n_updates) return;
+    const uint32_t s = slots[i];
+    if (s >= n_slots) return;
+    const float4 r = objects[(size_t)s * 8 + k];
+    if (k < 4) transforms[(size_t)s * 4 + k] = r;
+    else if (k == 4) spheres[s] = r;
+    else if (k == 7) {
+        if (__float_as_uint(r.y) != 0u) atomicOr(&enabled_bits[s >> 5], 1u << (s & 31u));
+        else atomicAnd(&enabled_bits[s >> 5], ~(1u << (s & 31u)));
+    }
+}
+
 template <bool BAKE, bool CULL, bool LIVE>
-__global__ void __launch_bounds__(CB_THREADS, 4)
-cull_bake_kernel(const float4* __restrict__ objects, float4* __restrict__ matrices, const uint32_t* __restrict__ live_bits,
-                 uint32_t* __restrict__ words, uint32_t* __restrict__ cta_counts, const __grid_constant__ CullBakeParams p) {
-    __shared__ float s_mat[32];
-    __shared__ float s_frustum[20];
-    __shared__ float4 s_sphere[CB_WARPS][32];
-    __shared__ uint32_t s_enabled[CB_WARPS][32];
+__global__ void __launch_bounds__(CB_THREADS)
+cull_bake_kernel(const float4* __restrict__ transforms, const float4* __restrict__ spheres, const uint32_t* __restrict__ enabled_bits,
+                 const uint32_t* __restrict__ live_bits, float4* __restrict__ matrices, uint32_t* __restrict__ words, uint32_t* __restrict__ cta_counts,
+                 const __grid_constant__ CullBakeParams p) {
     __shared__ uint32_t s_count[CB_WARPS];
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k = lane & 7, g = lane >> 3;
-    if (threadIdx.x < 32) s_mat[threadIdx.x] = threadIdx.x < 16 ? p.view[threadIdx.x] : p.view_proj[threadIdx.x - 16];
-    if (threadIdx.x >= 32 && threadIdx.x < 52) s_frustum[threadIdx.x - 32] = (&p.frustum[0][0])[threadIdx.x - 32];
-    __syncthreads();
-
+    const int col = lane & 3, sub = lane >> 2;   // transform column / slot within an 8-slot group
     uint32_t count = 0;
-#pragma unroll 1
+#pragma unroll 2
     for (int wt = 0; wt < CB_WT; ++wt) {
         const uint32_t wtile = (blockIdx.x * CB_WARPS + warp) * CB_WT + wt;   // visibility word index
         const uint32_t base = wtile * 32u;
         if (base >= p.object_count) break;
-        float4 r[8];
+        float4 t[4];
+        float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t enabled = 0u;
+        if (BAKE) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const uint32_t obj = base + it * 4 + g;
-            const bool want = BAKE ? true : (k == 4 || k == 7);
-            r[it] = (obj < p.object_count && want) ? __ldcs(&objects[(size_t)obj * 8 + k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int it = 0; it < 4; ++it) {
+                const uint32_t obj = base + it * 8 + sub;
+                t[it] = obj < p.object_count ? __ldcs(&transforms[(size_t)base * 4 + it * 32 + lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
+        if (CULL && base + lane < p.object_count) sp = __ldcs(&spheres[base + lane]);
+        if (BAKE || (CULL && !LIVE)) enabled = __ldg(&enabled_bits[wtile]);
+        if (BAKE) {
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const uint32_t obj = base + it * 4 + g;
-            // float4 #4 is the bounding sphere, float4 #7 carries `enabled` in .y: park them for the per-lane cull below
-            if (CULL && k == 4) s_sphere[warp][it * 4 + g] = r[it];
-            if (CULL && !LIVE && k == 7) s_enabled[warp][it * 4 + g] = __float_as_uint(r[it].y);
-            if (BAKE) {
-                const uint32_t enabled = __float_as_uint(__shfl_sync(0xFFFFFFFFu, r[it].y, (lane & 24) | 7));
-                const int src = (k < 4) ? lane : lane - 4;
-                const float cx = __shfl_sync(0xFFFFFFFFu, r[it].x, src), cy = __shfl_sync(0xFFFFFFFFu, r[it].y, src);
-                const float cz = __shfl_sync(0xFFFFFFFFu, r[it].z, src), cw = __shfl_sync(0xFFFFFFFFu, r[it].w, src);
-                const float4 o = mat_vec_rn(&s_mat[(k >> 2) * 16], cx, cy, cz, cw);
-                if (obj < p.object_count && enabled != 0u) __stcs(&matrices[(size_t)obj * 8 + k], o);
+            for (int it = 0; it < 4; ++it) {
+                const uint32_t slot = it * 8 + sub, obj = base + slot;
+                if (obj < p.object_count && ((enabled >> slot) & 1u)) {   // uniform_prep.wgsl:18-20 skips disabled slots
+                    float4* dst = &matrices[(size_t)obj * 8 + col];
+                    __stcs(dst, mat_vec_rn(p.view, t[it].x, t[it].y, t[it].z, t[it].w));
+                    __stcs(dst + 4, mat_vec_rn(p.view_proj, t[it].x, t[it].y, t[it].z, t[it].w));
+                }
             }
         }
         if (CULL) {
-            __syncwarp();
             // one object per lane: Plane::distance = abc.dot(center) + d with glam's scalar dot order (util/frustum.rs:79-81,148-161)
-            const uint32_t obj = base + lane;
-            const float4 sp = s_sphere[warp][lane];
-            bool live;
-            if (LIVE) live = (__ldg(&live_bits[wtile]) >> lane) & 1u;
-            else live = s_enabled[warp][lane] != 0u;
+            const uint32_t live = LIVE ? __ldg(&live_bits[wtile]) : enabled;
             const float neg_radius = -sp.w;
             bool inside = true;
 #pragma unroll
             for (int pl = 0; pl < 5; ++pl) {
-                const float d = add_rn(add_rn(add_rn(mul_rn(s_frustum[pl * 4 + 0], sp.x), mul_rn(s_frustum[pl * 4 + 1], sp.y)),
-                                              mul_rn(s_frustum[pl * 4 + 2], sp.z)), s_frustum[pl * 4 + 3]);
+                const float d = add_rn(add_rn(add_rn(mul_rn(p.frustum[pl][0], sp.x), mul_rn(p.frustum[pl][1], sp.y)), mul_rn(p.frustum[pl][2], sp.z)), p.frustum[pl][3]);
                 inside = inside && (d >= neg_radius);
             }
-            const uint32_t word = __ballot_sync(0xFFFFFFFFu, obj < p.object_count && live && inside);
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, base + lane < p.object_count && ((live >> lane) & 1u) && inside);
             if (lane == 0) words[wtile] = word;
             count += __popc(word);
-            __syncwarp();
         }
     }
     if (CULL) {
@@ -195,10 +223,11 @@ int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode) {
     R3_TRY(r3_reserve_t(c, &cam->d_tile_state, &cam->tile_state_cap, ((uint64_t)n_words + n_ctas + 3) / 2 + 1));
     uint32_t* words = reinterpret_cast<uint32_t*>(cam->d_tile_state);
     uint32_t* cta_counts = words + n_words;
-    const float4* obj = reinterpret_cast<const float4*>(c->d_objects);
+    if (!c->hot_valid) return r3_fail(c, R3_E_STATE, "object_uniform_upload before set_objects");
     float4* mats = reinterpret_cast<float4*>(cam->d_matrices);
     const bool live = c->have_live && cull;
-#define R3_CB_LAUNCH(B, C, L) cull_bake_kernel<B, C, L><<<n_ctas, CB_THREADS, 0, c->stream>>>(obj, mats, c->d_live_bits, words, cta_counts, p)
+#define R3_CB_LAUNCH(B, C, L) \
+    cull_bake_kernel<B, C, L><<<n_ctas, CB_THREADS, 0, c->stream>>>(c->d_hot_transform, c->d_hot_sphere, c->d_enabled_bits, c->d_live_bits, mats, words, cta_counts, p)
     if (bake && cull) { if (live) R3_CB_LAUNCH(true, true, true); else R3_CB_LAUNCH(true, true, false); }
     else if (bake) R3_CB_LAUNCH(true, false, false);
     else { if (live) R3_CB_LAUNCH(false, true, true); else R3_CB_LAUNCH(false, true, false); }
@@ -209,5 +238,37 @@ int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode) {
         compact_visible_kernel<<<n_tiles, CP_THREADS, 0, c->stream>>>(words, cta_counts, n_words, n_ctas, cam->d_visible, cam->d_visible_count);
         R3_CHECK_LAUNCH(c, "compact_visible_kernel");
     }
+    return R3_OK;
+}
+
+// (re)build the dense hot arrays from the AoS records (all slots)
+int r3_split_objects(r3_ctx* c) {
+    const uint32_t n = c->n_slots;
+    const uint64_t want = n ? n : 1;
+    if (want > c->hot_cap) {
+        cudaFree(c->d_hot_transform); cudaFree(c->d_hot_sphere); cudaFree(c->d_enabled_bits);
+        c->d_hot_transform = nullptr; c->d_hot_sphere = nullptr; c->d_enabled_bits = nullptr; c->hot_cap = 0;
+        uint64_t cap = 1024;
+        while (cap < want) cap *= 2;
+        if (cap > want + want / 8 && want > (1u << 20)) cap = want + want / 8;   // large worlds: 12.5% head room instead of a power of two
+        R3_CUDA(c, cudaMalloc((void**)&c->d_hot_transform, cap * 64));
+        R3_CUDA(c, cudaMalloc((void**)&c->d_hot_sphere, cap * 16));
+        R3_CUDA(c, cudaMalloc((void**)&c->d_enabled_bits, ((cap + 31) / 32 + 1) * 4));
+        c->hot_cap = cap;
+    }
+    if (n) {
+        const uint32_t warps = (n + 31) / 32;
+        split_objects_kernel<<<(warps + 7) / 8, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_objects), n, c->d_hot_transform, c->d_hot_sphere, c->d_enabled_bits);
+        R3_CHECK_LAUNCH(c, "split_objects_kernel");
+    }
+    c->hot_valid = true;
+    return R3_OK;
+}
+// refresh the hot copies of the `n` slots listed in d_slots (device pointer) after a scatter
+int r3_split_slots(r3_ctx* c, const uint32_t* d_slots, uint32_t n) {
+    if (!c->hot_valid || n == 0) return R3_OK;
+    split_slots_kernel<<<(n * 8 + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_objects), d_slots, n, c->n_slots, c->d_hot_transform, c->d_hot_sphere,
+                                                                    c->d_enabled_bits);
+    R3_CHECK_LAUNCH(c, "split_slots_kernel");
     return R3_OK;
 }
