@@ -44,7 +44,8 @@ __device__ __forceinline__ unsigned long long make_sort_key(const uint32_t* __re
 
 // cap <= SMALL_SORT_MAX: keys are unique (the low 24 bits are the position in the visible list), so an unstable
 // bitonic network yields the same order as the stable radix sort
-constexpr uint32_t SMALL_SORT_MAX = 2048;   // measured: the one-CTA network costs 170 us at 16384 keys, the multi-block radix ~50 us
+constexpr uint32_t SMALL_SORT_MAX = 8192;   // the network is sized by the VISIBLE count: ~30 us at 4096 keys, ~70 us at 8192 (170 us at 16384), against
+                                            // 15 launches (~60-75 us with their gaps) for the 5-pass multi-block radix sort
 __global__ void __launch_bounds__(1024) small_sort_kernel(const uint32_t* __restrict__ visible, const uint32_t* __restrict__ visible_count,
                                                           const uint8_t* __restrict__ key8, const float* __restrict__ loc, float vx, float vy, float vz,
                                                           unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ header) {
@@ -386,8 +387,7 @@ int r3_device_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], ui
             uint32_t pad = 1;
             while (pad < cap) pad <<= 1;
             const size_t smem = (size_t)pad * 8;
-            static bool attr_set = false;
-            if (!attr_set) { cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SORT_MAX * 8); attr_set = true; }
+            if (smem > 48 * 1024) cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SORT_MAX * 8);   // per device
             small_sort_kernel<<<1, 1024, smem, c->stream>>>(cam->d_visible, cam->d_visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2],
                                                             cam->d_sort_keys[0], j.d_header);
             R3_CHECK_LAUNCH(c, "small_sort_kernel");

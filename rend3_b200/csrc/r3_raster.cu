@@ -33,6 +33,7 @@ constexpr uint32_t BAND_CAP = 1u << 24;  // queued (sub-triangle, band) items (1
 constexpr int MODE_COLOUR = 0;           // opaque + cutout forward routines into the visibility buffer
 constexpr int MODE_DEPTH = 1;            // shadow passes into the atlas
 constexpr int MODE_BLEND = 2;            // blend routine: collect per-sample fragment lists
+constexpr int MODE_MSAA = 4;             // or-ed onto MODE_COLOUR / MODE_BLEND: SampleCount::Four (R7); keeps the 4-sample code out of the common kernels
 
 struct SubTri { int32_t x[3], y[3]; float z[3]; uint32_t rec; };   // oriented (area > 0), snapped 24.8
 static_assert(sizeof(SubTri) == 40, "SubTri");
@@ -53,7 +54,7 @@ struct RasterParams {
     uint32_t* depth_bits;                          // depth-only passes (shadow atlas)
     r3_tri_record* records;
     // queues
-    SubTri* large; uint2* bands; uint32_t* counters;   // [0] n_large, [1] n_bands, [2] band ticket, [3] blend fragment nodes
+    SubTri* large; uint2* bands; uint32_t* counters;   // [0] n_large, [1] n_bands, [2] band ticket, [3] blend fragment nodes, [4] setup ticket
     uint32_t* frag_heads; uint4* frag_nodes; uint32_t frag_cap;   // blend routine
     unsigned long long key_lo, key_hi;                 // material keys of the routine(s) drawing (forward.rs:286-313)
     unsigned long long* stats;
@@ -100,13 +101,21 @@ __device__ __noinline__ int clip_polygon(float4* poly, int n) {
     return n >= 3 ? n : 0;
 }
 
-struct EdgeSetup {
-    long long e0, e1, e2;          // biased edge values at the first pixel centre: >= 0 means inside
-    long long sx0, sx1, sx2;       // step for +1 pixel in x
-    long long sy0, sy1, sy2;       // step for +1 pixel in y
-    int b0, b1, b2;                // top-left biases folded into e* (0 for top/left edges, 1 otherwise)
+// Edge functions are evaluated in 64-bit integers in general (24.8 coordinates, guard band 64 x the viewport).  They are
+// translation invariant, so a triangle whose vertices and pixel box lie within +-11585 sub-pixel units (45 pixels) of its
+// first pixel centre can use 32-bit arithmetic relative to that centre: |E| <= 2 * (2 * 11585)^2 < 2^31.  Same integers,
+// same float conversions, half the integer instructions and no 64-bit I2F — that covers nearly every small and medium triangle.
+constexpr int FITS32_REACH = 11585;
+template <typename T>
+struct EdgeSetupT {
+    T e0, e1, e2;          // biased edge values at the first pixel centre: >= 0 means inside
+    T sx0, sx1, sx2;       // step for +1 pixel in x
+    T sy0, sy1, sy2;       // step for +1 pixel in y
+    int b0, b1, b2;        // top-left biases folded into e* (0 for top/left edges, 1 otherwise)
     float inv_area;
 };
+__device__ __forceinline__ float to_float_rn(long long v) { return __ll2float_rn(v); }
+__device__ __forceinline__ float to_float_rn(int v) { return __int2float_rn(v); }
 __device__ __forceinline__ long long edge_fn(int ax, int ay, int bx, int by, long long px, long long py) {
     return (long long)(bx - ax) * (py - ay) - (long long)(by - ay) * (px - ax);
 }
@@ -114,27 +123,39 @@ __device__ __forceinline__ int not_top_left(int ax, int ay, int bx, int by) {
     const int dx = bx - ax, dy = by - ay;
     return ((dy < 0) || (dy == 0 && dx > 0)) ? 0 : 1;
 }
+__device__ __forceinline__ bool fits32(const SubTri& s, int px0, int py0, int px1, int py1) {
+    const int ox = px0 * 256 + 128, oy = py0 * 256 + 128;
+    int reach = max((px1 - px0) * 256 + 128, (py1 - py0) * 256 + 128);   // +128: multisample offsets stay inside the pixel
+#pragma unroll
+    for (int k = 0; k < 3; ++k) reach = max(reach, max(abs(s.x[k] - ox), abs(s.y[k] - oy)));
+    return reach <= FITS32_REACH && abs(px0) < (1 << 20) && abs(py0) < (1 << 20);
+}
 // edge functions E_ab, E_bc, E_ca at pixel (px, py): e0 = E_bc (weight of a), e1 = E_ca (weight of b), e2 = E_ab (weight of c)
-__device__ __forceinline__ EdgeSetup make_edges(const SubTri& s, int px, int py) {
-    EdgeSetup e;
-    const long long cx = (long long)px * 256 + 128, cy = (long long)py * 256 + 128;
+template <typename T>
+__device__ __forceinline__ EdgeSetupT<T> make_edges(const SubTri& s, int px, int py) {
+    EdgeSetupT<T> e;
     e.b0 = not_top_left(s.x[1], s.y[1], s.x[2], s.y[2]);
     e.b1 = not_top_left(s.x[2], s.y[2], s.x[0], s.y[0]);
     e.b2 = not_top_left(s.x[0], s.y[0], s.x[1], s.y[1]);
-    e.e0 = edge_fn(s.x[1], s.y[1], s.x[2], s.y[2], cx, cy) - e.b0;
-    e.e1 = edge_fn(s.x[2], s.y[2], s.x[0], s.y[0], cx, cy) - e.b1;
-    e.e2 = edge_fn(s.x[0], s.y[0], s.x[1], s.y[1], cx, cy) - e.b2;
-    e.sx0 = -(long long)(s.y[2] - s.y[1]) * 256; e.sy0 = (long long)(s.x[2] - s.x[1]) * 256;
-    e.sx1 = -(long long)(s.y[0] - s.y[2]) * 256; e.sy1 = (long long)(s.x[0] - s.x[2]) * 256;
-    e.sx2 = -(long long)(s.y[1] - s.y[0]) * 256; e.sy2 = (long long)(s.x[1] - s.x[0]) * 256;
-    const long long area = edge_fn(s.x[0], s.y[0], s.x[1], s.y[1], s.x[2], s.y[2]);
-    e.inv_area = div_rn(1.0f, __ll2float_rn(area));
+    // vertices relative to the first pixel centre (exact: the edge functions only see differences)
+    const int ox = px * 256 + 128, oy = py * 256 + 128;
+    const T x0 = (T)s.x[0] - ox, y0 = (T)s.y[0] - oy, x1 = (T)s.x[1] - ox, y1 = (T)s.y[1] - oy, x2 = (T)s.x[2] - ox, y2 = (T)s.y[2] - oy;
+    // E(a, b, p) = (bx - ax) * (py - ay) - (by - ay) * (px - ax) at p = 0
+    e.e0 = (x2 - x1) * (-y1) - (y2 - y1) * (-x1) - e.b0;
+    e.e1 = (x0 - x2) * (-y2) - (y0 - y2) * (-x2) - e.b1;
+    e.e2 = (x1 - x0) * (-y0) - (y1 - y0) * (-x0) - e.b2;
+    e.sx0 = -(y2 - y1) * 256; e.sy0 = (x2 - x1) * 256;
+    e.sx1 = -(y0 - y2) * 256; e.sy1 = (x0 - x2) * 256;
+    e.sx2 = -(y1 - y0) * 256; e.sy2 = (x1 - x0) * 256;
+    const T area = (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0);
+    e.inv_area = div_rn(1.0f, to_float_rn(area));
     return e;
 }
 // R5 depth of a covered sample from the (biased) edge values
-__device__ __forceinline__ float sample_depth(const SubTri& s, const EdgeSetup& e, long long e0, long long e1, long long e2) {
-    const float la = mul_rn(__ll2float_rn(e0 + e.b0), e.inv_area), lb = mul_rn(__ll2float_rn(e1 + e.b1), e.inv_area),
-                lc = mul_rn(__ll2float_rn(e2 + e.b2), e.inv_area);
+template <typename T>
+__device__ __forceinline__ float sample_depth(const SubTri& s, const EdgeSetupT<T>& e, T e0, T e1, T e2) {
+    const float la = mul_rn(to_float_rn((T)(e0 + e.b0)), e.inv_area), lb = mul_rn(to_float_rn((T)(e1 + e.b1)), e.inv_area),
+                lc = mul_rn(to_float_rn((T)(e2 + e.b2)), e.inv_area);
     const float z = add_rn(add_rn(mul_rn(la, s.z[0]), mul_rn(lb, s.z[1])), mul_rn(lc, s.z[2]));
     return fminf(fmaxf(z, 0.0f), 1.0f);
 }
@@ -143,9 +164,9 @@ __device__ __forceinline__ uint32_t write_sample(const RasterParams& p, int px, 
     // the result of the atomic is never read, so it compiles to a fire-and-forget RED.MAX: a thread can have
     // hundreds of samples in flight instead of one L2 round trip per sample
     const size_t pi = (size_t)py * p.pitch + px;
-    if (MODE == MODE_DEPTH) {
+    if ((MODE & 3) == MODE_DEPTH) {
         atomicMax(&p.depth_bits[pi], __float_as_uint(z));
-    } else if (MODE == MODE_COLOUR) {
+    } else if ((MODE & 3) == MODE_COLOUR) {
         const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | ((unsigned long long)p.pass_bit << 31) | rec;
         atomicMax(&p.vis[pi * p.samples + k], key);
     } else {
@@ -169,20 +190,19 @@ __device__ __constant__ int c_sample_dx[4] = {-32, 96, -96, 32};
 __device__ __constant__ int c_sample_dy[4] = {-96, -32, 32, 96};
 
 // coverage + depth of one pixel given the biased edge values at its centre
-template <int MODE>
-__device__ __forceinline__ void emit_pixel(const RasterParams& p, const SubTri& s, const EdgeSetup& e, int px, int py, long long c0, long long c1, long long c2,
-                                           uint32_t& frags) {
-    if (MODE == MODE_DEPTH || p.samples == 1u) {
-        if ((c0 | c1 | c2) >= 0) frags += write_sample<MODE>(p, px, py, 0u, sample_depth(s, e, c0, c1, c2), s.rec);
+template <int MODE, typename T>
+__device__ __forceinline__ void emit_pixel(const RasterParams& p, const SubTri& s, const EdgeSetupT<T>& e, int px, int py, T c0, T c1, T c2, uint32_t& frags) {
+    if (!(MODE & MODE_MSAA)) {
+        if ((c0 | c1 | c2) >= 0) frags += write_sample<MODE>(p, px, py, 0u, sample_depth<T>(s, e, c0, c1, c2), s.rec);
         return;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         // E(centre + o) = E(centre) + (step_x * o.x + step_y * o.y) / 256 (the steps are exact multiples of 256)
-        const long long a0 = c0 + (e.sx0 >> 8) * c_sample_dx[k] + (e.sy0 >> 8) * c_sample_dy[k];
-        const long long a1 = c1 + (e.sx1 >> 8) * c_sample_dx[k] + (e.sy1 >> 8) * c_sample_dy[k];
-        const long long a2 = c2 + (e.sx2 >> 8) * c_sample_dx[k] + (e.sy2 >> 8) * c_sample_dy[k];
-        if ((a0 | a1 | a2) >= 0) frags += write_sample<MODE>(p, px, py, (uint32_t)k, sample_depth(s, e, a0, a1, a2), s.rec);
+        const T a0 = c0 + (e.sx0 >> 8) * c_sample_dx[k] + (e.sy0 >> 8) * c_sample_dy[k];
+        const T a1 = c1 + (e.sx1 >> 8) * c_sample_dx[k] + (e.sy1 >> 8) * c_sample_dy[k];
+        const T a2 = c2 + (e.sx2 >> 8) * c_sample_dx[k] + (e.sy2 >> 8) * c_sample_dy[k];
+        if ((a0 | a1 | a2) >= 0) frags += write_sample<MODE>(p, px, py, (uint32_t)k, sample_depth<T>(s, e, a0, a1, a2), s.rec);
     }
 }
 
@@ -199,18 +219,23 @@ __device__ __forceinline__ void pixel_bounds(const RasterParams& p, const SubTri
 }
 
 // one thread walks the pixel box of its own sub-triangle with incremental edge functions
-template <int MODE>
-__device__ __forceinline__ void raster_inline(const RasterParams& p, const SubTri& s, int px0, int py0, int px1, int py1, uint32_t& frags) {
-    const EdgeSetup e = make_edges(s, px0, py0);
-    long long r0 = e.e0, r1 = e.e1, r2 = e.e2;
+template <int MODE, typename T>
+__device__ __forceinline__ void raster_inline_t(const RasterParams& p, const SubTri& s, int px0, int py0, int px1, int py1, uint32_t& frags) {
+    const EdgeSetupT<T> e = make_edges<T>(s, px0, py0);
+    T r0 = e.e0, r1 = e.e1, r2 = e.e2;
     for (int py = py0; py <= py1; ++py) {
-        long long c0 = r0, c1 = r1, c2 = r2;
+        T c0 = r0, c1 = r1, c2 = r2;
         for (int px = px0; px <= px1; ++px) {
-            emit_pixel<MODE>(p, s, e, px, py, c0, c1, c2, frags);
+            emit_pixel<MODE, T>(p, s, e, px, py, c0, c1, c2, frags);
             c0 += e.sx0; c1 += e.sx1; c2 += e.sx2;
         }
         r0 += e.sy0; r1 += e.sy1; r2 += e.sy2;
     }
+}
+template <int MODE>
+__device__ __forceinline__ void raster_inline(const RasterParams& p, const SubTri& s, int px0, int py0, int px1, int py1, uint32_t& frags) {
+    if (fits32(s, px0, py0, px1, py1)) raster_inline_t<MODE, int>(p, s, px0, py0, px1, py1, frags);
+    else raster_inline_t<MODE, long long>(p, s, px0, py0, px1, py1, frags);
 }
 
 // R2-R4 for one sub-triangle: snap, orient, then pick the raster path by the size of its pixel bounding box:
@@ -281,21 +306,26 @@ __device__ bool process_subtriangle(const RasterParams& p, const float4 a, const
 }
 
 // medium triangles: all 32 lanes rasterise one sub-triangle; the lane grid is 32x1, 16x2 or 8x4 pixels depending on the box width
+template <int MODE, typename T>
+__device__ __forceinline__ void raster_cooperative_t(const RasterParams& p, const SubTri& s, int lane, int px0, int py0, int px1, int py1, uint32_t& frags) {
+    const int w = px1 - px0 + 1;
+    const int lw = w <= 8 ? 8 : (w <= 16 ? 16 : 32), lh = 32 / lw, lx = lane % lw, ly = lane / lw;
+    const EdgeSetupT<T> e = make_edges<T>(s, px0, py0);
+    for (int py = py0 + ly; py <= py1; py += lh) {
+        const T dy = py - py0;
+        T c0 = e.e0 + dy * e.sy0 + (T)lx * e.sx0, c1 = e.e1 + dy * e.sy1 + (T)lx * e.sx1, c2 = e.e2 + dy * e.sy2 + (T)lx * e.sx2;
+        for (int px = px0 + lx; px <= px1; px += lw) {
+            emit_pixel<MODE, T>(p, s, e, px, py, c0, c1, c2, frags);
+            c0 += lw * e.sx0; c1 += lw * e.sx1; c2 += lw * e.sx2;
+        }
+    }
+}
 template <int MODE>
 __device__ __forceinline__ void raster_cooperative(const RasterParams& p, const SubTri& s, int lane, uint32_t& frags) {
     int px0, py0, px1, py1;
     pixel_bounds(p, s, px0, py0, px1, py1);
-    const int w = px1 - px0 + 1;
-    const int lw = w <= 8 ? 8 : (w <= 16 ? 16 : 32), lh = 32 / lw, lx = lane % lw, ly = lane / lw;
-    const EdgeSetup e = make_edges(s, px0, py0);
-    for (int py = py0 + ly; py <= py1; py += lh) {
-        const long long dy = py - py0;
-        long long c0 = e.e0 + dy * e.sy0 + (long long)lx * e.sx0, c1 = e.e1 + dy * e.sy1 + (long long)lx * e.sx1, c2 = e.e2 + dy * e.sy2 + (long long)lx * e.sx2;
-        for (int px = px0 + lx; px <= px1; px += lw) {
-            emit_pixel<MODE>(p, s, e, px, py, c0, c1, c2, frags);
-            c0 += lw * e.sx0; c1 += lw * e.sx1; c2 += lw * e.sx2;
-        }
-    }
+    if (fits32(s, px0, py0, px1, py1)) raster_cooperative_t<MODE, int>(p, s, lane, px0, py0, px1, py1, frags);   // warp-uniform: same triangle in every lane
+    else raster_cooperative_t<MODE, long long>(p, s, lane, px0, py0, px1, py1, frags);
 }
 
 // vertex stage up to clip space, clipping and setup of listed triangle i; medium sub-triangles come back through `defer`
@@ -356,7 +386,7 @@ __device__ void setup_listed_triangle(const RasterParams& p, unsigned long long 
     }
     if (any) {
         set_up++;
-        if (MODE != MODE_DEPTH) {
+        if ((MODE & 3) != MODE_DEPTH) {
             r3_tri_record tr;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { tr.xyw[k][0] = clip[k].x; tr.xyw[k][1] = clip[k].y; tr.xyw[k][2] = clip[k].w; tr.vid[k] = vid[k]; }
@@ -374,8 +404,15 @@ __global__ void __launch_bounds__(RS_THREADS) raster_setup_kernel(const __grid_c
     const unsigned long long total = p.tri_prefix[n_regions];
     const int lane = threadIdx.x & 31;
     uint32_t frags = 0, set_up = 0;
-    // warp-uniform trip count: every iteration a warp takes 32 consecutive listed triangles
-    for (unsigned long long base = (unsigned long long)blockIdx.x * RS_THREADS + (threadIdx.x & ~31u); base < total; base += (unsigned long long)gridDim.x * RS_THREADS) {
+    // every iteration a warp draws a ticket for 32 consecutive listed triangles: the cost of a triangle varies by orders of
+    // magnitude (culled / a few pixels / a 32 x 32 box walked by the whole warp), so a static stride leaves most warps idle
+    // behind the slowest one (measured on the config-5 shadow passes: 18% active warps, 239 us -> see profiles/README.md)
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&p.counters[4], 1u);
+        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+        const unsigned long long base = (unsigned long long)tile * 32ull;
+        if (base >= total) break;
         const unsigned long long i = base + lane;
         SubTri med;
         bool has_med = false;
@@ -429,7 +466,7 @@ __global__ void __launch_bounds__(RS_THREADS) raster_band_kernel(const __grid_co
         pixel_bounds(p, s, px0, py0, px1, py1);
         const int by0 = max(py0, (int)it.y * BAND_ROWS), by1 = min(py1, (int)it.y * BAND_ROWS + BAND_ROWS - 1);
         if (by0 > by1) continue;
-        const EdgeSetup e = make_edges(s, px0, by0);
+        const EdgeSetupT<long long> e = make_edges<long long>(s, px0, by0);
         const int rows = by1 - by0 + 1;
         for (int bx = px0; bx <= px1; bx += 32) {
             // skip the 32 x rows block when it lies entirely outside one edge: evaluate the corner that maximises E
@@ -444,7 +481,7 @@ __global__ void __launch_bounds__(RS_THREADS) raster_band_kernel(const __grid_co
             const int px = bx + lane;
             long long c0 = e.e0 + (dx + lane) * e.sx0, c1 = e.e1 + (dx + lane) * e.sx1, c2 = e.e2 + (dx + lane) * e.sx2;
             for (int py = by0; py <= by1; ++py) {
-                if (px <= px1) emit_pixel<MODE>(p, s, e, px, py, c0, c1, c2, frags);
+                if (px <= px1) emit_pixel<MODE, long long>(p, s, e, px, py, c0, c1, c2, frags);
                 c0 += e.sy0; c1 += e.sy1; c2 += e.sy2;
             }
         }
@@ -553,13 +590,22 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, int mode,
         p.records = c->d_tris[pass];
     }
     const int grid = R3_SM_COUNT * 8;
-    if (mode == MODE_DEPTH) raster_setup_kernel<MODE_DEPTH><<<grid, RS_THREADS, 0, c->stream>>>(p);
-    else if (mode == MODE_COLOUR) raster_setup_kernel<MODE_COLOUR><<<grid, RS_THREADS, 0, c->stream>>>(p);
-    else raster_setup_kernel<MODE_BLEND><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    const int variant = mode | ((mode != MODE_DEPTH && c->samples == 4u) ? MODE_MSAA : 0);
+    switch (variant) {
+        case MODE_DEPTH: raster_setup_kernel<MODE_DEPTH><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
+        case MODE_COLOUR: raster_setup_kernel<MODE_COLOUR><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
+        case MODE_BLEND: raster_setup_kernel<MODE_BLEND><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
+        case MODE_COLOUR | MODE_MSAA: raster_setup_kernel<MODE_COLOUR | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
+        default: raster_setup_kernel<MODE_BLEND | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
+    }
     R3_CHECK_LAUNCH(c, "raster_setup_kernel");
-    if (mode == MODE_DEPTH) raster_band_kernel<MODE_DEPTH><<<grid, RS_THREADS, 0, c->stream>>>(p);
-    else if (mode == MODE_COLOUR) raster_band_kernel<MODE_COLOUR><<<grid, RS_THREADS, 0, c->stream>>>(p);
-    else raster_band_kernel<MODE_BLEND><<<grid, RS_THREADS, 0, c->stream>>>(p);
+    switch (variant) {
+        case MODE_DEPTH: raster_band_kernel<MODE_DEPTH><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
+        case MODE_COLOUR: raster_band_kernel<MODE_COLOUR><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
+        case MODE_BLEND: raster_band_kernel<MODE_BLEND><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
+        case MODE_COLOUR | MODE_MSAA: raster_band_kernel<MODE_COLOUR | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
+        default: raster_band_kernel<MODE_BLEND | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
+    }
     R3_CHECK_LAUNCH(c, "raster_band_kernel");
     return R3_OK;
 }

@@ -146,9 +146,12 @@ __device__ __forceinline__ VsOut vertex_stage(const ShadeParams& p, const uint32
     return o;
 }
 
-// vs_main outputs interpolated at the centre of pixel (px, py) + fs_main for triangle record `rec` of pass `pass`
-__device__ __forceinline__ float4 shade_fragment(const ShadeParams& p, const DirPrep* __restrict__ s_dir, const PointPrep* __restrict__ s_point,
-                                                 const r3_tri_record* tp, uint32_t px, uint32_t py) {
+// vs_main outputs interpolated at the centre of a pixel: what fs_main receives
+struct FragIn { float4 vp; float3 vnormal; float4 vcolor; uint32_t material_index; };
+struct LightMask { uint32_t w[MAX_SMEM_POINT / 32]; };   // point lights (the shared-memory resident ones) a fragment has to visit
+
+// vs_main for the three vertices of triangle record `tp` + interpolation at the centre of pixel (px, py)
+__device__ __forceinline__ FragIn fragment_inputs(const ShadeParams& p, const r3_tri_record* tp, uint32_t px, uint32_t py) {
     const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp)), q1 = __ldg(reinterpret_cast<const float4*>(tp) + 1),
                  q2 = __ldg(reinterpret_cast<const float4*>(tp) + 2);
     const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(tp) + 3);
@@ -187,6 +190,16 @@ __device__ __forceinline__ float4 shade_fragment(const ShadeParams& p, const Dir
     const float4 vcolor = make_float4(b0 * v0.color.x + b1 * v1.color.x + b2 * v2.color.x, b0 * v0.color.y + b1 * v1.color.y + b2 * v2.color.y,
                                       b0 * v0.color.z + b1 * v1.color.z + b2 * v2.color.z, b0 * v0.color.w + b1 * v1.color.w + b2 * v2.color.w);
 
+    FragIn f;
+    f.vp = vp; f.vnormal = vnormal; f.vcolor = vcolor; f.material_index = material_index;
+    return f;
+}
+
+// fs_main (opaque.wgsl:470-551).  `mask` lists the point lights that can reach the fragment (a conservative superset is fine:
+// every listed light still takes the exact per-fragment range test below).
+__device__ __forceinline__ float4 shade_inputs(const ShadeParams& p, const DirPrep* __restrict__ s_dir, const PointPrep* __restrict__ s_point, const FragIn& f,
+                                               const LightMask& mask) {
+    const float4 vp = f.vp; const float3 vnormal = f.vnormal; const float4 vcolor = f.vcolor; const uint32_t material_index = f.material_index;
     // get_pixel_data_inner for untextured materials (opaque.wgsl:203-424)
     const r3_material* m = &p.materials[material_index < p.n_materials ? material_index : 0u];
     const float4 malbedo = __ldg(reinterpret_cast<const float4*>(m->albedo));
@@ -240,22 +253,38 @@ __device__ __forceinline__ float4 shade_fragment(const ShadeParams& p, const Dir
             const float3 s = surface_shading(make_float3(L.l[0], L.l[1], L.l[2]), make_float3(L.color[0], L.color[1], L.color[2]), pxl, v, nov, shadow * ao);
             color.x += s.x; color.y += s.y; color.z += s.z;
         }
-        for (uint32_t i = 0; i < p.n_point; ++i) {                                 // opaque.wgsl:524-546
-            const PointPrep& L = i < MAX_SMEM_POINT ? s_point[i] : p.point[i];
-            const float3 delta = make_float3(L.pos[0] - vp.x, L.pos[1] - vp.y, L.pos[2] - vp.z);
-            const float d2 = dot3(delta, delta);
-            // att = (1 - s^2)^2 / (1 + s^2) with s = saturate(d / radius) is exactly 0 at and beyond the radius
-            if (d2 >= L.radius * L.radius && pxl.roughness > 0.0f) continue;
-            const float inv_d = rsqrtf(d2), d = d2 * inv_d;
-            const float sdist = saturate(d * rcp_approx(L.radius)), s2 = sdist * sdist, inv_s2 = 1.0f - s2;
-            const float att = inv_s2 * inv_s2 * rcp_approx(1.0f + s2);
-            const float3 s = surface_shading(make_float3(delta.x * inv_d, delta.y * inv_d, delta.z * inv_d),
-                                             make_float3(L.color[0] * att, L.color[1] * att, L.color[2] * att), pxl, v, nov, ao);
-            color.x += fmaxf(s.x, 0.0f); color.y += fmaxf(s.y, 0.0f); color.z += fmaxf(s.z, 0.0f);
+        const uint32_t n_smem_point = min(p.n_point, (uint32_t)MAX_SMEM_POINT);
+        for (uint32_t base = 0; base < p.n_point; base += 32u) {                   // opaque.wgsl:524-546, ascending light order
+            uint32_t m = base < n_smem_point ? mask.w[base >> 5] : 0xFFFFFFFFu;
+            if (p.n_point - base < 32u) m &= (1u << (p.n_point - base)) - 1u;
+            while (m) {
+                const uint32_t i = base + (uint32_t)__ffs(m) - 1u;
+                m &= m - 1u;
+                const PointPrep& L = i < MAX_SMEM_POINT ? s_point[i] : p.point[i];
+                const float3 delta = make_float3(L.pos[0] - vp.x, L.pos[1] - vp.y, L.pos[2] - vp.z);
+                const float d2 = dot3(delta, delta);
+                // att = (1 - s^2)^2 / (1 + s^2) with s = saturate(d / radius) is exactly 0 at and beyond the radius
+                if (d2 >= L.radius * L.radius && pxl.roughness > 0.0f) continue;
+                const float inv_d = rsqrtf(d2), d = d2 * inv_d;
+                const float sdist = saturate(d * rcp_approx(L.radius)), s2 = sdist * sdist, inv_s2 = 1.0f - s2;
+                const float att = inv_s2 * inv_s2 * rcp_approx(1.0f + s2);
+                const float3 s = surface_shading(make_float3(delta.x * inv_d, delta.y * inv_d, delta.z * inv_d),
+                                                 make_float3(L.color[0] * att, L.color[1] * att, L.color[2] * att), pxl, v, nov, ao);
+                color.x += fmaxf(s.x, 0.0f); color.y += fmaxf(s.y, 0.0f); color.z += fmaxf(s.z, 0.0f);
+            }
         }
         return make_float4(fmaxf(p.ambient[0] * albedo.x, color.x), fmaxf(p.ambient[1] * albedo.y, color.y), fmaxf(p.ambient[2] * albedo.z, color.z),
                           fmaxf(p.ambient[3] * albedo.w, albedo.w));
     }
+}
+
+// vs_main + fs_main for triangle record `tp` at pixel (px, py), every point light considered
+__device__ __forceinline__ float4 shade_fragment(const ShadeParams& p, const DirPrep* __restrict__ s_dir, const PointPrep* __restrict__ s_point,
+                                                 const r3_tri_record* tp, uint32_t px, uint32_t py) {
+    LightMask all;
+#pragma unroll
+    for (int k = 0; k < MAX_SMEM_POINT / 32; ++k) all.w[k] = 0xFFFFFFFFu;
+    return shade_inputs(p, s_dir, s_point, fragment_inputs(p, tp, px, py), all);
 }
 
 template <int SAMPLES>
@@ -272,18 +301,80 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
     }
     // CTA = 32 x 8 pixels: a warp is 32 consecutive pixels of one row (coalesced key reads / colour writes)
     const uint32_t px = blockIdx.x * 32u + (threadIdx.x & 31u), py = p.row_begin + blockIdx.y * 8u + (threadIdx.x >> 5);
-    if (px >= p.width || py >= p.row_end) return;
+    const bool in_target = px < p.width && py < p.row_end;
     const size_t pi = (size_t)py * p.width + px;
     float4 out;
     float depth;
     uint32_t n_shaded = 0;
     if (SAMPLES == 1) {
-        const unsigned long long key = p.vis[pi];
+        // tiled light culling: the CTA bounds the view-space positions of its fragments, then 32 lights per warp are tested
+        // against that box; fragments only visit the survivors (in ascending light order, so the sums are unchanged).  A light
+        // whose sphere misses the box by a 0.1% margin is beyond its radius for every fragment of the tile, where its
+        // attenuation is exactly 0 — unless a roughness-0 material needs the reference's 0 * inf = NaN (then nothing is culled).
+        __shared__ float s_box[8][6];
+        __shared__ uint32_t s_mask[MAX_SMEM_POINT / 32];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const unsigned long long key = in_target ? p.vis[pi] : 0ull;
         const uint32_t rec = (uint32_t)(key & 0x7FFFFFFFull), pass = (uint32_t)((key >> 31) & 1ull);
+        const bool covered = in_target && rec != 0u && rec <= (pass ? p.n_tris1 : p.n_tris0);
+        FragIn f;
+        f.vp = make_float4(0.f, 0.f, 0.f, 1.f); f.vnormal = make_float3(0.f, 0.f, 1.f); f.vcolor = make_float4(1.f, 1.f, 1.f, 1.f); f.material_index = 0u;
+        bool mirror = false;
+        if (covered) {
+            f = fragment_inputs(p, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py);
+            const r3_material* m = &p.materials[f.material_index < p.n_materials ? f.material_index : 0u];
+            // pixel.roughness as shade_inputs derives it (opaque.wgsl:392-399); anything not safely positive disables the culling
+            float perceptual = __ldg(&m->roughness);
+            const float cc = __ldg(&m->clear_coat);
+            if (cc != 0.0f) perceptual = perceptual * (1.0f - cc) + fmaxf(perceptual, __ldg(&m->clear_coat_roughness)) * cc;
+            mirror = !(perceptual * perceptual > 1.0e-30f);
+        }
+        const bool no_cull = __syncthreads_or(mirror ? 1 : 0) != 0;
+        if (p.n_point != 0u && !no_cull) {
+            const float big = 3.0e38f;
+            float lo[3] = {covered ? f.vp.x : big, covered ? f.vp.y : big, covered ? f.vp.z : big};
+            float hi[3] = {covered ? f.vp.x : -big, covered ? f.vp.y : -big, covered ? f.vp.z : -big};
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], sft));
+                    hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], sft));
+                }
+            if (lane == 0) { s_box[warp][0] = lo[0]; s_box[warp][1] = lo[1]; s_box[warp][2] = lo[2]; s_box[warp][3] = hi[0]; s_box[warp][4] = hi[1]; s_box[warp][5] = hi[2]; }
+            __syncthreads();
+            const uint32_t n_smem_point = min(p.n_point, (uint32_t)MAX_SMEM_POINT);
+            if (threadIdx.x < MAX_SMEM_POINT) {
+                bool reach = false;
+                if (threadIdx.x < n_smem_point) {
+                    float blo[3] = {big, big, big}, bhi[3] = {-big, -big, -big};
+#pragma unroll
+                    for (int w = 0; w < 8; ++w)
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) { blo[a] = fminf(blo[a], s_box[w][a]); bhi[a] = fmaxf(bhi[a], s_box[w][3 + a]); }
+                    const PointPrep& L = s_point[threadIdx.x];
+                    float d2 = 0.0f;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const float c = L.pos[a], e = fmaxf(fmaxf(blo[a] - c, c - bhi[a]), 0.0f);   // distance to the box along this axis
+                        d2 += e * e;
+                    }
+                    reach = blo[0] <= bhi[0] && d2 <= L.radius * L.radius * 1.001f;
+                }
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, reach);
+                if (lane == 0) s_mask[warp] = bal;
+            }
+            __syncthreads();
+        }
+        LightMask mask;
+#pragma unroll
+        for (int k = 0; k < MAX_SMEM_POINT / 32; ++k) mask.w[k] = (p.n_point != 0u && !no_cull) ? s_mask[k] : 0xFFFFFFFFu;
+        if (!in_target) return;
         out = make_float4(p.clear[0], p.clear[1], p.clear[2], p.clear[3]);
-        if (rec != 0u && rec <= (pass ? p.n_tris1 : p.n_tris0)) { out = shade_fragment(p, s_dir, s_point, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py); n_shaded = 1; }
+        if (covered) { out = shade_inputs(p, s_dir, s_point, f, mask); n_shaded = 1; }
         depth = __uint_as_float((uint32_t)(key >> 32));
     } else {
+        if (!in_target) return;
         // SampleCount::Four: a primitive is shaded once per pixel for all the samples it owns; the rgba16f samples are box-filtered
         // ((s0 + s1) + (s2 + s3)) * 0.25 like the resolve attachment (base.rs:245-255); depth resolves to the MIN over the samples
         unsigned long long keys[4];
