@@ -42,32 +42,83 @@ __device__ __forceinline__ unsigned long long make_sort_key(const uint32_t* __re
     return ((unsigned long long)(k >> 1) << 56) | ((unsigned long long)sortable_f32(d2) << 24) | (unsigned long long)j;
 }
 
-// cap <= SMALL_SORT_MAX: keys are unique (the low 24 bits are the position in the visible list), so an unstable
-// bitonic network yields the same order as the stable radix sort
-constexpr uint32_t SMALL_SORT_MAX = 8192;   // the network is sized by the VISIBLE count: ~30 us at 4096 keys, ~70 us at 8192 (170 us at 16384), against
-                                            // 15 launches (~60-75 us with their gaps) for the 5-pass multi-block radix sort
-__global__ void __launch_bounds__(1024) small_sort_kernel(const uint32_t* __restrict__ visible, const uint32_t* __restrict__ visible_count,
-                                                          const uint8_t* __restrict__ key8, const float* __restrict__ loc, float vx, float vy, float vz,
-                                                          unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ header) {
-    extern __shared__ unsigned long long s_keys[];
-    const uint32_t nv = *visible_count;
+// cap <= SMALL_SORT_MAX: key generation + the same stable LSD radix sort, but by ONE CTA entirely in shared memory — one launch
+// instead of 16, which is what a frame with a few thousand objects per camera is made of.  Warp w owns the w-th contiguous
+// chunk of the keys; per pass: per-warp digit counts (__match_any_sync, leader adds), a scan over (digit, warp), then the
+// warps re-walk their chunks in order and scatter (rank inside the round from the peer mask).  A pass whose digit is the same
+// for every key (typical for the material-key byte) is skipped.
+constexpr uint32_t SMALL_SORT_MAX = 8192;
+constexpr int SMALL_SORT_THREADS = 1024, SMALL_SORT_WARPS = SMALL_SORT_THREADS / 32;
+__host__ __device__ inline uint32_t small_sort_pad(uint32_t n) { return ((n + SMALL_SORT_THREADS - 1) / SMALL_SORT_THREADS) * SMALL_SORT_THREADS; }
+inline size_t small_sort_smem(uint32_t cap) { return (size_t)small_sort_pad(cap) * 16 + (size_t)SMALL_SORT_WARPS * 256 * 4 + 256 * 4; }
+__global__ void __launch_bounds__(SMALL_SORT_THREADS) small_sort_kernel(const uint32_t* __restrict__ visible, const uint32_t* __restrict__ visible_count,
+                                                                        const uint8_t* __restrict__ key8, const float* __restrict__ loc, float vx, float vy, float vz,
+                                                                        unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ header, uint32_t cap_pad) {
+    extern __shared__ unsigned long long s_keys[];                               // [2][cap_pad]
+    uint32_t* s_count = reinterpret_cast<uint32_t*>(s_keys + 2 * (size_t)cap_pad);   // [warps][256]
+    uint32_t* s_base = s_count + SMALL_SORT_WARPS * 256;                          // [256]
+    __shared__ uint32_t s_wsum[8];
+    __shared__ int s_skip;
+    const uint32_t nv = min(*visible_count, cap_pad);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { header[0] = nv; header[4] = 0u; }
-    uint32_t n_pad = 1;
-    while (n_pad < nv) n_pad <<= 1;
-    for (uint32_t j = threadIdx.x; j < n_pad; j += blockDim.x) s_keys[j] = j < nv ? make_sort_key(visible, key8, loc, vx, vy, vz, j) : ~0ull;
-    __syncthreads();
-    for (uint32_t k = 2; k <= n_pad; k <<= 1) {
-        for (uint32_t jj = k >> 1; jj > 0; jj >>= 1) {
-            for (uint32_t t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
-                const uint32_t i = ((t & ~(jj - 1u)) << 1) | (t & (jj - 1u)), l = i | jj;
-                const unsigned long long a = s_keys[i], b = s_keys[l];
-                const bool ascending = (i & k) == 0u;
-                if ((a > b) == ascending) { s_keys[i] = b; s_keys[l] = a; }
-            }
-            __syncthreads();
+    for (uint32_t j = threadIdx.x; j < nv; j += SMALL_SORT_THREADS) s_keys[j] = make_sort_key(visible, key8, loc, vx, vy, vz, j);
+    const uint32_t rounds = (nv + SMALL_SORT_THREADS - 1) / SMALL_SORT_THREADS, chunk = rounds * 32u;
+    int src = 0;
+    for (int pass = 0; pass < SORT_PASSES; ++pass) {
+        const int shift = KEY_SHIFT0 + 8 * pass;
+        const unsigned long long* in = s_keys + (size_t)src * cap_pad;
+        unsigned long long* out = s_keys + (size_t)(src ^ 1) * cap_pad;
+        for (uint32_t i = threadIdx.x; i < SMALL_SORT_WARPS * 256; i += SMALL_SORT_THREADS) s_count[i] = 0u;
+        if (threadIdx.x == 0) s_skip = 0;
+        __syncthreads();
+        for (uint32_t r = 0; r < rounds; ++r) {
+            const uint32_t idx = warp * chunk + r * 32u + lane;
+            const bool valid = idx < nv;
+            const uint32_t digit = valid ? (uint32_t)(in[idx] >> shift) & 255u : 256u + lane;
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, digit);
+            if (valid && lane == __ffs(peers) - 1) s_count[warp * 256 + digit] += __popc(peers);
+            __syncwarp();
         }
+        __syncthreads();
+        uint32_t total = 0, incl = 0;
+        if (threadIdx.x < 256) {
+            for (int w = 0; w < SMALL_SORT_WARPS; ++w) { const uint32_t t = s_count[w * 256 + threadIdx.x]; s_count[w * 256 + threadIdx.x] = total; total += t; }
+            if (total == nv) s_skip = 1;
+            incl = total;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += n; }
+            if (lane == 31) s_wsum[warp] = incl;
+        }
+        __syncthreads();
+        if (threadIdx.x < 256) {
+            uint32_t before = 0;
+            for (int w = 0; w < warp; ++w) before += s_wsum[w];
+            s_base[threadIdx.x] = before + incl - total;
+        }
+        __syncthreads();
+        const int skip = s_skip;
+        __syncthreads();        // s_skip is reset at the top of the next pass
+        if (skip) continue;     // block-uniform
+        for (uint32_t r = 0; r < rounds; ++r) {
+            const uint32_t idx = warp * chunk + r * 32u + lane;
+            const bool valid = idx < nv;
+            const unsigned long long key = valid ? in[idx] : 0ull;
+            const uint32_t digit = valid ? (uint32_t)(key >> shift) & 255u : 256u + lane;
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, digit);
+            if (valid) {
+                const uint32_t pos = s_base[digit] + s_count[warp * 256 + digit] + __popc(peers & ((1u << lane) - 1u));
+                out[pos] = key;
+            }
+            __syncwarp();
+            if (valid && lane == __ffs(peers) - 1) s_count[warp * 256 + digit] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        src ^= 1;
     }
-    for (uint32_t j = threadIdx.x; j < nv; j += blockDim.x) keys_out[j] = s_keys[j];
+    const unsigned long long* fin = s_keys + (size_t)src * cap_pad;
+    for (uint32_t j = threadIdx.x; j < nv; j += SMALL_SORT_THREADS) keys_out[j] = fin[j];
 }
 
 __global__ void keygen_kernel(const uint32_t* __restrict__ visible, const uint32_t* __restrict__ visible_count, const uint8_t* __restrict__ key8,
@@ -383,13 +434,11 @@ int r3_device_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], ui
     if (cap) {
         int src = 0;
         if (cap <= SMALL_SORT_MAX) {
-            // small worlds: key generation + a bitonic sort of the (unique) keys in shared memory, one CTA, one launch
-            uint32_t pad = 1;
-            while (pad < cap) pad <<= 1;
-            const size_t smem = (size_t)pad * 8;
-            if (smem > 48 * 1024) cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SORT_MAX * 8);   // per device
-            small_sort_kernel<<<1, 1024, smem, c->stream>>>(cam->d_visible, cam->d_visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2],
-                                                            cam->d_sort_keys[0], j.d_header);
+            // small worlds: key generation + radix sort by one CTA in shared memory, one launch
+            const size_t smem = small_sort_smem(cap);
+            cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_sort_smem(SMALL_SORT_MAX));   // per device
+            small_sort_kernel<<<1, SMALL_SORT_THREADS, smem, c->stream>>>(cam->d_visible, cam->d_visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2],
+                                                                          cam->d_sort_keys[0], j.d_header, small_sort_pad(cap));
             R3_CHECK_LAUNCH(c, "small_sort_kernel");
         } else {
             keygen_kernel<<<(cap + 255) / 256, 256, 0, c->stream>>>(cam->d_visible, cam->d_visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2],
