@@ -82,14 +82,14 @@ class ClockSampler:
                 mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
             except Exception:
                 mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-            self.rows.append((sm, self.max_mhz, mask))
+            self.rows.append((sm, self.max_mhz, mask, time.perf_counter()))
             return
         out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                              capture_output=True, text=True, timeout=5).stdout.strip()
         if out:
             c = [x.strip() for x in out.split(",")]
             mask = sum(bit for k, bit in zip(range(2, 6), (0x8, 0x40, 0x20, 0x4)) if len(c) > k and c[k].lower().startswith("active"))
-            self.rows.append((float(c[0]), float(c[1]), mask))
+            self.rows.append((float(c[0]), float(c[1]), mask, time.perf_counter()))
 
     def run(self):
         while not self.stop:
@@ -97,7 +97,13 @@ class ClockSampler:
                 self.sample()
             except Exception:
                 pass
-            time.sleep(0.0005 if self.nvml is not None else 0.1)
+            time.sleep(0.0002 if self.nvml is not None else 0.1)
+
+    def sample_now(self):
+        try:
+            self.sample()
+        except Exception:
+            pass
 
     def __enter__(self):
         self.t.start()
@@ -107,15 +113,29 @@ class ClockSampler:
         self.stop = True
         self.t.join(timeout=6)
 
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
     def summary(self):
+        """Samples stamped inside [mark_begin, mark_end] (the timed region).  The region is only milliseconds long, so when
+        fewer than 3 samples fell inside it the nearest samples of the surrounding warm-up / drain (same workload) are added."""
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0, "source": self.source}
-        sm = sorted(r[0] for r in self.rows)
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        inside = [r for r in self.rows if t0 <= r[3] <= t1]
+        used = inside
+        if len(inside) < 3:
+            mid = 0.5 * (t0 + min(t1, self.rows[-1][3]))
+            used = sorted(self.rows, key=lambda r: abs(r[3] - mid))[:max(3, len(inside))]
+        sm = sorted(r[0] for r in used)
         mask = 0
-        for r in self.rows:
+        for r in used:
             mask |= r[2]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": [k for k, bit in self.BITS.items() if mask & bit],
-                "samples": len(self.rows), "source": self.source}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": used[0][1], "reasons": [k for k, bit in self.BITS.items() if mask & bit],
+                "samples": len(used), "samples_in_timed_region": len(inside), "source": self.source}
 
 
 class DeviceView:
@@ -239,21 +259,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None))
+    clocks.__enter__()               # polls through warm-up, timed region and drain; only the stamped window is reported
     for _ in range(args.warmup):
         step_resident()
     barrier()
     launches0 = backend.launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    with ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) as clocks:
-        t_wall0 = time.perf_counter()
-        for i in range(args.steps):
-            starts[i].record(stream)
-            backend.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
-            ends[i].record(stream)
-            gather_visible()
-        barrier()
-        wall = time.perf_counter() - t_wall0
+    clocks.mark_begin()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        starts[i].record(stream)
+        backend.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+        ends[i].record(stream)
+        gather_visible()
+    clocks.sample_now()              # GPU busy with the queued steps
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks.mark_end()
+    clocks.__exit__()
     kernel_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = starts[0].elapsed_time(ends[-1]) if world == 1 else wall * 1e3
     launches = backend.launch_count() - launches0

@@ -146,34 +146,38 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_hist_kernel(const unsigned
     hist[threadIdx.x * nb + blockIdx.x] = s_hist[threadIdx.x];   // digit-major: a flat scan yields the scatter bases
 }
 
-__global__ void __launch_bounds__(1024) scan_u32_kernel(uint32_t* __restrict__ data, uint32_t n) {   // in-place exclusive scan, one block
+// in-place exclusive scan by one block: every thread owns a contiguous run (serial sum, one block scan of the 1024 run totals,
+// serial write-back) — three barriers in all instead of four per 1024 elements
+__global__ void __launch_bounds__(1024) scan_u32_kernel(uint32_t* __restrict__ data, uint32_t n) {
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n ? data[i] : 0u;
-        uint32_t incl = v;
+    const uint32_t per = (((n + 1023u) / 1024u) + 3u) & ~3u;          // multiple of 4: runs start 16-byte aligned
+    const uint32_t lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+    uint32_t sum = 0;
+    uint32_t i = lo;
+    for (; i + 4 <= hi; i += 4) { const uint4 v = *reinterpret_cast<const uint4*>(data + i); sum += v.x + v.y + v.z + v.w; }
+    for (; i < hi; ++i) sum += data[i];
+    uint32_t incl = sum;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t w = s_warp[lane];
-            uint32_t wi = w;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t wi = w;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += t; }
-            s_warp[lane] = wi - w;
-        }
-        __syncthreads();
-        const uint32_t excl = s_carry + s_warp[warp] + incl - v;
-        if (i < n) data[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = excl + v;
-        __syncthreads();
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += t; }
+        s_warp[lane] = wi - w;
     }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + incl - sum;
+    for (i = lo; i + 4 <= hi; i += 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(data + i);
+        uint4 o;
+        o.x = run; o.y = o.x + v.x; o.z = o.y + v.y; o.w = o.z + v.z; run = o.w + v.w;
+        *reinterpret_cast<uint4*>(data + i) = o;
+    }
+    for (; i < hi; ++i) { const uint32_t v = data[i]; data[i] = run; run += v; }
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) radix_scatter_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,

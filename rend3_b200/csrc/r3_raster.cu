@@ -332,6 +332,8 @@ __device__ __forceinline__ void raster_cooperative(const RasterParams& p, const 
 template <int MODE>
 __device__ void setup_listed_triangle(const RasterParams& p, unsigned long long i, uint32_t n_regions, uint32_t& frags, uint32_t& set_up, SubTri* defer, bool* deferred) {
     // region of listed triangle i: last r with tri_prefix[r] <= i
+    // (a warp-cooperative 32-ary bracket search was tried for the many-region case: no gain on config 3, and its extra live
+    //  state cost the shadow passes of config 5 30%)
     uint32_t lo = 0, hi = n_regions;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;

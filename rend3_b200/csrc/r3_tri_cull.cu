@@ -31,7 +31,7 @@ struct TriCullParams {
     const r3_object* objects;
     const r3_object_matrices* matrices;
     const r3_batch_data* batches;
-    const uint32_t* wg_info;             // per workgroup: (batch << 8) | batch-local object
+    const uint4* wg_info;                // per workgroup: WgRec (two uint4), everything the test needs about its object
     const uint32_t* region_first_inv;    // [n_regions + 1]
     const uint32_t* header;              // job header: [1] n_batches, [2] n_regions, [3] total_invocations (device-side counts)
     uint32_t* idx_pred; uint32_t* idx_resid;
@@ -105,15 +105,39 @@ __device__ bool execute_culling(const TriCullParams& p, const float* __restrict_
     return !(depth < occl);
 }
 
-__global__ void expand_wg_info_kernel(const r3_batch_data* __restrict__ batches, const uint32_t* __restrict__ header, uint32_t* __restrict__ wg_info) {
+// One record per 256-invocation workgroup, written once per frame by expand_wg_info_kernel: the test kernel would otherwise
+// walk workgroup -> batch -> object table -> Object record before it can fetch a single index (four dependent misses for
+// 1 M workgroups per frame on the 200k-object config).
+struct WgRec {
+    uint32_t object_id, first_index, pos_off, n_real;             // n_real: invocations of this workgroup that are triangles (rest = 256-padding)
+    uint32_t prev_invocation, flags, object_invocation, region;   // flags: bit0 atomic_capable | batch-local object << 8
+};
+static_assert(sizeof(WgRec) == 32, "WgRec");
+constexpr uint32_t WG_ATOMIC = 1u;
+
+__global__ void expand_wg_info_kernel(const r3_batch_data* __restrict__ batches, const uint32_t* __restrict__ header, const r3_object* __restrict__ objects,
+                                      uint4* __restrict__ wg_info) {
     const uint32_t b = blockIdx.x, o = threadIdx.x;
     if (b >= header[1]) return;
     const r3_batch_data* job = &batches[b];
     if (o >= job->total_objects) return;
-    const r3_object_culling_info info = job->object_culling_information[o];
+    const r3_object_culling_info info = job->object_culling_information[o];                 // find_object_info (cull.wgsl:181-207), hoisted
     const uint32_t n = info.invocation_end - info.invocation_start;
     const uint32_t first = (job->batch_base_invocation + info.invocation_start) >> 8, count = (n + 255u) >> 8;
-    for (uint32_t i = 0; i < count; ++i) wg_info[first + i] = (b << 8) | o;
+    const r3_object* obj = &objects[info.object_id];
+    const uint32_t first_index = obj->first_index, pos_off = obj->attr_offset[0] >> 2;
+    for (uint32_t i = 0; i < count; ++i) {
+        const uint32_t done = i << 8;
+        wg_info[2 * (size_t)(first + i)] = make_uint4(info.object_id, first_index, pos_off, min(n - done, 256u));
+        wg_info[2 * (size_t)(first + i) + 1] = make_uint4(info.previous_global_invocation, (info.atomic_capable == 1u ? WG_ATOMIC : 0u) | (o << 8), done, info.region_id);
+    }
+}
+__device__ __forceinline__ WgRec load_wg(const TriCullParams& p, uint32_t wg) {
+    const uint4 a = __ldg(&p.wg_info[2 * (size_t)wg]), b = __ldg(&p.wg_info[2 * (size_t)wg + 1]);
+    WgRec r;
+    r.object_id = a.x; r.first_index = a.y; r.pos_off = a.z; r.n_real = a.w;
+    r.prev_invocation = b.x; r.flags = b.y; r.object_invocation = b.z; r.region = b.w;
+    return r;
 }
 
 // ---- test: cull.wgsl::cs_main up to the visibility decision
@@ -123,34 +147,30 @@ __global__ void __launch_bounds__(TC_THREADS) triangle_test_kernel(const __grid_
     if (wg >= p.header[3] / TC_THREADS) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool shadow = p.cam.shadow_index != R3_CAMERA_VIEWPORT;
-    const uint32_t wi = __ldg(&p.wg_info[wg]);
-    const r3_batch_data* job = &p.batches[wi >> 8];
-    const uint32_t local_object = wi & 0xFFu;
-    const r3_object_culling_info info = job->object_culling_information[local_object];   // find_object_info (cull.wgsl:181-207)
+    const WgRec rec = load_wg(p, wg);
     const uint32_t global_invocation = wg * TC_THREADS + threadIdx.x;
-    const uint32_t gid = global_invocation - job->batch_base_invocation;                 // invocation within the batch
-    const bool real = gid < info.invocation_end;
-    const uint32_t object_invocation = gid - info.invocation_start;
+    const bool real = threadIdx.x < rec.n_real;
+    const uint32_t object_invocation = rec.object_invocation + threadIdx.x;
+    const bool atomic_capable = rec.flags & WG_ATOMIC;
+    const uint32_t local_object = rec.flags >> 8;
 
     bool passes = false, resid = false;
     uint32_t i0 = 0, i1 = 0, i2 = 0;
     if (real) {
-        const r3_object* obj = &p.objects[info.object_id];
-        const uint32_t first_index = obj->first_index, pos_off = obj->attr_offset[0] >> 2;
-        const uint64_t ib = (uint64_t)first_index + (uint64_t)object_invocation * 3u;      // vertex_fetch (cull.wgsl:9-32)
+        const uint64_t ib = (uint64_t)rec.first_index + (uint64_t)object_invocation * 3u;  // vertex_fetch (cull.wgsl:9-32)
         i0 = mesh_word(p, ib); i1 = mesh_word(p, ib + 1); i2 = mesh_word(p, ib + 2);
         float3 v[3];
         const uint32_t ids[3] = {i0, i1, i2};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const uint64_t f = (uint64_t)pos_off + (uint64_t)ids[k] * 3u;                  // extract_attribute_vec3_f32
+            const uint64_t f = (uint64_t)rec.pos_off + (uint64_t)ids[k] * 3u;              // extract_attribute_vec3_f32
             v[k] = make_float3(__uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));
         }
-        passes = execute_culling(p, p.matrices[info.object_id].model_view_proj, v[0], v[1], v[2]);
-        if (passes && !shadow && info.atomic_capable == 1u) {
+        passes = execute_culling(p, p.matrices[rec.object_id].model_view_proj, v[0], v[1], v[2]);
+        if (passes && !shadow && atomic_capable) {
             bool prev = false;                                                            // get_previous_culling_result (cull.wgsl:152-160)
-            if (info.previous_global_invocation != R3_NO_PREVIOUS) {
-                const uint64_t pgi = (uint64_t)object_invocation + info.previous_global_invocation;
+            if (rec.prev_invocation != R3_NO_PREVIOUS) {
+                const uint64_t pgi = (uint64_t)object_invocation + rec.prev_invocation;
                 const uint32_t mask = (pgi >> 5) < p.res_in_words ? p.res_in[pgi >> 5] : 0u;
                 prev = (mask >> (pgi & 31)) & 1u;
             }
@@ -163,7 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS) triangle_test_kernel(const __grid_
         p.res_out[global_invocation >> 5] = word_pred;                                     // save_culling_results (cull.wgsl:229-241)
         p.resid_bits[global_invocation >> 5] = word_resid;
     }
-    if (info.atomic_capable == 0u) {
+    if (!atomic_capable) {
         // non-atomic (blend) objects keep their slot: survivors in place, everything else INVALID (cull.wgsl:374-380,343-347)
         const uint64_t o = (uint64_t)global_invocation * 3u;
         const uint32_t hi = local_object << 24;
@@ -241,8 +261,7 @@ __global__ void __launch_bounds__(256) region_finish_kernel(const __grid_constan
         p.region_prefix[r] = before;
         if (end_inv > first_inv) {
             // the region's first object decides atomic / non-atomic for the whole region (one material key per region)
-            const uint32_t wi = p.wg_info[first_inv >> 8];
-            const bool atomic_region = p.batches[wi >> 8].object_culling_information[wi & 0xFFu].atomic_capable == 1u;
+            const bool atomic_region = load_wg(p, first_inv >> 8).flags & WG_ATOMIC;
             const unsigned long long cnt = after - before;
             r3_indirect_call pc, rc;
             pc.vertex_count = atomic_region ? 3u * (uint32_t)(cnt >> 32) : 0u;
@@ -284,17 +303,15 @@ __global__ void __launch_bounds__(SB_WORDS) triangle_compact_kernel(const __grid
     uint32_t base_pred = 0, base_resid = 0, idx_base = 0, hi = 0;
     bool atomic_word = false;
     if (wp | wr) {
-        const uint32_t wi = __ldg(&p.wg_info[w >> 3]);
-        const r3_batch_data* job = &p.batches[wi >> 8];
-        const r3_object_culling_info info = job->object_culling_information[wi & 0xFFu];
-        atomic_word = info.atomic_capable == 1u;
-        const unsigned long long rp = p.region_prefix[info.region_id];
-        const uint32_t region_first = p.region_first_inv[info.region_id];
+        const WgRec rec = load_wg(p, w >> 3);
+        atomic_word = rec.flags & WG_ATOMIC;
+        const unsigned long long rp = p.region_prefix[rec.region];
+        const uint32_t region_first = p.region_first_inv[rec.region];
         base_pred = region_first + (uint32_t)((excl - rp) >> 32);
         base_resid = region_first + (uint32_t)((excl & 0xFFFFFFFFull) - (rp & 0xFFFFFFFFull));
         // index of the first invocation of this word inside the mesh buffer
-        idx_base = p.objects[info.object_id].first_index + (w * 32u - job->batch_base_invocation - info.invocation_start) * 3u;
-        hi = (wi & 0xFFu) << 24;
+        idx_base = rec.first_index + (rec.object_invocation + (w & 7u) * 32u) * 3u;
+        hi = (rec.flags >> 8) << 24;
     }
     // the 32 words of a warp are expanded one after the other, one triangle per lane
     const uint32_t any = __ballot_sync(0xFFFFFFFFu, atomic_word && (wp | wr));
@@ -338,15 +355,15 @@ int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam) {
     if (n_wg == 0 || j.n_batches == 0 || j.n_regions == 0) return R3_OK;
 
     const uint32_t n_sb = (uint32_t)((words + SB_WORDS - 1) / SB_WORDS);
-    // scratch: wg_info [n_wg] | resid_bits [words]   and   sb_counts [n_sb + 1] | region_prefix [n_regions + 1]
-    R3_TRY(r3_reserve_t(c, &cam->d_resid_bits, &cam->resid_bits_cap, (uint64_t)n_wg + words + 2));
+    // scratch: wg records [8 words x n_wg] | resid_bits [words]   and   sb_counts [n_sb + 1] | region_prefix [n_regions + 1]
+    R3_TRY(r3_reserve_t(c, &cam->d_resid_bits, &cam->resid_bits_cap, (uint64_t)n_wg * 8 + words + 8));
     R3_TRY(r3_reserve_t(c, &cam->d_word_scan, &cam->word_scan_cap, (uint64_t)n_sb + j.n_regions + 4));
-    uint32_t* wg_info = cam->d_resid_bits;
-    uint32_t* resid_bits = wg_info + n_wg;
+    uint4* wg_info = reinterpret_cast<uint4*>(cam->d_resid_bits);
+    uint32_t* resid_bits = cam->d_resid_bits + (size_t)n_wg * 8;
     unsigned long long* sb_counts = cam->d_word_scan;
     unsigned long long* region_prefix = sb_counts + n_sb + 1;
     R3_CUDA(c, cudaMemsetAsync(sb_counts, 0, ((size_t)n_sb + 1) * 8, c->stream));
-    expand_wg_info_kernel<<<j.n_batches, 256, 0, c->stream>>>(j.d_batches, j.d_header, wg_info);
+    expand_wg_info_kernel<<<j.n_batches, 256, 0, c->stream>>>(j.d_batches, j.d_header, c->d_objects, wg_info);
     R3_CHECK_LAUNCH(c, "expand_wg_info_kernel");
 
     TriCullParams p;
