@@ -37,6 +37,7 @@ from rend3_b200.scenes import cloud_camera, cube_field_scene, object_cloud_recor
 METRIC = "culled objects/s (fused frustum cull + object-uniform bake)"
 BYTES_PER_OBJECT = 212   # 84 B read (transform 64 + sphere 16 + enabled 4) + 128 B MV/MVP written
 BYTES_PER_VISIBLE = 4
+NCU_TRAFFIC_PER_OBJECT = (801_563_648 + 1_213_981_000) / 10_000_000   # ncu --set full capture of cull_bake_kernel<bake,cull>, 10 M objects (profiles/)
 
 
 def measured_peak_gbs():
@@ -365,7 +366,8 @@ def main():
             "config": {"workload": "BASELINE config 4: fused frustum cull + uniform bake, 10 M object records per GPU (128 B std430 records, 1% disabled)",
                        "objects_per_gpu": n, "visible_fraction": n_vis / n, "parallelism": f"object-range shards x{world}, NCCL all-gather of the visibility words (1 bit/object)" if world > 1 else "single GPU",
                        "l2": "inputs (0.8 GB) + outputs (1.28 GB) per step exceed the 126 MB L2; no explicit flush"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_PER_OBJECT * n,
+                         "traffic_source": "profiles/r1_ncu_cull_bake_10M.txt: dram__bytes_read.sum + dram__bytes_write.sum of one 10 M-object launch, scaled per object",
                          "kernel": "cull_bake_kernel<bake,cull>", "kernel_ms": kern_s * 1e3, "algorithmic_bytes_per_launch": BYTES_PER_OBJECT * n + BYTES_PER_VISIBLE * n_vis,
                          "peak_source": peak_src},
             "cpu_baseline": cpu_baseline(n),
