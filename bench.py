@@ -239,14 +239,20 @@ def main():
     vis_host = torch.empty(n, dtype=torch.int32, pin_memory=True)
     gathered_words = torch.empty(world * ((n + 31) // 32), dtype=torch.int32, device=f"cuda:{local}")
 
+    side = torch.cuda.Stream(device=f"cuda:{local}") if world > 1 else None
+
     def gather_visible():
         """North-star exchange: every rank ends up with the visible set of all shards.  The set travels in its
         1-bit-per-object form (the stream kernel's visibility words, n/8 bytes per shard instead of 4 B per visible
-        object): fixed size, so no count exchange and no host synchronisation."""
+        object): fixed size, so no count exchange and no host synchronisation.  The library alternates between two
+        word buffers, so the all-gather of step k runs on a side stream while the cull of step k+1 streams."""
         if world == 1:
             return
         wptr, wbytes = backend.device_ptr(CAMERA_VIEWPORT, 4)
-        with torch.cuda.stream(stream):
+        done = torch.cuda.Event()
+        done.record(stream)
+        side.wait_event(done)
+        with torch.cuda.stream(side):
             mine = torch.as_tensor(DeviceView(wptr, wbytes, "<i4", 4), device=f"cuda:{local}")
             dist.all_gather_into_tensor(gathered_words, mine)
 

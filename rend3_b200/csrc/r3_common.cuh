@@ -42,7 +42,8 @@ struct r3_camera {
     r3_object_matrices* d_matrices = nullptr; uint32_t matrices_cap = 0;
     uint32_t* d_visible = nullptr; uint32_t visible_cap = 0;
     uint32_t* d_visible_count = nullptr;      // device scalar
-    unsigned long long* d_tile_state = nullptr; uint32_t tile_state_cap = 0;   // decoupled look-back descriptors (+ticket)
+    unsigned long long* d_tile_state = nullptr; uint32_t tile_state_cap = 0;   // visibility words + per-CTA counts (two alternating sets)
+    uint32_t* d_words = nullptr; uint32_t words_set = 0;                       // the set the last cull wrote
     int visible_count_host = -1;              // cached after a readback, -1 = unknown
     r3_jobs jobs[2]; int cur = 0;             // jobs[cur] = this frame, jobs[cur^1] = cached DrawCallSet (forward.rs:219)
     bool has_draw_call_set = false; int cache_idx = -1;   // cache_idx: which jobs[] the forward routine cached, -1 = none

@@ -439,7 +439,7 @@ R3_EXPORT int r3_device_ptr(r3_ctx* c, uint32_t camera, int which, void** p, uin
     else if (which == 1) { *p = c->d_hdr16; *nbytes = (uint64_t)c->width * c->height * 8; }
     else if (which == 2) { *p = cam->d_matrices; *nbytes = (uint64_t)cam->matrices_cap * 128; }
     else if (which == 3) { *p = cam->d_visible_count; *nbytes = 4; }
-    else if (which == 4) { *p = cam->d_tile_state; *nbytes = (((uint64_t)cam->header.object_count + 31) / 32) * 4; }   // 1 bit per object
+    else if (which == 4) { *p = cam->d_words; *nbytes = (((uint64_t)cam->header.object_count + 31) / 32) * 4; }   // 1 bit per object
     else return r3_fail(c, R3_E_INVALID, "device_ptr: which");
     return R3_OK;
 }

@@ -219,9 +219,14 @@ int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode) {
     memcpy(p.frustum, cam->header.frustum, 80);
     p.object_count = n;
     const uint32_t n_ctas = (n + CB_CTA_OBJECTS - 1) / CB_CTA_OBJECTS, n_words = (n + 31) / 32;
-    // scratch: visibility words [n_words] | stream-CTA counts [n_ctas]   (d_tile_state is a u64 array)
-    R3_TRY(r3_reserve_t(c, &cam->d_tile_state, &cam->tile_state_cap, ((uint64_t)n_words + n_ctas + 3) / 2 + 1));
-    uint32_t* words = reinterpret_cast<uint32_t*>(cam->d_tile_state);
+    // scratch: two sets of { visibility words [n_words] | stream-CTA counts [n_ctas] }, used alternately: the words of
+    // call k stay intact while call k+1 runs, so an exchange of the visible set (r3_device_ptr which = 4) can overlap the
+    // next cull on another stream.  (d_tile_state is a u64 array; each set is padded to a 256-byte multiple.)
+    const uint64_t set_words = (((uint64_t)n_words + n_ctas + 63) / 64) * 64;
+    R3_TRY(r3_reserve_t(c, &cam->d_tile_state, &cam->tile_state_cap, set_words + 2));
+    if (cull) cam->words_set ^= 1u;
+    uint32_t* words = reinterpret_cast<uint32_t*>(cam->d_tile_state) + (size_t)cam->words_set * set_words;
+    cam->d_words = words;
     uint32_t* cta_counts = words + n_words;
     if (!c->hot_valid) return r3_fail(c, R3_E_STATE, "object_uniform_upload before set_objects");
     float4* mats = reinterpret_cast<float4*>(cam->d_matrices);
