@@ -34,8 +34,16 @@
 #define R3_MAT_ALBEDO_ACTIVE 0x0001u
 #define R3_MAT_ALBEDO_BLEND 0x0002u
 #define R3_MAT_ALBEDO_VERTEX_SRGB 0x0004u
+#define R3_MAT_BICOMPONENT_NORMAL 0x0008u
+#define R3_MAT_SWIZZLED_NORMAL 0x0010u
+#define R3_MAT_YDOWN_NORMAL 0x0020u
 #define R3_MAT_AOMR_COMBINED 0x0040u
+#define R3_MAT_AOMR_SWIZZLED_SPLIT 0x0080u
+#define R3_MAT_AOMR_SPLIT 0x0100u
+#define R3_MAT_AOMR_BW_SPLIT 0x0200u
 #define R3_MAT_CC_GLTF_COMBINED 0x0400u
+#define R3_MAT_CC_GLTF_SPLIT 0x0800u
+#define R3_MAT_CC_BW_SPLIT 0x1000u
 #define R3_MAT_UNLIT 0x2000u
 #define R3_MAT_NEAREST 0x4000u
 
@@ -187,6 +195,23 @@ typedef struct r3_material {
 R3_STATIC_ASSERT(sizeof(r3_material) == 208, "GpuMaterialData");
 R3_STATIC_ASSERT(offsetof(r3_material, albedo) == 144, "albedo");
 R3_STATIC_ASSERT(offsetof(r3_material, flags) == 204, "flags");
+
+/* texture slots of r3_material.textures[] (material.wgsl:21-35): value = index into the texture table + 1, 0 = none */
+enum { R3_TEX_ALBEDO = 0, R3_TEX_NORMAL, R3_TEX_ROUGHNESS, R3_TEX_METALLIC, R3_TEX_REFLECTANCE, R3_TEX_CLEAR_COAT, R3_TEX_CLEAR_COAT_ROUGHNESS,
+       R3_TEX_EMISSIVE, R3_TEX_ANISOTROPY, R3_TEX_AMBIENT_OCCLUSION };
+
+/* One entry of the bindless `textures` array (TextureManager<D2>, rend3/src/managers/texture.rs; binding opaque.wgsl:35):
+ * a 2D texture with `mip_count` levels stored tightly one after the other (level l is max(w >> l, 1) x max(h >> l, 1))
+ * starting at `byte_offset` of the texel blob handed to r3_set_textures. */
+#define R3_TEXFMT_RGBA8_UNORM 0u
+#define R3_TEXFMT_RGBA8_UNORM_SRGB 1u   /* rgb decoded to linear before filtering, alpha linear */
+#define R3_TEXFMT_RGBA32_FLOAT 2u
+typedef struct r3_texture_desc {
+    uint32_t width, height, mip_count, format;
+    uint64_t byte_offset;
+    uint64_t _reserved;
+} r3_texture_desc;
+R3_STATIC_ASSERT(sizeof(r3_texture_desc) == 32, "r3_texture_desc");
 
 /* GpuSkinningInput — rend3-routine/src/skinning.rs:20-45, skinning.wgsl:3-26 (40 bytes, byte offsets into the mesh buffer,
  * R3_ATTR_ABSENT when an attribute is missing) */

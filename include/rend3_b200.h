@@ -74,6 +74,10 @@ int r3_set_object_sort_info(r3_ctx*, const uint64_t* material_key, const uint8_t
                             const float* location_xyz, uint32_t n_slots);
 int r3_set_mesh_buffer(r3_ctx*, const void* bytes, uint64_t nbytes);               /* eval_output.mesh_buffer (mesh.rs:99) */
 int r3_set_materials(r3_ctx*, const r3_material* records, uint32_t count);         /* material_manager.archetype_view::<M>().buffer() */
+/* the bindless d2 texture table the material records index (TextureManager::add / fill, rend3/src/managers/texture.rs;
+ * `textures[material.albedo_tex - 1u]`, opaque.wgsl:152-161): descriptors + one blob with every mip level.  Sampling is
+ * textureSampleGrad with the linear or nearest Repeat sampler of common/samplers.rs:42-56 (trilinear, no anisotropy). */
+int r3_set_textures(r3_ctx*, const r3_texture_desc* descs, uint32_t count, const void* texels, uint64_t nbytes);
 int r3_set_directional_lights(r3_ctx*, const void* bytes, uint64_t nbytes,
                               uint32_t atlas_width, uint32_t atlas_height);         /* directional.rs:135-156 */
 int r3_set_point_lights(r3_ctx*, const void* bytes, uint64_t nbytes);              /* point.rs:58-74 */

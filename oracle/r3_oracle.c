@@ -129,7 +129,7 @@ API int r3o_ctx_destroy(r3o_ctx* c) {
     free(c->vis); free(c->hdr); free(c->hdr16); free(c->depth); free(c->ldr); free(c->atlas);
     for (uint32_t i = 0; i < c->hiz_mips; ++i) free(c->hiz[i]);
     free(c->hiz); free(c->hiz_w); free(c->hiz_h);
-    free(c->tris[0]); free(c->tris[1]); free(c->tris[2]); free(c->sample_col16); free(c->blended);
+    free(c->tex_descs); free(c->texels); free(c->tris[0]); free(c->tris[1]); free(c->tris[2]); free(c->sample_col16); free(c->blended);
     free(c);
     return R3_OK;
 }
@@ -177,6 +177,26 @@ API int r3o_set_materials(r3o_ctx* c, const r3_material* recs, uint32_t n) {
     if (!c || (!recs && n)) return fail(c, R3_E_INVALID, "materials");
     REPLACE(c->materials, r3_material, recs, n);
     c->n_materials = n;
+    return R3_OK;
+}
+/* TextureManager<D2> table (rend3/src/managers/texture.rs): validated here so the samplers can index without checks */
+API int r3o_set_textures(r3o_ctx* c, const r3_texture_desc* descs, uint32_t n, const void* texels, uint64_t nbytes) {
+    if (!c || (!descs && n) || (!texels && nbytes)) return fail(c, R3_E_INVALID, "textures");
+    for (uint32_t i = 0; i < n; ++i) {
+        const r3_texture_desc* d = &descs[i];
+        if (!d->width || !d->height || !d->mip_count || d->mip_count > 32 || d->format > R3_TEXFMT_RGBA32_FLOAT) return fail(c, R3_E_INVALID, "textures: bad descriptor");
+        uint64_t bpp = d->format == R3_TEXFMT_RGBA32_FLOAT ? 16 : 4, total = 0;
+        for (uint32_t l = 0; l < d->mip_count; ++l) {
+            uint64_t w = (d->width >> l) ? (d->width >> l) : 1, h = (d->height >> l) ? (d->height >> l) : 1;
+            total += w * h * bpp;
+        }
+        if (d->byte_offset % 16 || d->byte_offset + total > nbytes) return fail(c, R3_E_INVALID, "textures: mip chain outside the texel blob");
+    }
+    REPLACE(c->tex_descs, r3_texture_desc, descs, n);
+    free(c->texels);
+    c->texels = (uint8_t*)malloc(nbytes + 16);
+    if (nbytes) memcpy(c->texels, texels, nbytes);
+    c->n_textures = n; c->texel_bytes = nbytes;
     return R3_OK;
 }
 API int r3o_set_directional_lights(r3o_ctx* c, const void* bytes, uint64_t nbytes, uint32_t aw, uint32_t ah) {
@@ -421,6 +441,10 @@ static void io_swap(r3o_iobuf* b, uint64_t new_elems) {
 
 /* ------------------------------------------------------------------ a8/a9: vertex fetch (vertex_attributes.wgsl:43-85) */
 static inline uint32_t mesh_word(const r3o_ctx* c, uint64_t idx) { return idx < c->mesh_words ? c->mesh[idx] : 0u; /* robust access */ }
+static inline void fetch_vec2(const r3o_ctx* c, uint32_t byte_off, uint32_t vertex, float* out) {   /* vertex_attributes.wgsl:43-49 */
+    uint64_t first = (uint64_t)(byte_off / 4u) + (uint64_t)vertex * 2u;
+    out[0] = u2f(mesh_word(c, first)); out[1] = u2f(mesh_word(c, first + 1));
+}
 static inline v3 fetch_vec3(const r3o_ctx* c, uint32_t byte_off, uint32_t vertex) {
     uint64_t first = (uint64_t)(byte_off / 4u) + (uint64_t)vertex * 3u;
     v3 r = {u2f(mesh_word(c, first)), u2f(mesh_word(c, first + 1)), u2f(mesh_word(c, first + 2))};

@@ -40,6 +40,7 @@ typedef struct r3o_ctx {
     uint64_t* sort_key; uint8_t* sort_flags; float* sort_loc; uint32_t sort_n;
     uint32_t* mesh; uint64_t mesh_words;
     r3_material* materials; uint32_t n_materials;
+    r3_texture_desc* tex_descs; uint32_t n_textures; uint8_t* texels; uint64_t texel_bytes;   /* bindless d2 texture table */
     r3_directional_light* dir_lights; uint32_t n_dir; uint32_t atlas_w, atlas_h;
     r3_point_light* point_lights; uint32_t n_point;
     r3_frame_uniforms uniforms;

@@ -68,7 +68,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (!c->objects_borrowed) cudaFree(c->d_objects);
-    cudaFree(c->d_hot_transform); cudaFree(c->d_hot_sphere); cudaFree(c->d_enabled_bits);
+    cudaFree(c->d_hot_transform); cudaFree(c->d_hot_sphere); cudaFree(c->d_enabled_bits); cudaFree(c->d_tex_descs); cudaFree(c->d_texels);
     cudaFree(c->d_sort_key8); cudaFree(c->d_sort_loc);
     cudaFree(c->d_live_bits); cudaFree(c->d_mesh); cudaFree(c->d_materials); cudaFree(c->d_dir); cudaFree(c->d_point);
     cudaFree(c->d_light_mats); cudaFree(c->d_atlas);
@@ -207,6 +207,25 @@ R3_EXPORT int r3_set_materials(r3_ctx* c, const r3_material* recs, uint32_t n) {
     if (n) R3_CUDA(c, cudaMemcpyAsync(c->d_materials, recs, (size_t)n * sizeof(r3_material), cudaMemcpyHostToDevice, c->stream));
     R3_CUDA(c, cudaStreamSynchronize(c->stream));
     c->n_materials = n;
+    return R3_OK;
+}
+R3_EXPORT int r3_set_textures(r3_ctx* c, const r3_texture_desc* descs, uint32_t n, const void* texels, uint64_t nbytes) {
+    if (!c || (!descs && n) || (!texels && nbytes)) return r3_fail(c, R3_E_INVALID, "set_textures: null");
+    for (uint32_t i = 0; i < n; ++i) {   // validated once here so the samplers index without checks
+        const r3_texture_desc& d = descs[i];
+        if (!d.width || !d.height || !d.mip_count || d.mip_count > 32 || d.format > R3_TEXFMT_RGBA32_FLOAT) return r3_fail(c, R3_E_INVALID, "set_textures: bad descriptor");
+        const uint64_t bpp = d.format == R3_TEXFMT_RGBA32_FLOAT ? 16 : 4;
+        uint64_t total = 0;
+        for (uint32_t l = 0; l < d.mip_count; ++l) total += (uint64_t)((d.width >> l) ? (d.width >> l) : 1u) * ((d.height >> l) ? (d.height >> l) : 1u) * bpp;
+        if (d.byte_offset % 16 || d.byte_offset + total > nbytes) return r3_fail(c, R3_E_INVALID, "set_textures: mip chain outside the texel blob");
+    }
+    cudaSetDevice(c->device);
+    R3_TRY(r3_reserve_t(c, &c->d_tex_descs, &c->tex_descs_cap, n));
+    R3_TRY(r3_reserve_t(c, &c->d_texels, &c->texels_cap, nbytes + 16));
+    if (n) R3_CUDA(c, cudaMemcpyAsync(c->d_tex_descs, descs, (size_t)n * sizeof(r3_texture_desc), cudaMemcpyHostToDevice, c->stream));
+    if (nbytes) R3_CUDA(c, cudaMemcpyAsync(c->d_texels, texels, nbytes, cudaMemcpyHostToDevice, c->stream));
+    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_textures = n;
     return R3_OK;
 }
 R3_EXPORT int r3_set_directional_lights(r3_ctx* c, const void* bytes, uint64_t nbytes, uint32_t aw, uint32_t ah) {

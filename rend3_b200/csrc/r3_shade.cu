@@ -31,6 +31,7 @@ struct ShadeParams {
     const r3_object* objects; const r3_object_matrices* matrices;
     const uint32_t* mesh; uint64_t mesh_words;
     const r3_material* materials; uint32_t n_materials;
+    const r3_texture_desc* tex; uint32_t n_tex; const uint8_t* texels;   // bindless d2 texture table (r3_set_textures)
     const DirPrep* dir; uint32_t n_dir; const PointPrep* point; uint32_t n_point;
     const float* atlas; uint32_t atlas_w, atlas_h;
     // blend routine (r3_forward_blend): triangle records of the key-2 regions + the per-sample fragment lists
@@ -195,27 +196,234 @@ __device__ __forceinline__ FragIn fragment_inputs(const ShadeParams& p, const r3
     return f;
 }
 
-// fs_main (opaque.wgsl:470-551).  `mask` lists the point lights that can reach the fragment (a conservative superset is fine:
-// every listed light still takes the exact per-fragment range test below).
-__device__ __forceinline__ float4 shade_inputs(const ShadeParams& p, const DirPrep* __restrict__ s_dir, const PointPrep* __restrict__ s_point, const FragIn& f,
-                                               const LightMask& mask) {
-    const float4 vp = f.vp; const float3 vnormal = f.vnormal; const float4 vcolor = f.vcolor; const uint32_t material_index = f.material_index;
-    // get_pixel_data_inner for untextured materials (opaque.wgsl:203-424)
-    const r3_material* m = &p.materials[material_index < p.n_materials ? material_index : 0u];
-    const float4 malbedo = __ldg(reinterpret_cast<const float4*>(m->albedo));
-    const float4 mA = __ldg(reinterpret_cast<const float4*>(m->emissive));        // emissive.xyz, roughness
-    const float4 mB = __ldg(reinterpret_cast<const float4*>(&m->metallic));       // metallic, reflectance, clear_coat, clear_coat_roughness
-    const float4 mC = __ldg(reinterpret_cast<const float4*>(&m->anisotropy));     // anisotropy, ambient_occlusion, alpha_cutout, flags
-    const uint32_t flags = __float_as_uint(mC.w);
-    float4 albedo = make_float4(0.f, 0.f, 0.f, 1.f);
-    if (flags & R3_MAT_ALBEDO_ACTIVE) {
-        albedo = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (flags & R3_MAT_ALBEDO_BLEND) {
-            if (flags & R3_MAT_ALBEDO_VERTEX_SRGB) albedo = make_float4(srgb_to_linear(vcolor.x), srgb_to_linear(vcolor.y), srgb_to_linear(vcolor.z), vcolor.w);
-            else albedo = vcolor;
+// ------------------------------------------------------------------ material textures (rule R9 of the oracle)
+// textureSampleGrad with the linear / nearest Repeat sampler of common/samplers.rs:42-56.  Everything that SELECTS texels or
+// levels (coordinates, floor) follows the oracle's order without contraction; the filter weights are continuous.
+__device__ __forceinline__ float4 texel_fetch(const ShadeParams& p, const r3_texture_desc& d, uint32_t level, long long x, long long y) {
+    unsigned long long off = d.byte_offset;
+    const unsigned long long bpp = d.format == R3_TEXFMT_RGBA32_FLOAT ? 16ull : 4ull;
+    for (uint32_t l = 0; l < level; ++l) off += (unsigned long long)max(d.width >> l, 1u) * max(d.height >> l, 1u) * bpp;
+    const long long w = max(d.width >> level, 1u), h = max(d.height >> level, 1u);
+    x = ((x % w) + w) % w; y = ((y % h) + h) % h;                                   // AddressMode::Repeat
+    const uint8_t* t = p.texels + off + (unsigned long long)(y * w + x) * bpp;
+    if (d.format == R3_TEXFMT_RGBA32_FLOAT) return __ldg(reinterpret_cast<const float4*>(t));
+    const uchar4 c = __ldg(reinterpret_cast<const uchar4*>(t));
+    float4 o = make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+    if (d.format == R3_TEXFMT_RGBA8_UNORM_SRGB) { o.x = srgb_to_linear(o.x); o.y = srgb_to_linear(o.y); o.z = srgb_to_linear(o.z); }
+    return o;
+}
+__device__ __forceinline__ float clamp_coord(float v) { return fminf(fmaxf(v, -1.0e9f), 1.0e9f); }
+__device__ __noinline__ float4 sample_level(const ShadeParams& p, const r3_texture_desc& d, uint32_t level, bool nearest, float u, float v) {
+    const float w = (float)max(d.width >> level, 1u), h = (float)max(d.height >> level, 1u);
+    if (nearest) {
+        float x = floorf(mul_rn(u, w)), y = floorf(mul_rn(v, h));
+        if (!(x == x)) x = 0.0f; if (!(y == y)) y = 0.0f;
+        return texel_fetch(p, d, level, (long long)clamp_coord(x), (long long)clamp_coord(y));
+    }
+    const float x = sub_rn(mul_rn(u, w), 0.5f), y = sub_rn(mul_rn(v, h), 0.5f);
+    float x0 = floorf(x), y0 = floorf(y), fx = sub_rn(x, x0), fy = sub_rn(y, y0);
+    if (!(x0 == x0)) { x0 = 0.0f; fx = 0.0f; } if (!(y0 == y0)) { y0 = 0.0f; fy = 0.0f; }
+    const long long ix = (long long)clamp_coord(x0), iy = (long long)clamp_coord(y0);
+    const float4 t00 = texel_fetch(p, d, level, ix, iy), t10 = texel_fetch(p, d, level, ix + 1, iy);
+    const float4 t01 = texel_fetch(p, d, level, ix, iy + 1), t11 = texel_fetch(p, d, level, ix + 1, iy + 1);
+    const float gx = 1.0f - fx, gy = 1.0f - fy;
+    return make_float4((t00.x * gx + t10.x * fx) * gy + (t01.x * gx + t11.x * fx) * fy, (t00.y * gx + t10.y * fx) * gy + (t01.y * gx + t11.y * fx) * fy,
+                       (t00.z * gx + t10.z * fx) * gy + (t01.z * gx + t11.z * fx) * fy, (t00.w * gx + t10.w * fx) * gy + (t01.w * gx + t11.w * fx) * fy);
+}
+struct TexCoords { float u, v, dudx, dvdx, dudy, dvdy; };
+// slot value = table index + 1; an index outside the table reads zeros (robust access)
+__device__ __noinline__ float4 texture_sample_grad(const ShadeParams& p, uint32_t slot_value, bool nearest, const TexCoords& c) {
+    if (slot_value == 0u || slot_value > p.n_tex) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const r3_texture_desc d = p.tex[slot_value - 1u];
+    const float w0 = (float)d.width, h0 = (float)d.height;
+    const float ax = c.dudx * w0, ay = c.dvdx * h0, bx = c.dudy * w0, by = c.dvdy * h0;
+    const float rho = fmaxf(sqrtf(ax * ax + ay * ay), sqrtf(bx * bx + by * by));
+    const float lambda = log2f(rho);
+    const uint32_t last = d.mip_count - 1u;
+    if (!(lambda > 0.0f)) return sample_level(p, d, 0u, nearest, c.u, c.v);
+    if (nearest) {
+        const float lv = floorf(lambda + 0.5f);
+        return sample_level(p, d, lv >= (float)last ? last : (uint32_t)lv, true, c.u, c.v);
+    }
+    const float l = fminf(lambda, (float)last), lo = floorf(l), fr = l - lo;
+    const uint32_t level = (uint32_t)lo;
+    const float4 a = sample_level(p, d, level, false, c.u, c.v);
+    if (level >= last || fr == 0.0f) return a;
+    const float4 b = sample_level(p, d, level + 1u, false, c.u, c.v);
+    const float g = 1.0f - fr;
+    return make_float4(a.x * g + b.x * fr, a.y * g + b.y * fr, a.z * g + b.z * fr, a.w * g + b.w * fr);
+}
+
+// what get_pixel_data_inner (opaque.wgsl:203-424) hands to the lighting code
+struct PixelInputs { float4 albedo; float3 normal; float ao, perceptual, metallic, reflectance, clear_coat, cc_rough; float3 emissive; };
+
+// get_pixel_data_inner for a material that references textures: texture coordinates + derivatives (R9: forward differences of the
+// primitive's own interpolation), tangent frame, every texture slot and layout flag
+__device__ __noinline__ void textured_pixel_data(const ShadeParams& p, const r3_material* m, const FragIn& f, const r3_tri_record* tp, uint32_t px, uint32_t py,
+                                                 PixelInputs* out) {
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp)), q1 = __ldg(reinterpret_cast<const float4*>(tp) + 1), q2 = __ldg(reinterpret_cast<const float4*>(tp) + 2);
+    const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(tp) + 3);
+    const float3 p0 = make_float3(q0.x, q0.y, q0.z), p1 = make_float3(q0.w, q1.x, q1.y), p2 = make_float3(q1.z, q1.w, q2.x);
+    const uint32_t oid = __float_as_uint(q2.y);
+    const uint32_t vid[3] = {__float_as_uint(q2.z), __float_as_uint(q2.w), q3.x};
+    const r3_object* obj = &p.objects[oid];
+    const uint32_t tangent_off = __ldg(&obj->attr_offset[2]), uv_off = __ldg(&obj->attr_offset[3]);
+    const uint32_t flags = __ldg(&m->flags);
+    const bool nearest = flags & R3_MAT_NEAREST;
+    uint32_t tex[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) tex[k] = __ldg(&m->textures[k]);
+
+    // perspective weights at the pixel centre and at the centres of the right / lower neighbours
+    float b[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float fx = (float)px + (k == 1 ? 1.5f : 0.5f), fy = (float)py + (k == 2 ? 1.5f : 0.5f);
+        const float nx = sub_rn(div_rn(fx, (float)p.width * 0.5f), 1.0f), ny = sub_rn(1.0f, div_rn(fy, (float)p.height * 0.5f));
+        const float b0 = cross_term_rn(p1, p2, nx, ny), b1 = cross_term_rn(p2, p0, nx, ny), b2 = cross_term_rn(p0, p1, nx, ny);
+        const float sum = add_rn(add_rn(b0, b1), b2);
+        b[k][0] = div_rn(b0, sum); b[k][1] = div_rn(b1, sum); b[k][2] = div_rn(b2, sum);
+    }
+    float uv[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    if (uv_off != R3_ATTR_ABSENT) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint64_t w = (uint64_t)(uv_off >> 2) + (uint64_t)vid[k] * 2u;
+            uv[k][0] = __uint_as_float(mesh_word(p, w)); uv[k][1] = __uint_as_float(mesh_word(p, w + 1));
         }
     }
-    albedo = make_float4(albedo.x * malbedo.x, albedo.y * malbedo.y, albedo.z * malbedo.z, albedo.w * malbedo.w);
+    const float4 ut0 = __ldg(reinterpret_cast<const float4*>(m->uv_transform0[0])), ut1 = __ldg(reinterpret_cast<const float4*>(m->uv_transform0[1])),
+                 ut2 = __ldg(reinterpret_cast<const float4*>(m->uv_transform0[2]));
+    float co[3][2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float u = lerp3_rn(b[k][0], b[k][1], b[k][2], uv[0][0], uv[1][0], uv[2][0]), v = lerp3_rn(b[k][0], b[k][1], b[k][2], uv[0][1], uv[1][1], uv[2][1]);
+        co[k][0] = add_rn(add_rn(mul_rn(ut0.x, u), mul_rn(ut1.x, v)), ut2.x);
+        co[k][1] = add_rn(add_rn(mul_rn(ut0.y, u), mul_rn(ut1.y, v)), ut2.y);
+    }
+    TexCoords tc;
+    tc.u = co[0][0]; tc.v = co[0][1];
+    tc.dudx = sub_rn(co[1][0], co[0][0]); tc.dvdx = sub_rn(co[1][1], co[0][1]); tc.dudy = sub_rn(co[2][0], co[0][0]); tc.dvdy = sub_rn(co[2][1], co[0][1]);
+
+    PixelInputs o;
+    const float4 malbedo = __ldg(reinterpret_cast<const float4*>(m->albedo));
+    o.albedo = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (flags & R3_MAT_ALBEDO_ACTIVE) {
+        o.albedo = tex[R3_TEX_ALBEDO] ? texture_sample_grad(p, tex[R3_TEX_ALBEDO], nearest, tc) : make_float4(1.f, 1.f, 1.f, 1.f);
+        if (flags & R3_MAT_ALBEDO_BLEND) {
+            const float4 vc = (flags & R3_MAT_ALBEDO_VERTEX_SRGB) ? make_float4(srgb_to_linear(f.vcolor.x), srgb_to_linear(f.vcolor.y), srgb_to_linear(f.vcolor.z), f.vcolor.w) : f.vcolor;
+            o.albedo = make_float4(o.albedo.x * vc.x, o.albedo.y * vc.y, o.albedo.z * vc.z, o.albedo.w * vc.w);
+        }
+    }
+    o.albedo = make_float4(o.albedo.x * malbedo.x, o.albedo.y * malbedo.y, o.albedo.z * malbedo.z, o.albedo.w * malbedo.w);
+    o.normal = f.vnormal;
+    if (tex[R3_TEX_NORMAL] && !(flags & R3_MAT_UNLIT)) {                               // opaque.wgsl:244-276
+        const float4 t = texture_sample_grad(p, tex[R3_TEX_NORMAL], nearest, tc);
+        float3 n;
+        if (flags & R3_MAT_BICOMPONENT_NORMAL) {
+            const float bx = ((flags & R3_MAT_SWIZZLED_NORMAL) ? t.w : t.x) * 2.0f - 1.0f, by = t.y * 2.0f - 1.0f;
+            n = make_float3(bx, by, sqrtf((1.0f - bx * bx) - by * by));
+        } else n = normalize3(make_float3(t.x * 2.0f - 1.0f, t.y * 2.0f - 1.0f, t.z * 2.0f - 1.0f));
+        if (flags & R3_MAT_YDOWN_NORMAL) n.y = -n.y;
+        // vs_out.tangent = normalize(mv3 * (inv_scale_sq * tangent)) per vertex, interpolated (opaque.wgsl:128)
+        float mv[12];
+        {
+            const float4* m4 = reinterpret_cast<const float4*>(p.matrices[oid].model_view);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const float4 c4 = __ldg(&m4[k]); mv[4 * k] = c4.x; mv[4 * k + 1] = c4.y; mv[4 * k + 2] = c4.z; mv[4 * k + 3] = c4.w; }
+        }
+        const float3 iss = make_float3(1.0f / (mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]), 1.0f / (mv[4] * mv[4] + mv[5] * mv[5] + mv[6] * mv[6]),
+                                       1.0f / (mv[8] * mv[8] + mv[9] * mv[9] + mv[10] * mv[10]));
+        float3 vt[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            vt[k] = make_float3(0.f, 0.f, 0.f);
+            if (tangent_off != R3_ATTR_ABSENT) {
+                const float3 t3 = fetch3(p, tangent_off, vid[k]);
+                const float3 st = make_float3(iss.x * t3.x, iss.y * t3.y, iss.z * t3.z);
+                vt[k] = normalize3(make_float3(mv[0] * st.x + mv[4] * st.y + mv[8] * st.z, mv[1] * st.x + mv[5] * st.y + mv[9] * st.z, mv[2] * st.x + mv[6] * st.y + mv[10] * st.z));
+            }
+        }
+        const float3 vtan = make_float3(b[0][0] * vt[0].x + b[0][1] * vt[1].x + b[0][2] * vt[2].x, b[0][0] * vt[0].y + b[0][1] * vt[1].y + b[0][2] * vt[2].y,
+                                        b[0][0] * vt[0].z + b[0][1] * vt[1].z + b[0][2] * vt[2].z);
+        const float3 nn = normalize3(f.vnormal), tn = normalize3(vtan);
+        const float3 bt = make_float3(nn.y * tn.z - tn.y * nn.z, nn.z * tn.x - tn.z * nn.x, nn.x * tn.y - tn.x * nn.y);
+        o.normal = make_float3(tn.x * n.x + bt.x * n.y + nn.x * n.z, tn.y * n.x + bt.y * n.y + nn.y * n.z, tn.z * n.x + bt.z * n.y + nn.z * n.z);
+    }
+    const float4 mA = __ldg(reinterpret_cast<const float4*>(m->emissive));        // emissive.xyz, roughness
+    const float4 mB = __ldg(reinterpret_cast<const float4*>(&m->metallic));       // metallic, reflectance, clear_coat, clear_coat_roughness
+    const float m_ao = __ldg(&m->ambient_occlusion);
+    o.ao = m_ao; o.perceptual = mA.w; o.metallic = mB.x;
+    if (!(flags & R3_MAT_UNLIT)) {
+        if (flags & R3_MAT_AOMR_COMBINED) {                                            // opaque.wgsl:280-295
+            if (tex[R3_TEX_ROUGHNESS]) { const float4 t = texture_sample_grad(p, tex[R3_TEX_ROUGHNESS], nearest, tc); o.ao = m_ao * t.x; o.perceptual = mA.w * t.y; o.metallic = mB.x * t.z; }
+        } else if (flags & R3_MAT_AOMR_BW_SPLIT) {
+            if (tex[R3_TEX_ROUGHNESS]) o.perceptual = mA.w * texture_sample_grad(p, tex[R3_TEX_ROUGHNESS], nearest, tc).x;
+            if (tex[R3_TEX_METALLIC]) o.metallic = mB.x * texture_sample_grad(p, tex[R3_TEX_METALLIC], nearest, tc).x;
+            if (tex[R3_TEX_AMBIENT_OCCLUSION]) o.ao = m_ao * texture_sample_grad(p, tex[R3_TEX_AMBIENT_OCCLUSION], nearest, tc).x;
+        } else {
+            if (tex[R3_TEX_ROUGHNESS]) {
+                const float4 t = texture_sample_grad(p, tex[R3_TEX_ROUGHNESS], nearest, tc);
+                const bool sw = flags & R3_MAT_AOMR_SWIZZLED_SPLIT;
+                o.perceptual = mA.w * (sw ? t.y : t.x); o.metallic = mB.x * (sw ? t.z : t.y);
+            }
+            if (tex[R3_TEX_AMBIENT_OCCLUSION]) o.ao = m_ao * texture_sample_grad(p, tex[R3_TEX_AMBIENT_OCCLUSION], nearest, tc).x;
+        }
+        o.reflectance = mB.y;
+        if (tex[R3_TEX_REFLECTANCE]) o.reflectance = mB.y * texture_sample_grad(p, tex[R3_TEX_REFLECTANCE], nearest, tc).x;
+        o.clear_coat = mB.z; o.cc_rough = mB.w;
+        if (flags & R3_MAT_CC_GLTF_COMBINED) {
+            if (tex[R3_TEX_CLEAR_COAT]) { const float4 t = texture_sample_grad(p, tex[R3_TEX_CLEAR_COAT], nearest, tc); o.clear_coat = mB.z * t.x; o.cc_rough = mB.w * t.y; }
+        } else {
+            if (tex[R3_TEX_CLEAR_COAT]) o.clear_coat = mB.z * texture_sample_grad(p, tex[R3_TEX_CLEAR_COAT], nearest, tc).x;
+            if (tex[R3_TEX_CLEAR_COAT_ROUGHNESS]) {
+                const float4 t = texture_sample_grad(p, tex[R3_TEX_CLEAR_COAT_ROUGHNESS], nearest, tc);
+                o.cc_rough = mB.w * ((flags & R3_MAT_CC_GLTF_SPLIT) ? t.y : t.x);
+            }
+        }
+        o.emissive = make_float3(mA.x, mA.y, mA.z);
+        if (tex[R3_TEX_EMISSIVE]) { const float4 t = texture_sample_grad(p, tex[R3_TEX_EMISSIVE], nearest, tc); o.emissive = make_float3(mA.x * t.x, mA.y * t.y, mA.z * t.z); }
+    }
+    *out = o;
+}
+
+// fs_main (opaque.wgsl:470-551).  `mask` lists the point lights that can reach the fragment (a conservative superset is fine:
+// every listed light still takes the exact per-fragment range test below).
+// TEX = the context holds a texture table: kernels are instantiated with and without the texture path, so that scenes without
+// textures keep the register budget (75 instead of 104) of the lean kernel.
+template <bool TEX>
+__device__ __forceinline__ float4 shade_inputs(const ShadeParams& p, const DirPrep* __restrict__ s_dir, const PointPrep* __restrict__ s_point, const FragIn& f,
+                                               const LightMask& mask, const r3_tri_record* tp, uint32_t px, uint32_t py) {
+    const float4 vp = f.vp; const float4 vcolor = f.vcolor; const uint32_t material_index = f.material_index;
+    float3 vnormal = f.vnormal;
+    const r3_material* m = &p.materials[material_index < p.n_materials ? material_index : 0u];
+    const float4 malbedo = __ldg(reinterpret_cast<const float4*>(m->albedo));
+    float4 mA = __ldg(reinterpret_cast<const float4*>(m->emissive));              // emissive.xyz, roughness
+    float4 mB = __ldg(reinterpret_cast<const float4*>(&m->metallic));             // metallic, reflectance, clear_coat, clear_coat_roughness
+    float4 mC = __ldg(reinterpret_cast<const float4*>(&m->anisotropy));           // anisotropy, ambient_occlusion, alpha_cutout, flags
+    const uint32_t flags = __float_as_uint(mC.w);
+    float4 albedo = make_float4(0.f, 0.f, 0.f, 1.f);
+    const uint4 ta = __ldg(reinterpret_cast<const uint4*>(m->textures)), tb = __ldg(reinterpret_cast<const uint4*>(m->textures) + 1);
+    const uint2 tc2 = __ldg(reinterpret_cast<const uint2*>(m->textures) + 4);
+    if (TEX && (ta.x | ta.y | ta.z | ta.w | tb.x | tb.y | tb.z | tb.w | tc2.x | tc2.y) != 0u) {
+        // the material references textures: get_pixel_data_inner out of line, results funnelled into the same variables
+        PixelInputs pi;
+        textured_pixel_data(p, m, f, tp, px, py, &pi);
+        albedo = pi.albedo; vnormal = pi.normal;
+        mA = make_float4(pi.emissive.x, pi.emissive.y, pi.emissive.z, pi.perceptual);
+        mB = make_float4(pi.metallic, pi.reflectance, pi.clear_coat, pi.cc_rough);
+        mC.y = pi.ao;
+    } else {
+        // get_pixel_data_inner for untextured materials (opaque.wgsl:203-424)
+        if (flags & R3_MAT_ALBEDO_ACTIVE) {
+            albedo = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (flags & R3_MAT_ALBEDO_BLEND) {
+                if (flags & R3_MAT_ALBEDO_VERTEX_SRGB) albedo = make_float4(srgb_to_linear(vcolor.x), srgb_to_linear(vcolor.y), srgb_to_linear(vcolor.z), vcolor.w);
+                else albedo = vcolor;
+            }
+        }
+        albedo = make_float4(albedo.x * malbedo.x, albedo.y * malbedo.y, albedo.z * malbedo.z, albedo.w * malbedo.w);
+    }
     if (flags & R3_MAT_UNLIT) {
         return albedo;                                                             // opaque.wgsl:476-478
     } else {
@@ -279,15 +487,16 @@ __device__ __forceinline__ float4 shade_inputs(const ShadeParams& p, const DirPr
 }
 
 // vs_main + fs_main for triangle record `tp` at pixel (px, py), every point light considered
+template <bool TEX>
 __device__ __forceinline__ float4 shade_fragment(const ShadeParams& p, const DirPrep* __restrict__ s_dir, const PointPrep* __restrict__ s_point,
                                                  const r3_tri_record* tp, uint32_t px, uint32_t py) {
     LightMask all;
 #pragma unroll
     for (int k = 0; k < MAX_SMEM_POINT / 32; ++k) all.w[k] = 0xFFFFFFFFu;
-    return shade_inputs(p, s_dir, s_point, fragment_inputs(p, tp, px, py), all);
+    return shade_inputs<TEX>(p, s_dir, s_point, fragment_inputs(p, tp, px, py), all, tp, px, py);
 }
 
-template <int SAMPLES>
+template <int SAMPLES, bool TEX>
 __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ ShadeParams p) {
     __shared__ DirPrep s_dir[MAX_SMEM_DIR];
     __shared__ PointPrep s_point[MAX_SMEM_POINT];
@@ -371,7 +580,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
         for (int k = 0; k < MAX_SMEM_POINT / 32; ++k) mask.w[k] = (p.n_point != 0u && !no_cull) ? s_mask[k] : 0xFFFFFFFFu;
         if (!in_target) return;
         out = make_float4(p.clear[0], p.clear[1], p.clear[2], p.clear[3]);
-        if (covered) { out = shade_inputs(p, s_dir, s_point, f, mask); n_shaded = 1; }
+        if (covered) { out = shade_inputs<TEX>(p, s_dir, s_point, f, mask, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py); n_shaded = 1; }
         depth = __uint_as_float((uint32_t)(key >> 32));
     } else {
         if (!in_target) return;
@@ -393,7 +602,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
                 int reuse = -1;
                 for (int q = 0; q < k; ++q) if ((uint32_t)keys[q] == id && reuse < 0) reuse = q;
                 if (reuse >= 0) col[k] = col[reuse];
-                else { col[k] = shade_fragment(p, s_dir, s_point, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py); n_shaded++; }
+                else { col[k] = shade_fragment<TEX>(p, s_dir, s_point, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py); n_shaded++; }
             }
             // each sample lives in the rgba16f multisampled target
             col[k] = make_float4(__half2float(__float2half_rn(col[k].x)), __half2float(__float2half_rn(col[k].y)), __half2float(__float2half_rn(col[k].z)),
@@ -419,7 +628,7 @@ __device__ __forceinline__ float f16_round(float v) { return __half2float(__floa
 // depth write (forward.rs:331-365), then BlendState::ALPHA_BLENDING (pbr/routine.rs:115-118) into the rgba16f target —
 // rule R8 of the oracle: rgb' = (src.rgb * src.a) + (dst.rgb * (1 - src.a)), a' = src.a + dst.a * (1 - src.a), rounded to
 // half precision after every primitive.  A primitive is shaded once per pixel for all the samples it covers (R7).
-template <int SAMPLES>
+template <int SAMPLES, bool TEX>
 __global__ void __launch_bounds__(256) blend_apply_kernel(const __grid_constant__ ShadeParams p) {
     __shared__ DirPrep s_dir[MAX_SMEM_DIR];
     __shared__ PointPrep s_point[MAX_SMEM_POINT];
@@ -462,7 +671,7 @@ __global__ void __launch_bounds__(256) blend_apply_kernel(const __grid_constant_
                 int reuse = -1;
                 for (int q = 0; q < k; ++q) if (ids[q] == ids[k] && reuse < 0) reuse = q;
                 if (reuse >= 0) col = dst[reuse];
-                else col = shade_fragment(p, s_dir, s_point, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py);
+                else col = shade_fragment<TEX>(p, s_dir, s_point, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py);
             }
             dst[k] = make_float4(f16_round(col.x), f16_round(col.y), f16_round(col.z), f16_round(col.w));
         }
@@ -494,7 +703,7 @@ __global__ void __launch_bounds__(256) blend_apply_kernel(const __grid_constant_
             }
             if (!found || z < zdst[k]) continue;   // GreaterEqual (reverse-Z bits order like the floats)
             zdst[k] = z;                            // depth write
-            if (!shaded) { src = shade_fragment(p, s_dir, s_point, p.tris2 + (next - 1u), px, py); shaded = true; }
+            if (!shaded) { src = shade_fragment<TEX>(p, s_dir, s_point, p.tris2 + (next - 1u), px, py); shaded = true; }
             const float inv_a = sub_rn(1.0f, src.w);
             dst[k] = make_float4(f16_round(add_rn(mul_rn(src.x, src.w), mul_rn(dst[k].x, inv_a))), f16_round(add_rn(mul_rn(src.y, src.w), mul_rn(dst[k].y, inv_a))),
                                  f16_round(add_rn(mul_rn(src.z, src.w), mul_rn(dst[k].z, inv_a))), f16_round(add_rn(src.w, mul_rn(dst[k].w, inv_a))));
@@ -683,6 +892,7 @@ static void fill_shade_params(r3_ctx* c, ShadeParams* out) {
     p.tris2 = c->d_tris[2]; p.n_tris2 = c->n_tris[2]; p.frag_heads = c->d_frag_heads; p.frag_nodes = c->d_frag_nodes;
     p.objects = c->d_objects; p.matrices = cam->d_matrices; p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;
     p.materials = c->d_materials; p.n_materials = c->n_materials;
+    p.tex = c->d_tex_descs; p.n_tex = c->n_textures; p.texels = c->d_texels;
     p.dir = d_dir; p.n_dir = c->n_dir; p.point = d_point; p.n_point = c->n_point;
     p.atlas = c->d_atlas; p.atlas_w = c->atlas_w; p.atlas_h = c->atlas_h;
     memcpy(p.ambient, c->uniforms.ambient, 16); memcpy(p.clear, c->clear_color, 16);
@@ -709,8 +919,9 @@ R3_EXPORT int r3_forward_resolve(r3_ctx* c) {
     const uint32_t rows = c->row_end - c->row_begin;
     if (rows) {
         const dim3 grid((c->width + 31) / 32, (rows + 7) / 8);
-        if (c->samples == 1) resolve_kernel<1><<<grid, 256, 0, c->stream>>>(p);
-        else resolve_kernel<4><<<grid, 256, 0, c->stream>>>(p);
+        const bool tex = c->n_textures != 0;
+        if (c->samples == 1) { if (tex) resolve_kernel<1, true><<<grid, 256, 0, c->stream>>>(p); else resolve_kernel<1, false><<<grid, 256, 0, c->stream>>>(p); }
+        else { if (tex) resolve_kernel<4, true><<<grid, 256, 0, c->stream>>>(p); else resolve_kernel<4, false><<<grid, 256, 0, c->stream>>>(p); }
         R3_CHECK_LAUNCH(c, "resolve_kernel");
     }
     return R3_OK;
@@ -726,8 +937,9 @@ R3_EXPORT int r3_forward_blend(r3_ctx* c) {
     ShadeParams p;
     fill_shade_params(c, &p);   // the lights were prepared by r3_forward_resolve of this frame
     const dim3 grid((c->width + 31) / 32, (rows + 7) / 8);
-    if (c->samples == 1) blend_apply_kernel<1><<<grid, 256, 0, c->stream>>>(p);
-    else blend_apply_kernel<4><<<grid, 256, 0, c->stream>>>(p);
+    const bool tex = c->n_textures != 0;
+    if (c->samples == 1) { if (tex) blend_apply_kernel<1, true><<<grid, 256, 0, c->stream>>>(p); else blend_apply_kernel<1, false><<<grid, 256, 0, c->stream>>>(p); }
+    else { if (tex) blend_apply_kernel<4, true><<<grid, 256, 0, c->stream>>>(p); else blend_apply_kernel<4, false><<<grid, 256, 0, c->stream>>>(p); }
     R3_CHECK_LAUNCH(c, "blend_apply_kernel");
     return R3_OK;
 }

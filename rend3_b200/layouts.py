@@ -19,8 +19,16 @@ PCU_MULTISAMPLED = 0x2
 MAT_ALBEDO_ACTIVE = 0x0001
 MAT_ALBEDO_BLEND = 0x0002
 MAT_ALBEDO_VERTEX_SRGB = 0x0004
+MAT_BICOMPONENT_NORMAL = 0x0008
+MAT_SWIZZLED_NORMAL = 0x0010
+MAT_YDOWN_NORMAL = 0x0020
 MAT_AOMR_COMBINED = 0x0040
+MAT_AOMR_SWIZZLED_SPLIT = 0x0080
+MAT_AOMR_SPLIT = 0x0100
+MAT_AOMR_BW_SPLIT = 0x0200
 MAT_CC_GLTF_COMBINED = 0x0400
+MAT_CC_GLTF_SPLIT = 0x0800
+MAT_CC_BW_SPLIT = 0x1000
 MAT_UNLIT = 0x2000
 MAT_NEAREST = 0x4000
 
@@ -146,6 +154,11 @@ MATERIAL_DTYPE = _dt(
     ],
     208,
 )
+
+TEXTURE_DESC_DTYPE = _dt([("width", u4, 0), ("height", u4, 4), ("mip_count", u4, 8), ("format", u4, 12), ("byte_offset", np.dtype("<u8"), 16)], 32)
+TEXFMT_RGBA8_UNORM, TEXFMT_RGBA8_UNORM_SRGB, TEXFMT_RGBA32_FLOAT = 0, 1, 2
+(TEX_ALBEDO, TEX_NORMAL, TEX_ROUGHNESS, TEX_METALLIC, TEX_REFLECTANCE, TEX_CLEAR_COAT, TEX_CLEAR_COAT_ROUGHNESS, TEX_EMISSIVE, TEX_ANISOTROPY,
+ TEX_AMBIENT_OCCLUSION) = range(10)
 
 SKINNING_INPUT_DTYPE = _dt(
     [

@@ -13,7 +13,7 @@ import numpy as np
 from . import glam
 from .layouts import ATTR_ABSENT, OBJECT_DTYPE
 from .runner import cube_mesh
-from .world import LEFT, Camera, DirectionalLight, EvalOutput, MeshBuilder, PbrMaterial, PointLight, Renderer
+from .world import LEFT, Camera, DirectionalLight, EvalOutput, MeshBuilder, Object, PbrMaterial, PointLight, Renderer
 
 f32 = np.float32
 
@@ -100,27 +100,87 @@ def cube_example_camera(pull_back: float = 1.0) -> Camera:
     return Camera(("perspective", 60.0, 0.1), view)
 
 
-def subdivided_cube_mesh(k: int):
-    """Cube [-1,1]^3 whose faces are k x k quads (12 k^2 triangles), same winding as rend3-test's cube."""
-    if k == 1:
+def subdivided_cube_mesh(k: int, with_uv: bool = False):
+    """Cube [-1,1]^3 whose faces are k x k quads (12 k^2 triangles), same winding as rend3-test's cube.  with_uv: every face
+    carries texture coordinates [0,1]^2 (MeshBuilder then derives tangents, lib.rs:720-836)."""
+    if k == 1 and not with_uv:
         return cube_mesh()
     faces = [  # origin corner, u edge, v edge chosen so (o, o+u, o+u+v, o+v) matches helpers.rs:78-109
         ((-1, -1, 1), (2, 0, 0), (0, 2, 0)), ((-1, 1, -1), (2, 0, 0), (0, -2, 0)), ((1, -1, -1), (0, 2, 0), (0, 0, 2)),
         ((-1, -1, 1), (0, 2, 0), (0, 0, -2)), ((1, 1, -1), (-2, 0, 0), (0, 0, 2)), ((1, -1, 1), (-2, 0, 0), (0, 0, -2)),
     ]
-    pos, idx = [], []
+    pos, idx, uvs = [], [], []
     for o, u, v in faces:
         o, u, v = (np.array(a, dtype=np.float64) for a in (o, u, v))
         base = len(pos)
         for j in range(k + 1):
             for i in range(k + 1):
                 pos.append(o + u * (i / k) + v * (j / k))
+                uvs.append((i / k, j / k))
         for j in range(k):
             for i in range(k):
                 a = base + j * (k + 1) + i
                 b, c, d = a + 1, a + 1 + (k + 1), a + (k + 1)
                 idx += [a, b, c, c, d, a]
-    return MeshBuilder.new(np.array(pos, dtype=f32), LEFT).with_indices(idx).build()
+    mb = MeshBuilder.new(np.array(pos, dtype=f32), LEFT).with_indices(idx)
+    if with_uv:
+        mb = mb.with_vertex_texture_coordinates_0(np.array(uvs, dtype=f32))
+    return mb.build()
+
+
+def textured_cube_scene(n_objects: int = 300, seed: int = 41, resolution: Tuple[int, int] = (320, 180), texture_size: int = 32,
+                        sample_type: str = "linear") -> EvalOutput:
+    """Cubes with texture coordinates and materials that exercise every texture slot and layout flag of PbrMaterial
+    (opaque.wgsl:203-424): sRGB albedo, tri- and bi-component normal maps, combined / split AO-metallic-roughness, reflectance,
+    clear coat, emissive, a scaled uv_transform0; one shadowed directional light and two point lights."""
+    from .world import Texture
+
+    rng = np.random.default_rng(seed)
+    r = Renderer(LEFT, aspect_ratio=resolution[0] / resolution[1])
+    meshes = [r.add_mesh(subdivided_cube_mesh(k, with_uv=True)) for k in (1, 2)]
+
+    def smooth(channels_lo, channels_hi):   # low-frequency random texture: a few random texels upsampled bilinearly
+        coarse = rng.uniform(channels_lo, channels_hi, (5, 5, 4))
+        t = np.linspace(0, 4, texture_size, endpoint=False)
+        i0 = np.floor(t).astype(int)
+        f = (t - i0)[:, None]
+        rows = coarse[i0] * (1 - f[..., None]) + coarse[np.minimum(i0 + 1, 4)] * f[..., None]
+        img = rows[:, i0] * (1 - f[None, :, :]) + rows[:, np.minimum(i0 + 1, 4)] * f[None, :, :]
+        return np.clip(np.rint(img * 255), 0, 255).astype(np.uint8)
+
+    albedo = r.add_texture_2d(Texture(smooth(0.2, 1.0), srgb=True))
+    normal = r.add_texture_2d(Texture(smooth((0.35, 0.35, 0.8, 0.35), (0.65, 0.65, 1.0, 0.65))))
+    aomr = r.add_texture_2d(Texture(smooth((0.6, 0.3, 0.0, 0.0), (1.0, 0.9, 0.6, 1.0))))
+    single = r.add_texture_2d(Texture(smooth(0.3, 0.9)))
+    emissive = r.add_texture_2d(Texture(smooth(0.0, 0.4), srgb=True))
+    f32tex = r.add_texture_2d(Texture(rng.uniform(0.2, 0.8, (8, 8, 4)).astype(f32), mips="none"))
+    ut = np.array([[2.0, 0, 0], [0, 1.5, 0], [0.25, 0.1, 1]], dtype=f32)
+    mats = [
+        PbrMaterial(albedo_texture=albedo, roughness_factor=0.5, sample_type=sample_type),
+        PbrMaterial(albedo_texture=albedo, albedo_value=(0.9, 0.8, 0.7, 1.0), normal_texture=normal, roughness_texture=aomr, roughness_factor=0.9, metallic_factor=0.8,
+                    ao_factor=0.9, sample_type=sample_type),
+        PbrMaterial(albedo_value=(0.6, 0.6, 0.6, 1.0), normal_texture=normal, normal_kind="bicomponent", normal_y_down=True, aomr_kind="bw_split",
+                    roughness_texture=single, metallic_texture=single, ao_texture=single, roughness_factor=0.8, metallic_factor=0.5, sample_type=sample_type),
+        PbrMaterial(albedo_texture=albedo, normal_texture=normal, normal_kind="bicomponent_swizzled", aomr_kind="swizzled_split", roughness_texture=aomr, ao_texture=single,
+                    roughness_factor=1.0, metallic_factor=1.0, reflectance_texture=single, reflectance=0.8, emissive=(1.0, 0.8, 0.6), emissive_texture=emissive,
+                    uv_transform0=ut, sample_type=sample_type),
+        PbrMaterial(albedo_texture=f32tex, aomr_kind="split", roughness_texture=aomr, roughness_factor=0.7, metallic_factor=0.4, clearcoat_factor=0.6,
+                    clearcoat_roughness_factor=0.5, clearcoat_texture=aomr, clearcoat_kind="gltf_combined", sample_type=sample_type),
+        PbrMaterial(albedo_texture=albedo, roughness_factor=0.6, clearcoat_factor=0.5, clearcoat_roughness_factor=0.8, clearcoat_kind="gltf_split",
+                    clearcoat_texture=single, clearcoat_roughness_texture=aomr, anisotropy=0.3, anisotropy_texture=single, sample_type=sample_type),
+        PbrMaterial(albedo_texture=albedo, unlit=True, sample_type=sample_type),
+    ]
+    mat_ids = [r.add_material(m) for m in mats]
+    r.set_camera_data(cube_example_camera(8.0))
+    r.add_directional_light(DirectionalLight(color=(1, 1, 1), intensity=1.0, direction=(-1.0, -4.0, 2.0), distance=80.0, resolution=256))
+    for _ in range(2):
+        r.add_point_light(PointLight(position=tuple(rng.uniform(-10, 10, 3)), color=tuple(rng.uniform(0.3, 1.0, 3)), radius=18.0, intensity=3.0))
+    centers = rng.uniform(-14.0, 14.0, (n_objects, 3)).astype(f32)
+    scale = rng.uniform(0.8, 3.0, (n_objects, 1)).astype(f32)
+    transforms = trs_matrices(centers, random_unit_quaternions(rng, n_objects), scale)
+    for i in range(n_objects):
+        r.add_object(Object(meshes[i % 2], mat_ids[i % len(mat_ids)], transforms[i]))
+    return r.evaluate()
 
 
 def cube_field_scene(n_objects: int = 10_000, seed: int = 1, resolution: Tuple[int, int] = (1920, 1080), extent: float = 50.0,

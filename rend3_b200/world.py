@@ -30,6 +30,19 @@ from .layouts import (
     ATTR_ABSENT,
     MAT_ALBEDO_ACTIVE,
     MAT_ALBEDO_BLEND,
+    MAT_AOMR_BW_SPLIT,
+    MAT_AOMR_SPLIT,
+    MAT_AOMR_SWIZZLED_SPLIT,
+    MAT_BICOMPONENT_NORMAL,
+    MAT_CC_BW_SPLIT,
+    MAT_CC_GLTF_SPLIT,
+    MAT_NEAREST,
+    MAT_SWIZZLED_NORMAL,
+    MAT_YDOWN_NORMAL,
+    TEXTURE_DESC_DTYPE,
+    TEXFMT_RGBA8_UNORM,
+    TEXFMT_RGBA8_UNORM_SRGB,
+    TEXFMT_RGBA32_FLOAT,
     MAT_ALBEDO_VERTEX_SRGB,
     MAT_AOMR_COMBINED,
     MAT_CC_GLTF_COMBINED,
@@ -107,10 +120,10 @@ class MeshBuilder:
             attrs.append((5, self.color0))
         if self.normals is None:
             attrs.append((1, calculate_normals(self.positions, indices, self.handedness == LEFT)))
-        # tangents are generated only when uv0 exists (lib.rs:720-728); the synthetic scenes are
-        # untextured, so a zero tangent array stands in (unused without a normal map).
+        # tangents are generated only when uv0 exists (lib.rs:720-728)
         if self.uv0 is not None:
-            attrs.append((2, np.zeros((n, 3), dtype=f32)))
+            normals = next(a for slot, a in attrs if slot == 1)
+            attrs.append((2, calculate_tangents(self.positions, normals, self.uv0, indices)))
         return Mesh(attrs, n, indices)
 
 
@@ -130,6 +143,26 @@ def calculate_normals(positions: np.ndarray, indices: np.ndarray, left_handed: b
     for i in range(len(normals)):
         normals[i] = glam.normalize_or_zero3(normals[i])
     return normals
+
+
+def calculate_tangents(positions: np.ndarray, normals: np.ndarray, uvs: np.ndarray, indices: np.ndarray) -> np.ndarray:
+    """Mesh::calculate_tangents_for_buffers (rend3-types/src/lib.rs:784-836), including its operator precedence:
+    tangent = edge1 * uv2.y - (edge2 * uv1.y) * r; then Gram-Schmidt against the normal, normalize_or_zero."""
+    tangents = np.zeros_like(positions, dtype=f32)
+    with np.errstate(all="ignore"):
+        for i0, i1, i2 in indices.reshape(-1, 3):
+            e1 = (positions[i1] - positions[i0]).astype(f32)
+            e2 = (positions[i2] - positions[i0]).astype(f32)
+            uv1 = (uvs[i1] - uvs[i0]).astype(f32)
+            uv2 = (uvs[i2] - uvs[i0]).astype(f32)
+            r = f32(1.0) / f32(f32(uv1[0] * uv2[1]) - f32(uv1[1] * uv2[0]))
+            t = ((e1 * uv2[1]).astype(f32) - ((e2 * uv1[1]).astype(f32) * r).astype(f32)).astype(f32)
+            for i in (i0, i1, i2):
+                tangents[i] = (tangents[i] + t).astype(f32)
+        for i in range(len(tangents)):
+            t = (tangents[i] - (normals[i] * glam.dot3(normals[i], tangents[i])).astype(f32)).astype(f32)
+            tangents[i] = glam.normalize_or_zero3(np.nan_to_num(t, nan=0.0, posinf=0.0, neginf=0.0).astype(f32))
+    return tangents
 
 
 def bounding_sphere_from_mesh(positions: np.ndarray):
@@ -154,6 +187,46 @@ def sphere_apply_transform(center, radius, m):
 
 # ----------------------------------------------------------------------------- materials
 @dataclass
+class Texture:
+    """rend3_types::Texture (rend3-types/src/lib.rs:843-870): RGBA texels + MipmapSource.  `data` is (h, w, 4) uint8 (Rgba8Unorm /
+    Rgba8UnormSrgb) or float32 (Rgba32Float); mips = "generated" (box filter, MipmapCount::Maximum) or 1 level."""
+
+    data: np.ndarray
+    srgb: bool = False
+    mips: str = "generated"
+
+    def levels(self) -> List[np.ndarray]:
+        lv = [np.ascontiguousarray(self.data)]
+        if self.mips != "generated":
+            return lv
+        while lv[-1].shape[0] > 1 or lv[-1].shape[1] > 1:
+            a = lv[-1].astype(np.float64)
+            if self.srgb and a.dtype != np.float32 and self.data.dtype == np.uint8:
+                lin = a / 255.0
+                rgb = np.where(lin[..., :3] > 0.04045, ((lin[..., :3] + 0.055) / 1.055) ** 2.4, lin[..., :3] / 12.92)
+                a = np.concatenate([rgb, lin[..., 3:]], axis=-1)
+            elif self.data.dtype == np.uint8:
+                a = a / 255.0
+            h, w = a.shape[:2]
+            nh, nw = max(h // 2, 1), max(w // 2, 1)
+            a = a[: nh * 2 if h > 1 else 1, : nw * 2 if w > 1 else 1]
+            a = a.reshape(nh, 2 if h > 1 else 1, nw, 2 if w > 1 else 1, 4).mean(axis=(1, 3))
+            if self.data.dtype == np.uint8:
+                if self.srgb:
+                    rgb = np.where(a[..., :3] > 0.0031308, 1.055 * a[..., :3] ** (1 / 2.4) - 0.055, a[..., :3] * 12.92)
+                    a = np.concatenate([rgb, a[..., 3:]], axis=-1)
+                lv.append(np.clip(np.rint(a * 255.0), 0, 255).astype(np.uint8))
+            else:
+                lv.append(a.astype(np.float32))
+        return lv
+
+    def format(self) -> int:
+        if self.data.dtype == np.float32:
+            return TEXFMT_RGBA32_FLOAT
+        return TEXFMT_RGBA8_UNORM_SRGB if self.srgb else TEXFMT_RGBA8_UNORM
+
+
+@dataclass
 class PbrMaterial:
     """Untextured subset of rend3-routine's PbrMaterial (pbr/material.rs:455-474)."""
 
@@ -170,6 +243,23 @@ class PbrMaterial:
     clearcoat_roughness_factor: Optional[float] = None
     emissive: Optional[Tuple[float, float, float]] = None
     anisotropy: Optional[float] = None
+    # texture handles (Renderer.add_texture_2d) per slot of GpuMaterialData (material.wgsl:21-35); None = no texture
+    albedo_texture: Optional[int] = None            # AlbedoComponent::Texture / TextureValue / TextureVertex...
+    normal_texture: Optional[int] = None            # NormalTexture::{Tricomponent, Bicomponent, BicomponentSwizzled}
+    normal_kind: str = "tricomponent"               # | "bicomponent" | "bicomponent_swizzled"
+    normal_y_down: bool = False                     # NormalTextureYDirection::Down
+    aomr_kind: str = "combined"                     # AoMRTextures: "combined" | "swizzled_split" | "split" | "bw_split"
+    roughness_texture: Optional[int] = None         # the mr / aomr texture slot
+    metallic_texture: Optional[int] = None
+    ao_texture: Optional[int] = None
+    reflectance_texture: Optional[int] = None
+    clearcoat_kind: str = "gltf_combined"           # ClearcoatTextures: "gltf_combined" | "gltf_split" | "bw_split"
+    clearcoat_texture: Optional[int] = None
+    clearcoat_roughness_texture: Optional[int] = None
+    emissive_texture: Optional[int] = None
+    anisotropy_texture: Optional[int] = None
+    sample_type: str = "linear"                     # SampleType::{Linear, Nearest}
+    uv_transform0: Optional[np.ndarray] = None      # 3x3, column-major like glam Mat3
 
     def key(self) -> int:  # Material::key (pbr/material.rs:497-499)
         return int(self.transparency)
@@ -184,6 +274,12 @@ class PbrMaterial:
         """ShaderMaterial::from_material (pbr/material.rs:549-582) inside the Gpu wrapper."""
         r = np.zeros((), dtype=MATERIAL_DTYPE)
         r["uv_transform0"] = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]]
+        if self.uv_transform0 is not None:
+            u = np.asarray(self.uv_transform0, dtype=f32).reshape(3, 3)   # u[col][row]
+            r["uv_transform0"] = [[u[0][0], u[0][1], u[0][2], 0], [u[1][0], u[1][1], u[1][2], 0], [u[2][0], u[2][1], u[2][2], 0]]
+        for slot, handle in enumerate((self.albedo_texture, self.normal_texture, self.roughness_texture, self.metallic_texture, self.reflectance_texture,
+                                       self.clearcoat_texture, self.clearcoat_roughness_texture, self.emissive_texture, self.anisotropy_texture, self.ao_texture)):
+            r["textures"][slot] = 0 if handle is None else handle + 1            # NonZeroU32 index + 1 (managers/texture.rs)
         r["uv_transform1"] = [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]]
         r["albedo"] = self.albedo_value if self.albedo_value is not None else (1, 1, 1, 1)
         r["emissive"] = self.emissive if self.emissive is not None else (0, 0, 0)
@@ -196,13 +292,24 @@ class PbrMaterial:
         r["ambient_occlusion"] = 1.0 if self.ao_factor is None else self.ao_factor
         r["alpha_cutout"] = self.alpha_cutout if self.transparency == CUTOUT else 0.0
         flags = 0
-        if self.albedo_value is not None or self.albedo_vertex is not None:
+        if self.albedo_value is not None or self.albedo_vertex is not None or self.albedo_texture is not None:
             flags |= MAT_ALBEDO_ACTIVE
         if self.albedo_vertex is not None:
             flags |= MAT_ALBEDO_BLEND
             if self.albedo_vertex == "srgb":
                 flags |= MAT_ALBEDO_VERTEX_SRGB
-        flags |= MAT_AOMR_COMBINED | MAT_CC_GLTF_COMBINED  # AoMRTextures::None / ClearcoatTextures::None
+        # pbr/material.rs:296-305,354-362: the texture-layout enums map to one flag each (None counts as Combined)
+        flags |= {"combined": MAT_AOMR_COMBINED, "swizzled_split": MAT_AOMR_SWIZZLED_SPLIT, "split": MAT_AOMR_SPLIT, "bw_split": MAT_AOMR_BW_SPLIT}[self.aomr_kind]
+        flags |= {"gltf_combined": MAT_CC_GLTF_COMBINED, "gltf_split": MAT_CC_GLTF_SPLIT, "bw_split": MAT_CC_BW_SPLIT}[self.clearcoat_kind]
+        if self.normal_texture is not None:
+            if self.normal_kind != "tricomponent":
+                flags |= MAT_BICOMPONENT_NORMAL
+            if self.normal_kind == "bicomponent_swizzled":
+                flags |= MAT_SWIZZLED_NORMAL
+            if self.normal_y_down:
+                flags |= MAT_YDOWN_NORMAL
+        if self.sample_type == "nearest":
+            flags |= MAT_NEAREST
         if self.unlit:
             flags |= MAT_UNLIT
         r["flags"] = flags
@@ -390,6 +497,8 @@ class EvalOutput:
     object_location: np.ndarray        # (capacity,3) f32  InternalObject::location (object.rs:256,306)
     mesh_buffer: np.ndarray            # (nwords,) u32
     material_buffer: np.ndarray        # (n,) MATERIAL_DTYPE
+    texture_descs: np.ndarray          # (n,) TEXTURE_DESC_DTYPE — the bindless d2 table
+    texture_texels: np.ndarray         # u8 blob holding every mip level
     directional_buffer: bytes          # u32 count @0, array @16 (stride 128)
     point_buffer: bytes                # u32 count @0, array @16 (stride 32)
     shadows: List[ShadowDesc]
@@ -408,6 +517,7 @@ class Renderer:
         self.meshes: list = []
         self.mesh_words = np.zeros(0, dtype=np.uint32)
         self.materials: List[PbrMaterial] = []
+        self.textures: List[Texture] = []
         self.objects: List[Optional[dict]] = []
         self.free_objects: List[int] = []
         self.delayed: List[int] = []
@@ -439,6 +549,23 @@ class Renderer:
             dict(ranges=ranges, index_start=index_start, index_count=len(mesh.indices), center=center, radius=radius)
         )
         return len(self.meshes) - 1
+
+    def add_texture_2d(self, texture: Texture) -> int:   # Renderer::add_texture_2d (renderer/mod.rs:213-241)
+        self.textures.append(texture)
+        return len(self.textures) - 1
+
+    def _texture_table(self):
+        descs = np.zeros(len(self.textures), dtype=TEXTURE_DESC_DTYPE)
+        blobs, cursor = [], 0
+        for i, t in enumerate(self.textures):
+            lv = t.levels()
+            descs[i]["width"], descs[i]["height"] = lv[0].shape[1], lv[0].shape[0]
+            descs[i]["mip_count"], descs[i]["format"], descs[i]["byte_offset"] = len(lv), t.format(), cursor
+            raw = np.concatenate([np.ascontiguousarray(l).view(np.uint8).reshape(-1) for l in lv])
+            pad = (-len(raw)) % 16
+            blobs.append(np.concatenate([raw, np.zeros(pad, dtype=np.uint8)]))
+            cursor += len(raw) + pad
+        return descs, (np.concatenate(blobs) if blobs else np.zeros(0, dtype=np.uint8))
 
     def add_material(self, material: PbrMaterial) -> int:
         self.materials.append(material)
@@ -583,6 +710,7 @@ class Renderer:
             pl[k]["radius"] = l.radius
         pbytes = np.array([len(pl), 0, 0, 0], dtype=np.uint32).tobytes() + pl.tobytes()
 
+        tex_descs, tex_blob = self._texture_table()
         return EvalOutput(
             object_buffer=self.obj_gpu.copy(),
             object_material_key=key,
@@ -592,6 +720,8 @@ class Renderer:
             object_location=location,
             mesh_buffer=self.mesh_words.copy(),
             material_buffer=mats,
+            texture_descs=tex_descs,
+            texture_texels=tex_blob,
             directional_buffer=dbytes,
             point_buffer=pbytes,
             shadows=shadows,

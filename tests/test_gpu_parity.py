@@ -358,6 +358,49 @@ def test_blend_routine_matches_oracle(cuda, samples):
         assert np.mean(np.abs(a - o) > TOL) < 0.02, "half-precision rounding flips must stay rare"
 
 
+@pytest.mark.parametrize("sample_type", ["linear", "nearest"])
+def test_texture_sampling_known_answers(cuda, sample_type):
+    """textureSampleGrad (rule R9) on the CUDA path against the texture itself: level 0 at one texel per pixel, mip 1 at half
+    resolution, Repeat tiling through uv_transform0, sRGB decode before filtering."""
+    import texture_case as tcase
+    from rend3_b200.world import Texture
+
+    data = tcase.checker_texture(64, seed=3)
+    for srgb in (False, True):
+        tex = Texture(data, srgb=srgb)
+        decode = tcase.srgb_decode if srgb else (lambda a: a.astype(np.float64) / 255.0)
+        for size, scale, want in ((64, 1.0, decode(data)), (32, 1.0, decode(tex.levels()[1])), (128, 2.0, np.tile(decode(data), (2, 2, 1)))):
+            b = load_cuda_backend(0)
+            tcase.build(b, tex, sample_type, uv_scale=scale).render_frame(size)
+            assert np.abs(b.readback_hdr_f32() - want).max() < 2e-5, (srgb, size, scale)
+            b.close()
+
+
+@pytest.mark.parametrize("sample_type,samples", [("linear", 1), ("nearest", 1), ("linear", 4)])
+def test_textured_materials_match_oracle(cuda, sample_type, samples):
+    """Every texture slot and layout flag of PbrMaterial (albedo sRGB / float, tri- and bi-component normal maps, combined /
+    split / bw AO-metallic-roughness, reflectance, clear coat, emissive, uv_transform0) under one shadowed directional light and
+    two point lights.  Texel and mip SELECTION is bit-identical by construction for the linear sampler; the nearest sampler may
+    pick the neighbouring mip where log2 of the footprint lands on x.5 (libm vs CUDA log2f), hence the small outlier budget."""
+    from rend3_b200.scenes import textured_cube_scene
+
+    res = (320, 180)
+    ev = textured_cube_scene(n_objects=500, resolution=res, sample_type=sample_type)
+    orc = load_oracle_backend()
+    for b in (cuda, orc):
+        BaseRenderGraph(b).add_to_graph(ev, res, samples, BaseRenderGraphSettings(clear_color=(0.05, 0.05, 0.1, 1.0)))
+    compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], check_pixels=False, what="textured")
+    assert np.array_equal(cuda.readback_depth().view(np.uint32), orc.readback_depth().view(np.uint32))
+    assert cuda.forward_stats()[:3] == orc.forward_stats()[:3] and orc.forward_stats()[2] > 10000
+    a, o = cuda.readback_hdr_f32().astype(np.float64), orc.readback_hdr_f32().astype(np.float64)
+    bound = TOL * np.maximum(1.0, np.abs(o)) + (np.maximum(np.abs(o) * 2.0 ** -10, 2.0 ** -24) if samples == 4 else 0.0)
+    off = np.abs(a - o) > bound
+    if sample_type == "linear":
+        assert not off.any(), f"{off.sum()} channel values differ (max {np.abs(a - o).max():.3e})"
+    else:
+        assert off.sum() <= 1e-3 * off.size, f"{off.sum()} channel values differ (max {np.abs(a - o).max():.3e})"
+
+
 def test_device_batching_equals_host_batching_and_oracle(cuda, monkeypatch):
     """batch_objects on the device (radix sort + block scans) against the host implementation and the oracle, with
     three material keys (opaque / cutout / blend: atomic and non-atomic regions, front-to-back and back-to-front)."""

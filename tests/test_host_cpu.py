@@ -211,6 +211,43 @@ def test_oracle_blend_routine_known_answer(far_first, samples):
     assert sorted(int(k) for k in regions["material_key"]) == [0, 2]
 
 
+@pytest.mark.parametrize("sample_type", ["linear", "nearest"])
+@pytest.mark.parametrize("srgb", [False, True])
+def test_oracle_texture_sampling_known_answers(sample_type, srgb):
+    """textureSampleGrad of the bindless d2 table (rule R9): texel centres on pixel centres reproduce the texture; half the
+    resolution selects mip 1 exactly; uv_transform0 x2 tiles it (Repeat); *Srgb formats decode before filtering."""
+    import texture_case as tcase
+    from rend3_b200.world import Texture
+
+    data = tcase.checker_texture(64, seed=3)
+    tex = Texture(data, srgb=srgb)
+    decode = tcase.srgb_decode if srgb else (lambda a: a.astype(np.float64) / 255.0)
+    orc = load_oracle_backend()
+    tcase.build(orc, tex, sample_type).render_frame(64)
+    hdr = orc.readback_hdr_f32()
+    assert np.abs(hdr - decode(data)).max() < 2e-5, "level 0 at one texel per pixel"
+    # one texel of mip 1 per pixel
+    orc = load_oracle_backend()
+    tcase.build(orc, tex, sample_type).render_frame(32)
+    assert np.abs(orc.readback_hdr_f32() - decode(tex.levels()[1])).max() < 2e-5, "lambda = 1 selects mip 1"
+    # two tiles per axis at 128 pixels: still one texel per pixel
+    orc = load_oracle_backend()
+    tcase.build(orc, tex, sample_type, uv_scale=2.0).render_frame(128)
+    assert np.abs(orc.readback_hdr_f32() - np.tile(decode(data), (2, 2, 1))).max() < 2e-5, "Repeat addressing"
+    if sample_type == "linear":
+        # magnification x2: pixel centres sit a quarter texel off the texel centres -> bilinear mix of four texels
+        orc = load_oracle_backend()
+        tcase.build(orc, Texture(data, srgb=srgb, mips="none"), "linear").render_frame(128)
+        d = decode(data)
+        pad = np.pad(d, ((1, 1), (1, 1), (0, 0)), mode="wrap")
+        y, x = np.mgrid[0:128, 0:128]
+        fx, fy = (x + 0.5) / 2 - 0.5, (y + 0.5) / 2 - 0.5
+        x0, y0 = np.floor(fx).astype(int), np.floor(fy).astype(int)
+        wx, wy = (fx - x0)[..., None], (fy - y0)[..., None]
+        want = (pad[y0 + 1, x0 + 1] * (1 - wx) + pad[y0 + 1, x0 + 2] * wx) * (1 - wy) + (pad[y0 + 2, x0 + 1] * (1 - wx) + pad[y0 + 2, x0 + 2] * wx) * wy
+        assert np.abs(orc.readback_hdr_f32() - want).max() < 2e-5, "bilinear magnification"
+
+
 def test_oracle_skinning_matches_float64_blend():
     """skinning.wgsl:37-94 restated: skinned positions equal the float64 4-joint blend, normals are unit length, and
     identity joints leave the mesh untouched."""
