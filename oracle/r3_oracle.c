@@ -129,7 +129,7 @@ API int r3o_ctx_destroy(r3o_ctx* c) {
     free(c->vis); free(c->hdr); free(c->hdr16); free(c->depth); free(c->ldr); free(c->atlas);
     for (uint32_t i = 0; i < c->hiz_mips; ++i) free(c->hiz[i]);
     free(c->hiz); free(c->hiz_w); free(c->hiz_h);
-    free(c->tex_descs); free(c->texels); free(c->tris[0]); free(c->tris[1]); free(c->tris[2]); free(c->sample_col16); free(c->blended);
+    free(c->tex_descs); free(c->texels); free(c->tris[0]); free(c->tris[1]); free(c->tris[2]); free(c->tris[3]); free(c->sample_col16); free(c->blended);
     free(c);
     return R3_OK;
 }

@@ -52,7 +52,7 @@ typedef struct r3o_ctx {
     float* hdr; uint16_t* hdr16; float* depth; uint8_t* ldr;
     float* atlas;
     float** hiz; uint32_t* hiz_w; uint32_t* hiz_h; uint32_t hiz_mips;
-    struct r3o_tri* tris[3]; uint64_t n_tris[3], cap_tris[3];   /* predicted, residual, blend */
+    struct r3o_tri* tris[4]; uint64_t n_tris[4], cap_tris[4];   /* predicted, residual, blend, shadow-pass scratch */
     uint16_t* sample_col16;   /* the rgba16f colour target per SAMPLE (what the blend routine reads and writes) */
     uint8_t* blended;         /* per pixel: touched by the blend routine this frame */
     uint64_t stats[4];

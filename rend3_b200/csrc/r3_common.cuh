@@ -91,7 +91,8 @@ struct r3_ctx {
     float* d_hdr32 = nullptr; uint16_t* d_hdr16 = nullptr; float* d_depth = nullptr; uint8_t* d_ldr = nullptr;
     std::vector<float*> d_hiz; std::vector<uint32_t> hiz_w, hiz_h;
     float** d_hiz_ptrs = nullptr; uint32_t* d_hiz_dims = nullptr;
-    r3_tri_record* d_tris[3] = {nullptr, nullptr, nullptr}; uint64_t tris_cap[3] = {0, 0, 0}; uint64_t n_tris[3] = {0, 0, 0};   // predicted, residual, blend
+    r3_tri_record* d_tris[4] = {nullptr, nullptr, nullptr, nullptr}; uint64_t tris_cap[4] = {0, 0, 0, 0}; uint64_t n_tris[4] = {0, 0, 0, 0};   // predicted, residual, blend, shadow scratch
+    bool any_frag_alpha = false;              // a material discards per fragment (cutout alpha from its albedo texture / vertex colour)
     unsigned long long* d_stats = nullptr;    // [8]: [0..3] forward statistics, [4] scratch of r3_compute_max_invocations
     // blend routine: per-sample fragment lists (head = node index + 1, 0 = empty; node = {record, depth bits, next, 0})
     bool any_blend = false;                   // some live object carries material key 2 (TransparencyType::Blend)

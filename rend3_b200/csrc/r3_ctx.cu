@@ -82,7 +82,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     cudaFree(c->d_vis); cudaFree(c->d_hdr32); cudaFree(c->d_hdr16); cudaFree(c->d_depth); cudaFree(c->d_ldr);
     for (float* p : c->d_hiz) cudaFree(p);
     cudaFree(c->d_hiz_ptrs); cudaFree(c->d_hiz_dims);
-    cudaFree(c->d_tris[0]); cudaFree(c->d_tris[1]); cudaFree(c->d_tris[2]); cudaFree(c->d_stats); cudaFree(c->d_scratch);
+    cudaFree(c->d_tris[0]); cudaFree(c->d_tris[1]); cudaFree(c->d_tris[2]); cudaFree(c->d_tris[3]); cudaFree(c->d_stats); cudaFree(c->d_scratch);
     cudaFree(c->d_frag_heads); cudaFree(c->d_frag_nodes);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -207,6 +207,9 @@ R3_EXPORT int r3_set_materials(r3_ctx* c, const r3_material* recs, uint32_t n) {
     if (n) R3_CUDA(c, cudaMemcpyAsync(c->d_materials, recs, (size_t)n * sizeof(r3_material), cudaMemcpyHostToDevice, c->stream));
     R3_CUDA(c, cudaStreamSynchronize(c->stream));
     c->n_materials = n;
+    c->any_frag_alpha = false;
+    for (uint32_t i = 0; i < n; ++i)
+        if ((recs[i].flags & R3_MAT_ALBEDO_ACTIVE) && recs[i].alpha_cutout > 0.0f && (recs[i].textures[R3_TEX_ALBEDO] || (recs[i].flags & R3_MAT_ALBEDO_BLEND))) c->any_frag_alpha = true;
     return R3_OK;
 }
 R3_EXPORT int r3_set_textures(r3_ctx* c, const r3_texture_desc* descs, uint32_t n, const void* texels, uint64_t nbytes) {

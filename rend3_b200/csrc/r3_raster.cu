@@ -19,6 +19,7 @@
 // All setup / coverage / depth arithmetic is __f*_rn in the order of the oracle's RASTER RULES R1-R5
 // (oracle/r3_oracle_forward.inc), integer edge functions with the top-left rule — bit-exact by construction.
 #include "r3_common.cuh"
+#include "r3_texture.cuh"
 
 namespace {
 
@@ -34,8 +35,11 @@ constexpr int MODE_COLOUR = 0;           // opaque + cutout forward routines int
 constexpr int MODE_DEPTH = 1;            // shadow passes into the atlas
 constexpr int MODE_BLEND = 2;            // blend routine: collect per-sample fragment lists
 constexpr int MODE_MSAA = 4;             // or-ed onto MODE_COLOUR / MODE_BLEND: SampleCount::Four (R7); keeps the 4-sample code out of the common kernels
+constexpr int MODE_ALPHA = 8;            // or-ed on when some cutout material discards per fragment (texture / vertex alpha): the call into the
+                                         // texture sampler would otherwise set the register budget of every kernel (80 -> 128 for the shadow passes)
 
-struct SubTri { int32_t x[3], y[3]; float z[3]; uint32_t rec; };   // oriented (area > 0), snapped 24.8
+struct SubTri { int32_t x[3], y[3]; float z[3]; uint32_t rec; };   // oriented (area > 0), snapped 24.8; rec bit 31 = per-fragment alpha test
+constexpr uint32_t REC_ALPHA_TESTED = 0x80000000u;
 static_assert(sizeof(SubTri) == 40, "SubTri");
 
 struct RasterParams {
@@ -47,6 +51,7 @@ struct RasterParams {
     const r3_object_matrices* matrices; uint32_t matrices_cap;
     const uint32_t* mesh; uint64_t mesh_words;
     const r3_material* materials; uint32_t n_materials;
+    TexTable tt;                                   // albedo textures of cutout materials (per-fragment discard)
     // target
     float ox, oy, vw, vh; int32_t x0, y0, x1, y1; uint32_t pitch; int positive_visible;
     uint32_t samples;                              // 1 or 4 (R7: standard 4x pattern); shadow passes are always single-sampled
@@ -167,7 +172,7 @@ __device__ __forceinline__ uint32_t write_sample(const RasterParams& p, int px, 
     if ((MODE & 3) == MODE_DEPTH) {
         atomicMax(&p.depth_bits[pi], __float_as_uint(z));
     } else if ((MODE & 3) == MODE_COLOUR) {
-        const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | ((unsigned long long)p.pass_bit << 31) | rec;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(z) << 32) | ((unsigned long long)p.pass_bit << 31) | (rec & ~REC_ALPHA_TESTED);
         atomicMax(&p.vis[pi * p.samples + k], key);
     } else {
         // blend routine: fragments must be applied in draw order, so they are only collected here (one list per sample).
@@ -177,7 +182,7 @@ __device__ __forceinline__ uint32_t write_sample(const RasterParams& p, int px, 
             const uint32_t node = atomicAdd(&p.counters[3], 1u);
             if (node < p.frag_cap) {
                 const uint32_t next = atomicExch(&p.frag_heads[si], node + 1u);
-                p.frag_nodes[node] = make_uint4(rec, __float_as_uint(z), next, 0u);
+                p.frag_nodes[node] = make_uint4(rec & ~REC_ALPHA_TESTED, __float_as_uint(z), next, 0u);
             }
         }
         return 0u;
@@ -189,20 +194,105 @@ __device__ __forceinline__ uint32_t write_sample(const RasterParams& p, int px, 
 __device__ __constant__ int c_sample_dx[4] = {-32, 96, -96, 32};
 __device__ __constant__ int c_sample_dy[4] = {-96, -32, 32, 96};
 
+// alpha of the cutout routines' fragment at the centre of pixel (px, py) against the material's threshold: true = discard.
+//   colour passes (opaque.wgsl:203-235, discard variant): albedo alpha of get_pixel_data_inner — coords through uv_transform0, the
+//     material's sampler, times vertex alpha when ALBEDO_BLEND, times material.albedo.a;
+//   depth passes  (depth.wgsl:101-127): the RAW coords0, uvdy = dpdx(coords) like uvdx (sic), always the linear sampler.
+// Same operation order as the oracle (this translation unit is compiled without contraction): the decision is bit-identical up to
+// the last-ulp difference of log2f in the mip fraction.
+template <int MODE>
+__device__ __noinline__ bool cutout_discards(const RasterParams& p, uint32_t rec, int px, int py) {
+    // the record was written earlier in THIS launch (by this thread, or by another lane of the warp before a __syncwarp): plain loads
+    const r3_tri_record* tp = p.records + ((rec & ~REC_ALPHA_TESTED) - 1u);
+    const float4 q0 = reinterpret_cast<const float4*>(tp)[0], q1 = reinterpret_cast<const float4*>(tp)[1], q2 = reinterpret_cast<const float4*>(tp)[2];
+    const uint4 q3 = reinterpret_cast<const uint4*>(tp)[3];
+    const float p0[3] = {q0.x, q0.y, q0.z}, p1[3] = {q0.w, q1.x, q1.y}, p2[3] = {q1.z, q1.w, q2.x};
+    const uint32_t oid = __float_as_uint(q2.y);
+    const uint32_t vid[3] = {__float_as_uint(q2.z), __float_as_uint(q2.w), q3.x};
+    const r3_object* obj = &p.objects[oid];
+    const r3_material* m = &p.materials[obj->material_index < p.n_materials ? obj->material_index : 0u];
+    const uint32_t flags = m->flags;
+    float alpha = 1.0f;
+    if (flags & R3_MAT_ALBEDO_ACTIVE) {
+        const float hw = p.vw * 0.5f, hh = p.vh * 0.5f;
+        float b[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float fx = ((float)px - p.ox) + (k == 1 ? 1.5f : 0.5f), fy = ((float)py - p.oy) + (k == 2 ? 1.5f : 0.5f);
+            const float nx = fx / hw - 1.0f, ny = 1.0f - fy / hh;
+            const float b0 = ((p1[1] * p2[2] - p1[2] * p2[1]) * nx + (p1[2] * p2[0] - p1[0] * p2[2]) * ny) + (p1[0] * p2[1] - p1[1] * p2[0]);
+            const float b1 = ((p2[1] * p0[2] - p2[2] * p0[1]) * nx + (p2[2] * p0[0] - p2[0] * p0[2]) * ny) + (p2[0] * p0[1] - p2[1] * p0[0]);
+            const float b2 = ((p0[1] * p1[2] - p0[2] * p1[1]) * nx + (p0[2] * p1[0] - p0[0] * p1[2]) * ny) + (p0[0] * p1[1] - p0[1] * p1[0]);
+            const float sum = (b0 + b1) + b2;
+            b[k][0] = b0 / sum; b[k][1] = b1 / sum; b[k][2] = b2 / sum;
+        }
+        const uint32_t albedo_tex = m->textures[R3_TEX_ALBEDO];
+        if (albedo_tex) {
+            float uv[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+            const uint32_t uv_off = obj->attr_offset[3];
+            if (uv_off != R3_ATTR_ABSENT) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint64_t w = (uint64_t)(uv_off >> 2) + (uint64_t)vid[k] * 2u;
+                    uv[k][0] = __uint_as_float(mesh_word(p, w)); uv[k][1] = __uint_as_float(mesh_word(p, w + 1));
+                }
+            }
+            float co[3][2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float u = (b[k][0] * uv[0][0] + b[k][1] * uv[1][0]) + b[k][2] * uv[2][0];
+                const float v = (b[k][0] * uv[0][1] + b[k][1] * uv[1][1]) + b[k][2] * uv[2][1];
+                if ((MODE & 3) == MODE_DEPTH) { co[k][0] = u; co[k][1] = v; }
+                else {
+                    co[k][0] = (m->uv_transform0[0][0] * u + m->uv_transform0[1][0] * v) + m->uv_transform0[2][0];
+                    co[k][1] = (m->uv_transform0[0][1] * u + m->uv_transform0[1][1] * v) + m->uv_transform0[2][1];
+                }
+            }
+            TexCoords tc;
+            tc.u = co[0][0]; tc.v = co[0][1];
+            tc.dudx = co[1][0] - co[0][0]; tc.dvdx = co[1][1] - co[0][1];
+            if ((MODE & 3) == MODE_DEPTH) { tc.dudy = tc.dudx; tc.dvdy = tc.dvdx; }
+            else { tc.dudy = co[2][0] - co[0][0]; tc.dvdy = co[2][1] - co[0][1]; }
+            alpha = texture_sample_grad(p.tt, albedo_tex, (MODE & 3) != MODE_DEPTH && (flags & R3_MAT_NEAREST), tc).w;
+        }
+        if (flags & R3_MAT_ALBEDO_BLEND) {
+            float va[3] = {1.0f, 1.0f, 1.0f};
+            const uint32_t col_off = obj->attr_offset[5];
+            if (col_off != R3_ATTR_ABSENT) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) va[k] = (float)(mesh_word(p, (uint64_t)(col_off >> 2) + vid[k]) >> 24) / 255.0f;
+            }
+            alpha *= (b[0][0] * va[0] + b[0][1] * va[1]) + b[0][2] * va[2];
+        }
+    }
+    return alpha * m->albedo[3] < m->alpha_cutout;
+}
+
 // coverage + depth of one pixel given the biased edge values at its centre
 template <int MODE, typename T>
 __device__ __forceinline__ void emit_pixel(const RasterParams& p, const SubTri& s, const EdgeSetupT<T>& e, int px, int py, T c0, T c1, T c2, uint32_t& frags) {
     if (!(MODE & MODE_MSAA)) {
-        if ((c0 | c1 | c2) >= 0) frags += write_sample<MODE>(p, px, py, 0u, sample_depth<T>(s, e, c0, c1, c2), s.rec);
+        if ((c0 | c1 | c2) >= 0) {
+            // cutout routines: the fragment shader `discard`s (opaque.wgsl:231-235, depth.wgsl:101-127)
+            if ((MODE & MODE_ALPHA) && (s.rec & REC_ALPHA_TESTED) && cutout_discards<MODE>(p, s.rec, px, py)) return;
+            frags += write_sample<MODE>(p, px, py, 0u, sample_depth<T>(s, e, c0, c1, c2), s.rec);
+        }
         return;
     }
+    bool tested = !(MODE & MODE_ALPHA) || !(s.rec & REC_ALPHA_TESTED);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         // E(centre + o) = E(centre) + (step_x * o.x + step_y * o.y) / 256 (the steps are exact multiples of 256)
         const T a0 = c0 + (e.sx0 >> 8) * c_sample_dx[k] + (e.sy0 >> 8) * c_sample_dy[k];
         const T a1 = c1 + (e.sx1 >> 8) * c_sample_dx[k] + (e.sy1 >> 8) * c_sample_dy[k];
         const T a2 = c2 + (e.sx2 >> 8) * c_sample_dx[k] + (e.sy2 >> 8) * c_sample_dy[k];
-        if ((a0 | a1 | a2) >= 0) frags += write_sample<MODE>(p, px, py, (uint32_t)k, sample_depth<T>(s, e, a0, a1, a2), s.rec);
+        if ((a0 | a1 | a2) >= 0) {
+            if (!tested) {   // once per pixel and primitive: a discard removes every sample
+                if (cutout_discards<MODE>(p, s.rec, px, py)) return;
+                tested = true;
+            }
+            frags += write_sample<MODE>(p, px, py, (uint32_t)k, sample_depth<T>(s, e, a0, a1, a2), s.rec);
+        }
     }
 }
 
@@ -350,11 +440,16 @@ __device__ void setup_listed_triangle(const RasterParams& p, unsigned long long 
     if (oid >= p.n_slots || oid >= p.matrices_cap) return;
     const r3_object* obj = &p.objects[oid];
     if (obj->enabled == 0u) return;                                                               // opaque.wgsl:108-112
+    bool alpha_tested = false;
     if (p.regions[r].material_key == 1ull) {
         // cutout routine (pbr/routine.rs:97-133, `discard` variant): untextured alpha = material.albedo.a, constant over the
         // object unless the vertex colour is blended in, so the discard (opaque.wgsl:231-235, depth.wgsl:186-207) is per triangle
         const r3_material* m = &p.materials[obj->material_index < p.n_materials ? obj->material_index : 0u];
-        if (!(m->flags & R3_MAT_ALBEDO_BLEND) && m->albedo[3] < m->alpha_cutout) return;
+        // alpha varies inside the object only through the albedo texture or a blended vertex colour: then the discard is
+        // evaluated per pixel (cutout_discards); otherwise alpha = material.albedo.a for every fragment of the object
+        alpha_tested = (m->flags & R3_MAT_ALBEDO_ACTIVE) && (m->textures[R3_TEX_ALBEDO] != 0u || ((m->flags & R3_MAT_ALBEDO_BLEND) && obj->attr_offset[5] != R3_ATTR_ABSENT));
+        if (!alpha_tested && m->albedo[3] < m->alpha_cutout) return;
+        if (!(MODE & MODE_ALPHA) || !p.records) alpha_tested = false;   // (run_raster picks the MODE_ALPHA kernels and provides records whenever such materials exist)
     }
     const uint32_t pos_off = obj->attr_offset[0] >> 2;
     const float* mvp = p.matrices[oid].model_view_proj;
@@ -376,7 +471,17 @@ __device__ void setup_listed_triangle(const RasterParams& p, unsigned long long 
         nan |= !(v.w == v.w);
     }
     if (nan || ox0 || ox1 || oy0 || oy1 || oz0 || oz1) return;
-    const uint32_t rec = (uint32_t)(i + 1);
+    const uint32_t rec = (uint32_t)(i + 1) | (alpha_tested ? REC_ALPHA_TESTED : 0u);
+    const auto store_record = [&]() {
+        r3_tri_record tr;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { tr.xyw[k][0] = clip[k].x; tr.xyw[k][1] = clip[k].y; tr.xyw[k][2] = clip[k].w; tr.vid[k] = vid[k]; }
+        tr.object_id = oid; tr._pad[0] = tr._pad[1] = tr._pad[2] = 0u;
+        float4* dst = reinterpret_cast<float4*>(&p.records[i]);
+        const float4* src = reinterpret_cast<const float4*>(&tr);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+    };
+    if (alpha_tested) store_record();   // the per-fragment discard reads it while this triangle is being rasterised
     bool any = false;
     if (!need_clip) {
         any = process_subtriangle<MODE>(p, clip[0], clip[1], clip[2], rec, frags, defer, deferred);
@@ -388,15 +493,7 @@ __device__ void setup_listed_triangle(const RasterParams& p, unsigned long long 
     }
     if (any) {
         set_up++;
-        if ((MODE & 3) != MODE_DEPTH) {
-            r3_tri_record tr;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { tr.xyw[k][0] = clip[k].x; tr.xyw[k][1] = clip[k].y; tr.xyw[k][2] = clip[k].w; tr.vid[k] = vid[k]; }
-            tr.object_id = oid; tr._pad[0] = tr._pad[1] = tr._pad[2] = 0u;
-            float4* dst = reinterpret_cast<float4*>(&p.records[i]);
-            const float4* src = reinterpret_cast<const float4*>(&tr);
-            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
-        }
+        if ((MODE & 3) != MODE_DEPTH && !alpha_tested) store_record();
     }
 }
 
@@ -419,6 +516,7 @@ __global__ void __launch_bounds__(RS_THREADS) raster_setup_kernel(const __grid_c
         SubTri med;
         bool has_med = false;
         if (i < total) setup_listed_triangle<MODE>(p, i, n_regions, frags, set_up, &med, &has_med);
+        if (MODE & MODE_ALPHA) __syncwarp();   // records of alpha-tested triangles are read by the other lanes below
         uint32_t m = __ballot_sync(0xFFFFFFFFu, has_med);
         if (__popc(m) >= COOP_MAX_LANES) {
             // most lanes hold a medium triangle: 32 boxes walked in parallel beat 32 boxes walked one after the other
@@ -582,7 +680,13 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, int mode,
     p.vis = c->d_vis; p.pass_bit = (uint32_t)(pass & 1); p.depth_bits = (uint32_t*)c->d_atlas;
     p.frag_heads = c->d_frag_heads; p.frag_nodes = c->d_frag_nodes; p.frag_cap = (uint32_t)c->frag_nodes_cap; p.key_lo = key_lo; p.key_hi = key_hi;
     p.large = large; p.bands = bands; p.counters = counters; p.stats = mode == MODE_COLOUR ? c->d_stats : nullptr;   // statistics describe the opaque + cutout passes
+    p.tt.tex = c->d_tex_descs; p.tt.n_tex = c->n_textures; p.tt.texels = c->d_texels;
     p.records = nullptr;
+    if (depth_only && c->any_frag_alpha) {
+        // cutout materials whose alpha comes from a texture / vertex colour: the shadow pass needs the triangle records too
+        R3_TRY(r3_reserve_t(c, &c->d_tris[3], &c->tris_cap[3], (uint64_t)j->total_invocations + 1));
+        p.records = c->d_tris[3];
+    }
     if (!depth_only) {
         // one record slot per listed triangle; the listed total is bounded by the partition size
         const uint64_t max_tris = (uint64_t)j->total_invocations;
@@ -592,23 +696,23 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, int mode,
         p.records = c->d_tris[pass];
     }
     const int grid = R3_SM_COUNT * 8;
-    const int variant = mode | ((mode != MODE_DEPTH && c->samples == 4u) ? MODE_MSAA : 0);
-    switch (variant) {
-        case MODE_DEPTH: raster_setup_kernel<MODE_DEPTH><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
-        case MODE_COLOUR: raster_setup_kernel<MODE_COLOUR><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
-        case MODE_BLEND: raster_setup_kernel<MODE_BLEND><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
-        case MODE_COLOUR | MODE_MSAA: raster_setup_kernel<MODE_COLOUR | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
-        default: raster_setup_kernel<MODE_BLEND | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
+    const int variant = mode | ((mode != MODE_DEPTH && c->samples == 4u) ? MODE_MSAA : 0) | ((c->any_frag_alpha && mode != MODE_BLEND) ? MODE_ALPHA : 0);
+#define R3_RASTER_LAUNCH(KERNEL)                                                                                          \
+    switch (variant) {                                                                                                    \
+        case MODE_DEPTH: KERNEL<MODE_DEPTH><<<grid, RS_THREADS, 0, c->stream>>>(p); break;                                \
+        case MODE_COLOUR: KERNEL<MODE_COLOUR><<<grid, RS_THREADS, 0, c->stream>>>(p); break;                              \
+        case MODE_BLEND: KERNEL<MODE_BLEND><<<grid, RS_THREADS, 0, c->stream>>>(p); break;                                \
+        case MODE_COLOUR | MODE_MSAA: KERNEL<MODE_COLOUR | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;      \
+        case MODE_BLEND | MODE_MSAA: KERNEL<MODE_BLEND | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;        \
+        case MODE_DEPTH | MODE_ALPHA: KERNEL<MODE_DEPTH | MODE_ALPHA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;      \
+        case MODE_COLOUR | MODE_ALPHA: KERNEL<MODE_COLOUR | MODE_ALPHA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;    \
+        default: KERNEL<MODE_COLOUR | MODE_MSAA | MODE_ALPHA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;              \
     }
+    R3_RASTER_LAUNCH(raster_setup_kernel)
     R3_CHECK_LAUNCH(c, "raster_setup_kernel");
-    switch (variant) {
-        case MODE_DEPTH: raster_band_kernel<MODE_DEPTH><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
-        case MODE_COLOUR: raster_band_kernel<MODE_COLOUR><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
-        case MODE_BLEND: raster_band_kernel<MODE_BLEND><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
-        case MODE_COLOUR | MODE_MSAA: raster_band_kernel<MODE_COLOUR | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
-        default: raster_band_kernel<MODE_BLEND | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;
-    }
+    R3_RASTER_LAUNCH(raster_band_kernel)
     R3_CHECK_LAUNCH(c, "raster_band_kernel");
+#undef R3_RASTER_LAUNCH
     return R3_OK;
 }
 

@@ -15,6 +15,7 @@
 #include <cuda_fp16.h>
 
 #include "r3_common.cuh"
+#include "r3_texture.cuh"
 
 namespace {
 
@@ -31,7 +32,7 @@ struct ShadeParams {
     const r3_object* objects; const r3_object_matrices* matrices;
     const uint32_t* mesh; uint64_t mesh_words;
     const r3_material* materials; uint32_t n_materials;
-    const r3_texture_desc* tex; uint32_t n_tex; const uint8_t* texels;   // bindless d2 texture table (r3_set_textures)
+    TexTable tt;                                                          // bindless d2 texture table (r3_set_textures)
     const DirPrep* dir; uint32_t n_dir; const PointPrep* point; uint32_t n_point;
     const float* atlas; uint32_t atlas_w, atlas_h;
     // blend routine (r3_forward_blend): triangle records of the key-2 regions + the per-sample fragment lists
@@ -50,7 +51,6 @@ __device__ __forceinline__ float3 fetch3(const ShadeParams& p, uint32_t byte_off
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ float3 normalize3(float3 a) { const float r = rsqrtf(dot3(a, a)); return make_float3(a.x * r, a.y * r, a.z * r); }
 __device__ __forceinline__ float saturate(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
-__device__ __forceinline__ float srgb_to_linear(float e) { return e > 0.04045f ? powf((e + 0.055f) / 1.055f, 2.4f) : e / 12.92f; }
 
 struct Pixel { float3 diffuse_pi, f0, normal; float roughness, f90; };   // diffuse_pi = diffuse_color * (1/pi)
 
@@ -196,64 +196,6 @@ __device__ __forceinline__ FragIn fragment_inputs(const ShadeParams& p, const r3
     return f;
 }
 
-// ------------------------------------------------------------------ material textures (rule R9 of the oracle)
-// textureSampleGrad with the linear / nearest Repeat sampler of common/samplers.rs:42-56.  Everything that SELECTS texels or
-// levels (coordinates, floor) follows the oracle's order without contraction; the filter weights are continuous.
-__device__ __forceinline__ float4 texel_fetch(const ShadeParams& p, const r3_texture_desc& d, uint32_t level, long long x, long long y) {
-    unsigned long long off = d.byte_offset;
-    const unsigned long long bpp = d.format == R3_TEXFMT_RGBA32_FLOAT ? 16ull : 4ull;
-    for (uint32_t l = 0; l < level; ++l) off += (unsigned long long)max(d.width >> l, 1u) * max(d.height >> l, 1u) * bpp;
-    const long long w = max(d.width >> level, 1u), h = max(d.height >> level, 1u);
-    x = ((x % w) + w) % w; y = ((y % h) + h) % h;                                   // AddressMode::Repeat
-    const uint8_t* t = p.texels + off + (unsigned long long)(y * w + x) * bpp;
-    if (d.format == R3_TEXFMT_RGBA32_FLOAT) return __ldg(reinterpret_cast<const float4*>(t));
-    const uchar4 c = __ldg(reinterpret_cast<const uchar4*>(t));
-    float4 o = make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
-    if (d.format == R3_TEXFMT_RGBA8_UNORM_SRGB) { o.x = srgb_to_linear(o.x); o.y = srgb_to_linear(o.y); o.z = srgb_to_linear(o.z); }
-    return o;
-}
-__device__ __forceinline__ float clamp_coord(float v) { return fminf(fmaxf(v, -1.0e9f), 1.0e9f); }
-__device__ __noinline__ float4 sample_level(const ShadeParams& p, const r3_texture_desc& d, uint32_t level, bool nearest, float u, float v) {
-    const float w = (float)max(d.width >> level, 1u), h = (float)max(d.height >> level, 1u);
-    if (nearest) {
-        float x = floorf(mul_rn(u, w)), y = floorf(mul_rn(v, h));
-        if (!(x == x)) x = 0.0f; if (!(y == y)) y = 0.0f;
-        return texel_fetch(p, d, level, (long long)clamp_coord(x), (long long)clamp_coord(y));
-    }
-    const float x = sub_rn(mul_rn(u, w), 0.5f), y = sub_rn(mul_rn(v, h), 0.5f);
-    float x0 = floorf(x), y0 = floorf(y), fx = sub_rn(x, x0), fy = sub_rn(y, y0);
-    if (!(x0 == x0)) { x0 = 0.0f; fx = 0.0f; } if (!(y0 == y0)) { y0 = 0.0f; fy = 0.0f; }
-    const long long ix = (long long)clamp_coord(x0), iy = (long long)clamp_coord(y0);
-    const float4 t00 = texel_fetch(p, d, level, ix, iy), t10 = texel_fetch(p, d, level, ix + 1, iy);
-    const float4 t01 = texel_fetch(p, d, level, ix, iy + 1), t11 = texel_fetch(p, d, level, ix + 1, iy + 1);
-    const float gx = 1.0f - fx, gy = 1.0f - fy;
-    return make_float4((t00.x * gx + t10.x * fx) * gy + (t01.x * gx + t11.x * fx) * fy, (t00.y * gx + t10.y * fx) * gy + (t01.y * gx + t11.y * fx) * fy,
-                       (t00.z * gx + t10.z * fx) * gy + (t01.z * gx + t11.z * fx) * fy, (t00.w * gx + t10.w * fx) * gy + (t01.w * gx + t11.w * fx) * fy);
-}
-struct TexCoords { float u, v, dudx, dvdx, dudy, dvdy; };
-// slot value = table index + 1; an index outside the table reads zeros (robust access)
-__device__ __noinline__ float4 texture_sample_grad(const ShadeParams& p, uint32_t slot_value, bool nearest, const TexCoords& c) {
-    if (slot_value == 0u || slot_value > p.n_tex) return make_float4(0.f, 0.f, 0.f, 0.f);
-    const r3_texture_desc d = p.tex[slot_value - 1u];
-    const float w0 = (float)d.width, h0 = (float)d.height;
-    const float ax = c.dudx * w0, ay = c.dvdx * h0, bx = c.dudy * w0, by = c.dvdy * h0;
-    const float rho = fmaxf(sqrtf(ax * ax + ay * ay), sqrtf(bx * bx + by * by));
-    const float lambda = log2f(rho);
-    const uint32_t last = d.mip_count - 1u;
-    if (!(lambda > 0.0f)) return sample_level(p, d, 0u, nearest, c.u, c.v);
-    if (nearest) {
-        const float lv = floorf(lambda + 0.5f);
-        return sample_level(p, d, lv >= (float)last ? last : (uint32_t)lv, true, c.u, c.v);
-    }
-    const float l = fminf(lambda, (float)last), lo = floorf(l), fr = l - lo;
-    const uint32_t level = (uint32_t)lo;
-    const float4 a = sample_level(p, d, level, false, c.u, c.v);
-    if (level >= last || fr == 0.0f) return a;
-    const float4 b = sample_level(p, d, level + 1u, false, c.u, c.v);
-    const float g = 1.0f - fr;
-    return make_float4(a.x * g + b.x * fr, a.y * g + b.y * fr, a.z * g + b.z * fr, a.w * g + b.w * fr);
-}
-
 // what get_pixel_data_inner (opaque.wgsl:203-424) hands to the lighting code
 struct PixelInputs { float4 albedo; float3 normal; float ao, perceptual, metallic, reflectance, clear_coat, cc_rough; float3 emissive; };
 
@@ -309,7 +251,7 @@ __device__ __noinline__ void textured_pixel_data(const ShadeParams& p, const r3_
     const float4 malbedo = __ldg(reinterpret_cast<const float4*>(m->albedo));
     o.albedo = make_float4(0.f, 0.f, 0.f, 1.f);
     if (flags & R3_MAT_ALBEDO_ACTIVE) {
-        o.albedo = tex[R3_TEX_ALBEDO] ? texture_sample_grad(p, tex[R3_TEX_ALBEDO], nearest, tc) : make_float4(1.f, 1.f, 1.f, 1.f);
+        o.albedo = tex[R3_TEX_ALBEDO] ? texture_sample_grad(p.tt, tex[R3_TEX_ALBEDO], nearest, tc) : make_float4(1.f, 1.f, 1.f, 1.f);
         if (flags & R3_MAT_ALBEDO_BLEND) {
             const float4 vc = (flags & R3_MAT_ALBEDO_VERTEX_SRGB) ? make_float4(srgb_to_linear(f.vcolor.x), srgb_to_linear(f.vcolor.y), srgb_to_linear(f.vcolor.z), f.vcolor.w) : f.vcolor;
             o.albedo = make_float4(o.albedo.x * vc.x, o.albedo.y * vc.y, o.albedo.z * vc.z, o.albedo.w * vc.w);
@@ -318,7 +260,7 @@ __device__ __noinline__ void textured_pixel_data(const ShadeParams& p, const r3_
     o.albedo = make_float4(o.albedo.x * malbedo.x, o.albedo.y * malbedo.y, o.albedo.z * malbedo.z, o.albedo.w * malbedo.w);
     o.normal = f.vnormal;
     if (tex[R3_TEX_NORMAL] && !(flags & R3_MAT_UNLIT)) {                               // opaque.wgsl:244-276
-        const float4 t = texture_sample_grad(p, tex[R3_TEX_NORMAL], nearest, tc);
+        const float4 t = texture_sample_grad(p.tt, tex[R3_TEX_NORMAL], nearest, tc);
         float3 n;
         if (flags & R3_MAT_BICOMPONENT_NORMAL) {
             const float bx = ((flags & R3_MAT_SWIZZLED_NORMAL) ? t.w : t.x) * 2.0f - 1.0f, by = t.y * 2.0f - 1.0f;
@@ -356,33 +298,33 @@ __device__ __noinline__ void textured_pixel_data(const ShadeParams& p, const r3_
     o.ao = m_ao; o.perceptual = mA.w; o.metallic = mB.x;
     if (!(flags & R3_MAT_UNLIT)) {
         if (flags & R3_MAT_AOMR_COMBINED) {                                            // opaque.wgsl:280-295
-            if (tex[R3_TEX_ROUGHNESS]) { const float4 t = texture_sample_grad(p, tex[R3_TEX_ROUGHNESS], nearest, tc); o.ao = m_ao * t.x; o.perceptual = mA.w * t.y; o.metallic = mB.x * t.z; }
+            if (tex[R3_TEX_ROUGHNESS]) { const float4 t = texture_sample_grad(p.tt, tex[R3_TEX_ROUGHNESS], nearest, tc); o.ao = m_ao * t.x; o.perceptual = mA.w * t.y; o.metallic = mB.x * t.z; }
         } else if (flags & R3_MAT_AOMR_BW_SPLIT) {
-            if (tex[R3_TEX_ROUGHNESS]) o.perceptual = mA.w * texture_sample_grad(p, tex[R3_TEX_ROUGHNESS], nearest, tc).x;
-            if (tex[R3_TEX_METALLIC]) o.metallic = mB.x * texture_sample_grad(p, tex[R3_TEX_METALLIC], nearest, tc).x;
-            if (tex[R3_TEX_AMBIENT_OCCLUSION]) o.ao = m_ao * texture_sample_grad(p, tex[R3_TEX_AMBIENT_OCCLUSION], nearest, tc).x;
+            if (tex[R3_TEX_ROUGHNESS]) o.perceptual = mA.w * texture_sample_grad(p.tt, tex[R3_TEX_ROUGHNESS], nearest, tc).x;
+            if (tex[R3_TEX_METALLIC]) o.metallic = mB.x * texture_sample_grad(p.tt, tex[R3_TEX_METALLIC], nearest, tc).x;
+            if (tex[R3_TEX_AMBIENT_OCCLUSION]) o.ao = m_ao * texture_sample_grad(p.tt, tex[R3_TEX_AMBIENT_OCCLUSION], nearest, tc).x;
         } else {
             if (tex[R3_TEX_ROUGHNESS]) {
-                const float4 t = texture_sample_grad(p, tex[R3_TEX_ROUGHNESS], nearest, tc);
+                const float4 t = texture_sample_grad(p.tt, tex[R3_TEX_ROUGHNESS], nearest, tc);
                 const bool sw = flags & R3_MAT_AOMR_SWIZZLED_SPLIT;
                 o.perceptual = mA.w * (sw ? t.y : t.x); o.metallic = mB.x * (sw ? t.z : t.y);
             }
-            if (tex[R3_TEX_AMBIENT_OCCLUSION]) o.ao = m_ao * texture_sample_grad(p, tex[R3_TEX_AMBIENT_OCCLUSION], nearest, tc).x;
+            if (tex[R3_TEX_AMBIENT_OCCLUSION]) o.ao = m_ao * texture_sample_grad(p.tt, tex[R3_TEX_AMBIENT_OCCLUSION], nearest, tc).x;
         }
         o.reflectance = mB.y;
-        if (tex[R3_TEX_REFLECTANCE]) o.reflectance = mB.y * texture_sample_grad(p, tex[R3_TEX_REFLECTANCE], nearest, tc).x;
+        if (tex[R3_TEX_REFLECTANCE]) o.reflectance = mB.y * texture_sample_grad(p.tt, tex[R3_TEX_REFLECTANCE], nearest, tc).x;
         o.clear_coat = mB.z; o.cc_rough = mB.w;
         if (flags & R3_MAT_CC_GLTF_COMBINED) {
-            if (tex[R3_TEX_CLEAR_COAT]) { const float4 t = texture_sample_grad(p, tex[R3_TEX_CLEAR_COAT], nearest, tc); o.clear_coat = mB.z * t.x; o.cc_rough = mB.w * t.y; }
+            if (tex[R3_TEX_CLEAR_COAT]) { const float4 t = texture_sample_grad(p.tt, tex[R3_TEX_CLEAR_COAT], nearest, tc); o.clear_coat = mB.z * t.x; o.cc_rough = mB.w * t.y; }
         } else {
-            if (tex[R3_TEX_CLEAR_COAT]) o.clear_coat = mB.z * texture_sample_grad(p, tex[R3_TEX_CLEAR_COAT], nearest, tc).x;
+            if (tex[R3_TEX_CLEAR_COAT]) o.clear_coat = mB.z * texture_sample_grad(p.tt, tex[R3_TEX_CLEAR_COAT], nearest, tc).x;
             if (tex[R3_TEX_CLEAR_COAT_ROUGHNESS]) {
-                const float4 t = texture_sample_grad(p, tex[R3_TEX_CLEAR_COAT_ROUGHNESS], nearest, tc);
+                const float4 t = texture_sample_grad(p.tt, tex[R3_TEX_CLEAR_COAT_ROUGHNESS], nearest, tc);
                 o.cc_rough = mB.w * ((flags & R3_MAT_CC_GLTF_SPLIT) ? t.y : t.x);
             }
         }
         o.emissive = make_float3(mA.x, mA.y, mA.z);
-        if (tex[R3_TEX_EMISSIVE]) { const float4 t = texture_sample_grad(p, tex[R3_TEX_EMISSIVE], nearest, tc); o.emissive = make_float3(mA.x * t.x, mA.y * t.y, mA.z * t.z); }
+        if (tex[R3_TEX_EMISSIVE]) { const float4 t = texture_sample_grad(p.tt, tex[R3_TEX_EMISSIVE], nearest, tc); o.emissive = make_float3(mA.x * t.x, mA.y * t.y, mA.z * t.z); }
     }
     *out = o;
 }
@@ -892,7 +834,7 @@ static void fill_shade_params(r3_ctx* c, ShadeParams* out) {
     p.tris2 = c->d_tris[2]; p.n_tris2 = c->n_tris[2]; p.frag_heads = c->d_frag_heads; p.frag_nodes = c->d_frag_nodes;
     p.objects = c->d_objects; p.matrices = cam->d_matrices; p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;
     p.materials = c->d_materials; p.n_materials = c->n_materials;
-    p.tex = c->d_tex_descs; p.n_tex = c->n_textures; p.texels = c->d_texels;
+    p.tt.tex = c->d_tex_descs; p.tt.n_tex = c->n_textures; p.tt.texels = c->d_texels;
     p.dir = d_dir; p.n_dir = c->n_dir; p.point = d_point; p.n_point = c->n_point;
     p.atlas = c->d_atlas; p.atlas_w = c->atlas_w; p.atlas_h = c->atlas_h;
     memcpy(p.ambient, c->uniforms.ambient, 16); memcpy(p.clear, c->clear_color, 16);

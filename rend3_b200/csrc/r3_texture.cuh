@@ -1,0 +1,72 @@
+// r3_texture.cuh — textureSampleGrad on the bindless d2 texture table (r3_set_textures), shared by the shading kernels
+// (r3_shade.cu) and the per-fragment alpha cutout of the rasteriser (r3_raster.cu).
+#ifndef R3_TEXTURE_CUH
+#define R3_TEXTURE_CUH
+#include "r3_common.cuh"
+
+namespace {
+
+struct TexTable { const r3_texture_desc* tex; uint32_t n_tex; const uint8_t* texels; };
+
+__device__ __forceinline__ float srgb_to_linear(float e) { return e > 0.04045f ? powf((e + 0.055f) / 1.055f, 2.4f) : e / 12.92f; }   // math/color.wgsl:3-9
+
+// ------------------------------------------------------------------ material textures (rule R9 of the oracle)
+// textureSampleGrad with the linear / nearest Repeat sampler of common/samplers.rs:42-56.  Everything that SELECTS texels or
+// levels (coordinates, floor) follows the oracle's order without contraction; the filter weights are continuous.
+__device__ __forceinline__ float4 texel_fetch(const TexTable& p, const r3_texture_desc& d, uint32_t level, long long x, long long y) {
+    unsigned long long off = d.byte_offset;
+    const unsigned long long bpp = d.format == R3_TEXFMT_RGBA32_FLOAT ? 16ull : 4ull;
+    for (uint32_t l = 0; l < level; ++l) off += (unsigned long long)max(d.width >> l, 1u) * max(d.height >> l, 1u) * bpp;
+    const long long w = max(d.width >> level, 1u), h = max(d.height >> level, 1u);
+    x = ((x % w) + w) % w; y = ((y % h) + h) % h;                                   // AddressMode::Repeat
+    const uint8_t* t = p.texels + off + (unsigned long long)(y * w + x) * bpp;
+    if (d.format == R3_TEXFMT_RGBA32_FLOAT) return __ldg(reinterpret_cast<const float4*>(t));
+    const uchar4 c = __ldg(reinterpret_cast<const uchar4*>(t));
+    float4 o = make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+    if (d.format == R3_TEXFMT_RGBA8_UNORM_SRGB) { o.x = srgb_to_linear(o.x); o.y = srgb_to_linear(o.y); o.z = srgb_to_linear(o.z); }
+    return o;
+}
+__device__ __forceinline__ float clamp_coord(float v) { return fminf(fmaxf(v, -1.0e9f), 1.0e9f); }
+__device__ __noinline__ float4 sample_level(const TexTable& p, const r3_texture_desc& d, uint32_t level, bool nearest, float u, float v) {
+    const float w = (float)max(d.width >> level, 1u), h = (float)max(d.height >> level, 1u);
+    if (nearest) {
+        float x = floorf(mul_rn(u, w)), y = floorf(mul_rn(v, h));
+        if (!(x == x)) x = 0.0f; if (!(y == y)) y = 0.0f;
+        return texel_fetch(p, d, level, (long long)clamp_coord(x), (long long)clamp_coord(y));
+    }
+    const float x = sub_rn(mul_rn(u, w), 0.5f), y = sub_rn(mul_rn(v, h), 0.5f);
+    float x0 = floorf(x), y0 = floorf(y), fx = sub_rn(x, x0), fy = sub_rn(y, y0);
+    if (!(x0 == x0)) { x0 = 0.0f; fx = 0.0f; } if (!(y0 == y0)) { y0 = 0.0f; fy = 0.0f; }
+    const long long ix = (long long)clamp_coord(x0), iy = (long long)clamp_coord(y0);
+    const float4 t00 = texel_fetch(p, d, level, ix, iy), t10 = texel_fetch(p, d, level, ix + 1, iy);
+    const float4 t01 = texel_fetch(p, d, level, ix, iy + 1), t11 = texel_fetch(p, d, level, ix + 1, iy + 1);
+    const float gx = 1.0f - fx, gy = 1.0f - fy;
+    return make_float4((t00.x * gx + t10.x * fx) * gy + (t01.x * gx + t11.x * fx) * fy, (t00.y * gx + t10.y * fx) * gy + (t01.y * gx + t11.y * fx) * fy,
+                       (t00.z * gx + t10.z * fx) * gy + (t01.z * gx + t11.z * fx) * fy, (t00.w * gx + t10.w * fx) * gy + (t01.w * gx + t11.w * fx) * fy);
+}
+struct TexCoords { float u, v, dudx, dvdx, dudy, dvdy; };
+// slot value = table index + 1; an index outside the table reads zeros (robust access)
+__device__ __noinline__ float4 texture_sample_grad(const TexTable& p, uint32_t slot_value, bool nearest, const TexCoords& c) {
+    if (slot_value == 0u || slot_value > p.n_tex) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const r3_texture_desc d = p.tex[slot_value - 1u];
+    const float w0 = (float)d.width, h0 = (float)d.height;
+    const float ax = c.dudx * w0, ay = c.dvdx * h0, bx = c.dudy * w0, by = c.dvdy * h0;
+    const float rho = fmaxf(sqrtf(ax * ax + ay * ay), sqrtf(bx * bx + by * by));
+    const float lambda = log2f(rho);
+    const uint32_t last = d.mip_count - 1u;
+    if (!(lambda > 0.0f)) return sample_level(p, d, 0u, nearest, c.u, c.v);
+    if (nearest) {
+        const float lv = floorf(lambda + 0.5f);
+        return sample_level(p, d, lv >= (float)last ? last : (uint32_t)lv, true, c.u, c.v);
+    }
+    const float l = fminf(lambda, (float)last), lo = floorf(l), fr = l - lo;
+    const uint32_t level = (uint32_t)lo;
+    const float4 a = sample_level(p, d, level, false, c.u, c.v);
+    if (level >= last || fr == 0.0f) return a;
+    const float4 b = sample_level(p, d, level + 1u, false, c.u, c.v);
+    const float g = 1.0f - fr;
+    return make_float4(a.x * g + b.x * fr, a.y * g + b.y * fr, a.z * g + b.z * fr, a.w * g + b.w * fr);
+}
+
+}  // namespace
+#endif

@@ -100,10 +100,10 @@ def cube_example_camera(pull_back: float = 1.0) -> Camera:
     return Camera(("perspective", 60.0, 0.1), view)
 
 
-def subdivided_cube_mesh(k: int, with_uv: bool = False):
+def subdivided_cube_mesh(k: int, with_uv: bool = False, vertex_alpha_seed: Optional[int] = None):
     """Cube [-1,1]^3 whose faces are k x k quads (12 k^2 triangles), same winding as rend3-test's cube.  with_uv: every face
     carries texture coordinates [0,1]^2 (MeshBuilder then derives tangents, lib.rs:720-836)."""
-    if k == 1 and not with_uv:
+    if k == 1 and not with_uv and vertex_alpha_seed is None:
         return cube_mesh()
     faces = [  # origin corner, u edge, v edge chosen so (o, o+u, o+u+v, o+v) matches helpers.rs:78-109
         ((-1, -1, 1), (2, 0, 0), (0, 2, 0)), ((-1, 1, -1), (2, 0, 0), (0, -2, 0)), ((1, -1, -1), (0, 2, 0), (0, 0, 2)),
@@ -125,11 +125,14 @@ def subdivided_cube_mesh(k: int, with_uv: bool = False):
     mb = MeshBuilder.new(np.array(pos, dtype=f32), LEFT).with_indices(idx)
     if with_uv:
         mb = mb.with_vertex_texture_coordinates_0(np.array(uvs, dtype=f32))
+    if vertex_alpha_seed is not None:   # vertex colours whose alpha straddles a 0.5 cutout
+        col = np.random.default_rng(vertex_alpha_seed).integers(0, 256, (len(pos), 4), dtype=np.uint8)
+        mb = mb.with_vertex_color_0(col)
     return mb.build()
 
 
 def textured_cube_scene(n_objects: int = 300, seed: int = 41, resolution: Tuple[int, int] = (320, 180), texture_size: int = 32,
-                        sample_type: str = "linear") -> EvalOutput:
+                        sample_type: str = "linear", cutout: bool = False) -> EvalOutput:
     """Cubes with texture coordinates and materials that exercise every texture slot and layout flag of PbrMaterial
     (opaque.wgsl:203-424): sRGB albedo, tri- and bi-component normal maps, combined / split AO-metallic-roughness, reflectance,
     clear coat, emissive, a scaled uv_transform0; one shadowed directional light and two point lights."""
@@ -170,6 +173,18 @@ def textured_cube_scene(n_objects: int = 300, seed: int = 41, resolution: Tuple[
                     clearcoat_texture=single, clearcoat_roughness_texture=aomr, anisotropy=0.3, anisotropy_texture=single, sample_type=sample_type),
         PbrMaterial(albedo_texture=albedo, unlit=True, sample_type=sample_type),
     ]
+    if cutout:
+        # cutout routine with per-fragment alpha: from the albedo texture, from the vertex colour, from both (opaque.wgsl:231-235,
+        # depth.wgsl:101-127); the holes also show in the shadow map
+        from .world import CUTOUT
+        meshes += [r.add_mesh(subdivided_cube_mesh(3, with_uv=True, vertex_alpha_seed=seed + 1))]
+        alpha_tex = r.add_texture_2d(Texture(smooth((0.3, 0.3, 0.3, 0.0), (1.0, 1.0, 1.0, 1.0)), srgb=True))
+        mats += [
+            PbrMaterial(albedo_texture=alpha_tex, roughness_factor=0.6, transparency=CUTOUT, alpha_cutout=0.5, sample_type=sample_type, uv_transform0=ut),
+            PbrMaterial(albedo_value=(0.8, 0.7, 0.3, 1.0), albedo_vertex="linear", roughness_factor=0.6, transparency=CUTOUT, alpha_cutout=0.5),
+            PbrMaterial(albedo_texture=alpha_tex, albedo_value=(1.0, 1.0, 1.0, 1.3), albedo_vertex="srgb", roughness_factor=0.6, transparency=CUTOUT, alpha_cutout=0.4,
+                        sample_type=sample_type),
+        ]
     mat_ids = [r.add_material(m) for m in mats]
     r.set_camera_data(cube_example_camera(8.0))
     r.add_directional_light(DirectionalLight(color=(1, 1, 1), intensity=1.0, direction=(-1.0, -4.0, 2.0), distance=80.0, resolution=256))
@@ -179,7 +194,9 @@ def textured_cube_scene(n_objects: int = 300, seed: int = 41, resolution: Tuple[
     scale = rng.uniform(0.8, 3.0, (n_objects, 1)).astype(f32)
     transforms = trs_matrices(centers, random_unit_quaternions(rng, n_objects), scale)
     for i in range(n_objects):
-        r.add_object(Object(meshes[i % 2], mat_ids[i % len(mat_ids)], transforms[i]))
+        mi = mat_ids[i % len(mat_ids)]
+        vertex_coloured = cutout and (i % len(mat_ids)) >= len(mat_ids) - 2
+        r.add_object(Object(meshes[2] if vertex_coloured else meshes[i % 2], mi, transforms[i]))
     return r.evaluate()
 
 

@@ -401,6 +401,37 @@ def test_textured_materials_match_oracle(cuda, sample_type, samples):
         assert off.sum() <= 1e-3 * off.size, f"{off.sum()} channel values differ (max {np.abs(a - o).max():.3e})"
 
 
+@pytest.mark.parametrize("samples", [1, 4])
+def test_per_fragment_cutout_matches_oracle(cuda, samples):
+    """Cutout materials whose alpha comes from the albedo texture and / or the vertex colour: the discard is per pixel and primitive,
+    in the forward passes (opaque.wgsl:231-235) and, with depth.wgsl's own coordinates and derivatives, in the shadow pass."""
+    from rend3_b200.scenes import textured_cube_scene
+
+    res = (320, 180)
+    ev = textured_cube_scene(n_objects=500, resolution=res, cutout=True)
+    assert set(int(k) for k in ev.object_material_key[ev.object_live != 0]) == {0, 1}
+    orc = load_oracle_backend()
+    graphs = {id(b): BaseRenderGraph(b) for b in (cuda, orc)}
+    for frame in range(2):
+        for b in (cuda, orc):
+            graphs[id(b)].add_to_graph(ev, res, samples, BaseRenderGraphSettings(clear_color=(0.05, 0.05, 0.1, 1.0)), upload=(frame == 0))
+        compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], check_pixels=False, what=f"cutout frame {frame}")
+        w, h = ev.shadow_target_size
+        sa, so = cuda.readback_shadow_atlas(w, h).view(np.uint32), orc.readback_shadow_atlas(w, h).view(np.uint32)
+        da, do = cuda.readback_depth().view(np.uint32), orc.readback_depth().view(np.uint32)
+        # the discard compares alpha with the threshold: identical arithmetic on both sides, a stray texel may still differ through log2f
+        assert np.count_nonzero(sa != so) <= 2 and np.count_nonzero(da != do) <= 2, (np.count_nonzero(sa != so), np.count_nonzero(da != do))
+        a, o = cuda.readback_hdr_f32().astype(np.float64), orc.readback_hdr_f32().astype(np.float64)
+        bound = TOL * np.maximum(1.0, np.abs(o)) + (np.maximum(np.abs(o) * 2.0 ** -10, 2.0 ** -24) if samples == 4 else 0.0)
+        assert np.count_nonzero(np.abs(a - o) > bound) <= 40, f"{np.count_nonzero(np.abs(a - o) > bound)} channel values differ"
+    # the holes are really there: the same scene without the discard covers more pixels
+    opaque = load_oracle_backend()
+    ev2 = textured_cube_scene(n_objects=500, resolution=res, cutout=True)
+    ev2.material_buffer["alpha_cutout"] = 0.0
+    BaseRenderGraph(opaque).add_to_graph(ev2, res, samples, BaseRenderGraphSettings(clear_color=(0.05, 0.05, 0.1, 1.0)))
+    assert np.count_nonzero(opaque.readback_depth() > 0) > np.count_nonzero(orc.readback_depth() > 0) + 200
+
+
 def test_device_batching_equals_host_batching_and_oracle(cuda, monkeypatch):
     """batch_objects on the device (radix sort + block scans) against the host implementation and the oracle, with
     three material keys (opaque / cutout / blend: atomic and non-atomic regions, front-to-back and back-to-front)."""
