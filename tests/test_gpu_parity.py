@@ -209,6 +209,20 @@ def test_config1_full_size_matches_oracle(cuda):
     assert cuda.visible_count(CAMERA_VIEWPORT) > 5000
 
 
+def test_config5_full_size_matches_oracle(cuda):
+    """BASELINE config 5 at full size (3840x2160, ~500k triangles, 64 point + 4 shadowed directional lights), one frame:
+    every integer artefact, the four shadow maps and the depth buffer bit-exact, the HDR pixels within TOL."""
+    from rend3_b200 import configs
+
+    ev, res = configs.config5()
+    orc = load_oracle_backend()
+    for b in (cuda, orc):
+        BaseRenderGraph(b).add_to_graph(ev, res, 1, BaseRenderGraphSettings(clear_color=(0.10, 0.05, 0.10, 1.0)))
+    compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0, 3], what="config 5")
+    st = cuda.forward_stats()
+    assert st[:3] == orc.forward_stats()[:3] and st[2] == res[0] * res[1], "the slabs close the frame: every pixel is shaded"
+
+
 def test_full_size_cull_bake_properties(cuda):
     """BASELINE configs 2 / 4 at full size (10 M object records on one GPU), checked through size-independent properties:
     sortedness, agreement with an independent float64 classification away from the plane boundaries, idempotence,
