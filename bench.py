@@ -239,15 +239,32 @@ def main():
     vis_host = torch.empty(n, dtype=torch.int32, pin_memory=True)
     gathered_words = torch.empty(world * ((n + 31) // 32), dtype=torch.int32, device=f"cuda:{local}")
 
-    side = torch.cuda.Stream(device=f"cuda:{local}") if world > 1 else None
+    # ---- north-star exchange: every rank ends up with the visible set of all shards, in its 1-bit-per-object form
+    # (n/8 bytes per shard instead of 4 B per visible object: fixed size, no count exchange, no host synchronisation).
+    # Preferred: the library's compaction kernel stores the words straight into every peer's buffer over NVLink (r3_exchange_*),
+    # so no collective kernel runs at all.  If the IPC set-up is not possible on this box the NCCL all-gather (on a high-priority
+    # side stream, overlapped with the next cull) takes over; the JSON line says which one ran.
+    exchange, exchange_kind = None, "single GPU"
+    side = None
+    if world > 1:
+        try:
+            from rend3_b200.parallel import VisibilityExchange
+            exchange = VisibilityExchange(backend, CAMERA_VIEWPORT, n, rank, world)
+            exchange_kind = "peer-memory stores fused into the compaction kernel (NVLink P2P, CUDA IPC)"
+        except Exception as e:   # noqa: BLE001
+            print(f"[rank {rank}] peer-memory exchange unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+            exchange = None
+        ok = torch.tensor([1 if exchange is not None else 0], device=f"cuda:{local}")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if exchange is not None:
+                exchange.close()
+            exchange, exchange_kind = None, "NCCL all-gather of the visibility words on a side stream"
+            side = torch.cuda.Stream(device=f"cuda:{local}", priority=-1)
 
     def gather_visible():
-        """North-star exchange: every rank ends up with the visible set of all shards.  The set travels in its
-        1-bit-per-object form (the stream kernel's visibility words, n/8 bytes per shard instead of 4 B per visible
-        object): fixed size, so no count exchange and no host synchronisation.  The library alternates between two
-        word buffers, so the all-gather of step k runs on a side stream while the cull of step k+1 streams."""
-        if world == 1:
-            return
+        if world == 1 or exchange is not None:
+            return   # nothing to launch: the exchange is part of r3_object_uniform_upload
         wptr, wbytes = backend.device_ptr(CAMERA_VIEWPORT, 4)
         done = torch.cuda.Event()
         done.record(stream)
@@ -271,6 +288,24 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     barrier()
+    exchange_verified = None
+    if exchange is not None:
+        # outside the timed region: the rows the peers stored must equal an NCCL all-gather of the same words
+        wptr, wbytes = backend.device_ptr(CAMERA_VIEWPORT, 4)
+        with torch.cuda.stream(stream):
+            mine = torch.as_tensor(DeviceView(wptr, wbytes, "<i4", 4), device=f"cuda:{local}")
+            ref = torch.empty(world * mine.numel(), dtype=torch.int32, device=f"cuda:{local}")
+            dist.all_gather_into_tensor(ref, mine)
+            got = exchange.gathered(f"cuda:{local}")[:, : mine.numel()].reshape(-1)
+            same = torch.tensor([1 if torch.equal(got, ref) else 0], device=f"cuda:{local}")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        exchange_verified = bool(int(same.item()))
+        if not exchange_verified:
+            print(f"[rank {rank}] peer-memory exchange does not match the NCCL all-gather; using NCCL", file=sys.stderr)
+            exchange.close()
+            exchange, exchange_kind = None, "NCCL all-gather of the visibility words on a side stream"
+            side = torch.cuda.Stream(device=f"cuda:{local}", priority=-1)
+        barrier()
     launches0 = backend.launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -370,7 +405,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "objects/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE config 4: fused frustum cull + uniform bake, 10 M object records per GPU (128 B std430 records, 1% disabled)",
-                       "objects_per_gpu": n, "visible_fraction": n_vis / n, "parallelism": f"object-range shards x{world}, NCCL all-gather of the visibility words (1 bit/object)" if world > 1 else "single GPU",
+                       "objects_per_gpu": n, "visible_fraction": n_vis / n, "parallelism": f"object-range shards x{world}; visible set (1 bit/object) exchanged by {exchange_kind}" if world > 1 else "single GPU",
+                       "exchange_verified_against_nccl": exchange_verified,
                        "l2": "inputs (0.8 GB) + outputs (1.28 GB) per step exceed the 126 MB L2; no explicit flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_PER_OBJECT * n,
                          "traffic_source": "profiles/r1_ncu_cull_bake_10M.txt: dram__bytes_read.sum + dram__bytes_write.sum of one 10 M-object launch, scaled per object",

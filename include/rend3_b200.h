@@ -159,6 +159,18 @@ int r3_forward_stats(r3_ctx*, uint64_t stats[4]);
  * host bounce.  which: 0 visible list (u32), 1 hdr f16 colour, 2 object matrices, 3 visible count (u32),
  * 4 visibility words (1 bit per object slot, bit i of word w = slot 32*w + i) */
 int r3_device_ptr(r3_ctx*, uint32_t camera, int which, void** device_ptr, uint64_t* nbytes);
+/* Exchange of the visible set between the GPUs of one node over NVLink / NVSwitch peer memory (one process per GPU, objects
+ * sharded in contiguous ranges).  r3_exchange_create allocates this rank's gathered[n_ranks][words_per_rank] buffer
+ * (1 bit per object slot, rows 256-byte aligned) and returns its CUDA IPC handle; the caller all-gathers the handles with whatever
+ * it already uses (torch.distributed, MPI) and hands them to r3_exchange_connect.  From then on every r3_object_uniform_upload(CULL)
+ * on that camera also stores its visibility words into row `my_rank` of EVERY rank's buffer, fused into the compaction kernel — no
+ * collective kernel runs.  The rows are complete once all ranks have synchronised their streams and met at a barrier. */
+#define R3_IPC_HANDLE_BYTES 64
+int r3_exchange_create(r3_ctx*, uint32_t camera, uint32_t n_ranks, uint32_t my_rank, uint32_t max_objects_per_rank,
+                       uint8_t handle_out[R3_IPC_HANDLE_BYTES]);
+int r3_exchange_connect(r3_ctx*, uint32_t camera, const uint8_t* handles /* n_ranks x R3_IPC_HANDLE_BYTES, rank order */);
+int r3_exchange_words(r3_ctx*, uint32_t camera, void** device_ptr, uint64_t* nbytes, uint32_t* words_per_rank);
+int r3_exchange_destroy(r3_ctx*, uint32_t camera);
 /* restrict rasterisation + shading to pixel rows [row_begin, row_end) (screen-tile split) */
 int r3_set_scissor_rows(r3_ctx*, uint32_t row_begin, uint32_t row_end);
 

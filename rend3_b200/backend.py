@@ -38,6 +38,7 @@ ENTRY_POINTS = [
     "shadow_pass", "forward_begin", "forward_pass", "hiz_build", "forward_resolve", "forward_blend", "tonemap",
     "readback_hdr_f32", "readback_hdr_f16", "readback_depth", "readback_ldr", "readback_shadow_atlas",
     "readback_hiz", "forward_stats", "device_ptr", "set_scissor_rows", "skin", "readback_mesh_buffer",
+    "exchange_create", "exchange_connect", "exchange_words", "exchange_destroy",
 ]
 
 
@@ -244,6 +245,24 @@ class Backend:
 
     def forward_resolve(self):
         self._call("forward_resolve")
+
+    # ---- multi-GPU exchange of the visible set over NVLink peer memory
+    def exchange_create(self, camera: int, n_ranks: int, my_rank: int, max_objects_per_rank: int) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self._call("exchange_create", C.c_uint32(camera), C.c_uint32(n_ranks), C.c_uint32(my_rank), C.c_uint32(max_objects_per_rank), h)
+        return bytes(h)
+
+    def exchange_connect(self, camera: int, handles: bytes):
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self._call("exchange_connect", C.c_uint32(camera), buf)
+
+    def exchange_words(self, camera: int):
+        p, n, w = C.c_void_p(), C.c_uint64(), C.c_uint32()
+        self._call("exchange_words", C.c_uint32(camera), C.byref(p), C.byref(n), C.byref(w))
+        return p.value, n.value, w.value
+
+    def exchange_destroy(self, camera: int):
+        self._call("exchange_destroy", C.c_uint32(camera))
 
     def forward_blend(self):
         self._call("forward_blend")

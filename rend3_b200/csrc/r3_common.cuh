@@ -36,6 +36,7 @@ struct r3_jobs {
     bool valid = false;
 };
 
+constexpr int R3_MAX_EXCHANGE_RANKS = 16;
 struct r3_camera {
     bool header_set = false;
     r3_camera_header header{};
@@ -44,6 +45,9 @@ struct r3_camera {
     uint32_t* d_visible_count = nullptr;      // device scalar
     unsigned long long* d_tile_state = nullptr; uint32_t tile_state_cap = 0;   // visibility words + per-CTA counts (two alternating sets)
     uint32_t* d_words = nullptr; uint32_t words_set = 0;                       // the set the last cull wrote
+    // multi-GPU exchange of the visible set over NVLink peer memory (r3_exchange_*): gathered[n_ranks][words_per_rank]
+    uint32_t* d_gathered = nullptr; uint32_t ex_ranks = 0, ex_rank = 0, ex_words_per_rank = 0; bool ex_connected = false;
+    uint32_t* ex_peers[R3_MAX_EXCHANGE_RANKS] = {};   // peer-mapped gathered buffers (ex_peers[ex_rank] == d_gathered)
     int visible_count_host = -1;              // cached after a readback, -1 = unknown
     r3_jobs jobs[2]; int cur = 0;             // jobs[cur] = this frame, jobs[cur^1] = cached DrawCallSet (forward.rs:219)
     bool has_draw_call_set = false; int cache_idx = -1;   // cache_idx: which jobs[] the forward routine cached, -1 = none
@@ -122,6 +126,10 @@ int r3_cuda_fail(r3_ctx* c, cudaError_t e, const char* where);
     } while (0)
 
 static inline int r3_cam_slot(uint32_t camera) { return camera == R3_CAMERA_VIEWPORT ? 0 : (int)camera + 1; }
+static inline r3_camera* r3_get_camera(r3_ctx* c, uint32_t camera) {
+    if (!c || (camera != R3_CAMERA_VIEWPORT && camera >= R3_MAX_SHADOWS)) return nullptr;
+    return &c->cams[r3_cam_slot(camera)];
+}
 #define R3_CAM_OR_FAIL(ctx, camera)                                                                              \
     if (!(ctx)) return R3_E_INVALID;                                                                             \
     if ((camera) != R3_CAMERA_VIEWPORT && (camera) >= R3_MAX_SHADOWS) return r3_fail((ctx), R3_E_INVALID, "bad camera"); \

@@ -150,9 +150,13 @@ cull_bake_kernel(const float4* __restrict__ transforms, const float4* __restrict
     }
 }
 
+// visible-set exchange fused into the compaction: every word this rank produced is also stored, coalesced, into the gathered
+// buffer of every rank (its own included) through NVLink peer mappings — no collective kernel, no extra pass over the words
+struct ExchangeParams { uint32_t* peers[R3_MAX_EXCHANGE_RANKS]; uint32_t n_ranks, word_offset, words_per_rank; };
+
 __global__ void __launch_bounds__(CP_THREADS)
 compact_visible_kernel(const uint32_t* __restrict__ words, const uint32_t* __restrict__ cta_counts, uint32_t n_words, uint32_t n_cta_counts,
-                       uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count) {
+                       uint32_t* __restrict__ visible, uint32_t* __restrict__ visible_count, const __grid_constant__ ExchangeParams ex) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -176,6 +180,10 @@ compact_visible_kernel(const uint32_t* __restrict__ words, const uint32_t* __res
     // (2) block-wide exclusive scan of the word popcounts (one word per thread)
     const uint32_t wi = blockIdx.x * CP_THREADS + threadIdx.x;
     const uint32_t word = wi < n_words ? __ldg(&words[wi]) : 0u;
+    if (ex.n_ranks && wi < ex.words_per_rank) {
+#pragma unroll 1
+        for (uint32_t r = 0; r < ex.n_ranks; ++r) ex.peers[r][ex.word_offset + wi] = word;
+    }
     const uint32_t c = __popc(word);
     uint32_t incl = c;
 #pragma unroll
@@ -240,7 +248,15 @@ int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode) {
     R3_CHECK_LAUNCH(c, "cull_bake_kernel");
     if (cull) {
         const uint32_t n_tiles = (n_words + CP_THREADS - 1) / CP_THREADS;
-        compact_visible_kernel<<<n_tiles, CP_THREADS, 0, c->stream>>>(words, cta_counts, n_words, n_ctas, cam->d_visible, cam->d_visible_count);
+        ExchangeParams ex{};
+        if (cam->ex_connected) {
+            if (n_words > cam->ex_words_per_rank) return r3_fail(c, R3_E_INVALID, "object_uniform_upload: more objects than the exchange was created for");
+            for (uint32_t r = 0; r < cam->ex_ranks; ++r) ex.peers[r] = cam->ex_peers[r];
+            ex.n_ranks = cam->ex_ranks; ex.word_offset = cam->ex_rank * cam->ex_words_per_rank; ex.words_per_rank = cam->ex_words_per_rank;
+        }
+        // with an exchange every slot of this rank's row is written each step (the tail beyond n_words as zeros)
+        const uint32_t n_tiles_ex = cam->ex_connected ? (cam->ex_words_per_rank + CP_THREADS - 1) / CP_THREADS : 0u;
+        compact_visible_kernel<<<n_tiles > n_tiles_ex ? n_tiles : n_tiles_ex, CP_THREADS, 0, c->stream>>>(words, cta_counts, n_words, n_ctas, cam->d_visible, cam->d_visible_count, ex);
         R3_CHECK_LAUNCH(c, "compact_visible_kernel");
     }
     return R3_OK;
@@ -275,5 +291,65 @@ int r3_split_slots(r3_ctx* c, const uint32_t* d_slots, uint32_t n) {
     split_slots_kernel<<<(n * 8 + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->d_objects), d_slots, n, c->n_slots, c->d_hot_transform, c->d_hot_sphere,
                                                                     c->d_enabled_bits);
     R3_CHECK_LAUNCH(c, "split_slots_kernel");
+    return R3_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU exchange of the visible set
+// One process per GPU.  Every rank owns gathered[n_ranks][words_per_rank]; rank r's compact kernel stores row r into the
+// buffer of every rank through CUDA IPC peer mappings over NVLink / NVSwitch.  The rows are complete once the ranks have
+// synchronised their streams and met at a barrier (the caller's: torch.distributed / MPI / the frame fence).
+R3_EXPORT int r3_exchange_create(r3_ctx* c, uint32_t camera, uint32_t n_ranks, uint32_t my_rank, uint32_t max_objects_per_rank, uint8_t handle_out[R3_IPC_HANDLE_BYTES]) {
+    if (!c || !handle_out) return r3_fail(c, R3_E_INVALID, "exchange_create: null");
+    if (n_ranks == 0 || n_ranks > R3_MAX_EXCHANGE_RANKS || my_rank >= n_ranks || max_objects_per_rank == 0) return r3_fail(c, R3_E_INVALID, "exchange_create: bad rank layout");
+    r3_camera* cam = r3_get_camera(c, camera);
+    if (!cam) return r3_fail(c, R3_E_INVALID, "exchange_create: bad camera");
+    static_assert(sizeof(cudaIpcMemHandle_t) == R3_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaSetDevice(c->device);
+    if (cam->d_gathered) return r3_fail(c, R3_E_STATE, "exchange_create: already created for this camera");
+    const uint32_t wpr = (((max_objects_per_rank + 31u) / 32u) + 63u) & ~63u;   // rows start 256-byte aligned
+    R3_CUDA(c, cudaMalloc((void**)&cam->d_gathered, (size_t)n_ranks * wpr * 4));
+    R3_CUDA(c, cudaMemsetAsync(cam->d_gathered, 0, (size_t)n_ranks * wpr * 4, c->stream));
+    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaIpcMemHandle_t h;
+    R3_CUDA(c, cudaIpcGetMemHandle(&h, cam->d_gathered));
+    memcpy(handle_out, &h, sizeof h);
+    cam->ex_ranks = n_ranks; cam->ex_rank = my_rank; cam->ex_words_per_rank = wpr; cam->ex_connected = false;
+    return R3_OK;
+}
+R3_EXPORT int r3_exchange_connect(r3_ctx* c, uint32_t camera, const uint8_t* handles) {
+    if (!c || !handles) return r3_fail(c, R3_E_INVALID, "exchange_connect: null");
+    r3_camera* cam = r3_get_camera(c, camera);
+    if (!cam || !cam->d_gathered) return r3_fail(c, R3_E_STATE, "exchange_connect before exchange_create");
+    cudaSetDevice(c->device);
+    for (uint32_t r = 0; r < cam->ex_ranks; ++r) {
+        if (r == cam->ex_rank) { cam->ex_peers[r] = cam->d_gathered; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * R3_IPC_HANDLE_BYTES, sizeof h);
+        void* p = nullptr;
+        R3_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));   // maps the peer allocation and enables NVLink peer access
+        cam->ex_peers[r] = (uint32_t*)p;
+    }
+    cam->ex_connected = true;
+    return R3_OK;
+}
+R3_EXPORT int r3_exchange_words(r3_ctx* c, uint32_t camera, void** device_ptr, uint64_t* nbytes, uint32_t* words_per_rank) {
+    if (!c || !device_ptr || !nbytes) return r3_fail(c, R3_E_INVALID, "exchange_words: null");
+    r3_camera* cam = r3_get_camera(c, camera);
+    if (!cam || !cam->d_gathered) return r3_fail(c, R3_E_STATE, "exchange_words before exchange_create");
+    *device_ptr = cam->d_gathered; *nbytes = (uint64_t)cam->ex_ranks * cam->ex_words_per_rank * 4;
+    if (words_per_rank) *words_per_rank = cam->ex_words_per_rank;
+    return R3_OK;
+}
+R3_EXPORT int r3_exchange_destroy(r3_ctx* c, uint32_t camera) {
+    if (!c) return R3_E_INVALID;
+    r3_camera* cam = r3_get_camera(c, camera);
+    if (!cam) return r3_fail(c, R3_E_INVALID, "exchange_destroy: bad camera");
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (uint32_t r = 0; r < cam->ex_ranks; ++r)
+        if (cam->ex_connected && r != cam->ex_rank && cam->ex_peers[r]) cudaIpcCloseMemHandle(cam->ex_peers[r]);
+    cudaFree(cam->d_gathered);
+    cam->d_gathered = nullptr; cam->ex_connected = false; cam->ex_ranks = 0;
+    for (auto& p : cam->ex_peers) p = nullptr;
     return R3_OK;
 }

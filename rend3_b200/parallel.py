@@ -48,3 +48,31 @@ def allgather_rows(image_rows: torch.Tensor, world: int) -> torch.Tensor:
     out = torch.empty((world,) + tuple(image_rows.shape), dtype=image_rows.dtype, device=image_rows.device)
     dist.all_gather_into_tensor(out, image_rows.contiguous())
     return out.reshape((-1,) + tuple(image_rows.shape[1:]))
+
+
+class VisibilityExchange:
+    """Every rank ends up with the visibility words (1 bit per object slot) of all shards, written by the cull's own compaction
+    kernel straight into the peers' memory over NVLink (r3_exchange_*, include/rend3_b200.h).  torch.distributed only carries
+    the 64-byte IPC handles once, at set-up."""
+
+    def __init__(self, backend, camera: int, objects_per_rank: int, rank: int, world: int):
+        self.backend, self.camera, self.rank, self.world = backend, camera, rank, world
+        handle = backend.exchange_create(camera, world, rank, objects_per_rank)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        backend.exchange_connect(camera, b"".join(handles))
+        self.ptr, self.nbytes, self.words_per_rank = backend.exchange_words(camera)
+        dist.barrier()   # every rank has mapped every buffer before anybody's cull writes into them
+
+    def gathered(self, device) -> torch.Tensor:
+        """(world, words_per_rank) int32 view of the local gathered buffer.  Valid after the ranks synchronised their streams and
+        passed a barrier."""
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (self.world, self.words_per_rank), "typestr": "<i4", "data": (self.ptr, False), "version": 2}
+        return torch.as_tensor(v, device=device)
+
+    def close(self):
+        dist.barrier()
+        self.backend.exchange_destroy(self.camera)
