@@ -6,6 +6,8 @@ visibility bits, depth, shadow atlas and hi-Z are integer / bit-pattern artefact
 shaded HDR pixels must agree within 1e-4 (absolute below 1.0, relative above — the target is HDR) on the f32
 shading result, and the rgba16f store within one f16 ulp of that.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -444,6 +446,35 @@ def test_per_fragment_cutout_matches_oracle(cuda, samples):
     ev2.material_buffer["alpha_cutout"] = 0.0
     BaseRenderGraph(opaque).add_to_graph(ev2, res, samples, BaseRenderGraphSettings(clear_color=(0.05, 0.05, 0.1, 1.0)))
     assert np.count_nonzero(opaque.readback_depth() > 0) > np.count_nonzero(orc.readback_depth() > 0) + 200
+
+
+def test_cpp_host_mirror_renders_the_same_frames(cuda, tmp_path):
+    """The native host layer (include/rend3_b200.hpp: GpuCuller / ForwardRoutine / BaseRenderGraph in base.rs order) driven by
+    rend3_b200/host/r3_frame on a dumped scene: two frames, same artefacts as the Python-driven context and the oracle."""
+    import subprocess
+
+    from rend3_b200.scene_io import dump_scene, load_outputs
+
+    res = (256, 144)
+    ev = cube_field_scene(n_objects=900, seed=17, resolution=res, n_dir_lights=1, n_point_lights=2, shadow_resolution=256, shadow_distance=100.0, pull_back=7.0,
+                          extent=14.0, subdivisions=(1, 2), material_count=6, mixed_transparency=True)
+    settings = BaseRenderGraphSettings(clear_color=(0.1, 0.2, 0.3, 1.0))
+    scene, out = tmp_path / "scene.r3s", tmp_path / "out.r3o"
+    dump_scene(str(scene), ev, res, 1, settings, True, frames=2)
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rend3_b200", "host", "r3_frame")
+    r = subprocess.run([exe, str(scene), str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = load_outputs(str(out))
+    orc = load_oracle_backend()
+    graphs = {id(b): BaseRenderGraph(b) for b in (cuda, orc)}
+    for frame in range(2):
+        for b in (cuda, orc):
+            graphs[id(b)].add_to_graph(ev, res, 1, settings, upload=(frame == 0))
+    assert np.array_equal(got["visible"], orc.readback_visible(CAMERA_VIEWPORT))
+    assert np.array_equal(got["depth"].view(np.uint32), orc.readback_depth().reshape(-1).view(np.uint32))
+    assert list(got["stats"][:3]) == list(orc.forward_stats()[:3])
+    assert np.array_equal(got["hdr"], cuda.readback_hdr_f32().reshape(-1)), "same library, same calls: the two host layers must agree bit for bit"
+    assert np.abs(got["ldr"].astype(int) - orc.readback_ldr().reshape(-1).astype(int)).max() <= 1
 
 
 def test_device_batching_equals_host_batching_and_oracle(cuda, monkeypatch):

@@ -75,6 +75,26 @@ def test_cuda_library_exports_every_entry_point_and_fails_loudly_without_a_gpu()
         assert rc == -4 and not ctx.value, "context creation must fail with R3_E_NO_DEVICE: there is no CPU fallback"
 
 
+def test_cpp_host_driver_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """include/rend3_b200.hpp + rend3_b200/host/r3_frame: the native host mirror links against the C ABI; without a CUDA device it
+    must stop with the library's error (no CPU path behind it)."""
+    import torch
+
+    from rend3_b200.scene_io import dump_scene
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "rend3_b200", "host", "r3_frame")
+    assert os.path.exists(exe), "__graft_entry__.build() compiles the host driver"
+    scene = tmp_path / "s.r3s"
+    ev = cube_field_scene(n_objects=20, seed=3, resolution=(64, 48), shadow_resolution=64, shadow_distance=40.0, pull_back=4.0, extent=4.0)
+    dump_scene(str(scene), ev, (64, 48))
+    assert os.path.getsize(scene) > 128 * 20
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the driver is exercised by tests/test_gpu_parity.py")
+    r = subprocess.run([exe, str(scene), str(tmp_path / "o.r3o")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr, r.stderr
+
+
 def test_product_never_touches_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py may reference oracle/."""
     pkg = os.path.join(ROOT, "rend3_b200")
