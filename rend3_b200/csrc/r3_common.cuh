@@ -71,6 +71,7 @@ struct r3_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    bool coop_launch_ok = false;              // cudaDevAttrCooperativeLaunch (grid-wide barriers inside one launch)
     // world
     r3_object* d_objects = nullptr; uint32_t n_slots = 0, objects_cap = 0; bool objects_borrowed = false;
     // dense copies of the fields the cull + bake stream reads (r3_cull_bake.cu): transform columns, bounding spheres, enabled bits

@@ -55,6 +55,7 @@ R3_EXPORT int r3_ctx_create(int device, r3_ctx** out) {
         cudaGetLastError();
         return R3_E_CUDA;
     }
+    { int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device); c->coop_launch_ok = coop != 0 && !getenv("R3_NO_COOP_SORT"); }
     if (cudaMalloc((void**)&c->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete c; return R3_E_OOM; }
     cudaMemsetAsync(c->d_stats, 0, 64, c->stream);
     *out = c;

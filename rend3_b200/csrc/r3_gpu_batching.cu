@@ -18,6 +18,8 @@
 // single batch exceeding max_compute_workgroups_per_dimension*256 invocations (reported through the overflow flag).
 #include <cstring>
 
+#include <cooperative_groups.h>
+
 #include "r3_common.cuh"
 
 namespace {
@@ -244,6 +246,88 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* s_warp
     return wbase + incl - v;
 }
 
+// Mid-sized worlds (more than one CTA's worth, up to 256 tiles = 524288 visible objects): the whole sort — key generation and
+// the five histogram / offset / scatter passes — in ONE cooperative launch with grid-wide barriers between the phases instead of
+// 16 launches.  Every CTA derives its own scatter bases from the raw digit-major histogram table (one pass over <= 256 columns
+// per thread), so no separate scan kernel runs.
+constexpr uint32_t COOP_SORT_MAX_BLOCKS = 256;
+struct SortCoopParams {
+    const uint32_t* visible; const uint32_t* visible_count; const uint8_t* key8; const float* loc; float vx, vy, vz;
+    unsigned long long* keys[2]; uint32_t* hist; uint32_t* header;
+};
+__global__ void __launch_bounds__(SORT_THREADS) radix_sort_coop_kernel(const __grid_constant__ SortCoopParams p) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_cnt[SORT_THREADS / 32][256];
+    __shared__ uint32_t s_run[256];
+    __shared__ uint32_t s_gbase[256];
+    __shared__ uint32_t s_warp[8];
+    const uint32_t nv = *p.visible_count, nb = gridDim.x, b = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t base = b * SORT_TILE;
+    if (b == 0 && threadIdx.x == 0) { p.header[0] = nv; p.header[4] = (nv >= (1u << 24)) ? 1u : 0u; }
+#pragma unroll 1
+    for (int r = 0; r < SORT_KEYS_PER_THREAD; ++r) {
+        const uint32_t i = base + r * SORT_THREADS + threadIdx.x;
+        if (i < nv) p.keys[0][i] = make_sort_key(p.visible, p.key8, p.loc, p.vx, p.vy, p.vz, i);
+    }
+    __syncthreads();
+    int src = 0;
+    for (int pass = 0; pass < SORT_PASSES; ++pass) {
+        const int shift = KEY_SHIFT0 + 8 * pass;
+        const unsigned long long* keys_in = p.keys[src];
+        unsigned long long* keys_out = p.keys[src ^ 1];
+        // histogram of this tile
+        s_hist[threadIdx.x] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < SORT_KEYS_PER_THREAD; ++r) {
+            const uint32_t i = base + r * SORT_THREADS + threadIdx.x;
+            if (i < nv) atomicAdd(&s_hist[(uint32_t)(keys_in[i] >> shift) & 0xFFu], 1u);
+        }
+        __syncthreads();
+        p.hist[threadIdx.x * nb + b] = s_hist[threadIdx.x];
+        grid.sync();
+        // scatter bases of this tile: digits below mine in every tile + my digit in the tiles in front of me
+        {
+            uint32_t before = 0, total = 0;
+            const uint32_t* col = p.hist + threadIdx.x * nb;
+            for (uint32_t k = 0; k < nb; ++k) { const uint32_t v = col[k]; total += v; if (k < b) before += v; }
+            uint32_t tot_all;
+            const uint32_t digit_base = block_scan_excl(total, s_warp, &tot_all);
+            s_gbase[threadIdx.x] = digit_base + before;
+            s_run[threadIdx.x] = 0;
+        }
+        __syncthreads();
+        // stable scatter, 256 keys per round
+#pragma unroll 1
+        for (int r = 0; r < SORT_KEYS_PER_THREAD; ++r) {
+#pragma unroll
+            for (int w = 0; w < SORT_THREADS / 32; ++w) s_cnt[w][threadIdx.x] = 0;
+            __syncthreads();
+            const uint32_t i = base + r * SORT_THREADS + threadIdx.x;
+            const bool valid = i < nv;
+            const unsigned long long key = valid ? keys_in[i] : 0ull;
+            const uint32_t d = valid ? ((uint32_t)(key >> shift) & 0xFFu) : 0x100u;
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+            const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+            if (valid && rank_in_warp == 0) s_cnt[warp][d] = __popc(peers);
+            __syncthreads();
+            uint32_t acc = 0;
+#pragma unroll
+            for (int w = 0; w < SORT_THREADS / 32; ++w) { const uint32_t c = s_cnt[w][threadIdx.x]; s_cnt[w][threadIdx.x] = acc; acc += c; }
+            __syncthreads();
+            if (valid) keys_out[s_gbase[d] + s_run[d] + s_cnt[warp][d] + rank_in_warp] = key;
+            __syncthreads();
+            s_run[threadIdx.x] += acc;
+            __syncthreads();
+        }
+        grid.sync();
+        src ^= 1;
+    }
+}
+
 __global__ void __launch_bounds__(256) batch_build_kernel(const __grid_constant__ BuildParams p) {
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_start[256];
@@ -444,6 +528,15 @@ int r3_device_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], ui
             small_sort_kernel<<<1, SMALL_SORT_THREADS, smem, c->stream>>>(cam->d_visible, cam->d_visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2],
                                                                           cam->d_sort_keys[0], j.d_header, small_sort_pad(cap));
             R3_CHECK_LAUNCH(c, "small_sort_kernel");
+        } else if (sort_blocks <= COOP_SORT_MAX_BLOCKS && c->coop_launch_ok) {
+            SortCoopParams sp;
+            sp.visible = cam->d_visible; sp.visible_count = cam->d_visible_count; sp.key8 = c->d_sort_key8; sp.loc = c->d_sort_loc;
+            sp.vx = vp_loc[0]; sp.vy = vp_loc[1]; sp.vz = vp_loc[2];
+            sp.keys[0] = cam->d_sort_keys[0]; sp.keys[1] = cam->d_sort_keys[1]; sp.hist = cam->d_sort_hist; sp.header = j.d_header;
+            void* args[] = {&sp};
+            R3_CUDA(c, cudaLaunchCooperativeKernel((const void*)radix_sort_coop_kernel, dim3(sort_blocks), dim3(SORT_THREADS), args, 0, c->stream));
+            c->launches++;
+            src = SORT_PASSES & 1;
         } else {
             keygen_kernel<<<(cap + 255) / 256, 256, 0, c->stream>>>(cam->d_visible, cam->d_visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2],
                                                                      cam->d_sort_keys[0], j.d_header);

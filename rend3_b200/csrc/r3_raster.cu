@@ -497,8 +497,9 @@ __device__ void setup_listed_triangle(const RasterParams& p, unsigned long long 
     }
 }
 
+// depth-only set-up is a chain of dependent gathers: 64 registers buy a fourth resident CTA per SM
 template <int MODE>
-__global__ void __launch_bounds__(RS_THREADS) raster_setup_kernel(const __grid_constant__ RasterParams p) {
+__global__ void __launch_bounds__(RS_THREADS, MODE == MODE_DEPTH ? 4 : 1) raster_setup_kernel(const __grid_constant__ RasterParams p) {
     const uint32_t n_regions = p.header[2];
     const unsigned long long total = p.tri_prefix[n_regions];
     const int lane = threadIdx.x & 31;
