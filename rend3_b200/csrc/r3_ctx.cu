@@ -75,6 +75,11 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     cudaFree(c->d_light_mats); cudaFree(c->d_atlas);
     for (auto& k : c->cams) {
         cudaFree(k.d_matrices); cudaFree(k.d_visible); cudaFree(k.d_visible_count); cudaFree(k.d_tile_state);
+        if (k.d_gathered) {   // visible-set exchange: unmap the peers' buffers, free ours
+            for (uint32_t r = 0; r < k.ex_ranks; ++r)
+                if (k.ex_connected && r != k.ex_rank && k.ex_peers[r]) cudaIpcCloseMemHandle(k.ex_peers[r]);
+            cudaFree(k.d_gathered);
+        }
         free_jobs(k.jobs[0]); free_jobs(k.jobs[1]);
         cudaFree(k.index_buffer.d); cudaFree(k.draw_call_buffer.d); cudaFree(k.results_buffer.d);
         cudaFree(k.d_resid_bits); cudaFree(k.d_word_scan); cudaFree(k.d_block_sums);
