@@ -334,6 +334,45 @@ def test_error_paths(cuda):
     hdr = per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (64, 64), 1, 9)   # object_count > buffer
     with pytest.raises(R3Error):
         cuda.object_uniform_upload(CAMERA_VIEWPORT, hdr)
+    # texture table: a mip chain that does not fit its blob, an unknown format
+    from rend3_b200.layouts import TEXTURE_DESC_DTYPE
+    d = np.zeros(1, dtype=TEXTURE_DESC_DTYPE)
+    d["width"], d["height"], d["mip_count"], d["format"] = 8, 8, 4, 0
+    with pytest.raises(R3Error):
+        cuda.set_textures(d, np.zeros(8 * 8 * 4, dtype=np.uint8))          # levels 1..3 missing
+    d["mip_count"], d["format"] = 1, 7
+    with pytest.raises(R3Error):
+        cuda.set_textures(d, np.zeros(8 * 8 * 4, dtype=np.uint8))
+    # exchange: connect before create, bad rank layout, more objects than announced
+    with pytest.raises(R3Error):
+        cuda.exchange_connect(CAMERA_VIEWPORT, bytes(64))
+    with pytest.raises(R3Error):
+        cuda.exchange_create(CAMERA_VIEWPORT, 4, 4, 100)
+    cuda.exchange_create(CAMERA_VIEWPORT, 1, 0, 2)
+    cuda.exchange_connect(CAMERA_VIEWPORT, bytes(64))                        # a single rank: its own buffer, no peer to open
+    cuda.set_objects(np.zeros(4096, dtype=OBJECT_DTYPE))
+    with pytest.raises(R3Error):
+        cuda.object_uniform_upload(CAMERA_VIEWPORT, per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (64, 64), 1, 4096))
+    cuda.exchange_destroy(CAMERA_VIEWPORT)
+    cuda.object_uniform_upload(CAMERA_VIEWPORT, per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (64, 64), 1, 4096))
+    # the single-rank exchange row mirrors the visibility words
+    rec = object_cloud_records(5000, seed=3)
+    cuda.set_objects(rec)
+    cuda.exchange_create(CAMERA_VIEWPORT, 1, 0, 5000)
+    cuda.exchange_connect(CAMERA_VIEWPORT, bytes(64))
+    cuda.object_uniform_upload(CAMERA_VIEWPORT, per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (1920, 1080), 1, 5000))
+    import torch
+
+    ptr, nbytes, wpr = cuda.exchange_words(CAMERA_VIEWPORT)
+
+    class _V:
+        __cuda_array_interface__ = {"shape": (wpr,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+    cuda.sync()
+    words = torch.as_tensor(_V(), device="cuda:0").cpu().numpy().view(np.uint32)
+    bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:5000]
+    assert np.array_equal(np.nonzero(bits)[0].astype(np.uint32), cuda.readback_visible(CAMERA_VIEWPORT))
+    cuda.exchange_destroy(CAMERA_VIEWPORT)
 
 
 @pytest.mark.parametrize("far_first", [True, False])
