@@ -129,7 +129,7 @@ API int r3o_ctx_destroy(r3o_ctx* c) {
     free(c->vis); free(c->hdr); free(c->hdr16); free(c->depth); free(c->ldr); free(c->atlas);
     for (uint32_t i = 0; i < c->hiz_mips; ++i) free(c->hiz[i]);
     free(c->hiz); free(c->hiz_w); free(c->hiz_h);
-    free(c->tex_descs); free(c->texels); free(c->tris[0]); free(c->tris[1]); free(c->tris[2]); free(c->tris[3]); free(c->sample_col16); free(c->blended);
+    free(c->tex_descs); free(c->texels); free(c->sky_texels); free(c->tris[0]); free(c->tris[1]); free(c->tris[2]); free(c->tris[3]); free(c->sample_col16); free(c->blended);
     free(c);
     return R3_OK;
 }
@@ -197,6 +197,22 @@ API int r3o_set_textures(r3o_ctx* c, const r3_texture_desc* descs, uint32_t n, c
     c->texels = (uint8_t*)malloc(nbytes + 16);
     if (nbytes) memcpy(c->texels, texels, nbytes);
     c->n_textures = n; c->texel_bytes = nbytes;
+    return R3_OK;
+}
+static uint64_t cube_face_bytes(const r3_texture_desc* d) {
+    uint64_t bpp = d->format == R3_TEXFMT_RGBA32_FLOAT ? 16 : 4, total = 0;
+    for (uint32_t l = 0; l < d->mip_count; ++l) { uint64_t w = (d->width >> l) ? (d->width >> l) : 1; total += w * w * bpp; }
+    return total;
+}
+API int r3o_set_skybox(r3o_ctx* c, const r3_texture_desc* desc, const void* texels, uint64_t nbytes) {
+    if (!c) return R3_E_INVALID;
+    free(c->sky_texels); c->sky_texels = NULL; c->has_skybox = 0;
+    if (!desc) return R3_OK;
+    if (!texels || !desc->width || !desc->mip_count || desc->mip_count > 32 || desc->format > R3_TEXFMT_RGBA32_FLOAT) return fail(c, R3_E_INVALID, "skybox: bad descriptor");
+    if (desc->byte_offset % 16 || desc->byte_offset + 6 * cube_face_bytes(desc) > nbytes) return fail(c, R3_E_INVALID, "skybox: faces outside the texel blob");
+    c->sky_texels = (uint8_t*)malloc(nbytes + 16);
+    memcpy(c->sky_texels, texels, nbytes);
+    c->sky_desc = *desc; c->sky_desc.height = desc->width; c->has_skybox = 1;
     return R3_OK;
 }
 API int r3o_set_directional_lights(r3o_ctx* c, const void* bytes, uint64_t nbytes, uint32_t aw, uint32_t ah) {

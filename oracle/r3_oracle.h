@@ -41,6 +41,7 @@ typedef struct r3o_ctx {
     uint32_t* mesh; uint64_t mesh_words;
     r3_material* materials; uint32_t n_materials;
     r3_texture_desc* tex_descs; uint32_t n_textures; uint8_t* texels; uint64_t texel_bytes;   /* bindless d2 texture table */
+    int has_skybox; r3_texture_desc sky_desc; uint8_t* sky_texels;                          /* cube map of the skybox routine */
     r3_directional_light* dir_lights; uint32_t n_dir; uint32_t atlas_w, atlas_h;
     r3_point_light* point_lights; uint32_t n_point;
     r3_frame_uniforms uniforms;

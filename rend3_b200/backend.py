@@ -30,7 +30,7 @@ CUDA_LIB_PATH = os.path.join(_ROOT, "librend3_b200.so")
 # every entry point of include/rend3_b200.h (tests check the .so exports all of them)
 ENTRY_POINTS = [
     "abi_version", "ctx_create", "ctx_destroy", "last_error", "sync", "get_stream", "launch_count",
-    "set_objects", "update_objects", "set_objects_device", "set_object_sort_info", "set_mesh_buffer", "set_textures",
+    "set_objects", "update_objects", "set_objects_device", "set_object_sort_info", "set_mesh_buffer", "set_textures", "set_skybox",
     "set_materials", "set_directional_lights", "set_point_lights", "set_frame_uniforms",
     "object_uniform_upload", "visible_count", "readback_visible", "readback_object_matrices",
     "batch_objects", "batch_counts", "readback_batches", "cull", "readback_indices",
@@ -132,6 +132,14 @@ class Backend:
         texels = np.ascontiguousarray(texels).view(np.uint8).reshape(-1)
         assert descs.dtype.itemsize == 32
         self._call("set_textures", _ptr(descs) if len(descs) else None, C.c_uint32(len(descs)), _ptr(texels) if len(texels) else None, C.c_uint64(len(texels)))
+
+    def set_skybox(self, desc: Optional[np.ndarray], texels: Optional[np.ndarray]):
+        if desc is None:
+            self._call("set_skybox", None, None, C.c_uint64(0))
+            return
+        desc = np.ascontiguousarray(desc).reshape(1)
+        texels = np.ascontiguousarray(texels).view(np.uint8).reshape(-1)
+        self._call("set_skybox", _ptr(desc), _ptr(texels), C.c_uint64(len(texels)))
 
     def set_directional_lights(self, data: bytes, atlas_w: int, atlas_h: int):
         self._call("set_directional_lights", C.c_char_p(data), C.c_uint64(len(data)), C.c_uint32(atlas_w), C.c_uint32(atlas_h))

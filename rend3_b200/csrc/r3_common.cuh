@@ -82,6 +82,7 @@ struct r3_ctx {
     uint64_t max_total_invocations = 0; bool max_invocations_valid = false;   // sum over all slots of round_up(tris, 256)
     uint32_t* d_mesh = nullptr; uint64_t mesh_words = 0, mesh_cap = 0;
     r3_material* d_materials = nullptr; uint32_t n_materials = 0, materials_cap = 0;
+    bool has_skybox = false; r3_texture_desc sky_desc{}; uint8_t* d_sky_texels = nullptr; uint64_t sky_cap = 0;   // cube map of the skybox routine
     r3_texture_desc* d_tex_descs = nullptr; uint32_t n_textures = 0, tex_descs_cap = 0; uint8_t* d_texels = nullptr; uint64_t texels_cap = 0;
     r3_directional_light* d_dir = nullptr; uint32_t n_dir = 0, dir_cap = 0;
     r3_point_light* d_point = nullptr; uint32_t n_point = 0, point_cap = 0;

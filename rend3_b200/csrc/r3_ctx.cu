@@ -69,7 +69,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (!c->objects_borrowed) cudaFree(c->d_objects);
-    cudaFree(c->d_hot_transform); cudaFree(c->d_hot_sphere); cudaFree(c->d_enabled_bits); cudaFree(c->d_tex_descs); cudaFree(c->d_texels);
+    cudaFree(c->d_hot_transform); cudaFree(c->d_hot_sphere); cudaFree(c->d_enabled_bits); cudaFree(c->d_tex_descs); cudaFree(c->d_texels); cudaFree(c->d_sky_texels);
     cudaFree(c->d_sort_key8); cudaFree(c->d_sort_loc);
     cudaFree(c->d_live_bits); cudaFree(c->d_mesh); cudaFree(c->d_materials); cudaFree(c->d_dir); cudaFree(c->d_point);
     cudaFree(c->d_light_mats); cudaFree(c->d_atlas);
@@ -235,6 +235,22 @@ R3_EXPORT int r3_set_textures(r3_ctx* c, const r3_texture_desc* descs, uint32_t 
     if (nbytes) R3_CUDA(c, cudaMemcpyAsync(c->d_texels, texels, nbytes, cudaMemcpyHostToDevice, c->stream));
     R3_CUDA(c, cudaStreamSynchronize(c->stream));
     c->n_textures = n;
+    return R3_OK;
+}
+R3_EXPORT int r3_set_skybox(r3_ctx* c, const r3_texture_desc* desc, const void* texels, uint64_t nbytes) {
+    if (!c) return R3_E_INVALID;
+    c->has_skybox = false;
+    if (!desc) return R3_OK;
+    if (!texels || !desc->width || !desc->mip_count || desc->mip_count > 32 || desc->format > R3_TEXFMT_RGBA32_FLOAT) return r3_fail(c, R3_E_INVALID, "set_skybox: bad descriptor");
+    const uint64_t bpp = desc->format == R3_TEXFMT_RGBA32_FLOAT ? 16 : 4;
+    uint64_t face = 0;
+    for (uint32_t l = 0; l < desc->mip_count; ++l) { const uint64_t w = (desc->width >> l) ? (desc->width >> l) : 1u; face += w * w * bpp; }
+    if (desc->byte_offset % 16 || desc->byte_offset + 6 * face > nbytes) return r3_fail(c, R3_E_INVALID, "set_skybox: faces outside the texel blob");
+    cudaSetDevice(c->device);
+    R3_TRY(r3_reserve_t(c, &c->d_sky_texels, &c->sky_cap, nbytes + 16));
+    R3_CUDA(c, cudaMemcpyAsync(c->d_sky_texels, texels, nbytes, cudaMemcpyHostToDevice, c->stream));
+    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->sky_desc = *desc; c->sky_desc.height = desc->width; c->has_skybox = true;
     return R3_OK;
 }
 R3_EXPORT int r3_set_directional_lights(r3_ctx* c, const void* bytes, uint64_t nbytes, uint32_t aw, uint32_t ah) {

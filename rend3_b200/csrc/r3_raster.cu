@@ -681,7 +681,7 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, int mode,
     p.vis = c->d_vis; p.pass_bit = (uint32_t)(pass & 1); p.depth_bits = (uint32_t*)c->d_atlas;
     p.frag_heads = c->d_frag_heads; p.frag_nodes = c->d_frag_nodes; p.frag_cap = (uint32_t)c->frag_nodes_cap; p.key_lo = key_lo; p.key_hi = key_hi;
     p.large = large; p.bands = bands; p.counters = counters; p.stats = mode == MODE_COLOUR ? c->d_stats : nullptr;   // statistics describe the opaque + cutout passes
-    p.tt.tex = c->d_tex_descs; p.tt.n_tex = c->n_textures; p.tt.texels = c->d_texels;
+    p.tt.tex = c->d_tex_descs; p.tt.n_tex = c->n_textures; p.tt.texels = c->d_texels; p.tt.clamp_to_edge = 0u;
     p.records = nullptr;
     if (depth_only && c->any_frag_alpha) {
         // cutout materials whose alpha comes from a texture / vertex colour: the shadow pass needs the triangle records too

@@ -33,6 +33,7 @@ struct ShadeParams {
     const uint32_t* mesh; uint64_t mesh_words;
     const r3_material* materials; uint32_t n_materials;
     TexTable tt;                                                          // bindless d2 texture table (r3_set_textures)
+    TexTable sky; r3_texture_desc sky_desc; float inv_origin_view_proj[16];   // skybox routine (r3_set_skybox)
     const DirPrep* dir; uint32_t n_dir; const PointPrep* point; uint32_t n_point;
     const float* atlas; uint32_t atlas_w, atlas_h;
     // blend routine (r3_forward_blend): triangle records of the key-2 regions + the per-sample fragment lists
@@ -331,6 +332,47 @@ __device__ __noinline__ void textured_pixel_data(const ShadeParams& p, const r3_
 
 // fs_main (opaque.wgsl:470-551).  `mask` lists the point lights that can reach the fragment (a conservative superset is fine:
 // every listed light still takes the exact per-fragment range test below).
+// skybox.wgsl::fs_main (rend3-routine/shaders/src/skybox.wgsl:24-36) at the centre of pixel (px, py); cube sampling by rule R10 of the
+// oracle (face + (s, t) by the major axis, forward-difference derivatives on the same face, trilinear, texels clamped to the face)
+__device__ __forceinline__ float3 skybox_direction(const ShadeParams& p, float fx, float fy) {
+    const float cx = sub_rn(div_rn(fx, (float)p.width * 0.5f), 1.0f), cy = sub_rn(1.0f, div_rn(fy, (float)p.height * 0.5f));
+    const float4 wu = mat_vec_rn(p.inv_origin_view_proj, cx, cy, 1.0f, 1.0f);
+    const float wx = div_rn(wu.x, wu.w), wy = div_rn(wu.y, wu.w), wz = div_rn(wu.z, wu.w);
+    const float len = sqrtf(add_rn(add_rn(mul_rn(wx, wx), mul_rn(wy, wy)), mul_rn(wz, wz)));
+    return make_float3(div_rn(wx, len), div_rn(wy, len), div_rn(wz, len));
+}
+__device__ __forceinline__ float2 cube_face_coords(const float3 d, int face) {
+    float sc, tc, ma;
+    switch (face) {
+        case 0: sc = -d.z; tc = -d.y; ma = fabsf(d.x); break;
+        case 1: sc = d.z; tc = -d.y; ma = fabsf(d.x); break;
+        case 2: sc = d.x; tc = d.z; ma = fabsf(d.y); break;
+        case 3: sc = d.x; tc = -d.z; ma = fabsf(d.y); break;
+        case 4: sc = d.x; tc = -d.y; ma = fabsf(d.z); break;
+        default: sc = -d.x; tc = -d.y; ma = fabsf(d.z); break;
+    }
+    return make_float2(mul_rn(0.5f, add_rn(div_rn(sc, ma), 1.0f)), mul_rn(0.5f, add_rn(div_rn(tc, ma), 1.0f)));
+}
+__device__ __noinline__ float4 skybox_at_pixel(const ShadeParams& p, uint32_t px, uint32_t py) {
+    const float3 d0 = skybox_direction(p, (float)px + 0.5f, (float)py + 0.5f);
+    const float3 dx = skybox_direction(p, (float)px + 1.5f, (float)py + 0.5f), dy = skybox_direction(p, (float)px + 0.5f, (float)py + 1.5f);
+    const float ax = fabsf(d0.x), ay = fabsf(d0.y), az = fabsf(d0.z);
+    int face;
+    if (ax >= ay && ax >= az) face = d0.x > 0.0f ? 0 : 1;
+    else if (ay >= az) face = d0.y > 0.0f ? 2 : 3;
+    else face = d0.z > 0.0f ? 4 : 5;
+    const float2 st = cube_face_coords(d0, face), stx = cube_face_coords(dx, face), sty = cube_face_coords(dy, face);
+    TexCoords tc;
+    tc.u = st.x; tc.v = st.y; tc.dudx = sub_rn(stx.x, st.x); tc.dvdx = sub_rn(stx.y, st.y); tc.dudy = sub_rn(sty.x, st.x); tc.dvdy = sub_rn(sty.y, st.y);
+    r3_texture_desc fd = p.sky_desc;
+    const unsigned long long bpp = fd.format == R3_TEXFMT_RGBA32_FLOAT ? 16ull : 4ull;
+    unsigned long long face_bytes = 0;
+    for (uint32_t l = 0; l < fd.mip_count; ++l) { const unsigned long long w = max(fd.width >> l, 1u); face_bytes += w * w * bpp; }
+    fd.byte_offset += (unsigned long long)face * face_bytes;
+    const float4 t = sample_grad_desc(p.sky, fd, false, tc);
+    return make_float4(t.x, t.y, t.z, 1.0f);
+}
+
 // TEX = the context holds a texture table: kernels are instantiated with and without the texture path, so that scenes without
 // textures keep the register budget (75 instead of 104) of the lean kernel.
 template <bool TEX>
@@ -530,6 +572,8 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
         // ((s0 + s1) + (s2 + s3)) * 0.25 like the resolve attachment (base.rs:245-255); depth resolves to the MIN over the samples
         unsigned long long keys[4];
         float4 col[4];
+        float4 sky = make_float4(0.f, 0.f, 0.f, 1.f);
+        bool have_sky = false;
         depth = 1.0f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -540,9 +584,13 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
         for (int k = 0; k < 4; ++k) {
             const uint32_t id = (uint32_t)keys[k], rec = id & 0x7FFFFFFFu, pass = id >> 31;
             col[k] = make_float4(p.clear[0], p.clear[1], p.clear[2], p.clear[3]);
-            if (rec != 0u && rec <= (pass ? p.n_tris1 : p.n_tris0)) {
+            if (p.sky.texels && (uint32_t)(keys[k] >> 32) == 0u) {
+                // SkyboxRoutine (skybox.rs:80-110, base.rs:175): depth 0, GreaterEqual -> every sample still at the clear depth
+                if (!have_sky) { sky = skybox_at_pixel(p, px, py); have_sky = true; }
+                col[k] = sky;
+            } else if (rec != 0u && rec <= (pass ? p.n_tris1 : p.n_tris0)) {
                 int reuse = -1;
-                for (int q = 0; q < k; ++q) if ((uint32_t)keys[q] == id && reuse < 0) reuse = q;
+                for (int q = 0; q < k; ++q) if ((uint32_t)keys[q] == id && (uint32_t)(keys[q] >> 32) != 0u && reuse < 0) reuse = q;
                 if (reuse >= 0) col[k] = col[reuse];
                 else { col[k] = shade_fragment<TEX>(p, s_dir, s_point, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py); n_shaded++; }
             }
@@ -609,9 +657,10 @@ __global__ void __launch_bounds__(256) blend_apply_kernel(const __grid_constant_
             ids[k] = (uint32_t)key; zdst[k] = (uint32_t)(key >> 32);
             const uint32_t rec = ids[k] & 0x7FFFFFFFu, pass = ids[k] >> 31;
             float4 col = make_float4(p.clear[0], p.clear[1], p.clear[2], p.clear[3]);
-            if (rec != 0u && rec <= (pass ? p.n_tris1 : p.n_tris0)) {
+            if (p.sky.texels && zdst[k] == 0u) col = skybox_at_pixel(p, px, py);
+            else if (rec != 0u && rec <= (pass ? p.n_tris1 : p.n_tris0)) {
                 int reuse = -1;
-                for (int q = 0; q < k; ++q) if (ids[q] == ids[k] && reuse < 0) reuse = q;
+                for (int q = 0; q < k; ++q) if (ids[q] == ids[k] && zdst[q] != 0u && reuse < 0) reuse = q;
                 if (reuse >= 0) col = dst[reuse];
                 else col = shade_fragment<TEX>(p, s_dir, s_point, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py);
             }
@@ -671,6 +720,19 @@ __global__ void __launch_bounds__(256) blend_apply_kernel(const __grid_constant_
         p.depth[pi] = depth;
         atomicAdd(&p.stats[3], (unsigned long long)n_blended);
     }
+}
+
+// SkyboxRoutine for single-sampled targets: a pass of its own after the opaque resolve (base.rs:175), so that resolve_kernel<1, .>
+// keeps its register budget — every pixel still at the clear depth takes the cube-map colour
+__global__ void __launch_bounds__(256) skybox_kernel(const __grid_constant__ ShadeParams p) {
+    const uint32_t px = blockIdx.x * 32u + (threadIdx.x & 31u), py = p.row_begin + blockIdx.y * 8u + (threadIdx.x >> 5);
+    if (px >= p.width || py >= p.row_end) return;
+    const size_t pi = (size_t)py * p.width + px;
+    if ((uint32_t)(p.vis[pi] >> 32) != 0u) return;
+    const float4 out = skybox_at_pixel(p, px, py);
+    p.hdr32[pi] = out;
+    const __half2 h01 = __floats2half2_rn(out.x, out.y), h23 = __floats2half2_rn(out.z, out.w);
+    p.hdr16[pi] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
 }
 
 // light prep: one thread per light (opaque.wgsl:491,519,528 hoisted out of the fragment loop)
@@ -834,7 +896,9 @@ static void fill_shade_params(r3_ctx* c, ShadeParams* out) {
     p.tris2 = c->d_tris[2]; p.n_tris2 = c->n_tris[2]; p.frag_heads = c->d_frag_heads; p.frag_nodes = c->d_frag_nodes;
     p.objects = c->d_objects; p.matrices = cam->d_matrices; p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;
     p.materials = c->d_materials; p.n_materials = c->n_materials;
-    p.tt.tex = c->d_tex_descs; p.tt.n_tex = c->n_textures; p.tt.texels = c->d_texels;
+    p.tt.tex = c->d_tex_descs; p.tt.n_tex = c->n_textures; p.tt.texels = c->d_texels; p.tt.clamp_to_edge = 0u;
+    p.sky.tex = nullptr; p.sky.n_tex = 0; p.sky.texels = c->has_skybox ? c->d_sky_texels : nullptr; p.sky.clamp_to_edge = 1u;
+    p.sky_desc = c->sky_desc; memcpy(p.inv_origin_view_proj, c->uniforms.inv_origin_view_proj, 64);
     p.dir = d_dir; p.n_dir = c->n_dir; p.point = d_point; p.n_point = c->n_point;
     p.atlas = c->d_atlas; p.atlas_w = c->atlas_w; p.atlas_h = c->atlas_h;
     memcpy(p.ambient, c->uniforms.ambient, 16); memcpy(p.clear, c->clear_color, 16);
@@ -865,6 +929,10 @@ R3_EXPORT int r3_forward_resolve(r3_ctx* c) {
         if (c->samples == 1) { if (tex) resolve_kernel<1, true><<<grid, 256, 0, c->stream>>>(p); else resolve_kernel<1, false><<<grid, 256, 0, c->stream>>>(p); }
         else { if (tex) resolve_kernel<4, true><<<grid, 256, 0, c->stream>>>(p); else resolve_kernel<4, false><<<grid, 256, 0, c->stream>>>(p); }
         R3_CHECK_LAUNCH(c, "resolve_kernel");
+        if (c->has_skybox && c->samples == 1) {
+            skybox_kernel<<<grid, 256, 0, c->stream>>>(p);
+            R3_CHECK_LAUNCH(c, "skybox_kernel");
+        }
     }
     return R3_OK;
 }

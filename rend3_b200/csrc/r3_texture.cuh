@@ -6,7 +6,7 @@
 
 namespace {
 
-struct TexTable { const r3_texture_desc* tex; uint32_t n_tex; const uint8_t* texels; };
+struct TexTable { const r3_texture_desc* tex; uint32_t n_tex; const uint8_t* texels; uint32_t clamp_to_edge; };   // clamp_to_edge: cube-map faces (skybox); 0 = Repeat
 
 __device__ __forceinline__ float srgb_to_linear(float e) { return e > 0.04045f ? powf((e + 0.055f) / 1.055f, 2.4f) : e / 12.92f; }   // math/color.wgsl:3-9
 
@@ -18,7 +18,8 @@ __device__ __forceinline__ float4 texel_fetch(const TexTable& p, const r3_textur
     const unsigned long long bpp = d.format == R3_TEXFMT_RGBA32_FLOAT ? 16ull : 4ull;
     for (uint32_t l = 0; l < level; ++l) off += (unsigned long long)max(d.width >> l, 1u) * max(d.height >> l, 1u) * bpp;
     const long long w = max(d.width >> level, 1u), h = max(d.height >> level, 1u);
-    x = ((x % w) + w) % w; y = ((y % h) + h) % h;                                   // AddressMode::Repeat
+    if (p.clamp_to_edge) { x = x < 0 ? 0 : (x >= w ? w - 1 : x); y = y < 0 ? 0 : (y >= h ? h - 1 : y); }   // texels clamped to the cube face
+    else { x = ((x % w) + w) % w; y = ((y % h) + h) % h; }                          // AddressMode::Repeat
     const uint8_t* t = p.texels + off + (unsigned long long)(y * w + x) * bpp;
     if (d.format == R3_TEXFMT_RGBA32_FLOAT) return __ldg(reinterpret_cast<const float4*>(t));
     const uchar4 c = __ldg(reinterpret_cast<const uchar4*>(t));
@@ -45,10 +46,7 @@ __device__ __noinline__ float4 sample_level(const TexTable& p, const r3_texture_
                        (t00.z * gx + t10.z * fx) * gy + (t01.z * gx + t11.z * fx) * fy, (t00.w * gx + t10.w * fx) * gy + (t01.w * gx + t11.w * fx) * fy);
 }
 struct TexCoords { float u, v, dudx, dvdx, dudy, dvdy; };
-// slot value = table index + 1; an index outside the table reads zeros (robust access)
-__device__ __noinline__ float4 texture_sample_grad(const TexTable& p, uint32_t slot_value, bool nearest, const TexCoords& c) {
-    if (slot_value == 0u || slot_value > p.n_tex) return make_float4(0.f, 0.f, 0.f, 0.f);
-    const r3_texture_desc d = p.tex[slot_value - 1u];
+__device__ __noinline__ float4 sample_grad_desc(const TexTable& p, const r3_texture_desc& d, bool nearest, const TexCoords& c) {
     const float w0 = (float)d.width, h0 = (float)d.height;
     const float ax = c.dudx * w0, ay = c.dvdx * h0, bx = c.dudy * w0, by = c.dvdy * h0;
     const float rho = fmaxf(sqrtf(ax * ax + ay * ay), sqrtf(bx * bx + by * by));
@@ -66,6 +64,11 @@ __device__ __noinline__ float4 texture_sample_grad(const TexTable& p, uint32_t s
     const float4 b = sample_level(p, d, level + 1u, false, c.u, c.v);
     const float g = 1.0f - fr;
     return make_float4(a.x * g + b.x * fr, a.y * g + b.y * fr, a.z * g + b.z * fr, a.w * g + b.w * fr);
+}
+// slot value = table index + 1; an index outside the table reads zeros (robust access)
+__device__ __forceinline__ float4 texture_sample_grad(const TexTable& p, uint32_t slot_value, bool nearest, const TexCoords& c) {
+    if (slot_value == 0u || slot_value > p.n_tex) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return sample_grad_desc(p, p.tex[slot_value - 1u], nearest, c);
 }
 
 }  // namespace

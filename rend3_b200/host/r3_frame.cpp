@@ -57,6 +57,10 @@ int main(int argc, char** argv) {
         ev.materials = as<r3_material>(s, "materials", &n); ev.n_materials = (uint32_t)n;
         ev.textures = as<r3_texture_desc>(s, "tex_descs", &n); ev.n_textures = (uint32_t)n;
         ev.texels = as<uint8_t>(s, "texels", &n); ev.texel_bytes = n;
+        if (s.count("skybox_desc") && !s.at("skybox_desc").empty()) {
+            ev.skybox = as<r3_texture_desc>(s, "skybox_desc");
+            ev.skybox_texels = as<uint8_t>(s, "skybox_texels", &n); ev.skybox_bytes = n;
+        }
         ev.directional_lights = as<uint8_t>(s, "dir_lights", &n); ev.directional_bytes = n;
         ev.point_lights = as<uint8_t>(s, "point_lights", &n); ev.point_bytes = n;
         const uint32_t* st = as<uint32_t>(s, "shadow_target");

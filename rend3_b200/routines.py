@@ -116,6 +116,7 @@ class BaseRenderGraph:
         b.set_object_sort_info(ev.object_material_key, flags.astype(np.uint8), loc)
         b.set_mesh_buffer(ev.mesh_buffer)
         b.set_textures(ev.texture_descs, ev.texture_texels)
+        b.set_skybox(ev.skybox_desc, ev.skybox_texels)
         b.set_materials(ev.material_buffer)
         b.set_directional_lights(ev.directional_buffer, ev.shadow_target_size[0], ev.shadow_target_size[1])
         b.set_point_lights(ev.point_buffer)

@@ -504,6 +504,8 @@ class EvalOutput:
     shadows: List[ShadowDesc]
     shadow_target_size: Tuple[int, int]
     camera: CameraState
+    skybox_desc: Optional[np.ndarray] = None    # TEXTURE_DESC_DTYPE scalar (width = face size), None = no skybox
+    skybox_texels: Optional[np.ndarray] = None  # six faces (+X -X +Y -Y +Z -Z), each with its mip chain
 
 
 class Renderer:
@@ -518,6 +520,7 @@ class Renderer:
         self.mesh_words = np.zeros(0, dtype=np.uint32)
         self.materials: List[PbrMaterial] = []
         self.textures: List[Texture] = []
+        self.skybox: Optional[List[Texture]] = None
         self.objects: List[Optional[dict]] = []
         self.free_objects: List[int] = []
         self.delayed: List[int] = []
@@ -553,6 +556,20 @@ class Renderer:
     def add_texture_2d(self, texture: Texture) -> int:   # Renderer::add_texture_2d (renderer/mod.rs:213-241)
         self.textures.append(texture)
         return len(self.textures) - 1
+
+    def set_skybox(self, faces, srgb: bool = True, mips: str = "generated"):
+        """SkyboxRoutine::set_background_texture with a cube texture (rend3-routine/src/skybox.rs:47-60): six square RGBA faces
+        in the order +X, -X, +Y, -Y, +Z, -Z; None removes it."""
+        self.skybox = None if faces is None else [Texture(np.ascontiguousarray(f), srgb=srgb, mips=mips) for f in faces]
+
+    def _skybox_blob(self):
+        if self.skybox is None:
+            return None, None
+        lv0 = self.skybox[0].levels()
+        desc = np.zeros((), dtype=TEXTURE_DESC_DTYPE)
+        desc["width"], desc["height"], desc["mip_count"], desc["format"], desc["byte_offset"] = lv0[0].shape[1], lv0[0].shape[0], len(lv0), self.skybox[0].format(), 0
+        raw = [np.ascontiguousarray(l).view(np.uint8).reshape(-1) for f in self.skybox for l in f.levels()]
+        return desc, np.concatenate(raw)
 
     def _texture_table(self):
         descs = np.zeros(len(self.textures), dtype=TEXTURE_DESC_DTYPE)
@@ -711,6 +728,7 @@ class Renderer:
         pbytes = np.array([len(pl), 0, 0, 0], dtype=np.uint32).tobytes() + pl.tobytes()
 
         tex_descs, tex_blob = self._texture_table()
+        sky_desc, sky_blob = self._skybox_blob()
         return EvalOutput(
             object_buffer=self.obj_gpu.copy(),
             object_material_key=key,
@@ -722,6 +740,8 @@ class Renderer:
             material_buffer=mats,
             texture_descs=tex_descs,
             texture_texels=tex_blob,
+            skybox_desc=sky_desc,
+            skybox_texels=sky_blob,
             directional_buffer=dbytes,
             point_buffer=pbytes,
             shadows=shadows,

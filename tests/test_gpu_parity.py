@@ -516,6 +516,42 @@ def test_cpp_host_mirror_renders_the_same_frames(cuda, tmp_path):
     assert np.abs(got["ldr"].astype(int) - orc.readback_ldr().reshape(-1).astype(int)).max() <= 1
 
 
+def test_skybox_known_answers_and_parity(cuda):
+    """SkyboxRoutine (skybox.wgsl, rule R10): the six axis views on CUDA, then a cube field with opaque, cutout and translucent objects
+    in front of a random cube map, single- and multi-sampled, against the oracle."""
+    import dataclasses
+
+    import skybox_case as sk
+
+    for f in range(6):
+        b = load_cuda_backend(0)
+        sk.build(b, sk.solid_faces(), f).render_frame(32)
+        want = np.append(sk.FACE_COLOURS[f][:3].astype(np.float32) / 255.0, 1.0)
+        assert np.array_equal(b.readback_hdr_f32().reshape(-1, 4), np.broadcast_to(want, (32 * 32, 4))), f
+        b.close()
+    from rend3_b200.world import Renderer
+
+    res = (320, 180)
+    ev = cube_field_scene(n_objects=400, seed=23, resolution=res, n_dir_lights=1, shadow_resolution=256, shadow_distance=100.0, pull_back=8.0, extent=14.0,
+                          subdivisions=(1, 2), material_count=6, mixed_transparency=True, scale_range=(0.5, 2.0))
+    rng = np.random.default_rng(9)
+    sky = Renderer()
+    sky.set_skybox([np.kron(rng.integers(0, 256, (8, 8, 4), dtype=np.uint8), np.ones((8, 8, 1), dtype=np.uint8)) for _ in range(6)], srgb=True)
+    desc, blob = sky._skybox_blob()
+    ev = dataclasses.replace(ev, skybox_desc=desc, skybox_texels=blob)
+    for samples in (1, 4):
+        orc, b = load_oracle_backend(), load_cuda_backend(0)
+        for x in (b, orc):
+            BaseRenderGraph(x).add_to_graph(ev, res, samples, BaseRenderGraphSettings(clear_color=(0.0, 0.0, 0.0, 1.0)))
+        a, o = b.readback_hdr_f32().astype(np.float64), orc.readback_hdr_f32().astype(np.float64)
+        assert np.count_nonzero(orc.readback_depth() == 0.0) > 5000, "the sky must be visible"
+        assert np.array_equal(b.readback_depth().view(np.uint32), orc.readback_depth().view(np.uint32))
+        # translucent layers (and MSAA samples) round to rgba16f before they are compared: a few half-precision ulps on top of TOL
+        bound = TOL * np.maximum(1.0, np.abs(o)) + 8.0 * np.maximum(np.abs(o) * 2.0 ** -10, 2.0 ** -24)
+        assert np.all(np.abs(a - o) <= bound), f"samples {samples}: {np.count_nonzero(np.abs(a - o) > bound)} channel values off (max {np.abs(a - o).max():.3e})"
+        b.close()
+
+
 def test_device_batching_equals_host_batching_and_oracle(cuda, monkeypatch):
     """batch_objects on the device (radix sort + block scans) against the host implementation and the oracle, with
     three material keys (opaque / cutout / blend: atomic and non-atomic regions, front-to-back and back-to-front)."""

@@ -268,6 +268,32 @@ def test_oracle_texture_sampling_known_answers(sample_type, srgb):
         assert np.abs(orc.readback_hdr_f32() - want).max() < 2e-5, "bilinear magnification"
 
 
+def test_oracle_skybox_known_answers():
+    """SkyboxRoutine + skybox.wgsl (rule R10): a 90-degree camera at the origin sees exactly one cube face per axis direction, with
+    Vulkan's (s, t) orientation — looking down +Z with +Y up the image IS the +Z face, texel for pixel."""
+    import skybox_case as sk
+
+    for f in range(6):
+        orc = load_oracle_backend()
+        sk.build(orc, sk.solid_faces(), f).render_frame(32)
+        want = np.append(sk.FACE_COLOURS[f][:3].astype(np.float32) / 255.0, 1.0)
+        assert np.array_equal(orc.readback_hdr_f32().reshape(-1, 4), np.broadcast_to(want, (32 * 32, 4))), f
+    rng = np.random.default_rng(5)
+    faces = [rng.integers(0, 256, (32, 32, 4), dtype=np.uint8) for _ in range(6)]
+    orc = load_oracle_backend()
+    sk.build(orc, faces, 4, mips="none").render_frame(32)          # +Z, one texel per pixel
+    got = orc.readback_hdr_f32()
+    assert np.abs(got[..., :3] - faces[4][..., :3].astype(np.float64) / 255.0).max() < 2e-5 and np.all(got[..., 3] == 1.0)
+    # an opaque object in front keeps its pixels: the skybox only fills samples still at the clear depth
+    orc = load_oracle_backend()
+    r = sk.build(orc, sk.solid_faces(), 4)
+    mat = r.add_unlit_material((0.25, 0.5, 0.75, 1.0))
+    r.cube(mat, glam.from_translation((0.0, 0.0, 5.0)))
+    r.render_frame(32)
+    h = orc.readback_hdr_f32()
+    assert np.allclose(h[16, 16], (0.25, 0.5, 0.75, 1.0)) and np.allclose(h[0, 0], (0.0, 1.0, 1.0, 1.0))
+
+
 def test_oracle_skinning_matches_float64_blend():
     """skinning.wgsl:37-94 restated: skinned positions equal the float64 4-joint blend, normals are unit length, and
     identity joints leave the mesh untouched."""
