@@ -25,7 +25,8 @@ namespace {
 constexpr int TC_THREADS = 256;                      // = the reference's workgroup.  (Quarter-workgroup CTAs, so that all-padding quarters retire early,
                                                      //  were measured 34% SLOWER on config 3: four times the CTAs to dispatch outweighs the occupancy they free;
                                                      //  one warp per word that holds work, from a compacted word list, measured no gain either: the test is bound
-                                                     //  by the sector traffic of its index / position gathers, not by the idle padding warps.)
+                                                     //  by the sector traffic of its index / position gathers, not by the idle padding warps; fetching each 12-byte
+                                                     //  triple with one or two aligned 16-byte loads instead of three 4-byte ones made config 3 14% slower.)
 constexpr int SB_WORDS = 1024;                       // words per superblock (32768 invocations, 128 workgroups)
 
 struct TriCullParams {
