@@ -225,6 +225,31 @@ def test_config5_full_size_matches_oracle(cuda):
     assert st[:3] == orc.forward_stats()[:3] and st[2] == res[0] * res[1], "the slabs close the frame: every pixel is shaded"
 
 
+def test_config3_full_size_matches_oracle(cuda):
+    """BASELINE config 3 at full size (200k objects over 1000 meshes / 20 M triangles, 4 shadow maps + 4 point lights, 3840x2160):
+    the first frame (all residual) artefact by artefact for the viewport and one shadow camera, then a second frame (predicted list,
+    hi-Z occlusion at scale) through its draw records and pixels."""
+    from rend3_b200 import configs
+
+    ev, res = configs.config3()
+    orc = load_oracle_backend()
+    graphs = {id(b): BaseRenderGraph(b) for b in (cuda, orc)}
+    settings = BaseRenderGraphSettings(clear_color=(0.10, 0.05, 0.10, 1.0))
+    for b in (cuda, orc):
+        graphs[id(b)].add_to_graph(ev, res, 1, settings)
+    compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 2], what="config 3 frame 0")
+    assert cuda.forward_stats()[:3] == orc.forward_stats()[:3]
+    for b in (cuda, orc):
+        graphs[id(b)].add_to_graph(ev, res, 1, settings, upload=False)
+    for part in (0, 1):
+        do = orc.readback_draw_calls(CAMERA_VIEWPORT, part)
+        assert cuda.readback_draw_calls(CAMERA_VIEWPORT, part)[:len(do)].tobytes() == do.tobytes(), f"frame 1 draw calls, partition {part}"
+    assert np.array_equal(cuda.readback_depth().view(np.uint32), orc.readback_depth().view(np.uint32))
+    hdr_close(cuda.readback_hdr_f32(), orc.readback_hdr_f32(), "config 3 frame 1 hdr")
+    sc, so = cuda.forward_stats(), orc.forward_stats()
+    assert sc[:3] == so[:3]
+
+
 def test_full_size_cull_bake_properties(cuda):
     """BASELINE configs 2 / 4 at full size (10 M object records on one GPU), checked through size-independent properties:
     sortedness, agreement with an independent float64 classification away from the plane boundaries, idempotence,
