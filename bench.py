@@ -364,9 +364,20 @@ def main():
         settings = BaseRenderGraphSettings(clear_color=(0.1, 0.05, 0.1, 1.0))
         rows = (res[1] * rank // world, res[1] * (rank + 1) // world)
 
+        n_shadows = len(ev.shadows)
+
+        def merge_shadow_maps():
+            # each rank rendered the shadow maps i with i % world == rank into its (cleared) atlas: an integer MAX all-reduce of the
+            # depth bits (reverse-Z, >= 0) gives every rank the complete atlas
+            ptr, nbytes = fb.device_ptr(CAMERA_VIEWPORT, 5)
+            with torch.cuda.stream(fstream):
+                atlas = torch.as_tensor(DeviceView(ptr, nbytes, "<i4", 4), device=f"cuda:{local}")
+                dist.all_reduce(atlas, op=dist.ReduceOp.MAX)
+
         def frame(upload):
-            graph.add_to_graph(ev, res, 1, settings, upload=upload, scissor_rows=rows if world > 1 else None)
             if world > 1:
+                graph.add_to_graph(ev, res, 1, settings, upload=upload, scissor_rows=rows, shadow_filter=lambda i: i % world == rank,
+                                   after_shadows=merge_shadow_maps if n_shadows else None)
                 ptr, nbytes = fb.device_ptr(CAMERA_VIEWPORT, 1)
                 with torch.cuda.stream(fstream):
                     img = torch.as_tensor(DeviceView(ptr, nbytes), device=f"cuda:{local}")
@@ -374,6 +385,26 @@ def main():
                     mine = img[rows[0] * row_bytes:rows[1] * row_bytes]
                     if res[1] % world == 0:
                         dist.all_gather_into_tensor(img, mine.clone())
+            else:
+                graph.add_to_graph(ev, res, 1, settings, upload=upload)
+
+        split_verified = None
+        if world > 1 and res[1] % world == 0:
+            # outside the timed region: the frame assembled from the ranks' row tiles and merged shadow maps must equal, bit for bit,
+            # the frame one GPU renders alone
+            frame(True)
+            barrier()
+            ptr, nbytes = fb.device_ptr(CAMERA_VIEWPORT, 1)
+            got = torch.as_tensor(DeviceView(ptr, nbytes), device=f"cuda:{local}").clone()
+            vb = load_cuda_backend(local)
+            BaseRenderGraph(vb).add_to_graph(ev, res, 1, settings)
+            vb.sync()
+            vptr, vbytes = vb.device_ptr(CAMERA_VIEWPORT, 1)
+            want = torch.as_tensor(DeviceView(vptr, vbytes), device=f"cuda:{local}")
+            same = torch.tensor([1 if torch.equal(got, want) else 0], device=f"cuda:{local}")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            split_verified = bool(int(same.item()))
+            vb.close()
         frame(True)
         for _ in range(2):
             frame(False)
@@ -398,7 +429,8 @@ def main():
                    "frame_ms": frame_ms, "shaded_mfrag_s": float(st[2].item()) / frame_ms / 1e3, "raster_mfrag_s": float(st[1].item()) / frame_ms / 1e3,
                    "shaded_fragments": int(st[2].item()), "depth_passing_fragments": int(st[1].item()), "triangles_after_cull": tris,
                    "gpu_launches_per_frame": (fb.launch_count() - l0) // max(args.forward_steps, 1),
-                   "split": f"{world} row tiles, rgba16f rows all-gathered" if world > 1 else "single GPU"}
+                   "split": f"{world} row tiles (rgba16f rows all-gathered), shadow maps split by light and merged with a MAX all-reduce" if world > 1 else "single GPU",
+                   "split_equals_single_gpu_frame": split_verified}
 
     if rank == 0:
         line = {

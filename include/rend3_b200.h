@@ -161,7 +161,8 @@ int r3_forward_stats(r3_ctx*, uint64_t stats[4]);
 /* ------------------------------------------------------------------ multi-GPU plumbing
  * raw device views so torch.distributed / NCCL can move the visible list and tile rows without a
  * host bounce.  which: 0 visible list (u32), 1 hdr f16 colour, 2 object matrices, 3 visible count (u32),
- * 4 visibility words (1 bit per object slot, bit i of word w = slot 32*w + i) */
+ * 4 visibility words (1 bit per object slot, bit i of word w = slot 32*w + i), 5 shadow atlas (depth32f: ranks that render
+ * different shadow maps merge them with an integer MAX all-reduce, the atlas being cleared to 0.0) */
 int r3_device_ptr(r3_ctx*, uint32_t camera, int which, void** device_ptr, uint64_t* nbytes);
 /* Exchange of the visible set between the GPUs of one node over NVLink / NVSwitch peer memory (one process per GPU, objects
  * sharded in contiguous ranges).  r3_exchange_create allocates this rank's gathered[n_ranks][words_per_rank] buffer

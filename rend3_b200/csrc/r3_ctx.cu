@@ -484,6 +484,7 @@ R3_EXPORT int r3_device_ptr(r3_ctx* c, uint32_t camera, int which, void** p, uin
     else if (which == 2) { *p = cam->d_matrices; *nbytes = (uint64_t)cam->matrices_cap * 128; }
     else if (which == 3) { *p = cam->d_visible_count; *nbytes = 4; }
     else if (which == 4) { *p = cam->d_words; *nbytes = (((uint64_t)cam->header.object_count + 31) / 32) * 4; }   // 1 bit per object
+    else if (which == 5) { *p = c->d_atlas; *nbytes = (uint64_t)c->atlas_w * c->atlas_h * 4; }   // shadow atlas (depth32f; reverse-Z depths order like their bits)
     else return r3_fail(c, R3_E_INVALID, "device_ptr: which");
     return R3_OK;
 }

@@ -123,9 +123,10 @@ class BaseRenderGraph:
 
     def add_to_graph(self, ev: EvalOutput, resolution: Tuple[int, int], samples: int = 1,
                      settings: BaseRenderGraphSettings = BaseRenderGraphSettings(), srgb_target: bool = True,
-                     upload: bool = True, scissor_rows: Optional[Tuple[int, int]] = None):
+                     upload: bool = True, scissor_rows: Optional[Tuple[int, int]] = None, shadow_filter=None, after_shadows=None):
         """One frame in the node order of base.rs:135-185.  `scissor_rows` restricts rasterisation and shading
-        to a band of pixel rows (the screen-tile split of the multi-GPU forward pass)."""
+        to a band of pixel rows (the screen-tile split of the multi-GPU forward pass); `shadow_filter(i)` selects the shadow
+        maps this rank renders and `after_shadows()` runs once they are in the atlas (the ranks merge their maps there)."""
         b, culler = self.backend, self.gpu_culler
         if upload:
             self.upload_world(ev)
@@ -137,12 +138,15 @@ class BaseRenderGraph:
         b.clear_shadow_atlas()                                                    # base.rs:139
         b.set_frame_uniforms(frame_uniforms(ev.camera, settings.ambient_color, resolution))  # :142
         # skinning (:145) — no animated meshes on this path
-        for i, s in enumerate(ev.shadows):                                        # :148
+        mine = [(i, s) for i, s in enumerate(ev.shadows) if shadow_filter is None or shadow_filter(i)]
+        for i, s in mine:                                                         # :148
             culler.object_uniform_upload(ev, s.camera, i, (s.size, s.size), 1)
-        for i, s in enumerate(ev.shadows):                                        # :150
+        for i, s in mine:                                                         # :150
             culler.cull(ev, i)
-        for i, s in enumerate(ev.shadows):                                        # :153
+        for i, s in mine:                                                         # :153
             b.shadow_pass(i, s.offset[0], s.offset[1], s.size)
+        if after_shadows is not None:
+            after_shadows()
         culler.object_uniform_upload(ev, ev.camera, CAMERA_VIEWPORT, resolution, samples)   # :156
         b.forward_begin()
         b.forward_pass(0)                                                         # :159 predicted triangles
