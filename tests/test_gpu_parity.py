@@ -577,6 +577,52 @@ def test_skybox_known_answers_and_parity(cuda):
         b.close()
 
 
+def test_ragged_meshes_and_batch_boundaries(cuda):
+    """Edge shapes of the invocation space: meshes with 0, 1, 255, 256 and 257 triangles (none / one / exactly one / two workgroups,
+    batching.rs:192,235 pads to 256), 257 objects per material so that batches fill to exactly 256 objects and regions split on key
+    changes, a disabled object in the middle; two frames."""
+    from rend3_b200.world import CUTOUT, LEFT, MeshBuilder, Object, PbrMaterial, Renderer
+
+    def strip_mesh(n_tris, seed):
+        # a fan of n_tris small triangles around the origin, all facing the camera (Cw in a left-handed world)
+        rng = np.random.default_rng(seed)
+        pos, idx = [], []
+        for t in range(n_tris):
+            a = 2 * np.pi * t / max(n_tris, 1)
+            c = np.array([0.8 * np.cos(a), 0.8 * np.sin(a), 0.0]) * (0.3 + 0.7 * rng.random())
+            base = len(pos)
+            pos += [c + (0.06, -0.05, 0), c + (-0.06, -0.05, 0), c + (0, 0.07, 0)]
+            idx += [base, base + 1, base + 2]
+        if not pos:
+            pos = [(0, 0, 0), (0, 0, 0), (0, 0, 0)]
+        return MeshBuilder.new(np.array(pos, dtype=np.float32), LEFT).with_indices(np.array(idx, dtype=np.uint32)).build()
+
+    res = (256, 256)
+    r = Renderer(LEFT, aspect_ratio=1.0)
+    meshes = [r.add_mesh(strip_mesh(n, 50 + n)) for n in (0, 1, 255, 256, 257)]
+    # the middle material is a cutout that never discards: material key 1, so a region boundary falls inside a batch
+    mats = [r.add_material(PbrMaterial(albedo_value=(0.2 + 0.2 * m, 0.5, 0.9 - 0.2 * m, 1.0), unlit=True, transparency=CUTOUT if m == 1 else 0)) for m in range(3)]
+    r.set_camera_data(Camera(("perspective", 60.0, 0.1), glam.look_at_lh(np.array([0, 0, -6], dtype=np.float32), np.zeros(3, dtype=np.float32),
+                                                                           np.array([0, 1, 0], dtype=np.float32))))
+    rng = np.random.default_rng(77)
+    handles = []
+    for i in range(3 * 257):
+        t = glam.mul(glam.from_translation(tuple(rng.uniform(-2.5, 2.5, 3))), glam.from_scale((0.5, 0.5, 0.5)))
+        handles.append(r.add_object(Object(meshes[i % 5], mats[i // 257], t)))
+    ev = r.evaluate()
+    ev.object_buffer["enabled"][handles[300]] = 0
+    orc = load_oracle_backend()
+    graphs = {id(b): BaseRenderGraph(b) for b in (cuda, orc)}
+    for frame in range(2):
+        for b in (cuda, orc):
+            graphs[id(b)].add_to_graph(ev, res, 1, BaseRenderGraphSettings(clear_color=(0, 0, 0, 1)), upload=(frame == 0))
+        compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT], what=f"ragged frame {frame}")
+    bo, ro = orc.readback_batches(CAMERA_VIEWPORT)
+    assert len(bo) >= 3 and int(bo[0]["total_objects"]) == 256, "the first batch must be full"
+    assert len(ro) > len(bo) and set(int(k) for k in ro["material_key"]) == {0, 1}, "a key change must split a batch into regions"
+    assert orc.forward_stats()[2] > 500
+
+
 def test_device_batching_equals_host_batching_and_oracle(cuda, monkeypatch):
     """batch_objects on the device (radix sort + block scans) against the host implementation and the oracle, with
     three material keys (opaque / cutout / blend: atomic and non-atomic regions, front-to-back and back-to-front)."""
