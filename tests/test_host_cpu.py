@@ -294,6 +294,52 @@ def test_oracle_skybox_known_answers():
     assert np.allclose(h[16, 16], (0.25, 0.5, 0.75, 1.0)) and np.allclose(h[0, 0], (0.0, 1.0, 1.0, 1.0))
 
 
+def test_shard_and_tile_partitions_cover_everything():
+    """parallel.shard_range / tile_rows: contiguous, disjoint, complete for every world size, including ragged ones."""
+    from rend3_b200.parallel import shard_range, tile_rows
+
+    for n in (0, 1, 7, 1000, 1_000_003, 10_000_000):
+        for world in (1, 2, 3, 4, 8):
+            edges = [shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:])) and all(lo <= hi for lo, hi in edges)
+            assert max(hi - lo for lo, hi in edges) - min(hi - lo for lo, hi in edges) <= 1
+    for h in (1, 270, 1080, 2160, 2161):
+        for world in (1, 2, 4, 8):
+            rows = [tile_rows(h, r, world) for r in range(world)]
+            assert rows[0][0] == 0 and rows[-1][1] == h and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+
+
+def test_oracle_frustum_boundary_and_degenerate_records():
+    """Frustum::contains_sphere is inclusive (`distance >= -radius`, util/frustum.rs:148-161); NaN centres fail every comparison and are
+    culled; zero-radius spheres on a plane stay; disabled slots neither bake nor list."""
+    n = 6
+    rec = np.zeros(n, dtype=layouts.OBJECT_DTYPE)
+    rec["transform"] = np.tile(glam.identity().reshape(16), (n, 1))
+    rec["enabled"] = 1
+    hdr = per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (64, 64), 1, n)
+    plane = hdr["frustum"][0]                                          # (a, b, c, d) of the left plane, unit normal
+    on_plane = (-plane[3] * plane[:3]).astype(np.float32)              # a point with distance exactly 0 (up to rounding)
+    inward = plane[:3]
+    rec["sphere_center"][0] = on_plane + inward * 5.0; rec["sphere_radius"][0] = 1.0      # clearly inside the left plane
+    rec["sphere_center"][1] = on_plane - inward * 2.0; rec["sphere_radius"][1] = 1.0      # clearly outside
+    rec["sphere_center"][2] = on_plane - inward * 1.0; rec["sphere_radius"][2] = 1.5      # centre outside, sphere reaches in
+    rec["sphere_center"][3] = np.nan; rec["sphere_radius"][3] = 1.0
+    rec["sphere_center"][4] = on_plane + inward * 5.0; rec["sphere_radius"][4] = 1.0; rec["enabled"][4] = 0
+    rec["sphere_center"][5] = on_plane + inward * 5.0; rec["sphere_radius"][5] = 0.0
+    orc = load_oracle_backend()
+    orc.set_objects(rec)
+    orc.object_uniform_upload(CAMERA_VIEWPORT, hdr, CB_BAKE | CB_CULL)
+    vis = set(int(v) for v in orc.readback_visible(CAMERA_VIEWPORT))
+    # whether 0, 2 and 5 survive the OTHER four planes depends on the camera; membership relative to each other is what is pinned
+    assert 1 not in vis and 3 not in vis and 4 not in vis
+    assert (0 in vis) == (5 in vis) and ((0 not in vis) or (2 in vis))
+    mats = orc.readback_object_matrices(CAMERA_VIEWPORT, 0, n)
+    raw = mats.view(np.uint8).reshape(n, 128)
+    assert not raw[4].any(), "disabled slots are not baked (uniform_prep.wgsl:18-20)"
+    assert raw[0].any()
+
+
 def test_oracle_skinning_matches_float64_blend():
     """skinning.wgsl:37-94 restated: skinned positions equal the float64 4-joint blend, normals are unit length, and
     identity joints leave the mesh untouched."""
