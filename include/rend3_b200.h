@@ -61,6 +61,13 @@ int r3_get_stream(r3_ctx* ctx, void** stream);
 /* number of kernel launches issued by this context since creation (bench.py gpu_launches) */
 int r3_launch_count(r3_ctx* ctx, uint64_t* launches);
 
+/* optional per-stage device timing (off by default): when enabled, CUDA event pairs are recorded around the kernels below and
+ * r3_stage_times returns, per stage, the summed duration in ms and the number of launches since the last call (it synchronises).
+ * stage ids: 0 triangle_test_kernel, 1 raster_setup_kernel (colour passes), 2 raster_setup_kernel (shadow passes), 3 raster_band_kernel,
+ * 4 resolve_kernel, 5 the batch_objects sort, 6 cull_bake_kernel, 7 triangle_compact_kernel. */
+int r3_set_stage_timing(r3_ctx* ctx, int enabled);
+int r3_stage_times(r3_ctx* ctx, double ms[8], uint32_t launches[8]);
+
 /* ------------------------------------------------------------------ world data
  * same bytes as the wgpu buffers named on the right */
 int r3_set_objects(r3_ctx*, const r3_object* records, uint32_t n_slots);           /* object_manager.buffer::<M>() (object.rs:193) */
@@ -113,6 +120,12 @@ int r3_readback_object_matrices(r3_ctx*, uint32_t camera, r3_object_matrices* ou
 int r3_batch_objects(r3_ctx*, uint32_t camera, const float viewport_location[3], uint32_t max_dispatch_count);
 int r3_batch_counts(r3_ctx*, uint32_t camera, uint32_t* n_batches, uint32_t* n_regions, uint32_t* total_invocations);
 int r3_readback_batches(r3_ctx*, uint32_t camera, r3_batch_data* batches, r3_region* regions);
+/* which implementation of batch_objects ran last for this camera, and what it built: info[0] = 0 none / 1 on the device (radix sort +
+ * block scans, no host sync) / 2 on the host (material keys >= 64, >= 2^24 slots, or a mesh large enough that a batch could reach the
+ * max_dispatch_count x 256 split of batching.rs:196, which only the host path implements) / 3 on the device, order taken from the
+ * frame-wide sort the cameras of one frame share (the sort key does not depend on the camera, batching.rs:156-157); info[1] = device overflow flag (always 0
+ * given the check above; kept as a tripwire); info[2] = batches, info[3] = regions.  Blocks (one 32-byte readback). */
+int r3_batching_info(r3_ctx*, uint32_t camera, uint32_t info[4]);
 /* GpuCuller::cull (culler.rs:531-659) + cull.wgsl.  batches/regions == NULL uses the jobs of the last
  * r3_batch_objects call; otherwise the caller's own ShaderBatchDatas (a Rust batch_objects). */
 int r3_cull(r3_ctx*, uint32_t camera, const r3_batch_data* batches, uint32_t n_batches,
@@ -147,7 +160,11 @@ int r3_forward_resolve(r3_ctx*);
 int r3_forward_blend(r3_ctx*);
 int r3_tonemap(r3_ctx*, int srgb_target);                                           /* tonemapping.rs:108-147 */
 
-int r3_readback_hdr_f32(r3_ctx*, float* rgba, uint64_t capacity_floats);            /* pre-f16 shading result (parity) */
+/* Parity instrumentation, OFF by default: when enabled the shading kernels also store their f32 result before the rgba16f rounding
+ * (16 B per pixel more than the reference's targets write) so that tests can hold fs_main to 1e-4 without the half-precision step.
+ * r3_readback_hdr_f32 fails with R3_E_STATE while it is off. */
+int r3_set_parity_target(r3_ctx*, int enabled);
+int r3_readback_hdr_f32(r3_ctx*, float* rgba, uint64_t capacity_floats);            /* pre-f16 shading result (parity target) */
 int r3_readback_hdr_f16(r3_ctx*, uint16_t* rgba, uint64_t capacity_halfs);          /* the Rgba16Float target */
 int r3_readback_depth(r3_ctx*, float* depth, uint64_t capacity);
 int r3_readback_ldr(r3_ctx*, uint8_t* rgba8, uint64_t capacity);
@@ -157,6 +174,9 @@ int r3_readback_hiz(r3_ctx*, uint32_t mip, float* depth, uint64_t capacity, uint
  * to the depth test), [2] fragments shaded by r3_forward_resolve (fs_main invocations), [3] sample fragments blended by
  * r3_forward_blend (depth-test survivors of the blend routine) */
 int r3_forward_stats(r3_ctx*, uint64_t stats[4]);
+/* surface_shading evaluations (opaque.wgsl:440-468) of the last r3_forward_resolve, summed over its fragments (single-sampled targets):
+ * directional lights + the point lights that survived the tile culling and the per-fragment range test — the flop count of the pass */
+int r3_forward_light_evaluations(r3_ctx*, uint64_t* evaluations);
 
 /* ------------------------------------------------------------------ multi-GPU plumbing
  * raw device views so torch.distributed / NCCL can move the visible list and tile rows without a
@@ -165,17 +185,42 @@ int r3_forward_stats(r3_ctx*, uint64_t stats[4]);
  * different shadow maps merge them with an integer MAX all-reduce, the atlas being cleared to 0.0) */
 int r3_device_ptr(r3_ctx*, uint32_t camera, int which, void** device_ptr, uint64_t* nbytes);
 /* Exchange of the visible set between the GPUs of one node over NVLink / NVSwitch peer memory (one process per GPU, objects
- * sharded in contiguous ranges).  r3_exchange_create allocates this rank's gathered[n_ranks][words_per_rank] buffer
- * (1 bit per object slot, rows 256-byte aligned) and returns its CUDA IPC handle; the caller all-gathers the handles with whatever
- * it already uses (torch.distributed, MPI) and hands them to r3_exchange_connect.  From then on every r3_object_uniform_upload(CULL)
- * on that camera also stores its visibility words into row `my_rank` of EVERY rank's buffer, fused into the compaction kernel — no
- * collective kernel runs.  The rows are complete once all ranks have synchronised their streams and met at a barrier. */
+ * sharded in contiguous ranges).  r3_exchange_create allocates this rank's buffer — epoch flags + rows[2][n_ranks][words_per_rank]
+ * (1 bit per object slot, rows 256-byte aligned, two parities) — and returns its CUDA IPC handle; the caller all-gathers the handles with
+ * whatever it already uses (torch.distributed, MPI) and hands them to r3_exchange_connect.  From then on every r3_object_uniform_upload(CULL)
+ * on that camera is one EPOCH e: its compaction kernel also stores the visibility words into row (e & 1, my_rank) of EVERY rank's buffer and
+ * publishes them with flags[e & 1][my_rank] = e (st.release.sys, after system-scope fences) — no collective kernel runs.
+ * r3_exchange_merge is the consumer: two kernels on this context's stream that wait for the n_ranks flags of the current epoch with
+ * ld.acquire.sys ON THE DEVICE (no host barrier) and expand the rows into the global ascending visible list (r3_exchange_merged returns its
+ * device pointers; rank_base == NULL numbers the shards r * max_objects_per_rank).  Protocol: the ranks cull in lockstep; a rank consumes
+ * epoch e (or meets the others at a host barrier) before issuing epoch e + 2, which reuses the parity. */
 #define R3_IPC_HANDLE_BYTES 64
 int r3_exchange_create(r3_ctx*, uint32_t camera, uint32_t n_ranks, uint32_t my_rank, uint32_t max_objects_per_rank,
                        uint8_t handle_out[R3_IPC_HANDLE_BYTES]);
 int r3_exchange_connect(r3_ctx*, uint32_t camera, const uint8_t* handles /* n_ranks x R3_IPC_HANDLE_BYTES, rank order */);
+/* rows [n_ranks][words_per_rank] of the LAST epoch in this rank's buffer (complete for a host reader after a stream sync + a barrier) */
 int r3_exchange_words(r3_ctx*, uint32_t camera, void** device_ptr, uint64_t* nbytes, uint32_t* words_per_rank);
+int r3_exchange_merge(r3_ctx*, uint32_t camera, const uint32_t* rank_objects /* n_ranks */, const uint32_t* rank_base /* n_ranks or NULL */);
+int r3_exchange_merged(r3_ctx*, uint32_t camera, void** device_list /* u32 global ids */, void** device_count /* u32 */, uint64_t* capacity);
 int r3_exchange_destroy(r3_ctx*, uint32_t camera);
+/* Peer-memory plumbing of the multi-GPU forward pass (shadow maps split by light, screen split in row tiles; one process per
+ * GPU on one NVLink / NVSwitch node).  r3_peer_create (after r3_set_directional_lights and r3_set_render_target: the atlas and the rgba16f
+ * target must exist and must not be reallocated afterwards) returns three CUDA IPC handles — flag block, shadow atlas, colour target; the
+ * caller all-gathers them and calls r3_peer_connect.  Then, all stream-ordered and without host synchronisation:
+ *   r3_peer_send_atlas_rect  copies a rect of the local atlas into the same rect of EVERY peer's atlas (plain stores over NVLink);
+ *   r3_peer_send_rows        copies rows of the local rgba16f target into the peers' targets (root >= 0: only into that rank's);
+ *   r3_peer_signal(kind)     publishes everything sent so far: flags[kind][my_rank] = ++epoch on every rank (st.release.sys);
+ *   r3_peer_wait(kind, e[])  a one-CTA kernel on this context's stream that spins (ld.acquire.sys) until flags[kind][r] >= e[r] for all r.
+ * kinds: 0 shadow atlas, 1 colour rows, 2 frame done, 3 spare.  rend3_b200/parallel.py::ForwardSplit shows the per-frame protocol. */
+int r3_peer_create(r3_ctx*, uint32_t n_ranks, uint32_t my_rank, uint8_t handles_out[3 * R3_IPC_HANDLE_BYTES]);
+int r3_peer_connect(r3_ctx*, const uint8_t* handles /* n_ranks x 3 x R3_IPC_HANDLE_BYTES, rank order */);
+int r3_peer_send_atlas_rect(r3_ctx*, uint32_t offset_x, uint32_t offset_y, uint32_t width, uint32_t height);
+int r3_peer_send_rows(r3_ctx*, uint32_t row_begin, uint32_t row_end, int root /* -1 = every peer */);
+int r3_peer_signal(r3_ctx*, uint32_t kind);
+int r3_peer_wait(r3_ctx*, uint32_t kind, const uint32_t* expected_epochs /* n_ranks */);
+int r3_peer_destroy(r3_ctx*);
+/* clear one shadow map's rect (a rank that renders only some of the lights clears only theirs; the others arrive from their owners) */
+int r3_clear_shadow_rect(r3_ctx*, uint32_t offset_x, uint32_t offset_y, uint32_t width, uint32_t height);
 /* restrict rasterisation + shading to pixel rows [row_begin, row_end) (screen-tile split) */
 int r3_set_scissor_rows(r3_ctx*, uint32_t row_begin, uint32_t row_end);
 

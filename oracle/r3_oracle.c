@@ -20,6 +20,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../include/rend3_b200.h" /* status codes + the entry-point list being mirrored (r3_ -> r3o_) */
 #include "r3_oracle.h"
@@ -122,7 +125,7 @@ API int r3o_ctx_destroy(r3o_ctx* c) {
     free(c->dir_lights); free(c->point_lights);
     for (int i = 0; i < R3O_MAX_CAMERAS; ++i) {
         r3o_camera* k = &c->cams[i];
-        free(k->matrices); free(k->visible); free(k->batches); free(k->regions); free(k->prev_batches); free(k->prev_regions);
+        free(k->matrices); free(k->visible); free(k->flag); free(k->batches); free(k->regions); free(k->prev_batches); free(k->prev_regions);
         free(k->prev_invocation);
         iobuf_free(&k->index_buffer); iobuf_free(&k->draw_call_buffer); iobuf_free(&k->results_buffer);
     }
@@ -274,24 +277,54 @@ API int r3o_object_uniform_upload(r3o_ctx* c, uint32_t camera, const r3_camera_h
         cam->visible = (uint32_t*)malloc(((size_t)n + 1) * 4);
         cam->visible_cap = n;
     }
-    uint8_t* flag = (uint8_t*)malloc((size_t)n + 1);
+    if (cam->flag_cap < n) {
+        free(cam->flag);
+        cam->flag = (uint8_t*)malloc((size_t)n + 1);
+        cam->flag_cap = n;
+    }
+    uint8_t* flag = cam->flag;
     if (!flag || !cam->matrices || !cam->visible) return fail(c, R3_E_OOM, "out of memory");
     int have_live = c->sort_flags && c->sort_n >= n;
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < (int64_t)n; ++i) {
-        const r3_object* o = &c->objects[i];
-        if ((mode & R3_CB_BAKE) && o->enabled != 0) {
-            mat_mul(h->view, o->transform, cam->matrices[i].model_view);
-            mat_mul(h->view_proj, o->transform, cam->matrices[i].model_view_proj);
+    /* every host thread owns one contiguous range of slots: bake + test it, count its survivors, then — after an exclusive prefix over
+     * the per-thread counts — write them at their final positions.  The visible list stays ascending; nothing is allocated per call. */
+    uint32_t counts[R3O_MAX_THREADS + 1];
+    int n_threads = 1;
+#pragma omp parallel
+    {
+#ifdef _OPENMP
+        const int t = omp_get_thread_num(), nt = omp_get_num_threads() < R3O_MAX_THREADS ? omp_get_num_threads() : R3O_MAX_THREADS;
+#else
+        const int t = 0, nt = 1;
+#endif
+        if (t == 0) n_threads = nt;
+        if (t < nt) {
+            const uint64_t lo = (uint64_t)n * t / nt, hi = (uint64_t)n * (t + 1) / nt;
+            uint32_t cnt = 0;
+            for (uint64_t i = lo; i < hi; ++i) {
+                const r3_object* o = &c->objects[i];
+                if ((mode & R3_CB_BAKE) && o->enabled != 0) {
+                    mat_mul(h->view, o->transform, cam->matrices[i].model_view);
+                    mat_mul(h->view_proj, o->transform, cam->matrices[i].model_view_proj);
+                }
+                int live = have_live ? (c->sort_flags[i] & 1) : (o->enabled != 0);
+                uint8_t f = (uint8_t)((mode & R3_CB_CULL) && live && frustum_contains_sphere(h->frustum, o->sphere_center, o->sphere_radius));
+                flag[i] = f;
+                cnt += f;
+            }
+            counts[t] = cnt;
         }
-        int live = have_live ? (c->sort_flags[i] & 1) : (o->enabled != 0);
-        flag[i] = (uint8_t)((mode & R3_CB_CULL) && live && frustum_contains_sphere(h->frustum, o->sphere_center, o->sphere_radius));
+#pragma omp barrier
+        if (t < nt && (mode & R3_CB_CULL)) {
+            uint32_t pos = 0;
+            for (int k = 0; k < t; ++k) pos += counts[k];
+            const uint64_t lo = (uint64_t)n * t / nt, hi = (uint64_t)n * (t + 1) / nt;
+            for (uint64_t i = lo; i < hi; ++i)
+                if (flag[i]) cam->visible[pos++] = (uint32_t)i;
+        }
     }
     uint32_t cnt = 0;
-    for (uint32_t i = 0; i < n; ++i)
-        if (flag[i]) cam->visible[cnt++] = i;
+    for (int k = 0; k < n_threads; ++k) cnt += counts[k];
     cam->visible_count = (mode & R3_CB_CULL) ? cnt : 0;
-    free(flag);
     return R3_OK;
 }
 API int r3o_visible_count(r3o_ctx* c, uint32_t camera, uint32_t* count) {
@@ -319,14 +352,19 @@ API int r3o_readback_object_matrices(r3o_ctx* c, uint32_t camera, r3_object_matr
 /* ------------------------------------------------------------------ a4: batch_objects (batching.rs:120-250) */
 typedef struct { uint64_t material_key; uint32_t reason; float distance; uint32_t handle; } sort_item;
 /* ShaderJobSortingKey::cmp (batching.rs:53-79); bind_group_index is DUMMY (equal) in the GpuDriven
- * profile (batching.rs:151).  OrderedFloat total order on the distance.  sort_unstable leaves ties
- * unspecified; ties are resolved by handle so the oracle is deterministic. */
+ * profile (batching.rs:151).  OrderedFloat total order on the distance: NaN is greater than every number and
+ * equal to itself, -0.0 == +0.0 (ordered-float's Ord).  sort_unstable leaves ties unspecified; ties are resolved
+ * by handle so the oracle is deterministic. */
 static int sort_cmp(const void* pa, const void* pb) {
     const sort_item* a = (const sort_item*)pa; const sort_item* b = (const sort_item*)pb;
     if (a->material_key != b->material_key) return a->material_key < b->material_key ? -1 : 1;
     if (a->reason != b->reason) return a->reason < b->reason ? -1 : 1;
-    if (a->distance < b->distance) return -1;
-    if (a->distance > b->distance) return 1;
+    const int an = a->distance != a->distance, bn = b->distance != b->distance;
+    if (an != bn) return an < bn ? -1 : 1;
+    if (!an) {
+        if (a->distance < b->distance) return -1;
+        if (a->distance > b->distance) return 1;
+    }
     return a->handle < b->handle ? -1 : (a->handle > b->handle ? 1 : 0);
 }
 static uint32_t round_up_u32(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
@@ -418,6 +456,16 @@ API int r3o_batch_counts(r3o_ctx* c, uint32_t camera, uint32_t* nb, uint32_t* nr
     if (tot) *tot = cam->total_invocations;
     return R3_OK;
 }
+API int r3o_batching_info(r3o_ctx* c, uint32_t camera, uint32_t info[4]) {
+    CAM_OR_FAIL(c, camera);
+    if (!info) return fail(c, R3_E_INVALID, "null");
+    info[0] = cam->batches ? 2u : 0u; info[1] = 0; info[2] = cam->n_batches; info[3] = cam->n_regions;   /* the oracle batches on the host */
+    return R3_OK;
+}
+API int r3o_forward_light_evaluations(r3o_ctx* c, uint64_t* n) { if (!c || !n) return R3_E_INVALID; *n = 0; return R3_OK; }   /* statistics of the CUDA path only */
+API int r3o_set_stage_timing(r3o_ctx* c, int enabled) { (void)enabled; return c ? R3_OK : R3_E_INVALID; }
+API int r3o_stage_times(r3o_ctx* c, double ms[8], uint32_t launches[8]) { if (!c || !ms || !launches) return R3_E_INVALID; for (int k = 0; k < 8; ++k) { ms[k] = 0.0; launches[k] = 0; } return R3_OK; }
+API int r3o_set_parity_target(r3o_ctx* c, int enabled) { (void)enabled; return c ? R3_OK : R3_E_INVALID; }   /* the oracle always keeps the f32 result */
 API int r3o_readback_batches(r3o_ctx* c, uint32_t camera, r3_batch_data* b, r3_region* r) {
     CAM_OR_FAIL(c, camera);
     if (b && cam->n_batches) memcpy(b, cam->batches, (size_t)cam->n_batches * sizeof *b);

@@ -11,6 +11,7 @@
 #include "../include/r3_layouts.h"
 
 #define R3O_MAX_CAMERAS 64
+#define R3O_MAX_THREADS 1024
 
 /* InputOutputBuffer — rend3-routine/src/culling/suballoc.rs:17-223 (header kept out of `data`) */
 typedef struct {
@@ -24,6 +25,7 @@ typedef struct {
     r3_camera_header header;
     r3_object_matrices* matrices; uint32_t matrices_cap;
     uint32_t* visible; uint32_t visible_count, visible_cap;
+    uint8_t* flag; uint32_t flag_cap;          /* per-slot survivor flags of the last cull (scratch kept across calls) */
     /* batch_objects products (this frame) and the cached DrawCallSet of the previous frame (forward.rs:219) */
     r3_batch_data* batches; uint32_t n_batches;
     r3_region* regions; uint32_t n_regions; uint32_t total_invocations;

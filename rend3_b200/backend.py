@@ -29,16 +29,17 @@ CUDA_LIB_PATH = os.path.join(_ROOT, "librend3_b200.so")
 
 # every entry point of include/rend3_b200.h (tests check the .so exports all of them)
 ENTRY_POINTS = [
-    "abi_version", "ctx_create", "ctx_destroy", "last_error", "sync", "get_stream", "launch_count",
+    "abi_version", "ctx_create", "ctx_destroy", "last_error", "sync", "get_stream", "launch_count", "set_stage_timing", "stage_times",
     "set_objects", "update_objects", "set_objects_device", "set_object_sort_info", "set_mesh_buffer", "set_textures", "set_skybox",
     "set_materials", "set_directional_lights", "set_point_lights", "set_frame_uniforms",
     "object_uniform_upload", "visible_count", "readback_visible", "readback_object_matrices",
-    "batch_objects", "batch_counts", "readback_batches", "cull", "readback_indices",
+    "batch_objects", "batch_counts", "readback_batches", "batching_info", "cull", "readback_indices",
     "readback_draw_calls", "readback_culling_results", "set_render_target", "clear_shadow_atlas",
     "shadow_pass", "forward_begin", "forward_pass", "hiz_build", "forward_resolve", "forward_blend", "tonemap",
-    "readback_hdr_f32", "readback_hdr_f16", "readback_depth", "readback_ldr", "readback_shadow_atlas",
-    "readback_hiz", "forward_stats", "device_ptr", "set_scissor_rows", "skin", "readback_mesh_buffer",
-    "exchange_create", "exchange_connect", "exchange_words", "exchange_destroy",
+    "set_parity_target", "readback_hdr_f32", "readback_hdr_f16", "readback_depth", "readback_ldr", "readback_shadow_atlas",
+    "readback_hiz", "forward_stats", "forward_light_evaluations", "device_ptr", "set_scissor_rows", "skin", "readback_mesh_buffer",
+    "exchange_create", "exchange_connect", "exchange_words", "exchange_merge", "exchange_merged", "exchange_destroy",
+    "peer_create", "peer_connect", "peer_send_atlas_rect", "peer_send_rows", "peer_signal", "peer_wait", "peer_destroy", "clear_shadow_rect",
 ]
 
 
@@ -96,6 +97,16 @@ class Backend:
         n = C.c_uint64()
         self._call("launch_count", C.byref(n))
         return n.value
+
+    STAGES = ("triangle_test", "raster_setup_colour", "raster_setup_depth", "raster_bands", "resolve", "sort", "cull_bake", "triangle_compact")
+
+    def set_stage_timing(self, enabled: bool = True):
+        self._call("set_stage_timing", C.c_int(1 if enabled else 0))
+
+    def stage_times(self):
+        ms, n = (C.c_double * 8)(), (C.c_uint32 * 8)()
+        self._call("stage_times", ms, n)
+        return {name: {"ms": float(ms[i]), "launches": int(n[i])} for i, name in enumerate(self.STAGES)}
 
     # ---- world data
     def set_objects(self, records: np.ndarray):
@@ -204,6 +215,11 @@ class Backend:
         self._call("readback_batches", C.c_uint32(camera), _ptr(batches), _ptr(regions))
         return batches[:nb], regions[:nr]
 
+    def batching_info(self, camera: int):
+        info = (C.c_uint32 * 4)()
+        self._call("batching_info", C.c_uint32(camera), info)
+        return {"path": {0: "none", 1: "device", 2: "host", 3: "device, frame-wide sort"}[info[0]], "overflow": int(info[1]), "batches": int(info[2]), "regions": int(info[3])}
+
     def cull(self, camera: int, batches: Optional[np.ndarray] = None, regions: Optional[np.ndarray] = None):
         if batches is None:
             self._call("cull", C.c_uint32(camera), None, C.c_uint32(0), None, C.c_uint32(0))
@@ -269,14 +285,56 @@ class Backend:
         self._call("exchange_words", C.c_uint32(camera), C.byref(p), C.byref(n), C.byref(w))
         return p.value, n.value, w.value
 
+    def exchange_merge(self, camera: int, rank_objects, rank_base=None):
+        ro = np.ascontiguousarray(rank_objects, dtype=np.uint32)
+        rb = None if rank_base is None else np.ascontiguousarray(rank_base, dtype=np.uint32)
+        self._call("exchange_merge", C.c_uint32(camera), _ptr(ro), _ptr(rb))
+
+    def exchange_merged(self, camera: int):
+        lst, cnt, cap = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._call("exchange_merged", C.c_uint32(camera), C.byref(lst), C.byref(cnt), C.byref(cap))
+        return lst.value, cnt.value, cap.value
+
     def exchange_destroy(self, camera: int):
         self._call("exchange_destroy", C.c_uint32(camera))
+
+    # ---- peer-memory plumbing of the multi-GPU forward pass
+    def peer_create(self, n_ranks: int, my_rank: int) -> bytes:
+        h = (C.c_uint8 * 192)()
+        self._call("peer_create", C.c_uint32(n_ranks), C.c_uint32(my_rank), h)
+        return bytes(h)
+
+    def peer_connect(self, handles: bytes):
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self._call("peer_connect", buf)
+
+    def peer_send_atlas_rect(self, ox: int, oy: int, w: int, h: int):
+        self._call("peer_send_atlas_rect", C.c_uint32(ox), C.c_uint32(oy), C.c_uint32(w), C.c_uint32(h))
+
+    def peer_send_rows(self, row_begin: int, row_end: int, root: int = -1):
+        self._call("peer_send_rows", C.c_uint32(row_begin), C.c_uint32(row_end), C.c_int(root))
+
+    def peer_signal(self, kind: int):
+        self._call("peer_signal", C.c_uint32(kind))
+
+    def peer_wait(self, kind: int, expected):
+        e = np.ascontiguousarray(expected, dtype=np.uint32)
+        self._call("peer_wait", C.c_uint32(kind), _ptr(e))
+
+    def peer_destroy(self):
+        self._call("peer_destroy")
+
+    def clear_shadow_rect(self, ox: int, oy: int, w: int, h: int):
+        self._call("clear_shadow_rect", C.c_uint32(ox), C.c_uint32(oy), C.c_uint32(w), C.c_uint32(h))
 
     def forward_blend(self):
         self._call("forward_blend")
 
     def tonemap(self, srgb_target: bool = True):
         self._call("tonemap", C.c_int(1 if srgb_target else 0))
+
+    def set_parity_target(self, enabled: bool = True):
+        self._call("set_parity_target", C.c_int(1 if enabled else 0))
 
     def readback_hdr_f32(self) -> np.ndarray:
         out = np.empty((self.height, self.width, 4), dtype=np.float32)
@@ -315,6 +373,11 @@ class Backend:
         self._call("forward_stats", s)
         return list(s)
 
+    def forward_light_evaluations(self) -> int:
+        n = C.c_uint64()
+        self._call("forward_light_evaluations", C.byref(n))
+        return n.value
+
     def device_ptr(self, camera: int, which: int):
         p, n = C.c_void_p(), C.c_uint64()
         self._call("device_ptr", C.c_uint32(camera), C.c_int(which), C.byref(p), C.byref(n))
@@ -331,5 +394,12 @@ def load_cuda_library() -> C.CDLL:
     return C.CDLL(CUDA_LIB_PATH)
 
 
-def load_cuda_backend(device: int = 0) -> Backend:
-    return Backend(load_cuda_library(), "r3_", device)
+def load_cuda_backend(device: int = 0, parity_target: Optional[bool] = None) -> Backend:
+    """`parity_target` switches the library's rgba32f parity instrumentation on (r3_set_parity_target); left at None it follows the
+    R3_PARITY_TARGET environment variable, which only the test suite sets — bench.py and the tools run the production configuration."""
+    b = Backend(load_cuda_library(), "r3_", device)
+    if parity_target is None:
+        parity_target = os.environ.get("R3_PARITY_TARGET", "0") not in ("", "0")
+    if parity_target:
+        b.set_parity_target(True)
+    return b

@@ -21,8 +21,13 @@ struct SortItem {
 inline bool sort_less(const SortItem& a, const SortItem& b) {
     if (a.material_key != b.material_key) return a.material_key < b.material_key;
     if (a.reason != b.reason) return a.reason < b.reason;
-    if (a.distance < b.distance) return true;
-    if (a.distance > b.distance) return false;
+    // OrderedFloat: NaN is greater than every number and equal to itself, -0.0 == +0.0 — a strict weak order for std::sort
+    const bool an = a.distance != a.distance, bn = b.distance != b.distance;
+    if (an != bn) return bn;
+    if (!an) {
+        if (a.distance < b.distance) return true;
+        if (a.distance > b.distance) return false;
+    }
     return a.handle < b.handle;
 }
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }

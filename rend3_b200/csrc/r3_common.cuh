@@ -36,7 +36,27 @@ struct r3_jobs {
     bool valid = false;
 };
 
+// optional per-stage device timing (r3_set_stage_timing / r3_stage_times): CUDA event pairs around the kernels named below, so that
+// bench.py can put a measured duration next to each kernel's algorithmic bytes / flops.  Off by default: no events are recorded.
+enum { R3_STAGE_TRIANGLE_TEST = 0, R3_STAGE_RASTER_SETUP_COLOUR, R3_STAGE_RASTER_SETUP_DEPTH, R3_STAGE_RASTER_BANDS, R3_STAGE_RESOLVE, R3_STAGE_SORT,
+       R3_STAGE_CULL_BAKE, R3_STAGE_TRIANGLE_COMPACT, R3_STAGE_COUNT };
+struct r3_stage_timer {
+    bool enabled = false;
+    std::vector<cudaEvent_t> pool;            // recycled events: [2 k] start, [2 k + 1] stop
+    std::vector<int> stage_of;                // stage of pair k
+    size_t used = 0;
+};
 constexpr int R3_MAX_EXCHANGE_RANKS = 16;
+// peer-memory plumbing of the multi-GPU forward pass (r3_peer.cu): kinds of epoch flags
+constexpr uint32_t R3_PEER_KINDS = 4;        // 0 shadow atlas rects, 1 colour rows, 2 frame done, 3 spare
+struct r3_peer_state {
+    bool created = false, connected = false, has_atlas = false;
+    uint32_t n_ranks = 0, rank = 0;
+    uint32_t* d_flags = nullptr;              // this rank's flags[R3_PEER_KINDS][R3_MAX_EXCHANGE_RANKS]
+    uint32_t* flags[R3_MAX_EXCHANGE_RANKS] = {}; float* atlas[R3_MAX_EXCHANGE_RANKS] = {}; uint16_t* hdr16[R3_MAX_EXCHANGE_RANKS] = {};   // peer mappings
+    uint32_t sent[R3_PEER_KINDS] = {0, 0, 0, 0};
+    const void* atlas_at_create = nullptr; const void* hdr_at_create = nullptr;
+};
 struct r3_camera {
     bool header_set = false;
     r3_camera_header header{};
@@ -48,8 +68,12 @@ struct r3_camera {
     // multi-GPU exchange of the visible set over NVLink peer memory (r3_exchange_*): gathered[n_ranks][words_per_rank]
     uint32_t* d_gathered = nullptr; uint32_t ex_ranks = 0, ex_rank = 0, ex_words_per_rank = 0; bool ex_connected = false;
     uint32_t* ex_peers[R3_MAX_EXCHANGE_RANKS] = {};   // peer-mapped gathered buffers (ex_peers[ex_rank] == d_gathered)
+    uint32_t ex_epoch = 0, ex_objects = 0; uint32_t* d_ex_done = nullptr;       // step counter (parity = epoch & 1), CTA arrival counter of the publishing kernel
+    uint32_t* d_global_visible = nullptr; uint64_t global_visible_cap = 0; uint32_t* d_merge_counts = nullptr; uint64_t merge_counts_cap = 0;   // r3_exchange_merge
     int visible_count_host = -1;              // cached after a readback, -1 = unknown
     r3_jobs jobs[2]; int cur = 0;             // jobs[cur] = this frame, jobs[cur^1] = cached DrawCallSet (forward.rs:219)
+    int batching_path = 0;                    // which batch_objects ran last for this camera: 0 none, 1 device, 2 host, 3 device with the frame-wide sort (r3_batching_info)
+    uint64_t gsort_epoch_used = ~0ull;        // frame epoch in which this camera last batched (r3_gpu_batching.cu)
     bool has_draw_call_set = false; int cache_idx = -1;   // cache_idx: which jobs[] the forward routine cached, -1 = none
     std::vector<uint32_t> prev_invocation;    // PerCameraPreviousInvocationsMap (batching.rs:102-118), host batching
     uint32_t* d_prev_inv[2] = {nullptr, nullptr}; uint32_t prev_inv_cap = 0; int prev_inv_cur = 0;   // same map, device batching
@@ -79,7 +103,11 @@ struct r3_ctx {
     std::vector<uint64_t> sort_key; std::vector<uint8_t> sort_flags; std::vector<float> sort_loc;
     uint32_t* d_live_bits = nullptr; uint32_t live_bits_cap = 0; bool have_live = false;
     uint8_t* d_sort_key8 = nullptr; float* d_sort_loc = nullptr; uint32_t sort_dev_cap = 0; bool gpu_batching_ok = false;
-    uint64_t max_total_invocations = 0; bool max_invocations_valid = false;   // sum over all slots of round_up(tris, 256)
+    // frame-wide sort shared by the cameras of one frame (r3_gpu_batching.cu)
+    unsigned long long* d_gsort_keys[2] = {nullptr, nullptr}; uint64_t gsort_cap[2] = {0, 0}; uint32_t* d_gsort_hist = nullptr; uint64_t gsort_hist_cap = 0;
+    uint32_t* d_gsort_header = nullptr; int gsort_src = 0; uint32_t gsort_n = 0; bool gsort_valid = false; float gsort_loc[3] = {0, 0, 0};
+    uint64_t gsort_epoch = 0, gsort_sorted_epoch = ~0ull; uint32_t gsort_cameras_this_epoch = 0, gsort_cameras_last_epoch = 0;
+    uint64_t max_total_invocations = 0, max_object_invocations = 0; bool max_invocations_valid = false;   // sum / max over all slots of round_up(tris, 256)
     uint32_t* d_mesh = nullptr; uint64_t mesh_words = 0, mesh_cap = 0;
     r3_material* d_materials = nullptr; uint32_t n_materials = 0, materials_cap = 0;
     bool has_skybox = false; r3_texture_desc sky_desc{}; uint8_t* d_sky_texels = nullptr; uint64_t sky_cap = 0;   // cube map of the skybox routine
@@ -94,6 +122,7 @@ struct r3_ctx {
     uint32_t width = 0, height = 0, samples = 1; float clear_color[4] = {0, 0, 0, 0};
     uint32_t row_begin = 0, row_end = 0;
     unsigned long long* d_vis = nullptr;      // (depth bits << 32) | (pass << 31) | record
+    bool parity_target = false;               // also keep the f32 shading result before the rgba16f store (tests; off in production)
     float* d_hdr32 = nullptr; uint16_t* d_hdr16 = nullptr; float* d_depth = nullptr; uint8_t* d_ldr = nullptr;
     std::vector<float*> d_hiz; std::vector<uint32_t> hiz_w, hiz_h;
     float** d_hiz_ptrs = nullptr; uint32_t* d_hiz_dims = nullptr;
@@ -105,6 +134,8 @@ struct r3_ctx {
     uint32_t* d_frag_heads = nullptr; uint64_t frag_heads_cap = 0;
     uint4* d_frag_nodes = nullptr; uint64_t frag_nodes_cap = 0;
     void* d_scratch = nullptr; uint64_t scratch_cap = 0;
+    r3_stage_timer timer;
+    r3_peer_state peer;
 };
 
 // ---- error plumbing (nothing throws across the C boundary)
@@ -127,6 +158,9 @@ int r3_cuda_fail(r3_ctx* c, cudaError_t e, const char* where);
         if (rc__ != R3_OK) return rc__;                                   \
     } while (0)
 
+// stage timing: no-ops unless enabled
+void r3_stage_begin(r3_ctx* c, int stage);
+void r3_stage_end(r3_ctx* c);
 static inline int r3_cam_slot(uint32_t camera) { return camera == R3_CAMERA_VIEWPORT ? 0 : (int)camera + 1; }
 static inline r3_camera* r3_get_camera(r3_ctx* c, uint32_t camera) {
     if (!c || (camera != R3_CAMERA_VIEWPORT && camera >= R3_MAX_SHADOWS)) return nullptr;
@@ -157,6 +191,7 @@ int r3_upload_jobs(r3_ctx* c, r3_camera* cam);
 int r3_device_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], uint32_t max_dispatch_count);
 int r3_download_jobs(r3_ctx* c, r3_camera* cam);          // device-built jobs -> host vectors (readbacks / tests)
 int r3_compute_max_invocations(r3_ctx* c);
+void r3_new_frame_epoch(r3_ctx* c);          // the frame-wide sort of the previous frame is stale from here on
 int r3_blend_collect(r3_ctx* c, bool* ran);   // r3_raster.cu: per-sample fragment lists of the blend routine
 int r3_iobuf_new(r3_ctx* c, r3_iobuf* b, uint64_t elems, uint64_t elem_size, bool clear_on_swap);
 int r3_iobuf_swap(r3_ctx* c, r3_iobuf* b, uint64_t new_elems);

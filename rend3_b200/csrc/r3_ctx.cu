@@ -68,9 +68,10 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     if (!c) return R3_E_INVALID;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    r3_peer_destroy(c);
     if (!c->objects_borrowed) cudaFree(c->d_objects);
     cudaFree(c->d_hot_transform); cudaFree(c->d_hot_sphere); cudaFree(c->d_enabled_bits); cudaFree(c->d_tex_descs); cudaFree(c->d_texels); cudaFree(c->d_sky_texels);
-    cudaFree(c->d_sort_key8); cudaFree(c->d_sort_loc);
+    cudaFree(c->d_sort_key8); cudaFree(c->d_sort_loc); cudaFree(c->d_gsort_keys[0]); cudaFree(c->d_gsort_keys[1]); cudaFree(c->d_gsort_hist); cudaFree(c->d_gsort_header);
     cudaFree(c->d_live_bits); cudaFree(c->d_mesh); cudaFree(c->d_materials); cudaFree(c->d_dir); cudaFree(c->d_point);
     cudaFree(c->d_light_mats); cudaFree(c->d_atlas);
     for (auto& k : c->cams) {
@@ -80,6 +81,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
                 if (k.ex_connected && r != k.ex_rank && k.ex_peers[r]) cudaIpcCloseMemHandle(k.ex_peers[r]);
             cudaFree(k.d_gathered);
         }
+        cudaFree(k.d_ex_done); cudaFree(k.d_global_visible); cudaFree(k.d_merge_counts);
         free_jobs(k.jobs[0]); free_jobs(k.jobs[1]);
         cudaFree(k.index_buffer.d); cudaFree(k.draw_call_buffer.d); cudaFree(k.results_buffer.d);
         cudaFree(k.d_resid_bits); cudaFree(k.d_word_scan); cudaFree(k.d_block_sums);
@@ -90,6 +92,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     cudaFree(c->d_hiz_ptrs); cudaFree(c->d_hiz_dims);
     cudaFree(c->d_tris[0]); cudaFree(c->d_tris[1]); cudaFree(c->d_tris[2]); cudaFree(c->d_tris[3]); cudaFree(c->d_stats); cudaFree(c->d_scratch);
     cudaFree(c->d_frag_heads); cudaFree(c->d_frag_nodes);
+    for (cudaEvent_t e : c->timer.pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
     return R3_OK;
@@ -108,6 +111,45 @@ R3_EXPORT int r3_get_stream(r3_ctx* c, void** s) {
 R3_EXPORT int r3_launch_count(r3_ctx* c, uint64_t* n) {
     if (!c || !n) return R3_E_INVALID;
     *n = c->launches;
+    return R3_OK;
+}
+
+// ------------------------------------------------------------------ stage timing
+void r3_stage_begin(r3_ctx* c, int stage) {
+    r3_stage_timer& t = c->timer;
+    if (!t.enabled) return;
+    if (t.pool.size() < 2 * (t.used + 1)) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { t.enabled = false; return; }
+        t.pool.push_back(a); t.pool.push_back(b); t.stage_of.push_back(stage);
+    }
+    t.stage_of[t.used] = stage;
+    cudaEventRecord(t.pool[2 * t.used], c->stream);
+}
+void r3_stage_end(r3_ctx* c) {
+    r3_stage_timer& t = c->timer;
+    if (!t.enabled) return;
+    cudaEventRecord(t.pool[2 * t.used + 1], c->stream);
+    t.used++;
+}
+R3_EXPORT int r3_set_stage_timing(r3_ctx* c, int enabled) {
+    if (!c) return R3_E_INVALID;
+    cudaSetDevice(c->device);
+    c->timer.enabled = enabled != 0;
+    c->timer.used = 0;
+    return R3_OK;
+}
+R3_EXPORT int r3_stage_times(r3_ctx* c, double ms[8], uint32_t launches[8]) {
+    if (!c || !ms || !launches) return R3_E_INVALID;
+    cudaSetDevice(c->device);
+    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 8; ++k) { ms[k] = 0.0; launches[k] = 0; }
+    r3_stage_timer& t = c->timer;
+    for (size_t k = 0; k < t.used; ++k) {
+        float e = 0.f;
+        if (cudaEventElapsedTime(&e, t.pool[2 * k], t.pool[2 * k + 1]) == cudaSuccess && t.stage_of[k] >= 0 && t.stage_of[k] < 8) { ms[t.stage_of[k]] += e; launches[t.stage_of[k]]++; }
+    }
+    t.used = 0;
     return R3_OK;
 }
 
@@ -193,6 +235,7 @@ R3_EXPORT int r3_set_object_sort_info(r3_ctx* c, const uint64_t* key, const uint
         R3_CUDA(c, cudaMemcpyAsync(c->d_sort_loc, loc, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
     }
     R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    r3_new_frame_epoch(c);
     c->have_live = true;
     c->gpu_batching_ok = ok && n < (1u << 24) && !getenv("R3_HOST_BATCHING");
     return R3_OK;
@@ -283,8 +326,15 @@ R3_EXPORT int r3_set_point_lights(r3_ctx* c, const void* bytes, uint64_t nbytes)
     c->n_point = n;
     return R3_OK;
 }
+void r3_new_frame_epoch(r3_ctx* c) {
+    c->gsort_epoch++;
+    c->gsort_valid = false;
+    if (c->gsort_cameras_this_epoch) c->gsort_cameras_last_epoch = c->gsort_cameras_this_epoch;
+    c->gsort_cameras_this_epoch = 0;
+}
 R3_EXPORT int r3_set_frame_uniforms(r3_ctx* c, const r3_frame_uniforms* u) {
     if (!c || !u) return r3_fail(c, R3_E_INVALID, "set_frame_uniforms: null");
+    r3_new_frame_epoch(c);   // base.rs:142: once per frame, before any camera batches
     c->uniforms = *u;
     c->uniforms_set = true;
     return R3_OK;
@@ -425,8 +475,33 @@ R3_EXPORT int r3_batch_objects(r3_ctx* c, uint32_t camera, const float vp_loc[3]
     R3_CAM_OR_FAIL(c, camera);
     if (!vp_loc) return r3_fail(c, R3_E_INVALID, "batch_objects: null location");
     cudaSetDevice(c->device);
-    if (c->gpu_batching_ok && c->sort_key.size() >= cam->header.object_count) return r3_device_batch_objects(c, cam, vp_loc, max_dispatch_count);
+    // The device path never splits a batch at the dispatch limit (batching.rs:196); it is only taken when no batch can reach it:
+    // 256 objects x the largest padded triangle count of any slot stays below max_dispatch_count x 256 invocations.  Worlds with
+    // such meshes (> ~65k triangles in one object), material keys >= 64 or >= 2^24 slots take the host path, which splits.
+    bool device = c->gpu_batching_ok && c->sort_key.size() >= cam->header.object_count;
+    if (device) {
+        R3_TRY(r3_compute_max_invocations(c));   // cached: one small reduction per object upload, never per frame
+        device = c->max_object_invocations * R3_BATCH_SIZE < (uint64_t)max_dispatch_count * R3_WORKGROUP_SIZE;
+    }
+    cam->batching_path = device ? 1 : 2;   // the device path raises it to 3 when it takes the frame-wide sort
+    if (device) return r3_device_batch_objects(c, cam, vp_loc, max_dispatch_count);
     return r3_host_batch_objects(c, cam, vp_loc, max_dispatch_count);
+}
+R3_EXPORT int r3_batching_info(r3_ctx* c, uint32_t camera, uint32_t info[4]) {
+    R3_CAM_OR_FAIL(c, camera);
+    if (!info) return r3_fail(c, R3_E_INVALID, "batching_info: null");
+    cudaSetDevice(c->device);
+    info[0] = (uint32_t)cam->batching_path; info[1] = 0; info[2] = 0; info[3] = 0;
+    const r3_jobs& j = cam->jobs[cam->cur];
+    if ((cam->batching_path == 1 || cam->batching_path == 3) && j.d_header) {
+        uint32_t hdr[8] = {0};
+        R3_CUDA(c, cudaMemcpyAsync(hdr, j.d_header, 32, cudaMemcpyDeviceToHost, c->stream));
+        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        info[1] = hdr[4]; info[2] = hdr[1]; info[3] = hdr[2];
+    } else if (cam->batching_path == 2) {
+        info[2] = (uint32_t)j.batches.size(); info[3] = (uint32_t)j.regions.size();
+    }
+    return R3_OK;
 }
 R3_EXPORT int r3_batch_counts(r3_ctx* c, uint32_t camera, uint32_t* nb, uint32_t* nr, uint32_t* tot) {
     R3_CAM_OR_FAIL(c, camera);

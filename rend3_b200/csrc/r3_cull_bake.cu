@@ -152,7 +152,16 @@ cull_bake_kernel(const float4* __restrict__ transforms, const float4* __restrict
 
 // visible-set exchange fused into the compaction: every word this rank produced is also stored, coalesced, into the gathered
 // buffer of every rank (its own included) through NVLink peer mappings — no collective kernel, no extra pass over the words
-struct ExchangeParams { uint32_t* peers[R3_MAX_EXCHANGE_RANKS]; uint32_t n_ranks, word_offset, words_per_rank; };
+// Buffer of every rank (one allocation, mapped into every process): [ flags[2][R3_MAX_EXCHANGE_RANKS] | pad to EX_HEADER_WORDS ] then
+// rows[2][n_ranks][words_per_rank].  A step with epoch e uses parity e & 1: rank r stores its words into row (e & 1, r) of every
+// buffer and then publishes them with flags[e & 1][r] = e (st.release.sys by the last CTA to finish, after every CTA fenced its stores
+// at system scope).  A consumer waits with ld.acquire.sys on the flag of the row it needs — on the device, no host barrier — and the
+// other parity keeps epoch e - 1 intact while epoch e + 1 is written.
+constexpr uint32_t EX_HEADER_WORDS = 256;
+struct ExchangeParams { uint32_t* peers[R3_MAX_EXCHANGE_RANKS]; uint32_t n_ranks, word_offset, words_per_rank, flag_offset, epoch; uint32_t* done; };
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 __global__ void __launch_bounds__(CP_THREADS)
 compact_visible_kernel(const uint32_t* __restrict__ words, const uint32_t* __restrict__ cta_counts, uint32_t n_words, uint32_t n_cta_counts,
@@ -182,7 +191,7 @@ compact_visible_kernel(const uint32_t* __restrict__ words, const uint32_t* __res
     const uint32_t word = wi < n_words ? __ldg(&words[wi]) : 0u;
     if (ex.n_ranks && wi < ex.words_per_rank) {
 #pragma unroll 1
-        for (uint32_t r = 0; r < ex.n_ranks; ++r) ex.peers[r][ex.word_offset + wi] = word;
+        for (uint32_t r = 0; r < ex.n_ranks; ++r) ex.peers[r][(size_t)ex.word_offset + wi] = word;
     }
     const uint32_t c = __popc(word);
     uint32_t incl = c;
@@ -212,6 +221,107 @@ compact_visible_kernel(const uint32_t* __restrict__ words, const uint32_t* __res
         const uint32_t wj = __shfl_sync(0xFFFFFFFFu, word, j), ej = __shfl_sync(0xFFFFFFFFu, excl, j);
         if ((wj >> lane) & 1u) visible[ej + __popc(wj & ((1u << lane) - 1u))] = (blockIdx.x * CP_THREADS + warp * 32 + j) * 32u + lane;
     }
+    if (ex.n_ranks) {
+        // publish the row: every thread orders its peer stores at system scope, the last CTA to arrive writes the epoch flags
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t arrived = atomicAdd(ex.done, 1u);
+            if (arrived == gridDim.x - 1u) {
+                *ex.done = 0u;                                  // next launch of this camera starts from zero (stream-ordered)
+                __threadfence_system();
+                for (uint32_t r = 0; r < ex.n_ranks; ++r) st_release_sys(ex.peers[r] + ex.flag_offset, ex.epoch);
+            }
+        }
+    }
+}
+
+// ---- consumer side: the GLOBAL visible list (ascending global object ids) out of the gathered rows, chained on the epoch flags.
+//   wait + count : CTA (row r, tile t): one thread spins on flags[parity][r] with ld.acquire.sys until the row's epoch arrived, then the CTA
+//                  counts the survivors of its 1024 words;
+//   expand       : survivors in front of the tile (sum of the counts before it), block scan, ordered expansion — as the local compaction.
+struct MergeParams {
+    const uint32_t* gathered;            // this rank's buffer (flags + rows)
+    uint32_t n_ranks, words_per_rank, parity, epoch, tiles_per_rank;
+    uint32_t rank_base[R3_MAX_EXCHANGE_RANKS];   // global id of slot 0 of every rank's shard
+    uint32_t rank_objects[R3_MAX_EXCHANGE_RANKS];
+    uint32_t* tile_counts; uint32_t* out; uint32_t* out_count; uint32_t out_cap;
+};
+__device__ __forceinline__ uint32_t merge_word(const MergeParams& p, uint32_t r, uint32_t w) {
+    if (w >= p.words_per_rank) return 0u;
+    uint32_t word = __ldcg(p.gathered + EX_HEADER_WORDS + ((size_t)p.parity * p.n_ranks + r) * p.words_per_rank + w);   // written by a peer: L2, never a stale L1 line
+    const uint32_t n = p.rank_objects[r];                   // bits beyond the shard's object count are never listed
+    if (w * 32u >= n) return 0u;
+    if (n - w * 32u < 32u) word &= (1u << (n - w * 32u)) - 1u;
+    return word;
+}
+__global__ void __launch_bounds__(CP_THREADS) exchange_wait_count_kernel(const __grid_constant__ MergeParams p) {
+    const uint32_t r = blockIdx.x / p.tiles_per_rank, t = blockIdx.x % p.tiles_per_rank;
+    if (threadIdx.x == 0) {
+        const uint32_t* flag = p.gathered + p.parity * R3_MAX_EXCHANGE_RANKS + r;
+        while ((int32_t)(ld_acquire_sys(flag) - p.epoch) < 0) __nanosleep(64);
+    }
+    __syncthreads();
+    const uint32_t word = merge_word(p, r, t * CP_THREADS + threadIdx.x);
+    uint32_t cnt = __popc(word);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, s);
+    __shared__ uint32_t s_warp[32];
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v = s_warp[threadIdx.x];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, s);
+        if (threadIdx.x == 0) p.tile_counts[blockIdx.x] = v;
+    }
+}
+__global__ void __launch_bounds__(CP_THREADS) exchange_expand_kernel(const __grid_constant__ MergeParams p) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x / p.tiles_per_rank, t = blockIdx.x % p.tiles_per_rank;
+    uint32_t before = 0;
+    for (uint32_t i = threadIdx.x; i < blockIdx.x; i += CP_THREADS) before += p.tile_counts[i];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, s);
+    if (lane == 0) s_warp[warp] = before;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_warp[lane];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, s);
+        if (lane == 0) s_base = v;
+    }
+    __syncthreads();
+    const uint32_t tile_base = s_base;
+    __syncthreads();
+    const uint32_t word = merge_word(p, r, t * CP_THREADS + threadIdx.x);
+    const uint32_t c = __popc(word);
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += n; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, d); if (lane >= d) wi += n; }
+        s_warp[lane] = wi - w;
+        if (lane == 31 && blockIdx.x == gridDim.x - 1) *p.out_count = tile_base + wi;
+    }
+    __syncthreads();
+    const uint32_t excl = tile_base + s_warp[warp] + incl - c;
+    const uint32_t id_base = p.rank_base[r] + (t * CP_THREADS + warp * 32u) * 32u;
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t wj = __shfl_sync(0xFFFFFFFFu, word, j), ej = __shfl_sync(0xFFFFFFFFu, excl, j);
+        if ((wj >> lane) & 1u) {
+            const uint32_t pos = ej + __popc(wj & ((1u << lane) - 1u));
+            if (pos < p.out_cap) p.out[pos] = id_base + j * 32u + lane;
+        }
+    }
 }
 
 }  // namespace
@@ -238,13 +348,17 @@ int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode) {
     uint32_t* cta_counts = words + n_words;
     if (!c->hot_valid) return r3_fail(c, R3_E_STATE, "object_uniform_upload before set_objects");
     float4* mats = reinterpret_cast<float4*>(cam->d_matrices);
-    const bool live = c->have_live && cull;
+    // the live mask of r3_set_object_sort_info is only trusted when it covers every slot of this launch; a shorter (stale) one would be
+    // read out of bounds — then `enabled` decides, as without sort info
+    const bool live = c->have_live && cull && c->sort_flags.size() >= (size_t)n;
 #define R3_CB_LAUNCH(B, C, L) \
     cull_bake_kernel<B, C, L><<<n_ctas, CB_THREADS, 0, c->stream>>>(c->d_hot_transform, c->d_hot_sphere, c->d_enabled_bits, c->d_live_bits, mats, words, cta_counts, p)
+    r3_stage_begin(c, R3_STAGE_CULL_BAKE);
     if (bake && cull) { if (live) R3_CB_LAUNCH(true, true, true); else R3_CB_LAUNCH(true, true, false); }
     else if (bake) R3_CB_LAUNCH(true, false, false);
     else { if (live) R3_CB_LAUNCH(false, true, true); else R3_CB_LAUNCH(false, true, false); }
 #undef R3_CB_LAUNCH
+    r3_stage_end(c);
     R3_CHECK_LAUNCH(c, "cull_bake_kernel");
     if (cull) {
         const uint32_t n_tiles = (n_words + CP_THREADS - 1) / CP_THREADS;
@@ -252,7 +366,11 @@ int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode) {
         if (cam->ex_connected) {
             if (n_words > cam->ex_words_per_rank) return r3_fail(c, R3_E_INVALID, "object_uniform_upload: more objects than the exchange was created for");
             for (uint32_t r = 0; r < cam->ex_ranks; ++r) ex.peers[r] = cam->ex_peers[r];
-            ex.n_ranks = cam->ex_ranks; ex.word_offset = cam->ex_rank * cam->ex_words_per_rank; ex.words_per_rank = cam->ex_words_per_rank;
+            const uint32_t epoch = ++cam->ex_epoch, parity = epoch & 1u;
+            ex.n_ranks = cam->ex_ranks; ex.words_per_rank = cam->ex_words_per_rank;
+            ex.word_offset = EX_HEADER_WORDS + (parity * cam->ex_ranks + cam->ex_rank) * cam->ex_words_per_rank;
+            ex.flag_offset = parity * R3_MAX_EXCHANGE_RANKS + cam->ex_rank; ex.epoch = epoch; ex.done = cam->d_ex_done;
+            cam->ex_objects = n;
         }
         // with an exchange every slot of this rank's row is written each step (the tail beyond n_words as zeros)
         const uint32_t n_tiles_ex = cam->ex_connected ? (cam->ex_words_per_rank + CP_THREADS - 1) / CP_THREADS : 0u;
@@ -295,9 +413,11 @@ int r3_split_slots(r3_ctx* c, const uint32_t* d_slots, uint32_t n) {
 }
 
 // ------------------------------------------------------------------ multi-GPU exchange of the visible set
-// One process per GPU.  Every rank owns gathered[n_ranks][words_per_rank]; rank r's compact kernel stores row r into the
-// buffer of every rank through CUDA IPC peer mappings over NVLink / NVSwitch.  The rows are complete once the ranks have
-// synchronised their streams and met at a barrier (the caller's: torch.distributed / MPI / the frame fence).
+// One process per GPU.  Every rank owns flags + rows[2][n_ranks][words_per_rank]; rank r's compact kernel stores row r of the step's
+// parity into the buffer of every rank through CUDA IPC peer mappings over NVLink / NVSwitch and publishes it with an epoch flag
+// (st.release.sys).  Consumers (r3_exchange_merge, or any kernel of the host's) wait for the flag with ld.acquire.sys on the device.
+// Protocol: the ranks call r3_object_uniform_upload(CULL) in lockstep (same number of steps); a rank consumes epoch e (or meets the
+// others at a host barrier) before it issues epoch e + 2, which reuses the parity — then no row is overwritten while it is read.
 R3_EXPORT int r3_exchange_create(r3_ctx* c, uint32_t camera, uint32_t n_ranks, uint32_t my_rank, uint32_t max_objects_per_rank, uint8_t handle_out[R3_IPC_HANDLE_BYTES]) {
     if (!c || !handle_out) return r3_fail(c, R3_E_INVALID, "exchange_create: null");
     if (n_ranks == 0 || n_ranks > R3_MAX_EXCHANGE_RANKS || my_rank >= n_ranks || max_objects_per_rank == 0) return r3_fail(c, R3_E_INVALID, "exchange_create: bad rank layout");
@@ -307,9 +427,13 @@ R3_EXPORT int r3_exchange_create(r3_ctx* c, uint32_t camera, uint32_t n_ranks, u
     cudaSetDevice(c->device);
     if (cam->d_gathered) return r3_fail(c, R3_E_STATE, "exchange_create: already created for this camera");
     const uint32_t wpr = (((max_objects_per_rank + 31u) / 32u) + 63u) & ~63u;   // rows start 256-byte aligned
-    R3_CUDA(c, cudaMalloc((void**)&cam->d_gathered, (size_t)n_ranks * wpr * 4));
-    R3_CUDA(c, cudaMemsetAsync(cam->d_gathered, 0, (size_t)n_ranks * wpr * 4, c->stream));
+    const size_t total_words = EX_HEADER_WORDS + (size_t)2 * n_ranks * wpr;    // flags | two parities of n_ranks rows
+    R3_CUDA(c, cudaMalloc((void**)&cam->d_gathered, total_words * 4));
+    R3_CUDA(c, cudaMemsetAsync(cam->d_gathered, 0, total_words * 4, c->stream));
+    if (!cam->d_ex_done) R3_CUDA(c, cudaMalloc((void**)&cam->d_ex_done, 16));
+    R3_CUDA(c, cudaMemsetAsync(cam->d_ex_done, 0, 16, c->stream));
     R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    cam->ex_epoch = 0; cam->ex_objects = 0;
     cudaIpcMemHandle_t h;
     R3_CUDA(c, cudaIpcGetMemHandle(&h, cam->d_gathered));
     memcpy(handle_out, &h, sizeof h);
@@ -336,8 +460,49 @@ R3_EXPORT int r3_exchange_words(r3_ctx* c, uint32_t camera, void** device_ptr, u
     if (!c || !device_ptr || !nbytes) return r3_fail(c, R3_E_INVALID, "exchange_words: null");
     r3_camera* cam = r3_get_camera(c, camera);
     if (!cam || !cam->d_gathered) return r3_fail(c, R3_E_STATE, "exchange_words before exchange_create");
-    *device_ptr = cam->d_gathered; *nbytes = (uint64_t)cam->ex_ranks * cam->ex_words_per_rank * 4;
+    // the rows of the LAST step (epoch parity); complete once their flags carry the epoch — r3_exchange_merge waits for that on the device,
+    // a host reader synchronises its stream and meets the other ranks at a barrier first
+    *device_ptr = cam->d_gathered + EX_HEADER_WORDS + (size_t)(cam->ex_epoch & 1u) * cam->ex_ranks * cam->ex_words_per_rank;
+    *nbytes = (uint64_t)cam->ex_ranks * cam->ex_words_per_rank * 4;
     if (words_per_rank) *words_per_rank = cam->ex_words_per_rank;
+    return R3_OK;
+}
+// Consumer of the exchange: the global visible list on this rank.  rank_objects[r] = slots of rank r's shard in the last step,
+// rank_base[r] = global id of its slot 0 (NULL: r * max_objects_per_rank).  Chained on the epoch flags on the device; no host barrier.
+R3_EXPORT int r3_exchange_merge(r3_ctx* c, uint32_t camera, const uint32_t* rank_objects, const uint32_t* rank_base) {
+    if (!c || !rank_objects) return r3_fail(c, R3_E_INVALID, "exchange_merge: null");
+    r3_camera* cam = r3_get_camera(c, camera);
+    if (!cam || !cam->d_gathered || !cam->ex_connected) return r3_fail(c, R3_E_STATE, "exchange_merge before exchange_connect");
+    if (cam->ex_epoch == 0) return r3_fail(c, R3_E_STATE, "exchange_merge before the first cull of the exchange");
+    cudaSetDevice(c->device);
+    MergeParams p{};
+    uint64_t total = 0;
+    for (uint32_t r = 0; r < cam->ex_ranks; ++r) {
+        if ((rank_objects[r] + 31u) / 32u > cam->ex_words_per_rank) return r3_fail(c, R3_E_INVALID, "exchange_merge: a shard is larger than the exchange was created for");
+        p.rank_objects[r] = rank_objects[r];
+        p.rank_base[r] = rank_base ? rank_base[r] : r * cam->ex_words_per_rank * 32u;
+        total += rank_objects[r];
+    }
+    if (total >= (1ull << 32)) return r3_fail(c, R3_E_INVALID, "exchange_merge: more than 2^32 objects");
+    p.gathered = cam->d_gathered; p.n_ranks = cam->ex_ranks; p.words_per_rank = cam->ex_words_per_rank;
+    p.epoch = cam->ex_epoch; p.parity = cam->ex_epoch & 1u;
+    p.tiles_per_rank = (cam->ex_words_per_rank + CP_THREADS - 1) / CP_THREADS;
+    const uint32_t n_tiles = p.tiles_per_rank * cam->ex_ranks;
+    R3_TRY(r3_reserve_t(c, &cam->d_global_visible, &cam->global_visible_cap, total + 1));
+    R3_TRY(r3_reserve_t(c, &cam->d_merge_counts, &cam->merge_counts_cap, (uint64_t)n_tiles + 4));
+    p.tile_counts = cam->d_merge_counts + 4; p.out = cam->d_global_visible; p.out_count = cam->d_merge_counts; p.out_cap = (uint32_t)total;
+    exchange_wait_count_kernel<<<n_tiles, CP_THREADS, 0, c->stream>>>(p);
+    R3_CHECK_LAUNCH(c, "exchange_wait_count_kernel");
+    exchange_expand_kernel<<<n_tiles, CP_THREADS, 0, c->stream>>>(p);
+    R3_CHECK_LAUNCH(c, "exchange_expand_kernel");
+    return R3_OK;
+}
+R3_EXPORT int r3_exchange_merged(r3_ctx* c, uint32_t camera, void** device_list, void** device_count, uint64_t* capacity) {
+    if (!c || !device_list || !device_count) return r3_fail(c, R3_E_INVALID, "exchange_merged: null");
+    r3_camera* cam = r3_get_camera(c, camera);
+    if (!cam || !cam->d_global_visible) return r3_fail(c, R3_E_STATE, "exchange_merged before exchange_merge");
+    *device_list = cam->d_global_visible; *device_count = cam->d_merge_counts;
+    if (capacity) *capacity = cam->global_visible_cap;
     return R3_OK;
 }
 R3_EXPORT int r3_exchange_destroy(r3_ctx* c, uint32_t camera) {
@@ -349,7 +514,7 @@ R3_EXPORT int r3_exchange_destroy(r3_ctx* c, uint32_t camera) {
     for (uint32_t r = 0; r < cam->ex_ranks; ++r)
         if (cam->ex_connected && r != cam->ex_rank && cam->ex_peers[r]) cudaIpcCloseMemHandle(cam->ex_peers[r]);
     cudaFree(cam->d_gathered);
-    cam->d_gathered = nullptr; cam->ex_connected = false; cam->ex_ranks = 0;
+    cam->d_gathered = nullptr; cam->ex_connected = false; cam->ex_ranks = 0; cam->ex_epoch = 0;
     for (auto& p : cam->ex_peers) p = nullptr;
     return R3_OK;
 }

@@ -29,14 +29,16 @@ constexpr int SORT_KEYS_PER_THREAD = 8;
 constexpr int SORT_TILE = SORT_THREADS * SORT_KEYS_PER_THREAD;   // 2048 keys per block
 constexpr int KEY_SHIFT0 = 24, SORT_PASSES = 5;
 
-__device__ __forceinline__ uint32_t sortable_f32(float f) {   // order-preserving map of the f32 total order used by OrderedFloat
-    const uint32_t b = __float_as_uint(f);
+// order-preserving map of OrderedFloat's total order (batching.rs:37): every NaN is one value above +inf, -0.0 == +0.0
+__device__ __forceinline__ uint32_t sortable_f32(float f) {
+    if (f != f) return 0xFFC00000u;                              // the image of the canonical quiet NaN 0x7FC00000
+    const uint32_t b = __float_as_uint(f) == 0x80000000u ? 0u : __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
 __device__ __forceinline__ unsigned long long make_sort_key(const uint32_t* __restrict__ visible, const uint8_t* __restrict__ key8, const float* __restrict__ loc,
                                                             float vx, float vy, float vz, uint32_t j) {
-    const uint32_t h = visible[j];
+    const uint32_t h = visible ? visible[j] : j;                 // visible == nullptr: the frame-wide sort over every slot (see r3_device_batch_objects)
     const uint8_t k = key8[h];                                   // (material_key << 1 | reason) << 1 | back_to_front
     const float dx = sub_rn(vx, loc[3 * (size_t)h]), dy = sub_rn(vy, loc[3 * (size_t)h + 1]), dz = sub_rn(vz, loc[3 * (size_t)h + 2]);
     float d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));   // Vec3A::distance_squared (batching.rs:156-157)
@@ -55,13 +57,13 @@ __host__ __device__ inline uint32_t small_sort_pad(uint32_t n) { return ((n + SM
 inline size_t small_sort_smem(uint32_t cap) { return (size_t)small_sort_pad(cap) * 16 + (size_t)SMALL_SORT_WARPS * 256 * 4 + 256 * 4; }
 __global__ void __launch_bounds__(SMALL_SORT_THREADS) small_sort_kernel(const uint32_t* __restrict__ visible, const uint32_t* __restrict__ visible_count,
                                                                         const uint8_t* __restrict__ key8, const float* __restrict__ loc, float vx, float vy, float vz,
-                                                                        unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ header, uint32_t cap_pad) {
+                                                                        unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ header, uint32_t cap_pad, uint32_t count_imm) {
     extern __shared__ unsigned long long s_keys[];                               // [2][cap_pad]
     uint32_t* s_count = reinterpret_cast<uint32_t*>(s_keys + 2 * (size_t)cap_pad);   // [warps][256]
     uint32_t* s_base = s_count + SMALL_SORT_WARPS * 256;                          // [256]
     __shared__ uint32_t s_wsum[8];
     __shared__ int s_skip;
-    const uint32_t nv = min(*visible_count, cap_pad);
+    const uint32_t nv = min(visible_count ? *visible_count : count_imm, cap_pad);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { header[0] = nv; header[4] = 0u; }
     for (uint32_t j = threadIdx.x; j < nv; j += SMALL_SORT_THREADS) s_keys[j] = make_sort_key(visible, key8, loc, vx, vy, vz, j);
@@ -124,8 +126,9 @@ __global__ void __launch_bounds__(SMALL_SORT_THREADS) small_sort_kernel(const ui
 }
 
 __global__ void keygen_kernel(const uint32_t* __restrict__ visible, const uint32_t* __restrict__ visible_count, const uint8_t* __restrict__ key8,
-                              const float* __restrict__ loc, float vx, float vy, float vz, unsigned long long* __restrict__ keys, uint32_t* __restrict__ header) {
-    const uint32_t nv = *visible_count;
+                              const float* __restrict__ loc, float vx, float vy, float vz, unsigned long long* __restrict__ keys, uint32_t* __restrict__ header,
+                              uint32_t count_imm) {
+    const uint32_t nv = visible_count ? *visible_count : count_imm;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == 0) { header[0] = nv; header[4] = (nv >= (1u << 24)) ? 1u : 0u; }
     if (j >= nv) return;
@@ -229,6 +232,7 @@ struct BuildParams {
     r3_region* regions; uint32_t* region_first_inv;
     const uint32_t* prev_map; uint32_t* cur_map; uint32_t map_cap;
     uint32_t n_batches_cap; uint64_t dispatch_limit;
+    uint32_t keys_hold_slots;                             // low 24 key bits = the object slot (frame-wide sort) instead of a position in `visible`
 };
 
 __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* s_warp, uint32_t* total) {
@@ -253,7 +257,7 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* s_warp
 constexpr uint32_t COOP_SORT_MAX_BLOCKS = 256;
 struct SortCoopParams {
     const uint32_t* visible; const uint32_t* visible_count; const uint8_t* key8; const float* loc; float vx, vy, vz;
-    unsigned long long* keys[2]; uint32_t* hist; uint32_t* header;
+    unsigned long long* keys[2]; uint32_t* hist; uint32_t* header; uint32_t count_imm;
 };
 __global__ void __launch_bounds__(SORT_THREADS) radix_sort_coop_kernel(const __grid_constant__ SortCoopParams p) {
     namespace cg = cooperative_groups;
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_sort_coop_kernel(const __g
     __shared__ uint32_t s_run[256];
     __shared__ uint32_t s_gbase[256];
     __shared__ uint32_t s_warp[8];
-    const uint32_t nv = *p.visible_count, nb = gridDim.x, b = blockIdx.x;
+    const uint32_t nv = p.visible_count ? *p.visible_count : p.count_imm, nb = gridDim.x, b = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t base = b * SORT_TILE;
     if (b == 0 && threadIdx.x == 0) { p.header[0] = nv; p.header[4] = (nv >= (1u << 24)) ? 1u : 0u; }
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(256) batch_build_kernel(const __grid_constant_
     uint32_t h = 0, tri = 0;
     if (valid) {
         key = p.keys[j];
-        h = p.visible[(uint32_t)(key & 0xFFFFFFull)];
+        h = p.keys_hold_slots ? (uint32_t)(key & 0xFFFFFFull) : p.visible[(uint32_t)(key & 0xFFFFFFull)];
         tri = p.objects[h].index_count / 3u;                                  // batching.rs:192
         if (j > 0) prev_key = p.keys[j - 1];
     }
@@ -449,12 +453,69 @@ __global__ void __launch_bounds__(256) batch_finalize_kernel(const __grid_consta
     }
 }
 
-__global__ void max_invocations_kernel(const r3_object* __restrict__ objects, uint32_t n, unsigned long long* __restrict__ out) {
-    unsigned long long acc = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc += ((objects[i].index_count / 3u) + 255u) & ~255u;
+// ---- frame-wide sort shared by the cameras of a frame.  batch_objects sorts by (material key, sorting reason, distance to the
+// VIEWPORT camera) for every camera, shadow cameras included (batching.rs:156-157 uses viewport_camera_state) — the key of an object
+// is the same in all of them, only the visible sets differ.  So the slots are sorted ONCE per frame and each camera takes its
+// visible objects out of that order with a stream compaction (ties resolve by slot in both forms: the results are identical).
+// On config 3 this replaces five 148-us cooperative sorts by one sort and five ~10-us compactions.
+constexpr int RC_THREADS = 1024;
+__device__ __forceinline__ bool rank_visible(const unsigned long long* __restrict__ gkeys, uint32_t r, uint32_t n, const uint32_t* __restrict__ words, uint32_t cap,
+                                             unsigned long long* key) {
+    if (r >= n) return false;
+    const unsigned long long k = gkeys[r];
+    const uint32_t slot = (uint32_t)(k & 0xFFFFFFull);
+    *key = k;
+    return slot < cap && ((__ldg(&words[slot >> 5]) >> (slot & 31u)) & 1u);
+}
+__global__ void __launch_bounds__(RC_THREADS) rank_count_kernel(const unsigned long long* __restrict__ gkeys, uint32_t n, const uint32_t* __restrict__ words, uint32_t cap,
+                                                                uint32_t* __restrict__ tile_counts) {
+    unsigned long long k;
+    const int c = __syncthreads_count(rank_visible(gkeys, blockIdx.x * RC_THREADS + threadIdx.x, n, words, cap, &k) ? 1 : 0);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = (uint32_t)c;
+}
+__global__ void __launch_bounds__(RC_THREADS) rank_scatter_kernel(const unsigned long long* __restrict__ gkeys, uint32_t n, const uint32_t* __restrict__ words, uint32_t cap,
+                                                                  const uint32_t* __restrict__ tile_counts, unsigned long long* __restrict__ keys_out,
+                                                                  uint32_t* __restrict__ header) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t before = 0;
+    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += RC_THREADS) before += __ldg(&tile_counts[t]);
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, s);
-    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+    for (int sft = 16; sft > 0; sft >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, sft);
+    if (lane == 0) s_warp[warp] = before;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_warp[lane];
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, sft);
+        if (lane == 0) s_base = v;
+    }
+    __syncthreads();
+    const uint32_t base = s_base;
+    __syncthreads();
+    unsigned long long key = 0ull;
+    const bool vis = rank_visible(gkeys, blockIdx.x * RC_THREADS + threadIdx.x, n, words, cap, &key);
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, vis);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) { const uint32_t c = s_warp[w]; if (w < warp) wbase += c; total += c; }
+    if (vis) keys_out[base + wbase + __popc(bal & ((1u << lane) - 1u))] = key;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { header[0] = base + total; header[4] = 0u; }
+}
+
+// out[0] = sum over the slots of round_up(triangles, 256), out[1] = the largest such term
+__global__ void max_invocations_kernel(const r3_object* __restrict__ objects, uint32_t n, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0, big = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long v = ((objects[i].index_count / 3u) + 255u) & ~255u;
+        acc += v; big = max(big, v);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) { acc += __shfl_xor_sync(0xFFFFFFFFu, acc, s); big = max(big, __shfl_xor_sync(0xFFFFFFFFu, big, s)); }
+    if ((threadIdx.x & 31) == 0 && acc) { atomicAdd(out, acc); atomicMax(out + 1, big); }
 }
 
 }  // namespace
@@ -463,17 +524,86 @@ __global__ void max_invocations_kernel(const r3_object* __restrict__ objects, ui
 // totals stay on the device.  One small reduction + 8-byte readback at upload time, never per frame.
 int r3_compute_max_invocations(r3_ctx* c) {
     if (c->max_invocations_valid) return R3_OK;
-    c->max_total_invocations = 0;
+    c->max_total_invocations = 0; c->max_object_invocations = 0;
     if (c->n_slots) {
-        R3_CUDA(c, cudaMemsetAsync(c->d_stats + 4, 0, 8, c->stream));
+        R3_CUDA(c, cudaMemsetAsync(c->d_stats + 4, 0, 16, c->stream));
         max_invocations_kernel<<<R3_SM_COUNT * 4, 256, 0, c->stream>>>(c->d_objects, c->n_slots, c->d_stats + 4);
         R3_CHECK_LAUNCH(c, "max_invocations_kernel");
-        unsigned long long v = 0;
-        R3_CUDA(c, cudaMemcpyAsync(&v, c->d_stats + 4, 8, cudaMemcpyDeviceToHost, c->stream));
+        unsigned long long v[2] = {0, 0};
+        R3_CUDA(c, cudaMemcpyAsync(v, c->d_stats + 4, 16, cudaMemcpyDeviceToHost, c->stream));
         R3_CUDA(c, cudaStreamSynchronize(c->stream));
-        c->max_total_invocations = v;
+        c->max_total_invocations = v[0]; c->max_object_invocations = v[1];
     }
     c->max_invocations_valid = true;
+    return R3_OK;
+}
+
+// key generation + stable LSD radix sort of `cap` candidates: the entries of `visible` (count on the device) or, with visible == nullptr,
+// the slots [0, cap) themselves.  keys[*src_out] holds the result.
+static int r3_launch_sort(r3_ctx* c, const uint32_t* visible, const uint32_t* visible_count, uint32_t cap, const float vp_loc[3], unsigned long long* keys[2],
+                          uint32_t** hist, uint64_t* hist_cap, uint32_t* header, int* src_out) {
+    int src = 0;
+    const uint32_t sort_blocks = (cap + SORT_TILE - 1) / SORT_TILE;
+    R3_TRY(r3_reserve_t(c, hist, hist_cap, (uint64_t)sort_blocks * 256 + 1));
+    r3_stage_begin(c, R3_STAGE_SORT);
+    if (cap <= SMALL_SORT_MAX) {
+        // small worlds: key generation + radix sort by one CTA in shared memory, one launch
+        const size_t smem = small_sort_smem(cap);
+        cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_sort_smem(SMALL_SORT_MAX));   // per device
+        small_sort_kernel<<<1, SMALL_SORT_THREADS, smem, c->stream>>>(visible, visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2], keys[0], header,
+                                                                      small_sort_pad(cap), cap);
+        R3_CHECK_LAUNCH(c, "small_sort_kernel");
+    } else if (sort_blocks <= COOP_SORT_MAX_BLOCKS && c->coop_launch_ok) {
+        SortCoopParams sp;
+        sp.visible = visible; sp.visible_count = visible_count; sp.key8 = c->d_sort_key8; sp.loc = c->d_sort_loc;
+        sp.vx = vp_loc[0]; sp.vy = vp_loc[1]; sp.vz = vp_loc[2];
+        sp.keys[0] = keys[0]; sp.keys[1] = keys[1]; sp.hist = *hist; sp.header = header; sp.count_imm = cap;
+        void* args[] = {&sp};
+        R3_CUDA(c, cudaLaunchCooperativeKernel((const void*)radix_sort_coop_kernel, dim3(sort_blocks), dim3(SORT_THREADS), args, 0, c->stream));
+        c->launches++;
+        src = SORT_PASSES & 1;
+    } else {
+        keygen_kernel<<<(cap + 255) / 256, 256, 0, c->stream>>>(visible, visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2], keys[0], header, cap);
+        R3_CHECK_LAUNCH(c, "keygen_kernel");
+        for (int pass = 0; pass < SORT_PASSES; ++pass) {
+            const int shift = KEY_SHIFT0 + 8 * pass;
+            radix_hist_kernel<<<sort_blocks, SORT_THREADS, 0, c->stream>>>(keys[src], header, shift, *hist);
+            R3_CHECK_LAUNCH(c, "radix_hist_kernel");
+            scan_u32_kernel<<<1, 1024, 0, c->stream>>>(*hist, sort_blocks * 256u);
+            R3_CHECK_LAUNCH(c, "scan_u32_kernel");
+            radix_scatter_kernel<<<sort_blocks, SORT_THREADS, 0, c->stream>>>(keys[src], keys[src ^ 1], header, shift, *hist);
+            R3_CHECK_LAUNCH(c, "radix_scatter_kernel");
+            src ^= 1;
+        }
+    }
+    r3_stage_end(c);
+    *src_out = src;
+    return R3_OK;
+}
+
+// Should this camera take its order from the frame-wide sort?  Yes when several cameras batch per frame (known from the previous
+// frame; on a first frame: when shadow-casting lights exist) and the world is small enough that sorting every slot once beats
+// sorting each camera's visible set.  R3_FRAME_SORT=0 / 1 forces the choice (tests run both).
+static bool r3_frame_sort_wanted(r3_ctx* c, r3_camera* cam, const float vp_loc[3]) {
+    // a camera batching a second time or another viewport location starts a new frame epoch (as do r3_set_frame_uniforms and new sort data)
+    if (cam->gsort_epoch_used == c->gsort_epoch || (c->gsort_cameras_this_epoch > 0 && memcmp(c->gsort_loc, vp_loc, 12) != 0)) r3_new_frame_epoch(c);
+    if (c->gsort_cameras_this_epoch == 0) memcpy(c->gsort_loc, vp_loc, 12);
+    cam->gsort_epoch_used = c->gsort_epoch;
+    c->gsort_cameras_this_epoch++;
+    const char* force = getenv("R3_FRAME_SORT");
+    if (force) return force[0] != '0';
+    if (c->n_slots > (1u << 22)) return false;
+    return c->gsort_cameras_last_epoch >= 2 || (c->gsort_cameras_last_epoch == 0 && c->n_dir >= 1);
+}
+static int r3_frame_sort(r3_ctx* c, const float vp_loc[3]) {
+    if (c->gsort_valid && c->gsort_sorted_epoch == c->gsort_epoch) return R3_OK;   // the location is fixed within an epoch
+    const uint32_t n = (uint32_t)(c->sort_flags.size() < c->n_slots ? c->sort_flags.size() : c->n_slots);
+    R3_TRY(r3_reserve_t(c, &c->d_gsort_keys[0], &c->gsort_cap[0], (uint64_t)n + 1));
+    R3_TRY(r3_reserve_t(c, &c->d_gsort_keys[1], &c->gsort_cap[1], (uint64_t)n + 1));
+    if (!c->d_gsort_header) R3_CUDA(c, cudaMalloc((void**)&c->d_gsort_header, 32));
+    int src = 0;
+    if (n) R3_TRY(r3_launch_sort(c, nullptr, nullptr, n, vp_loc, c->d_gsort_keys, &c->d_gsort_hist, &c->gsort_hist_cap, c->d_gsort_header, &src));
+    c->gsort_src = src; c->gsort_n = n; c->gsort_valid = true; c->gsort_sorted_epoch = c->gsort_epoch;
     return R3_OK;
 }
 
@@ -516,48 +646,37 @@ int r3_device_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], ui
         cam->prev_inv_cap = cap;
     }
     const int prev = cam->prev_inv_cur, cur = prev ^ 1;
-    R3_CUDA(c, cudaMemsetAsync(cam->d_prev_inv[cur], 0xFF, (size_t)cap * 4, c->stream));   // get_and_reset_camera (batching.rs:111-113)
+    // get_and_reset_camera (batching.rs:111-113): the WHOLE map starts empty, also the entries beyond this frame's object_count
+    // (a world that shrinks and grows again must not see invocations from two frames ago)
+    R3_CUDA(c, cudaMemsetAsync(cam->d_prev_inv[cur], 0xFF, (size_t)cam->prev_inv_cap * 4, c->stream));
     R3_CUDA(c, cudaMemsetAsync(j.d_header, 0, 32, c->stream));
 
     if (cap) {
         int src = 0;
-        if (cap <= SMALL_SORT_MAX) {
-            // small worlds: key generation + radix sort by one CTA in shared memory, one launch
-            const size_t smem = small_sort_smem(cap);
-            cudaFuncSetAttribute(small_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_sort_smem(SMALL_SORT_MAX));   // per device
-            small_sort_kernel<<<1, SMALL_SORT_THREADS, smem, c->stream>>>(cam->d_visible, cam->d_visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2],
-                                                                          cam->d_sort_keys[0], j.d_header, small_sort_pad(cap));
-            R3_CHECK_LAUNCH(c, "small_sort_kernel");
-        } else if (sort_blocks <= COOP_SORT_MAX_BLOCKS && c->coop_launch_ok) {
-            SortCoopParams sp;
-            sp.visible = cam->d_visible; sp.visible_count = cam->d_visible_count; sp.key8 = c->d_sort_key8; sp.loc = c->d_sort_loc;
-            sp.vx = vp_loc[0]; sp.vy = vp_loc[1]; sp.vz = vp_loc[2];
-            sp.keys[0] = cam->d_sort_keys[0]; sp.keys[1] = cam->d_sort_keys[1]; sp.hist = cam->d_sort_hist; sp.header = j.d_header;
-            void* args[] = {&sp};
-            R3_CUDA(c, cudaLaunchCooperativeKernel((const void*)radix_sort_coop_kernel, dim3(sort_blocks), dim3(SORT_THREADS), args, 0, c->stream));
-            c->launches++;
-            src = SORT_PASSES & 1;
+        const unsigned long long* sorted_keys = nullptr;
+        bool keys_hold_slots = false;
+        if (r3_frame_sort_wanted(c, cam, vp_loc)) {
+            // one sort for the frame's cameras, then this camera's visible objects in that order
+            R3_TRY(r3_frame_sort(c, vp_loc));
+            const uint32_t n = c->gsort_n, tiles = (n + RC_THREADS - 1) / RC_THREADS;
+            R3_TRY(r3_reserve_t(c, &cam->d_sort_hist, &cam->sort_hist_cap, (uint64_t)tiles + 1));
+            rank_count_kernel<<<tiles, RC_THREADS, 0, c->stream>>>(c->d_gsort_keys[c->gsort_src], n, cam->d_words, cap, cam->d_sort_hist);
+            R3_CHECK_LAUNCH(c, "rank_count_kernel");
+            rank_scatter_kernel<<<tiles, RC_THREADS, 0, c->stream>>>(c->d_gsort_keys[c->gsort_src], n, cam->d_words, cap, cam->d_sort_hist, cam->d_sort_keys[0], j.d_header);
+            R3_CHECK_LAUNCH(c, "rank_scatter_kernel");
+            sorted_keys = cam->d_sort_keys[0];
+            keys_hold_slots = true;
+            cam->batching_path = 3;
         } else {
-            keygen_kernel<<<(cap + 255) / 256, 256, 0, c->stream>>>(cam->d_visible, cam->d_visible_count, c->d_sort_key8, c->d_sort_loc, vp_loc[0], vp_loc[1], vp_loc[2],
-                                                                     cam->d_sort_keys[0], j.d_header);
-            R3_CHECK_LAUNCH(c, "keygen_kernel");
-            for (int pass = 0; pass < SORT_PASSES; ++pass) {
-                const int shift = KEY_SHIFT0 + 8 * pass;
-                radix_hist_kernel<<<sort_blocks, SORT_THREADS, 0, c->stream>>>(cam->d_sort_keys[src], j.d_header, shift, cam->d_sort_hist);
-                R3_CHECK_LAUNCH(c, "radix_hist_kernel");
-                scan_u32_kernel<<<1, 1024, 0, c->stream>>>(cam->d_sort_hist, sort_blocks * 256u);
-                R3_CHECK_LAUNCH(c, "scan_u32_kernel");
-                radix_scatter_kernel<<<sort_blocks, SORT_THREADS, 0, c->stream>>>(cam->d_sort_keys[src], cam->d_sort_keys[src ^ 1], j.d_header, shift, cam->d_sort_hist);
-                R3_CHECK_LAUNCH(c, "radix_scatter_kernel");
-                src ^= 1;
-            }
+            R3_TRY(r3_launch_sort(c, cam->d_visible, cam->d_visible_count, cap, vp_loc, cam->d_sort_keys, &cam->d_sort_hist, &cam->sort_hist_cap, j.d_header, &src));
+            sorted_keys = cam->d_sort_keys[src];
         }
         BuildParams p;
-        p.keys = cam->d_sort_keys[src]; p.visible = cam->d_visible; p.objects = c->d_objects;
+        p.keys = sorted_keys; p.visible = cam->d_visible; p.objects = c->d_objects; p.keys_hold_slots = keys_hold_slots ? 1u : 0u;
         p.batches = j.d_batches; p.header = j.d_header;
         p.batch_inv = cam->d_batch_tmp; p.batch_regions = p.batch_inv + nb_cap; p.region_key = p.batch_regions + nb_cap; p.region_start = p.region_key + (size_t)nb_cap * 256;
         p.regions = j.d_regions; p.region_first_inv = j.d_region_first_inv;
-        p.prev_map = cam->d_prev_inv[prev]; p.cur_map = cam->d_prev_inv[cur]; p.map_cap = cap;
+        p.prev_map = cam->d_prev_inv[prev]; p.cur_map = cam->d_prev_inv[cur]; p.map_cap = cam->prev_inv_cap;
         p.n_batches_cap = nb_cap; p.dispatch_limit = (uint64_t)max_dispatch_count * R3_WORKGROUP_SIZE;
         batch_build_kernel<<<nb_cap - 1, 256, 0, c->stream>>>(p);
         R3_CHECK_LAUNCH(c, "batch_build_kernel");

@@ -198,8 +198,8 @@ __device__ __constant__ int c_sample_dy[4] = {-96, -32, 32, 96};
 //   colour passes (opaque.wgsl:203-235, discard variant): albedo alpha of get_pixel_data_inner — coords through uv_transform0, the
 //     material's sampler, times vertex alpha when ALBEDO_BLEND, times material.albedo.a;
 //   depth passes  (depth.wgsl:101-127): the RAW coords0, uvdy = dpdx(coords) like uvdx (sic), always the linear sampler.
-// Same operation order as the oracle (this translation unit is compiled without contraction): the decision is bit-identical up to
-// the last-ulp difference of log2f in the mip fraction.
+// Same operation order as the oracle (this translation unit is compiled without contraction; the mip fraction comes from rule R9's
+// log2_r9, a fixed sequence of IEEE operations): the decision is bit-identical.
 template <int MODE>
 __device__ __noinline__ bool cutout_discards(const RasterParams& p, uint32_t rec, int px, int py) {
     // the record was written earlier in THIS launch (by this thread, or by another lane of the warp before a __syncwarp): plain loads
@@ -709,9 +709,13 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, int mode,
         case MODE_COLOUR | MODE_ALPHA: KERNEL<MODE_COLOUR | MODE_ALPHA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;    \
         default: KERNEL<MODE_COLOUR | MODE_MSAA | MODE_ALPHA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;              \
     }
+    r3_stage_begin(c, depth_only ? R3_STAGE_RASTER_SETUP_DEPTH : R3_STAGE_RASTER_SETUP_COLOUR);
     R3_RASTER_LAUNCH(raster_setup_kernel)
+    r3_stage_end(c);
     R3_CHECK_LAUNCH(c, "raster_setup_kernel");
+    r3_stage_begin(c, R3_STAGE_RASTER_BANDS);
     R3_RASTER_LAUNCH(raster_band_kernel)
+    r3_stage_end(c);
     R3_CHECK_LAUNCH(c, "raster_band_kernel");
 #undef R3_RASTER_LAUNCH
     return R3_OK;

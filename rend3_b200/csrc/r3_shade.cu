@@ -377,7 +377,7 @@ __device__ __noinline__ float4 skybox_at_pixel(const ShadeParams& p, uint32_t px
 // textures keep the register budget (75 instead of 104) of the lean kernel.
 template <bool TEX>
 __device__ __forceinline__ float4 shade_inputs(const ShadeParams& p, const DirPrep* __restrict__ s_dir, const PointPrep* __restrict__ s_point, const FragIn& f,
-                                               const LightMask& mask, const r3_tri_record* tp, uint32_t px, uint32_t py) {
+                                               const LightMask& mask, const r3_tri_record* tp, uint32_t px, uint32_t py, uint32_t* lights_evaluated = nullptr) {
     const float4 vp = f.vp; const float4 vcolor = f.vcolor; const uint32_t material_index = f.material_index;
     float3 vnormal = f.vnormal;
     const r3_material* m = &p.materials[material_index < p.n_materials ? material_index : 0u];
@@ -445,6 +445,7 @@ __device__ __forceinline__ float4 shade_inputs(const ShadeParams& p, const DirPr
             const float3 s = surface_shading(make_float3(L.l[0], L.l[1], L.l[2]), make_float3(L.color[0], L.color[1], L.color[2]), pxl, v, nov, shadow * ao);
             color.x += s.x; color.y += s.y; color.z += s.z;
         }
+        uint32_t n_eval = p.n_dir;
         const uint32_t n_smem_point = min(p.n_point, (uint32_t)MAX_SMEM_POINT);
         for (uint32_t base = 0; base < p.n_point; base += 32u) {                   // opaque.wgsl:524-546, ascending light order
             uint32_t m = base < n_smem_point ? mask.w[base >> 5] : 0xFFFFFFFFu;
@@ -463,8 +464,10 @@ __device__ __forceinline__ float4 shade_inputs(const ShadeParams& p, const DirPr
                 const float3 s = surface_shading(make_float3(delta.x * inv_d, delta.y * inv_d, delta.z * inv_d),
                                                  make_float3(L.color[0] * att, L.color[1] * att, L.color[2] * att), pxl, v, nov, ao);
                 color.x += fmaxf(s.x, 0.0f); color.y += fmaxf(s.y, 0.0f); color.z += fmaxf(s.z, 0.0f);
+                n_eval++;
             }
         }
+        if (lights_evaluated) *lights_evaluated = n_eval;
         return make_float4(fmaxf(p.ambient[0] * albedo.x, color.x), fmaxf(p.ambient[1] * albedo.y, color.y), fmaxf(p.ambient[2] * albedo.z, color.z),
                           fmaxf(p.ambient[3] * albedo.w, albedo.w));
     }
@@ -498,7 +501,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
     const size_t pi = (size_t)py * p.width + px;
     float4 out;
     float depth;
-    uint32_t n_shaded = 0;
+    uint32_t n_shaded = 0, n_lights = 0;   // n_lights: surface_shading evaluations of this fragment (statistics: flops of the pass)
     if (SAMPLES == 1) {
         // tiled light culling: the CTA bounds the view-space positions of its fragments, then 32 lights per warp are tested
         // against that box; fragments only visit the survivors (in ascending light order, so the sums are unchanged).  A light
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
         for (int k = 0; k < MAX_SMEM_POINT / 32; ++k) mask.w[k] = (p.n_point != 0u && !no_cull) ? s_mask[k] : 0xFFFFFFFFu;
         if (!in_target) return;
         out = make_float4(p.clear[0], p.clear[1], p.clear[2], p.clear[3]);
-        if (covered) { out = shade_inputs<TEX>(p, s_dir, s_point, f, mask, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py); n_shaded = 1; }
+        if (covered) { out = shade_inputs<TEX>(p, s_dir, s_point, f, mask, (pass ? p.tris1 : p.tris0) + (rec - 1u), px, py, &n_lights); n_shaded = 1; }
         depth = __uint_as_float((uint32_t)(key >> 32));
     } else {
         if (!in_target) return;
@@ -601,13 +604,13 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Sh
         out = make_float4(((col[0].x + col[1].x) + (col[2].x + col[3].x)) * 0.25f, ((col[0].y + col[1].y) + (col[2].y + col[3].y)) * 0.25f,
                           ((col[0].z + col[1].z) + (col[2].z + col[3].z)) * 0.25f, ((col[0].w + col[1].w) + (col[2].w + col[3].w)) * 0.25f);
     }
-    p.hdr32[pi] = out;
+    if (p.hdr32) p.hdr32[pi] = out;   // pre-rounding shading result: only when the parity target is enabled (r3_set_parity_target)
     const __half2 h01 = __floats2half2_rn(out.x, out.y), h23 = __floats2half2_rn(out.z, out.w);
     p.hdr16[pi] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
     p.depth[pi] = depth;
     const uint32_t active = __activemask();
-    const uint32_t total = __reduce_add_sync(active, n_shaded);
-    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(active) - 1) && total) atomicAdd(&p.stats[2], (unsigned long long)total);
+    const uint32_t total = __reduce_add_sync(active, n_shaded), total_lights = __reduce_add_sync(active, n_lights);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs(active) - 1) && total) { atomicAdd(&p.stats[2], (unsigned long long)total); atomicAdd(&p.stats[6], (unsigned long long)total_lights); }
 }
 
 
@@ -714,7 +717,7 @@ __global__ void __launch_bounds__(256) blend_apply_kernel(const __grid_constant_
 #pragma unroll
             for (int k = 0; k < SAMPLES; ++k) depth = fminf(depth, __uint_as_float(zdst[k]));
         }
-        p.hdr32[pi] = out;
+        if (p.hdr32) p.hdr32[pi] = out;
         const __half2 h01 = __floats2half2_rn(out.x, out.y), h23 = __floats2half2_rn(out.z, out.w);
         p.hdr16[pi] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
         p.depth[pi] = depth;
@@ -730,7 +733,7 @@ __global__ void __launch_bounds__(256) skybox_kernel(const __grid_constant__ Sha
     const size_t pi = (size_t)py * p.width + px;
     if ((uint32_t)(p.vis[pi] >> 32) != 0u) return;
     const float4 out = skybox_at_pixel(p, px, py);
-    p.hdr32[pi] = out;
+    if (p.hdr32) p.hdr32[pi] = out;
     const __half2 h01 = __floats2half2_rn(out.x, out.y), h23 = __floats2half2_rn(out.z, out.w);
     p.hdr16[pi] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
 }
@@ -826,7 +829,7 @@ R3_EXPORT int r3_set_render_target(r3_ctx* c, uint32_t w, uint32_t h, uint32_t s
         c->d_vis = nullptr; c->d_hdr32 = nullptr; c->d_hdr16 = nullptr; c->d_depth = nullptr; c->d_ldr = nullptr; c->d_hiz_ptrs = nullptr; c->d_hiz_dims = nullptr;
         const size_t n = (size_t)w * h;
         R3_CUDA(c, cudaMalloc((void**)&c->d_vis, n * 8 * samples));
-        R3_CUDA(c, cudaMalloc((void**)&c->d_hdr32, n * 16));
+        if (c->parity_target) R3_CUDA(c, cudaMalloc((void**)&c->d_hdr32, n * 16));
         R3_CUDA(c, cudaMalloc((void**)&c->d_hdr16, n * 8));
         R3_CUDA(c, cudaMalloc((void**)&c->d_depth, n * 4));
         R3_CUDA(c, cudaMalloc((void**)&c->d_ldr, n * 4));
@@ -854,6 +857,17 @@ R3_EXPORT int r3_set_render_target(r3_ctx* c, uint32_t w, uint32_t h, uint32_t s
     c->row_begin = 0; c->row_end = h;
     return R3_OK;
 }
+R3_EXPORT int r3_set_parity_target(r3_ctx* c, int enabled) {
+    if (!c) return R3_E_INVALID;
+    cudaSetDevice(c->device);
+    c->parity_target = enabled != 0;
+    if (!c->parity_target && c->d_hdr32) { R3_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_hdr32); c->d_hdr32 = nullptr; }
+    if (c->parity_target && !c->d_hdr32 && c->d_vis) {
+        R3_CUDA(c, cudaMalloc((void**)&c->d_hdr32, (size_t)c->width * c->height * 16));
+        R3_CUDA(c, cudaMemsetAsync(c->d_hdr32, 0, (size_t)c->width * c->height * 16, c->stream));
+    }
+    return R3_OK;
+}
 R3_EXPORT int r3_set_scissor_rows(r3_ctx* c, uint32_t a, uint32_t b) {
     if (!c || a > b || b > c->height) return r3_fail(c, R3_E_INVALID, "set_scissor_rows: bad range");
     c->row_begin = a; c->row_end = b;
@@ -870,6 +884,7 @@ R3_EXPORT int r3_forward_begin(r3_ctx* c) {
     cudaSetDevice(c->device);
     R3_CUDA(c, cudaMemsetAsync(c->d_vis, 0, (size_t)c->width * c->height * 8 * c->samples, c->stream));
     R3_CUDA(c, cudaMemsetAsync(c->d_stats, 0, 32, c->stream));
+    R3_CUDA(c, cudaMemsetAsync(c->d_stats + 6, 0, 8, c->stream));
     c->n_tris[0] = c->n_tris[1] = c->n_tris[2] = 0;
     return R3_OK;
 }
@@ -926,8 +941,10 @@ R3_EXPORT int r3_forward_resolve(r3_ctx* c) {
     if (rows) {
         const dim3 grid((c->width + 31) / 32, (rows + 7) / 8);
         const bool tex = c->n_textures != 0;
+        r3_stage_begin(c, R3_STAGE_RESOLVE);
         if (c->samples == 1) { if (tex) resolve_kernel<1, true><<<grid, 256, 0, c->stream>>>(p); else resolve_kernel<1, false><<<grid, 256, 0, c->stream>>>(p); }
         else { if (tex) resolve_kernel<4, true><<<grid, 256, 0, c->stream>>>(p); else resolve_kernel<4, false><<<grid, 256, 0, c->stream>>>(p); }
+        r3_stage_end(c);
         R3_CHECK_LAUNCH(c, "resolve_kernel");
         if (c->has_skybox && c->samples == 1) {
             skybox_kernel<<<grid, 256, 0, c->stream>>>(p);
@@ -970,7 +987,11 @@ static int copy_out(r3_ctx* c, const void* src, void* out, uint64_t cap, uint64_
     R3_CUDA(c, cudaStreamSynchronize(c->stream));
     return R3_OK;
 }
-R3_EXPORT int r3_readback_hdr_f32(r3_ctx* c, float* out, uint64_t cap) { return c ? copy_out(c, c->d_hdr32, out, cap, (uint64_t)c->width * c->height * 4, 4) : R3_E_INVALID; }
+R3_EXPORT int r3_readback_hdr_f32(r3_ctx* c, float* out, uint64_t cap) {
+    if (!c) return R3_E_INVALID;
+    if (!c->parity_target) return r3_fail(c, R3_E_STATE, "readback_hdr_f32: the rgba32f parity target is off (r3_set_parity_target)");
+    return copy_out(c, c->d_hdr32, out, cap, (uint64_t)c->width * c->height * 4, 4);
+}
 R3_EXPORT int r3_readback_hdr_f16(r3_ctx* c, uint16_t* out, uint64_t cap) { return c ? copy_out(c, c->d_hdr16, out, cap, (uint64_t)c->width * c->height * 4, 2) : R3_E_INVALID; }
 R3_EXPORT int r3_readback_depth(r3_ctx* c, float* out, uint64_t cap) { return c ? copy_out(c, c->d_depth, out, cap, (uint64_t)c->width * c->height, 4) : R3_E_INVALID; }
 R3_EXPORT int r3_readback_ldr(r3_ctx* c, uint8_t* out, uint64_t cap) { return c ? copy_out(c, c->d_ldr, out, cap, (uint64_t)c->width * c->height * 4, 1) : R3_E_INVALID; }
@@ -981,6 +1002,13 @@ R3_EXPORT int r3_readback_hiz(r3_ctx* c, uint32_t mip, float* out, uint64_t cap,
     if (h) *h = c->hiz_h[mip];
     if (!out) return R3_OK;
     return copy_out(c, c->d_hiz[mip], out, cap, (uint64_t)c->hiz_w[mip] * c->hiz_h[mip], 4);
+}
+R3_EXPORT int r3_forward_light_evaluations(r3_ctx* c, uint64_t* n) {
+    if (!c || !n) return R3_E_INVALID;
+    cudaSetDevice(c->device);
+    R3_CUDA(c, cudaMemcpyAsync(n, c->d_stats + 6, 8, cudaMemcpyDeviceToHost, c->stream));
+    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    return R3_OK;
 }
 R3_EXPORT int r3_forward_stats(r3_ctx* c, uint64_t stats[4]) {
     if (!c || !stats) return R3_E_INVALID;

@@ -46,18 +46,38 @@ __device__ __noinline__ float4 sample_level(const TexTable& p, const r3_texture_
                        (t00.z * gx + t10.z * fx) * gy + (t01.z * gx + t11.z * fx) * fy, (t00.w * gx + t10.w * fx) * gy + (t01.w * gx + t11.w * fx) * fy);
 }
 struct TexCoords { float u, v, dudx, dvdx, dudy, dvdy; };
+// log2 of the footprint, rule R9: WGSL leaves the LOD arithmetic of textureSampleGrad to the driver; the rule fixes it as a sequence of
+// IEEE f32 operations (no MUFU.LG2, no libm) so that the level picked at a footprint of 2^(k+0.5) texels is one bit pattern:
+// x = 2^e * m, m in [sqrt(1/2), sqrt(2)), s = (m - 1) / (m + 1), log2 x = e + (2 / ln 2) * s * (1 + s^2/3 + s^4/5 + s^6/7 + s^8/9).
+__device__ __forceinline__ float log2_r9(float x) {
+    if (!(x > 0.0f)) return x == 0.0f ? -__int_as_float(0x7F800000) : __int_as_float(0x7FC00000);
+    const uint32_t b = __float_as_uint(x);
+    if (b >= 0x7F800000u) return __int_as_float(0x7F800000);
+    int e = (int)(b >> 23) - 127;
+    if (e == -127) return -127.0f;
+    float m = __uint_as_float((b & 0x7FFFFFu) | 0x3F800000u);
+    if (m > 1.41421356f) { m = mul_rn(m, 0.5f); e += 1; }
+    const float s = div_rn(sub_rn(m, 1.0f), add_rn(m, 1.0f)), s2 = mul_rn(s, s);
+    float q = 0.11111111f;
+    q = add_rn(mul_rn(q, s2), 0.14285715f);
+    q = add_rn(mul_rn(q, s2), 0.2f);
+    q = add_rn(mul_rn(q, s2), 0.33333334f);
+    q = add_rn(mul_rn(q, s2), 1.0f);
+    return add_rn((float)e, mul_rn(mul_rn(s, q), 2.88539008f));
+}
 __device__ __noinline__ float4 sample_grad_desc(const TexTable& p, const r3_texture_desc& d, bool nearest, const TexCoords& c) {
+    // level SELECTION in the oracle's operation order, never contracted (this header is also compiled into the FMA-enabled shading unit)
     const float w0 = (float)d.width, h0 = (float)d.height;
-    const float ax = c.dudx * w0, ay = c.dvdx * h0, bx = c.dudy * w0, by = c.dvdy * h0;
-    const float rho = fmaxf(sqrtf(ax * ax + ay * ay), sqrtf(bx * bx + by * by));
-    const float lambda = log2f(rho);
+    const float ax = mul_rn(c.dudx, w0), ay = mul_rn(c.dvdx, h0), bx = mul_rn(c.dudy, w0), by = mul_rn(c.dvdy, h0);
+    const float rho = fmaxf(__fsqrt_rn(add_rn(mul_rn(ax, ax), mul_rn(ay, ay))), __fsqrt_rn(add_rn(mul_rn(bx, bx), mul_rn(by, by))));
+    const float lambda = log2_r9(rho);
     const uint32_t last = d.mip_count - 1u;
     if (!(lambda > 0.0f)) return sample_level(p, d, 0u, nearest, c.u, c.v);
     if (nearest) {
-        const float lv = floorf(lambda + 0.5f);
+        const float lv = floorf(add_rn(lambda, 0.5f));
         return sample_level(p, d, lv >= (float)last ? last : (uint32_t)lv, true, c.u, c.v);
     }
-    const float l = fminf(lambda, (float)last), lo = floorf(l), fr = l - lo;
+    const float l = fminf(lambda, (float)last), lo = floorf(l), fr = sub_rn(l, lo);
     const uint32_t level = (uint32_t)lo;
     const float4 a = sample_level(p, d, level, false, c.u, c.v);
     if (level >= last || fr == 0.0f) return a;

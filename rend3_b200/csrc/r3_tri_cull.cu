@@ -87,21 +87,24 @@ __device__ bool execute_culling(const TriCullParams& p, const float* __restrict_
     const bool positive = p.cam.flags & R3_PCU_POSITIVE_AREA_VISIBLE;
     if (positive && det <= 0.0f) return false;
     if (!positive && det >= 0.0f) return false;
-    const float n0x = div_rn(p0.x, p0.w), n0y = div_rn(p0.y, p0.w), n0z = div_rn(p0.z, p0.w);
-    const float n1x = div_rn(p1.x, p1.w), n1y = div_rn(p1.y, p1.w), n1z = div_rn(p1.z, p1.w);
-    const float n2x = div_rn(p2.x, p2.w), n2y = div_rn(p2.y, p2.w), n2z = div_rn(p2.z, p2.w);
+    float n0x = p0.x, n0y = p0.y, n0z = p0.z, n1x = p1.x, n1y = p1.y, n1z = p1.z, n2x = p2.x, n2y = p2.y, n2z = p2.z;
+    if (!(p0.w == 1.0f && p1.w == 1.0f && p2.w == 1.0f)) {   // x / 1.0f == x: orthographic (shadow) cameras skip the perspective divide
+        n0x = div_rn(p0.x, p0.w); n0y = div_rn(p0.y, p0.w); n0z = div_rn(p0.z, p0.w);
+        n1x = div_rn(p1.x, p1.w); n1y = div_rn(p1.y, p1.w); n1z = div_rn(p1.z, p1.w);
+        n2x = div_rn(p2.x, p2.w); n2y = div_rn(p2.y, p2.w); n2z = div_rn(p2.z, p2.w);
+    }
     const float minx = fminf(n0x, fminf(n1x, n2x)), miny = fminf(n0y, fminf(n1y, n2y));
     const float maxx = fmaxf(n0x, fmaxf(n1x, n2x)), maxy = fmaxf(n0y, fmaxf(n1y, n2y));
-    const float hrx = div_rn(p.cam.resolution[0], 2.0f), hry = div_rn(p.cam.resolution[1], 2.0f);
+    const float hrx = mul_rn(p.cam.resolution[0], 0.5f), hry = mul_rn(p.cam.resolution[1], 0.5f);   // x / 2 == x * 0.5 for every float
     const float minsx = mul_rn(add_rn(minx, 1.0f), hrx), minsy = mul_rn(add_rn(miny, 1.0f), hry);
     const float maxsx = mul_rn(add_rn(maxx, 1.0f), hrx), maxsy = mul_rn(add_rn(maxy, 1.0f), hry);
     if (!(p.cam.flags & R3_PCU_MULTISAMPLED)) {
         if (rintf(minsx) == rintf(maxsx) || rintf(minsy) == rintf(maxsy)) return false;   // WGSL round(): ties to even
     }
     if (p.cam.shadow_index != R3_CAMERA_VIEWPORT) return true;
-    const float mintx = div_rn(add_rn(minx, 1.0f), 2.0f), minty = sub_rn(1.0f, div_rn(add_rn(miny, 1.0f), 2.0f));
-    const float maxtx = div_rn(add_rn(maxx, 1.0f), 2.0f), maxty = sub_rn(1.0f, div_rn(add_rn(maxy, 1.0f), 2.0f));
-    const float u = div_rn(add_rn(maxtx, mintx), 2.0f), v = div_rn(add_rn(maxty, minty), 2.0f);
+    const float mintx = mul_rn(add_rn(minx, 1.0f), 0.5f), minty = sub_rn(1.0f, mul_rn(add_rn(miny, 1.0f), 0.5f));
+    const float maxtx = mul_rn(add_rn(maxx, 1.0f), 0.5f), maxty = sub_rn(1.0f, mul_rn(add_rn(maxy, 1.0f), 0.5f));
+    const float u = mul_rn(add_rn(maxtx, mintx), 0.5f), v = mul_rn(add_rn(maxty, minty), 0.5f);
     const float ex = sub_rn(maxsx, minsx), ey = sub_rn(maxsy, minsy);
     const uint32_t mip = ceil_log2_f32(fmaxf(fmaxf(ex, ey), 1.0f));
     const float depth = fmaxf(fmaxf(n0z, n1z), n2z);
@@ -145,64 +148,75 @@ __device__ __forceinline__ WgRec load_wg(const TriCullParams& p, uint32_t wg) {
 }
 
 // ---- test: cull.wgsl::cs_main up to the visibility decision
-__global__ void __launch_bounds__(TC_THREADS) triangle_test_kernel(const __grid_constant__ TriCullParams p) {
-    __shared__ uint32_t s_pred[8], s_resid[8];
-    const uint32_t wg = blockIdx.x;
-    if (wg >= p.header[3] / TC_THREADS) return;
+// Persistent grid (R3_SM_COUNT x 8 CTAs of 8 warps = every warp slot of the GPU), each CTA striding over the reference's workgroups;
+// warp w of the CTA owns invocations [32 w, 32 w + 32) of the workgroup = one visibility word.  The warps never meet: no shared
+// memory, no barrier (the round-2 profile of the barrier version, profiles/README.md: 62-70% issue-active with `barrier` the largest
+// stall reason, 7 of 8 warps of a 12-triangle object idling through the block reduction, 2.08 M warps launched for 0.46 M with work).
+//   * padding words (past the object's last triangle) cost one predicated store pair and the warp moves on;
+//   * survivor counts go to the superblock counters with one 64-bit RED per word that has survivors (most have none);
+//   * an orthographic camera (every shadow camera) produces w == 1.0f exactly, where x / w == x bit for bit: the nine IEEE divisions of
+//     the perspective divide — a third of the instructions of the test — are skipped; x / 2.0f is evaluated as x * 0.5f (identical
+//     for every float, subnormals included); the mesh-buffer bound is checked once per triple instead of once per word.
+__device__ __forceinline__ float3 load_position(const TriCullParams& p, uint32_t pos_off, uint32_t vid) {
+    const uint64_t f = (uint64_t)pos_off + (uint64_t)vid * 3u;                                 // extract_attribute_vec3_f32
+    if (f + 2u < p.mesh_words) return make_float3(__uint_as_float(__ldg(&p.mesh[f])), __uint_as_float(__ldg(&p.mesh[f + 1])), __uint_as_float(__ldg(&p.mesh[f + 2])));
+    return make_float3(__uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));   // robust access at the buffer end
+}
+__global__ void __launch_bounds__(TC_THREADS, 6) triangle_test_kernel(const __grid_constant__ TriCullParams p) {
+    const uint32_t n_wg = __ldg(&p.header[3]) / TC_THREADS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool shadow = p.cam.shadow_index != R3_CAMERA_VIEWPORT;
-    const WgRec rec = load_wg(p, wg);
-    const uint32_t global_invocation = wg * TC_THREADS + threadIdx.x;
-    const bool real = threadIdx.x < rec.n_real;
-    const uint32_t object_invocation = rec.object_invocation + threadIdx.x;
-    const bool atomic_capable = rec.flags & WG_ATOMIC;
-    const uint32_t local_object = rec.flags >> 8;
-
-    bool passes = false, resid = false;
-    uint32_t i0 = 0, i1 = 0, i2 = 0;
-    if (real) {
-        const uint64_t ib = (uint64_t)rec.first_index + (uint64_t)object_invocation * 3u;  // vertex_fetch (cull.wgsl:9-32)
-        i0 = mesh_word(p, ib); i1 = mesh_word(p, ib + 1); i2 = mesh_word(p, ib + 2);
-        float3 v[3];
-        const uint32_t ids[3] = {i0, i1, i2};
+    for (uint32_t wg = blockIdx.x; wg < n_wg; wg += gridDim.x) {
+        const WgRec rec = load_wg(p, wg);
+        const uint32_t word = wg * (TC_THREADS / 32) + warp;                                   // global_invocation >> 5
+        const uint32_t local = warp * 32u + lane;                                              // invocation inside the workgroup
+        const bool atomic_capable = rec.flags & WG_ATOMIC;
+        const bool real = local < rec.n_real;
+        bool passes = false, resid = false;
+        uint32_t i0 = 0, i1 = 0, i2 = 0;
+        if (warp * 32u < rec.n_real) {
+            if (real) {
+                const uint32_t object_invocation = rec.object_invocation + local;
+                const uint64_t ib = (uint64_t)rec.first_index + (uint64_t)object_invocation * 3u;  // vertex_fetch (cull.wgsl:9-32)
+                if (ib + 2u < p.mesh_words) { i0 = __ldg(&p.mesh[ib]); i1 = __ldg(&p.mesh[ib + 1]); i2 = __ldg(&p.mesh[ib + 2]); }
+                else { i0 = mesh_word(p, ib); i1 = mesh_word(p, ib + 1); i2 = mesh_word(p, ib + 2); }
+                const float3 v0 = load_position(p, rec.pos_off, i0), v1 = load_position(p, rec.pos_off, i1), v2 = load_position(p, rec.pos_off, i2);
+                float mvp[16];
+                const float4* m4 = reinterpret_cast<const float4*>(p.matrices[rec.object_id].model_view_proj);   // 64-byte aligned: four 16-byte loads
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const uint64_t f = (uint64_t)rec.pos_off + (uint64_t)ids[k] * 3u;              // extract_attribute_vec3_f32
-            v[k] = make_float3(__uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));
-        }
-        passes = execute_culling(p, p.matrices[rec.object_id].model_view_proj, v[0], v[1], v[2]);
-        if (passes && !shadow && atomic_capable) {
-            bool prev = false;                                                            // get_previous_culling_result (cull.wgsl:152-160)
-            if (rec.prev_invocation != R3_NO_PREVIOUS) {
-                const uint64_t pgi = (uint64_t)object_invocation + rec.prev_invocation;
-                const uint32_t mask = (pgi >> 5) < p.res_in_words ? p.res_in[pgi >> 5] : 0u;
-                prev = (mask >> (pgi & 31)) & 1u;
+                for (int k = 0; k < 4; ++k) { const float4 c4 = __ldg(&m4[k]); mvp[4 * k] = c4.x; mvp[4 * k + 1] = c4.y; mvp[4 * k + 2] = c4.z; mvp[4 * k + 3] = c4.w; }
+                passes = execute_culling(p, mvp, v0, v1, v2);
+                if (passes && !shadow && atomic_capable) {
+                    bool prev = false;                                                         // get_previous_culling_result (cull.wgsl:152-160)
+                    if (rec.prev_invocation != R3_NO_PREVIOUS) {
+                        const uint64_t pgi = (uint64_t)object_invocation + rec.prev_invocation;
+                        const uint32_t mask = (pgi >> 5) < p.res_in_words ? p.res_in[pgi >> 5] : 0u;
+                        prev = (mask >> (pgi & 31)) & 1u;
+                    }
+                    resid = !prev;
+                }
             }
-            resid = !prev;
+            const uint32_t word_pred = __ballot_sync(0xFFFFFFFFu, passes);
+            const uint32_t word_resid = __ballot_sync(0xFFFFFFFFu, resid);
+            if (lane == 0) {
+                p.res_out[word] = word_pred;                                                   // save_culling_results (cull.wgsl:229-241)
+                p.resid_bits[word] = word_resid;
+                // every visibility word is counted (atomic or not) so that the prefix over words is one consistent global scan
+                const unsigned long long t = ((unsigned long long)__popc(word_pred) << 32) | __popc(word_resid);
+                if (t) atomicAdd(&p.sb_counts[word / SB_WORDS], t);
+            }
+        } else if (lane == 0) {
+            p.res_out[word] = 0u;
+            p.resid_bits[word] = 0u;
         }
-    }
-    const uint32_t word_pred = __ballot_sync(0xFFFFFFFFu, passes);
-    const uint32_t word_resid = __ballot_sync(0xFFFFFFFFu, resid);
-    if (lane == 0) {
-        p.res_out[global_invocation >> 5] = word_pred;                                     // save_culling_results (cull.wgsl:229-241)
-        p.resid_bits[global_invocation >> 5] = word_resid;
-    }
-    if (!atomic_capable) {
-        // non-atomic (blend) objects keep their slot: survivors in place, everything else INVALID (cull.wgsl:374-380,343-347)
-        const uint64_t o = (uint64_t)global_invocation * 3u;
-        const uint32_t hi = local_object << 24;
-        p.idx_resid[o] = passes ? (hi | (i0 & 0xFFFFFFu)) : R3_INVALID_VERTEX;
-        p.idx_resid[o + 1] = passes ? (hi | (i1 & 0xFFFFFFu)) : R3_INVALID_VERTEX;
-        p.idx_resid[o + 2] = passes ? (hi | (i2 & 0xFFFFFFu)) : R3_INVALID_VERTEX;
-    }
-    // every visibility word is counted (atomic or not) so that the prefix over words is one consistent global scan
-    if (lane == 0) { s_pred[warp] = __popc(word_pred); s_resid[warp] = __popc(word_resid); }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long t = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += ((unsigned long long)s_pred[w] << 32) | s_resid[w];
-        if (t) atomicAdd(&p.sb_counts[wg / (SB_WORDS / 8)], t);
+        if (!atomic_capable) {
+            // non-atomic (blend) objects keep their slot: survivors in place, everything else INVALID (cull.wgsl:374-380,343-347)
+            const uint64_t o = ((uint64_t)word * 32u + lane) * 3u;
+            const uint32_t hi = (rec.flags >> 8) << 24;
+            p.idx_resid[o] = passes ? (hi | (i0 & 0xFFFFFFu)) : R3_INVALID_VERTEX;
+            p.idx_resid[o + 1] = passes ? (hi | (i1 & 0xFFFFFFu)) : R3_INVALID_VERTEX;
+            p.idx_resid[o + 2] = passes ? (hi | (i2 & 0xFFFFFFu)) : R3_INVALID_VERTEX;
+        }
     }
 }
 
@@ -386,13 +400,22 @@ int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam) {
     const bool viewport = cam->header.shadow_index == R3_CAMERA_VIEWPORT;
     p.hiz = c->d_hiz_ptrs; p.hiz_dims = c->d_hiz_dims; p.hiz_mips = viewport ? (uint32_t)c->d_hiz.size() : 0u;
 
-    triangle_test_kernel<<<n_wg, TC_THREADS, 0, c->stream>>>(p);
+    static int test_ctas_per_sm = 0;   // resident CTAs per SM of the persistent test kernel (a property of the binary)
+    if (!test_ctas_per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&test_ctas_per_sm, triangle_test_kernel, TC_THREADS, 0) != cudaSuccess || test_ctas_per_sm < 1) test_ctas_per_sm = 4;
+    }
+    const uint32_t test_grid = (uint32_t)R3_SM_COUNT * (uint32_t)test_ctas_per_sm;
+    r3_stage_begin(c, R3_STAGE_TRIANGLE_TEST);
+    triangle_test_kernel<<<n_wg < test_grid ? n_wg : test_grid, TC_THREADS, 0, c->stream>>>(p);
+    r3_stage_end(c);
     R3_CHECK_LAUNCH(c, "triangle_test_kernel");
     superblock_scan_kernel<<<1, 1024, 0, c->stream>>>(sb_counts, j.d_header);
     R3_CHECK_LAUNCH(c, "superblock_scan_kernel");
     region_finish_kernel<<<j.n_regions, 256, 0, c->stream>>>(p);
     R3_CHECK_LAUNCH(c, "region_finish_kernel");
+    r3_stage_begin(c, R3_STAGE_TRIANGLE_COMPACT);
     triangle_compact_kernel<<<n_sb, SB_WORDS, 0, c->stream>>>(p);
+    r3_stage_end(c);
     R3_CHECK_LAUNCH(c, "triangle_compact_kernel");
     return R3_OK;
 }

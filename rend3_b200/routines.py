@@ -123,10 +123,14 @@ class BaseRenderGraph:
 
     def add_to_graph(self, ev: EvalOutput, resolution: Tuple[int, int], samples: int = 1,
                      settings: BaseRenderGraphSettings = BaseRenderGraphSettings(), srgb_target: bool = True,
-                     upload: bool = True, scissor_rows: Optional[Tuple[int, int]] = None, shadow_filter=None, after_shadows=None):
+                     upload: bool = True, scissor_rows: Optional[Tuple[int, int]] = None, shadow_filter=None, after_shadows=None,
+                     after_target=None, tonemap: bool = True):
         """One frame in the node order of base.rs:135-185.  `scissor_rows` restricts rasterisation and shading
         to a band of pixel rows (the screen-tile split of the multi-GPU forward pass); `shadow_filter(i)` selects the shadow
-        maps this rank renders and `after_shadows()` runs once they are in the atlas (the ranks merge their maps there)."""
+        maps this rank renders — it then clears only their rects, the others arrive from their owners — and `after_shadows()`
+        runs once they are in the atlas (the ranks exchange their maps there); `after_target()` runs once the render target and
+        the atlas exist (peer mappings are created there); `tonemap=False` leaves the blit to the caller (the assembling rank
+        runs it after the other ranks' rows have arrived)."""
         b, culler = self.backend, self.gpu_culler
         if upload:
             self.upload_world(ev)
@@ -135,7 +139,14 @@ class BaseRenderGraph:
             self._resolution = (resolution, samples, tuple(settings.clear_color))
         if scissor_rows is not None:
             b.set_scissor_rows(scissor_rows[0], scissor_rows[1])
-        b.clear_shadow_atlas()                                                    # base.rs:139
+        if after_target is not None:
+            after_target()
+        if shadow_filter is None:
+            b.clear_shadow_atlas()                                                # base.rs:139
+        else:
+            for i, s in enumerate(ev.shadows):
+                if shadow_filter(i):
+                    b.clear_shadow_rect(s.offset[0], s.offset[1], s.size, s.size)
         b.set_frame_uniforms(frame_uniforms(ev.camera, settings.ambient_color, resolution))  # :142
         # skinning (:145) — no animated meshes on this path
         mine = [(i, s) for i, s in enumerate(ev.shadows) if shadow_filter is None or shadow_filter(i)]
@@ -156,4 +167,5 @@ class BaseRenderGraph:
         b.forward_resolve()                                                       # fs_main of the opaque + cutout fragments
         # skybox (:175) is outside this path
         b.forward_blend()                                                         # :181 transparent objects, back to front
-        b.tonemap(srgb_target)                                                    # :184
+        if tonemap:
+            b.tonemap(srgb_target)                                                # :184

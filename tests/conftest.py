@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("R3_PARITY_TARGET", "1")   # tests compare the f32 shading result; production keeps that target off
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

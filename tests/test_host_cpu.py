@@ -406,3 +406,46 @@ def test_two_rank_object_sharding_over_gloo():
                             "--master-port", "29541", script], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert r.stdout.count("ok") == 2
+
+
+def test_rule_r9_log2_is_exact_at_powers_of_two_and_close_elsewhere():
+    """Rule R9's log2 (the mip-level selection of textureSampleGrad): a fixed sequence of IEEE f32 operations.  Exact at powers of two
+    (so integer footprints select exact levels), within 4e-7 of the real log2 elsewhere (inside Vulkan's 2^-21 bound on [0.5, 2])."""
+    import ctypes
+
+    import oracle
+    lib = ctypes.CDLL(oracle.build())
+    lib.r3o_log2_r9.restype = ctypes.c_float
+    lib.r3o_log2_r9.argtypes = [ctypes.c_float]
+    for e in range(-20, 40):
+        assert lib.r3o_log2_r9(float(2.0 ** e)) == float(e)
+    rng = np.random.default_rng(5)
+    xs = np.exp(rng.uniform(np.log(1e-3), np.log(1e6), 20000)).astype(np.float32)
+    got = np.array([lib.r3o_log2_r9(float(x)) for x in xs], dtype=np.float64)
+    want = np.log2(xs.astype(np.float64))
+    assert np.abs(got - want).max() < 4e-7 + 1.2e-7 * np.abs(want).max()
+    assert lib.r3o_log2_r9(0.0) == -np.inf and np.isnan(lib.r3o_log2_r9(-1.0)) and lib.r3o_log2_r9(float("inf")) == np.inf
+
+
+def test_oracle_sort_orders_nan_distances_last_like_ordered_float():
+    """ShaderJobSortingKey compares OrderedFloat distances (batching.rs:37): NaN is greater than every number and equal to itself.
+    Objects with NaN locations must land at the end of their (material, reason) group, in handle order."""
+    from rend3_b200.routines import per_camera_header
+    from rend3_b200.scenes import cloud_camera, object_cloud_records
+
+    n = 600
+    rec = object_cloud_records(n, seed=21, extent=50.0, disabled_fraction=0.0)
+    rec["sphere_radius"][:] = 1.0e6          # everything visible
+    loc = rec["sphere_center"].copy()
+    bad = np.array([5, 17, 300, 599])
+    loc[bad] = np.nan
+    b = load_oracle_backend()
+    b.set_objects(rec)
+    b.set_object_sort_info(np.zeros(n, dtype=np.uint64), np.full(n, 3, dtype=np.uint8), loc)
+    b.object_uniform_upload(CAMERA_VIEWPORT, per_camera_header(cloud_camera(), CAMERA_VIEWPORT, (640, 480), 1, n))
+    b.batch_objects(CAMERA_VIEWPORT, np.zeros(3, dtype=np.float32))
+    batches, _ = b.readback_batches(CAMERA_VIEWPORT)
+    order = np.concatenate([bt["object_culling_information"]["object_id"][: int(bt["total_objects"])] for bt in batches])
+    assert len(order) == n and list(order[-4:]) == list(bad)
+    d2 = ((loc[order[:-4]].astype(np.float32)) ** 2).sum(axis=1)
+    assert np.all(np.diff(d2) >= 0)
