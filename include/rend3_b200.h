@@ -18,8 +18,16 @@
  *     device memory.  Buffers are the std430 bytes rend3's managers already produce
  *     (r3_layouts.h), so the Rust side uploads exactly what it uploads to wgpu today.
  *   - one context per GPU; calls on a context must be externally serialised (this is the
- *     `data_core` mutex of the reference, rend3/src/graph/graph.rs:265).  Work is
- *     stream-ordered and asynchronous; only r3_sync() and r3_readback_*() block.
+ *     `data_core` mutex of the reference, rend3/src/graph/graph.rs:265).  The per-frame entry points
+ *     (r3_object_uniform_upload, r3_batch_objects, r3_cull, r3_shadow_pass, r3_forward_*, r3_hiz_build, r3_tonemap,
+ *     r3_skin's kernel, r3_exchange_merge, r3_peer_*) only enqueue work on the context's stream and return.
+ *     What BLOCKS the calling thread until the stream has drained: r3_sync, every r3_readback_*, r3_visible_count,
+ *     r3_batch_counts / r3_batching_info / r3_forward_stats / r3_stage_times (small device-to-host reads), and the
+ *     uploads that borrow a HOST pointer — r3_set_objects, r3_update_objects, r3_set_object_sort_info,
+ *     r3_set_mesh_buffer, r3_set_materials, r3_set_textures, r3_set_skybox, r3_set_*_lights, r3_skin's joint upload —
+ *     because the pointer is only valid for the duration of the call (they are the counterpart of queue.write_buffer,
+ *     which copies before it returns).  r3_set_objects_device borrows device memory and does not block.  A buffer that
+ *     has to grow (first frame, larger world, new resolution) is reallocated with a stream synchronisation as well.
  *   - `camera` is R3_CAMERA_VIEWPORT or a shadow index 0..R3_MAX_SHADOWS-1
  *     (CameraSpecifier, rend3-routine/src/common/camera.rs).
  */
@@ -60,6 +68,17 @@ int r3_sync(r3_ctx* ctx);
 int r3_get_stream(r3_ctx* ctx, void** stream);
 /* number of kernel launches issued by this context since creation (bench.py gpu_launches) */
 int r3_launch_count(r3_ctx* ctx, uint64_t* launches);
+
+/* Frame submission as ONE CUDA graph launch (the reference submits once per frame, rend3/src/graph/graph.rs:510).  Optional: bracket
+ * the per-frame calls (r3_clear_shadow_atlas ... r3_tonemap) with r3_frame_begin / r3_frame_end.  The stream work in between is recorded
+ * by stream capture instead of being launched; r3_frame_end turns it into a graph — the instantiated graph of the previous frame of the
+ * same parity is updated in place (cudaGraphExecUpdate: same kernels, this frame's arguments and ping-pong pointers), so steady-state
+ * frames pay no instantiation — and launches it.  A call that has to wait for the stream inside the bracket (a buffer that must grow, a
+ * host-side batch_objects, a readback) submits what was recorded so far, waits, and the rest of the frame runs eagerly; results are the
+ * same either way.  stats: [0] frames ended, [1] frames submitted as a graph, [2] early flushes, [3] graph (re)instantiations. */
+int r3_frame_begin(r3_ctx* ctx);
+int r3_frame_end(r3_ctx* ctx);
+int r3_frame_graph_stats(r3_ctx* ctx, uint64_t stats[4]);
 
 /* optional per-stage device timing (off by default): when enabled, CUDA event pairs are recorded around the kernels below and
  * r3_stage_times returns, per stage, the summed duration in ms and the number of launches since the last call (it synchronises).

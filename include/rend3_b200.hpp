@@ -4,6 +4,7 @@
 // meaning and call order follow the reference:
 //
 //   r3::GpuCuller::object_uniform_upload      rend3-routine/src/culling/culler.rs:427-529
+//   r3::GpuSkinner::add_skinning_to_graph     skinning.rs:54-199 (node position base.rs:145)
 //   r3::GpuCuller::add_culling_to_graph       culler.rs:682-713 (batch_objects, batching.rs:120-250, then cull, culler.rs:531-659)
 //   r3::ForwardRoutine::add_forward_to_graph  forward.rs:192-315      r3::HiZRoutine::add_hi_z_to_graph   hi_z.rs:161-234
 //   r3::TonemappingRoutine::add_to_graph      tonemapping.rs:108-147  r3::BaseRenderGraph::add_to_graph   base.rs:129-185
@@ -63,6 +64,8 @@ struct EvalOutput {
     r3_camera_header viewport{};              // PerCameraUniform header of the viewport camera for this target
     r3_frame_uniforms uniforms{};             // FrameUniforms::new
     float viewport_location[3] = {0, 0, 0};   // CameraState::location()
+    // GPU skinning (skinning.rs:54-199): one record per skeleton + the global joint matrices; empty = no animated meshes this frame
+    const r3_skinning_input* skinning_inputs = nullptr; uint32_t n_skeletons = 0; const float* joint_matrices = nullptr; uint32_t n_joints = 0;
 };
 
 struct BaseRenderGraphSettings {              // base.rs:95-98
@@ -113,6 +116,13 @@ public:
     }
 };
 
+class GpuSkinner {   // skinning.rs:54-199: add_skinning_to_graph — skinned positions / normals / tangents into the skeletons' overridden mesh ranges
+public:
+    void add_skinning_to_graph(Renderer& r, const EvalOutput& ev) const {
+        if (ev.n_skeletons) r.check(r3_skin(r.raw(), ev.skinning_inputs, ev.n_skeletons, ev.joint_matrices, ev.n_joints));
+    }
+};
+
 class ForwardRoutine {   // forward.rs:85-315; opaque + cutout routines share one call, the blend routine has its own
 public:
     void add_forward_to_graph(Renderer& r, CullingSource source) const { r.check(r3_forward_pass(r.raw(), source == CullingSource::Predicted ? 0 : 1)); }
@@ -137,15 +147,19 @@ public:
 class BaseRenderGraph {
 public:
     GpuCuller gpu_culler;
+    GpuSkinner gpu_skinner;
     ForwardRoutine forward;
     HiZRoutine hi_z;
     TonemappingRoutine tonemapping;
+    bool submit_as_graph = false;             // record the frame and submit it as one CUDA graph launch (graph.rs:510: one submit per frame)
 
     void add_to_graph(Renderer& r, const EvalOutput& ev, uint32_t width, uint32_t height, SampleCount samples, const BaseRenderGraphSettings& settings,
                       bool target_is_srgb = true) {
         r.check(r3_set_render_target(r.raw(), width, height, (uint32_t)samples, settings.clear_color.data()));
+        if (submit_as_graph) r.check(r3_frame_begin(r.raw()));
         r.check(r3_clear_shadow_atlas(r.raw()));                                                     // base.rs:139
         r.check(r3_set_frame_uniforms(r.raw(), &ev.uniforms));                                       // :142
+        gpu_skinner.add_skinning_to_graph(r, ev);                                                    // :145 state.skinning — before any camera culls
         for (uint32_t i = 0; i < ev.shadows.size(); ++i) gpu_culler.object_uniform_upload(r, CameraSpecifier::Shadow(i), ev.shadows[i].header);   // :148
         for (uint32_t i = 0; i < ev.shadows.size(); ++i) gpu_culler.add_culling_to_graph(r, CameraSpecifier::Shadow(i), ev.viewport_location);     // :150
         for (uint32_t i = 0; i < ev.shadows.size(); ++i) forward.add_shadow_to_graph(r, i, ev.shadows[i]);                                         // :153
@@ -158,6 +172,7 @@ public:
         forward.resolve(r);
         forward.add_transparent_to_graph(r);                                                         // :181
         tonemapping.add_to_graph(r, target_is_srgb);                                                 // :184
+        if (submit_as_graph) r.check(r3_frame_end(r.raw()));
     }
 };
 

@@ -463,6 +463,9 @@ API int r3o_batching_info(r3o_ctx* c, uint32_t camera, uint32_t info[4]) {
     return R3_OK;
 }
 API int r3o_forward_light_evaluations(r3o_ctx* c, uint64_t* n) { if (!c || !n) return R3_E_INVALID; *n = 0; return R3_OK; }   /* statistics of the CUDA path only */
+API int r3o_frame_begin(r3o_ctx* c) { return c ? R3_OK : R3_E_INVALID; }   /* submission is a property of the CUDA path */
+API int r3o_frame_end(r3o_ctx* c) { return c ? R3_OK : R3_E_INVALID; }
+API int r3o_frame_graph_stats(r3o_ctx* c, uint64_t stats[4]) { if (!c || !stats) return R3_E_INVALID; stats[0] = stats[1] = stats[2] = stats[3] = 0; return R3_OK; }
 API int r3o_set_stage_timing(r3o_ctx* c, int enabled) { (void)enabled; return c ? R3_OK : R3_E_INVALID; }
 API int r3o_stage_times(r3o_ctx* c, double ms[8], uint32_t launches[8]) { if (!c || !ms || !launches) return R3_E_INVALID; for (int k = 0; k < 8; ++k) { ms[k] = 0.0; launches[k] = 0; } return R3_OK; }
 API int r3o_set_parity_target(r3o_ctx* c, int enabled) { (void)enabled; return c ? R3_OK : R3_E_INVALID; }   /* the oracle always keeps the f32 result */

@@ -29,7 +29,7 @@ CUDA_LIB_PATH = os.path.join(_ROOT, "librend3_b200.so")
 
 # every entry point of include/rend3_b200.h (tests check the .so exports all of them)
 ENTRY_POINTS = [
-    "abi_version", "ctx_create", "ctx_destroy", "last_error", "sync", "get_stream", "launch_count", "set_stage_timing", "stage_times",
+    "abi_version", "ctx_create", "ctx_destroy", "last_error", "sync", "get_stream", "launch_count", "set_stage_timing", "stage_times", "frame_begin", "frame_end", "frame_graph_stats",
     "set_objects", "update_objects", "set_objects_device", "set_object_sort_info", "set_mesh_buffer", "set_textures", "set_skybox",
     "set_materials", "set_directional_lights", "set_point_lights", "set_frame_uniforms",
     "object_uniform_upload", "visible_count", "readback_visible", "readback_object_matrices",
@@ -99,6 +99,17 @@ class Backend:
         return n.value
 
     STAGES = ("triangle_test", "raster_setup_colour", "raster_setup_depth", "raster_bands", "resolve", "sort", "cull_bake", "triangle_compact")
+
+    def frame_begin(self):
+        self._call("frame_begin")
+
+    def frame_end(self):
+        self._call("frame_end")
+
+    def frame_graph_stats(self):
+        s = (C.c_uint64 * 4)()
+        self._call("frame_graph_stats", s)
+        return {"frames": int(s[0]), "graphed": int(s[1]), "flushed": int(s[2]), "instantiations": int(s[3])}
 
     def set_stage_timing(self, enabled: bool = True):
         self._call("set_stage_timing", C.c_int(1 if enabled else 0))

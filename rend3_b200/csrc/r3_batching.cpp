@@ -48,7 +48,7 @@ int r3_host_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], uint
     uint32_t nv = 0;
     if (cam->d_visible_count) {
         R3_CUDA(c, cudaMemcpyAsync(&nv, cam->d_visible_count, 4, cudaMemcpyDeviceToHost, c->stream));
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
     }
     cam->visible_count_host = (int)nv;
     std::vector<uint32_t> visible(nv), index_count(nv);
@@ -58,7 +58,7 @@ int r3_host_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], uint
         R3_CHECK_LAUNCH(c, "gather_index_count_kernel");
         R3_CUDA(c, cudaMemcpyAsync(visible.data(), cam->d_visible, (size_t)nv * 4, cudaMemcpyDeviceToHost, c->stream));
         R3_CUDA(c, cudaMemcpyAsync(index_count.data(), c->d_scratch, (size_t)nv * 4, cudaMemcpyDeviceToHost, c->stream));
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
     }
     std::vector<SortItem> items(nv);
     for (uint32_t i = 0; i < nv; ++i) {
@@ -153,7 +153,7 @@ int r3_upload_jobs(r3_ctx* c, r3_camera* cam) {
     if (!j.d_header) R3_CUDA(c, cudaMalloc((void**)&j.d_header, 32));
     const uint32_t hdr[8] = {(uint32_t)(cam->visible_count_host < 0 ? 0 : cam->visible_count_host), nb, nr, j.total_invocations, 0, 0, 0, 0};
     R3_CUDA(c, cudaMemcpyAsync(j.d_header, hdr, 32, cudaMemcpyHostToDevice, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));   // `first` and the vectors are pageable host memory
+    R3_CUDA(c, r3_stream_sync(c));   // `first` and the vectors are pageable host memory
     j.n_batches = nb; j.n_regions = nr; j.valid = true;
     return R3_OK;
 }

@@ -136,6 +136,10 @@ struct r3_ctx {
     void* d_scratch = nullptr; uint64_t scratch_cap = 0;
     r3_stage_timer timer;
     r3_peer_state peer;
+    // frame graph
+    bool capturing = false;                   // between r3_frame_begin and the submission (or an early flush)
+    cudaGraphExec_t frame_exec[2] = {nullptr, nullptr};   // instantiated graphs of even / odd frames (the culling buffers ping-pong), updated in place
+    uint64_t frame_index = 0, frames_graphed = 0, frames_flushed = 0, graph_reinstantiations = 0;
 };
 
 // ---- error plumbing (nothing throws across the C boundary)
@@ -158,6 +162,10 @@ int r3_cuda_fail(r3_ctx* c, cudaError_t e, const char* where);
         if (rc__ != R3_OK) return rc__;                                   \
     } while (0)
 
+// Frame graph (r3_frame_begin / r3_frame_end): the stream work of one frame is recorded by stream capture and submitted as ONE CUDA graph
+// launch (the reference submits once per frame, graph.rs:510).  Anything that has to wait for the stream inside a frame first flushes what
+// was recorded so far (r3_stream_sync does that), after which the rest of the frame runs eagerly.
+cudaError_t r3_stream_sync(r3_ctx* c);
 // stage timing: no-ops unless enabled
 void r3_stage_begin(r3_ctx* c, int stage);
 void r3_stage_end(r3_ctx* c);

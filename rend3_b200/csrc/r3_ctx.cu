@@ -27,7 +27,7 @@ int r3_reserve(r3_ctx* c, void** ptr, uint64_t* cap, uint64_t need, size_t elem,
     if (zero_new) R3_CUDA(c, cudaMemsetAsync(n, 0, ncap * elem, c->stream));
     if (*ptr) {
         if (keep && *cap) R3_CUDA(c, cudaMemcpyAsync(n, *ptr, *cap * elem, cudaMemcpyDeviceToDevice, c->stream));
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
         cudaFree(*ptr);
     }
     *ptr = n;
@@ -67,7 +67,7 @@ static void free_jobs(r3_jobs& j) { cudaFree(j.d_batches); cudaFree(j.d_regions)
 R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     if (!c) return R3_E_INVALID;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    r3_stream_sync(c);
     r3_peer_destroy(c);
     if (!c->objects_borrowed) cudaFree(c->d_objects);
     cudaFree(c->d_hot_transform); cudaFree(c->d_hot_sphere); cudaFree(c->d_enabled_bits); cudaFree(c->d_tex_descs); cudaFree(c->d_texels); cudaFree(c->d_sky_texels);
@@ -93,6 +93,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     cudaFree(c->d_tris[0]); cudaFree(c->d_tris[1]); cudaFree(c->d_tris[2]); cudaFree(c->d_tris[3]); cudaFree(c->d_stats); cudaFree(c->d_scratch);
     cudaFree(c->d_frag_heads); cudaFree(c->d_frag_nodes);
     for (cudaEvent_t e : c->timer.pool) cudaEventDestroy(e);
+    for (auto& x : c->frame_exec) if (x) cudaGraphExecDestroy(x);
     cudaStreamDestroy(c->stream);
     delete c;
     return R3_OK;
@@ -100,7 +101,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
 R3_EXPORT const char* r3_last_error(const r3_ctx* c) { return c ? c->err.c_str() : "null context"; }
 R3_EXPORT int r3_sync(r3_ctx* c) {
     if (!c) return R3_E_INVALID;
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     return R3_OK;
 }
 R3_EXPORT int r3_get_stream(r3_ctx* c, void** s) {
@@ -114,10 +115,80 @@ R3_EXPORT int r3_launch_count(r3_ctx* c, uint64_t* n) {
     return R3_OK;
 }
 
+// ------------------------------------------------------------------ frame graph
+// End the capture (if one is running) and submit what it recorded.  `slot` >= 0: keep the instantiated graph of that frame parity and
+// update it in place next time (cudaGraphExecUpdate: same topology, new kernel arguments / pointers); slot < 0: one-off (an early flush).
+static cudaError_t r3_submit_capture(r3_ctx* c, int slot) {
+    if (!c->capturing) return cudaSuccess;
+    c->capturing = false;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (e != cudaSuccess || !g) return e != cudaSuccess ? e : cudaErrorUnknown;
+    if (slot < 0) {
+        cudaGraphExec_t x = nullptr;
+        e = cudaGraphInstantiate(&x, g, 0);
+        if (e == cudaSuccess) e = cudaGraphLaunch(x, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // the one-off exec is destroyed right away: wait for it
+        if (x) cudaGraphExecDestroy(x);
+        cudaGraphDestroy(g);
+        return e;
+    }
+    cudaGraphExec_t& x = c->frame_exec[slot];
+    if (x) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(x, g, &info) != cudaSuccess) {   // another topology (new buffers sizes, another routine set): instantiate again
+            cudaGetLastError();
+            cudaGraphExecDestroy(x);
+            x = nullptr;
+        }
+    }
+    if (!x) {
+        e = cudaGraphInstantiate(&x, g, 0);
+        c->graph_reinstantiations++;
+    }
+    if (e == cudaSuccess) e = cudaGraphLaunch(x, c->stream);
+    cudaGraphDestroy(g);
+    return e;
+}
+cudaError_t r3_stream_sync(r3_ctx* c) {
+    if (c->capturing) {
+        // a stage needs the stream to drain in the middle of a recorded frame (a buffer grows, a host path reads back): submit what
+        // was recorded, wait, and let the rest of the frame run eagerly
+        const cudaError_t e = r3_submit_capture(c, -1);
+        c->frames_flushed++;
+        if (e != cudaSuccess) return e;
+    }
+    return cudaStreamSynchronize(c->stream);
+}
+R3_EXPORT int r3_frame_begin(r3_ctx* c) {
+    if (!c) return R3_E_INVALID;
+    cudaSetDevice(c->device);
+    if (c->capturing) return r3_fail(c, R3_E_STATE, "frame_begin: a frame is already being recorded");
+    if (c->timer.enabled) return R3_OK;       // per-kernel timing needs real event records: the frame runs eagerly
+    R3_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    c->capturing = true;
+    return R3_OK;
+}
+R3_EXPORT int r3_frame_end(r3_ctx* c) {
+    if (!c) return R3_E_INVALID;
+    cudaSetDevice(c->device);
+    const bool was = c->capturing;
+    const cudaError_t e = r3_submit_capture(c, (int)(c->frame_index & 1u));
+    c->frame_index++;
+    if (was) c->frames_graphed++;
+    if (e != cudaSuccess) return r3_cuda_fail(c, e, "frame_end (graph submission)");
+    return R3_OK;
+}
+R3_EXPORT int r3_frame_graph_stats(r3_ctx* c, uint64_t stats[4]) {
+    if (!c || !stats) return R3_E_INVALID;
+    stats[0] = c->frame_index; stats[1] = c->frames_graphed; stats[2] = c->frames_flushed; stats[3] = c->graph_reinstantiations;
+    return R3_OK;
+}
+
 // ------------------------------------------------------------------ stage timing
 void r3_stage_begin(r3_ctx* c, int stage) {
     r3_stage_timer& t = c->timer;
-    if (!t.enabled) return;
+    if (!t.enabled || c->capturing) return;
     if (t.pool.size() < 2 * (t.used + 1)) {
         cudaEvent_t a = nullptr, b = nullptr;
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { t.enabled = false; return; }
@@ -128,7 +199,7 @@ void r3_stage_begin(r3_ctx* c, int stage) {
 }
 void r3_stage_end(r3_ctx* c) {
     r3_stage_timer& t = c->timer;
-    if (!t.enabled) return;
+    if (!t.enabled || c->capturing) return;
     cudaEventRecord(t.pool[2 * t.used + 1], c->stream);
     t.used++;
 }
@@ -142,7 +213,7 @@ R3_EXPORT int r3_set_stage_timing(r3_ctx* c, int enabled) {
 R3_EXPORT int r3_stage_times(r3_ctx* c, double ms[8], uint32_t launches[8]) {
     if (!c || !ms || !launches) return R3_E_INVALID;
     cudaSetDevice(c->device);
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     for (int k = 0; k < 8; ++k) { ms[k] = 0.0; launches[k] = 0; }
     r3_stage_timer& t = c->timer;
     for (size_t k = 0; k < t.used; ++k) {
@@ -163,7 +234,7 @@ R3_EXPORT int r3_set_objects(r3_ctx* c, const r3_object* recs, uint32_t n) {
     c->n_slots = n;
     c->max_invocations_valid = false;
     R3_TRY(r3_split_objects(c));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));   // host pointer is only borrowed for the call
+    R3_CUDA(c, r3_stream_sync(c));   // host pointer is only borrowed for the call
     return R3_OK;
 }
 R3_EXPORT int r3_set_objects_device(r3_ctx* c, const void* dptr, uint32_t n) {
@@ -198,7 +269,7 @@ R3_EXPORT int r3_update_objects(r3_ctx* c, const uint32_t* slots, const r3_objec
     R3_CHECK_LAUNCH(c, "scatter_objects_kernel");
     R3_TRY(r3_split_slots(c, d_slots, n));
     c->max_invocations_valid = false;
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     return R3_OK;
 }
 R3_EXPORT int r3_set_object_sort_info(r3_ctx* c, const uint64_t* key, const uint8_t* flags, const float* loc, uint32_t n) {
@@ -234,7 +305,7 @@ R3_EXPORT int r3_set_object_sort_info(r3_ctx* c, const uint64_t* key, const uint
         R3_CUDA(c, cudaMemcpyAsync(c->d_sort_key8, key8.data(), n, cudaMemcpyHostToDevice, c->stream));
         R3_CUDA(c, cudaMemcpyAsync(c->d_sort_loc, loc, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
     }
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     r3_new_frame_epoch(c);
     c->have_live = true;
     c->gpu_batching_ok = ok && n < (1u << 24) && !getenv("R3_HOST_BATCHING");
@@ -245,7 +316,7 @@ R3_EXPORT int r3_set_mesh_buffer(r3_ctx* c, const void* bytes, uint64_t nbytes) 
     cudaSetDevice(c->device);
     R3_TRY(r3_reserve_t(c, &c->d_mesh, &c->mesh_cap, nbytes / 4 + 4));
     if (nbytes) R3_CUDA(c, cudaMemcpyAsync(c->d_mesh, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     c->mesh_words = nbytes / 4;
     return R3_OK;
 }
@@ -254,7 +325,7 @@ R3_EXPORT int r3_set_materials(r3_ctx* c, const r3_material* recs, uint32_t n) {
     cudaSetDevice(c->device);
     R3_TRY(r3_reserve_t(c, &c->d_materials, &c->materials_cap, n));
     if (n) R3_CUDA(c, cudaMemcpyAsync(c->d_materials, recs, (size_t)n * sizeof(r3_material), cudaMemcpyHostToDevice, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     c->n_materials = n;
     c->any_frag_alpha = false;
     for (uint32_t i = 0; i < n; ++i)
@@ -276,7 +347,7 @@ R3_EXPORT int r3_set_textures(r3_ctx* c, const r3_texture_desc* descs, uint32_t 
     R3_TRY(r3_reserve_t(c, &c->d_texels, &c->texels_cap, nbytes + 16));
     if (n) R3_CUDA(c, cudaMemcpyAsync(c->d_tex_descs, descs, (size_t)n * sizeof(r3_texture_desc), cudaMemcpyHostToDevice, c->stream));
     if (nbytes) R3_CUDA(c, cudaMemcpyAsync(c->d_texels, texels, nbytes, cudaMemcpyHostToDevice, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     c->n_textures = n;
     return R3_OK;
 }
@@ -292,7 +363,7 @@ R3_EXPORT int r3_set_skybox(r3_ctx* c, const r3_texture_desc* desc, const void* 
     cudaSetDevice(c->device);
     R3_TRY(r3_reserve_t(c, &c->d_sky_texels, &c->sky_cap, nbytes + 16));
     R3_CUDA(c, cudaMemcpyAsync(c->d_sky_texels, texels, nbytes, cudaMemcpyHostToDevice, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     c->sky_desc = *desc; c->sky_desc.height = desc->width; c->has_skybox = true;
     return R3_OK;
 }
@@ -305,14 +376,14 @@ R3_EXPORT int r3_set_directional_lights(r3_ctx* c, const void* bytes, uint64_t n
     if (n) R3_CUDA(c, cudaMemcpyAsync(c->d_dir, (const uint8_t*)bytes + 16, (size_t)n * sizeof(r3_directional_light), cudaMemcpyHostToDevice, c->stream));
     c->n_dir = n;
     if (aw != c->atlas_w || ah != c->atlas_h || !c->d_atlas) {
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
         cudaFree(c->d_atlas);
         c->d_atlas = nullptr;
         R3_CUDA(c, cudaMalloc((void**)&c->d_atlas, (size_t)aw * ah * 4 + 16));
         R3_CUDA(c, cudaMemsetAsync(c->d_atlas, 0, (size_t)aw * ah * 4, c->stream));
         c->atlas_w = aw; c->atlas_h = ah;
     }
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     return R3_OK;
 }
 R3_EXPORT int r3_set_point_lights(r3_ctx* c, const void* bytes, uint64_t nbytes) {
@@ -322,7 +393,7 @@ R3_EXPORT int r3_set_point_lights(r3_ctx* c, const void* bytes, uint64_t nbytes)
     if (nbytes < 16 + (uint64_t)n * sizeof(r3_point_light)) return r3_fail(c, R3_E_INVALID, "set_point_lights: short buffer");
     R3_TRY(r3_reserve_t(c, &c->d_point, &c->point_cap, n));
     if (n) R3_CUDA(c, cudaMemcpyAsync(c->d_point, (const uint8_t*)bytes + 16, (size_t)n * sizeof(r3_point_light), cudaMemcpyHostToDevice, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     c->n_point = n;
     return R3_OK;
 }
@@ -352,7 +423,7 @@ R3_EXPORT int r3_object_uniform_upload(r3_ctx* c, uint32_t camera, const r3_came
     if (mode & R3_CB_BAKE) {
         // a resized per-camera buffer starts zeroed (culler.rs:459-476: new buffer when the size changes)
         if (cam->matrices_cap < n || !cam->d_matrices) {
-            R3_CUDA(c, cudaStreamSynchronize(c->stream));
+            R3_CUDA(c, r3_stream_sync(c));
             cudaFree(cam->d_matrices);
             cam->d_matrices = nullptr;
             R3_CUDA(c, cudaMalloc((void**)&cam->d_matrices, ((size_t)n + 1) * sizeof(r3_object_matrices)));
@@ -376,7 +447,7 @@ R3_EXPORT int r3_visible_count(r3_ctx* c, uint32_t camera, uint32_t* count) {
     if (cam->visible_count_host < 0) {
         uint32_t v = 0;
         R3_CUDA(c, cudaMemcpyAsync(&v, cam->d_visible_count, 4, cudaMemcpyDeviceToHost, c->stream));
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
         cam->visible_count_host = (int)v;
     }
     *count = (uint32_t)cam->visible_count_host;
@@ -390,7 +461,7 @@ R3_EXPORT int r3_readback_visible(r3_ctx* c, uint32_t camera, uint32_t* out, uin
     if (out && n) {
         if (cap < n) return r3_fail(c, R3_E_INVALID, "readback_visible: capacity too small");
         R3_CUDA(c, cudaMemcpyAsync(out, cam->d_visible, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
     }
     return R3_OK;
 }
@@ -399,7 +470,7 @@ R3_EXPORT int r3_readback_object_matrices(r3_ctx* c, uint32_t camera, r3_object_
     if (!out || (uint64_t)first + n > cam->matrices_cap) return r3_fail(c, R3_E_INVALID, "readback_object_matrices: range");
     cudaSetDevice(c->device);
     if (n) R3_CUDA(c, cudaMemcpyAsync(out, cam->d_matrices + first, (size_t)n * sizeof *out, cudaMemcpyDeviceToHost, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     return R3_OK;
 }
 
@@ -429,7 +500,7 @@ int r3_iobuf_swap(r3_ctx* c, r3_iobuf* b, uint64_t new_elems) {
             if (bytes > room) bytes = room;
             if (bytes) R3_CUDA(c, cudaMemcpyAsync(nd + b->in_off() * b->elem_size, b->d + old_out * b->elem_size, bytes, cudaMemcpyDeviceToDevice, c->stream));
         }
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
         cudaFree(b->d);
         b->d = nd;
     } else if (b->clear_on_swap) {
@@ -447,7 +518,7 @@ static int io_read(r3_ctx* c, const r3_iobuf* b, int partition, void* out, uint6
     if (out && elems) {
         if (cap < elems) return r3_fail(c, R3_E_INVALID, "readback: capacity too small");
         R3_CUDA(c, cudaMemcpyAsync(out, b->d + off * b->elem_size, elems * b->elem_size, cudaMemcpyDeviceToHost, c->stream));
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
     }
     return R3_OK;
 }
@@ -496,7 +567,7 @@ R3_EXPORT int r3_batching_info(r3_ctx* c, uint32_t camera, uint32_t info[4]) {
     if ((cam->batching_path == 1 || cam->batching_path == 3) && j.d_header) {
         uint32_t hdr[8] = {0};
         R3_CUDA(c, cudaMemcpyAsync(hdr, j.d_header, 32, cudaMemcpyDeviceToHost, c->stream));
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
         info[1] = hdr[4]; info[2] = hdr[1]; info[3] = hdr[2];
     } else if (cam->batching_path == 2) {
         info[2] = (uint32_t)j.batches.size(); info[3] = (uint32_t)j.regions.size();

@@ -432,7 +432,7 @@ R3_EXPORT int r3_exchange_create(r3_ctx* c, uint32_t camera, uint32_t n_ranks, u
     R3_CUDA(c, cudaMemsetAsync(cam->d_gathered, 0, total_words * 4, c->stream));
     if (!cam->d_ex_done) R3_CUDA(c, cudaMalloc((void**)&cam->d_ex_done, 16));
     R3_CUDA(c, cudaMemsetAsync(cam->d_ex_done, 0, 16, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     cam->ex_epoch = 0; cam->ex_objects = 0;
     cudaIpcMemHandle_t h;
     R3_CUDA(c, cudaIpcGetMemHandle(&h, cam->d_gathered));
@@ -510,7 +510,7 @@ R3_EXPORT int r3_exchange_destroy(r3_ctx* c, uint32_t camera) {
     r3_camera* cam = r3_get_camera(c, camera);
     if (!cam) return r3_fail(c, R3_E_INVALID, "exchange_destroy: bad camera");
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    r3_stream_sync(c);
     for (uint32_t r = 0; r < cam->ex_ranks; ++r)
         if (cam->ex_connected && r != cam->ex_rank && cam->ex_peers[r]) cudaIpcCloseMemHandle(cam->ex_peers[r]);
     cudaFree(cam->d_gathered);

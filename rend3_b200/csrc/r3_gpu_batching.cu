@@ -531,7 +531,7 @@ int r3_compute_max_invocations(r3_ctx* c) {
         R3_CHECK_LAUNCH(c, "max_invocations_kernel");
         unsigned long long v[2] = {0, 0};
         R3_CUDA(c, cudaMemcpyAsync(v, c->d_stats + 4, 16, cudaMemcpyDeviceToHost, c->stream));
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
         c->max_total_invocations = v[0]; c->max_object_invocations = v[1];
     }
     c->max_invocations_valid = true;
@@ -638,7 +638,7 @@ int r3_device_batch_objects(r3_ctx* c, r3_camera* cam, const float vp_loc[3], ui
             R3_CUDA(c, cudaMemsetAsync(n, 0xFF, ((size_t)cap + 1) * 4, c->stream));
             if (cam->d_prev_inv[k]) {   // keep last frame's entries across a capacity growth
                 R3_CUDA(c, cudaMemcpyAsync(n, cam->d_prev_inv[k], (size_t)cam->prev_inv_cap * 4, cudaMemcpyDeviceToDevice, c->stream));
-                R3_CUDA(c, cudaStreamSynchronize(c->stream));
+                R3_CUDA(c, r3_stream_sync(c));
                 cudaFree(cam->d_prev_inv[k]);
             }
             cam->d_prev_inv[k] = n;
@@ -699,12 +699,12 @@ int r3_download_jobs(r3_ctx* c, r3_camera* cam) {
     if (!j.device_built || !j.batches.empty() || !j.d_header) return R3_OK;
     uint32_t hdr[8] = {0};
     R3_CUDA(c, cudaMemcpyAsync(hdr, j.d_header, 32, cudaMemcpyDeviceToHost, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     if (hdr[4]) return r3_fail(c, R3_E_INVALID, "device batch_objects overflow (batch beyond the dispatch limit or > 2^24 visible objects): use host batching");
     j.batches.resize(hdr[1]); j.regions.resize(hdr[2]);
     if (hdr[1]) R3_CUDA(c, cudaMemcpyAsync(j.batches.data(), j.d_batches, (size_t)hdr[1] * sizeof(r3_batch_data), cudaMemcpyDeviceToHost, c->stream));
     if (hdr[2]) R3_CUDA(c, cudaMemcpyAsync(j.regions.data(), j.d_regions, (size_t)hdr[2] * sizeof(r3_region), cudaMemcpyDeviceToHost, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     // the 8448-byte records carry 244 bytes of padding the host path leaves zero
     for (auto& b : j.batches) {
         std::memset(b._pad, 0, sizeof b._pad);

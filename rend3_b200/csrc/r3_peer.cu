@@ -72,7 +72,7 @@ R3_EXPORT int r3_peer_create(r3_ctx* c, uint32_t n_ranks, uint32_t my_rank, uint
     cudaSetDevice(c->device);
     R3_CUDA(c, cudaMalloc((void**)&c->peer.d_flags, 1024));
     R3_CUDA(c, cudaMemsetAsync(c->peer.d_flags, 0, 1024, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     memset(handles_out, 0, 3 * R3_IPC_HANDLE_BYTES);
     cudaIpcMemHandle_t h;
     R3_CUDA(c, cudaIpcGetMemHandle(&h, c->peer.d_flags));
@@ -159,7 +159,7 @@ R3_EXPORT int r3_peer_destroy(r3_ctx* c) {
     if (!c) return R3_E_INVALID;
     if (!c->peer.created) return R3_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    r3_stream_sync(c);
     if (c->peer.connected)
         for (uint32_t r = 0; r < c->peer.n_ranks; ++r) {
             if (r == c->peer.rank) continue;

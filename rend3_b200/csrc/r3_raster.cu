@@ -342,7 +342,9 @@ __device__ bool process_subtriangle(const RasterParams& p, const float4 a, const
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (!(v[k].w > 0.0f)) return false;
-        const float nx = div_rn(v[k].x, v[k].w), ny = div_rn(v[k].y, v[k].w), nz = div_rn(v[k].z, v[k].w);
+        // x / 1.0f == x bit for bit: orthographic cameras (every shadow pass) skip the three IEEE divisions per vertex
+        const bool unit_w = v[k].w == 1.0f;
+        const float nx = unit_w ? v[k].x : div_rn(v[k].x, v[k].w), ny = unit_w ? v[k].y : div_rn(v[k].y, v[k].w), nz = unit_w ? v[k].z : div_rn(v[k].z, v[k].w);
         const float fx = add_rn(p.ox, mul_rn(add_rn(nx, 1.0f), hw)), fy = add_rn(p.oy, mul_rn(sub_rn(1.0f, ny), hh));
         const float qx = rintf(mul_rn(fx, 256.0f)), qy = rintf(mul_rn(fy, 256.0f));
         if (!(fabsf(qx) < 1.0e9f) || !(fabsf(qy) < 1.0e9f)) return false;
@@ -452,13 +454,19 @@ __device__ void setup_listed_triangle(const RasterParams& p, unsigned long long 
         if (!(MODE & MODE_ALPHA) || !p.records) alpha_tested = false;   // (run_raster picks the MODE_ALPHA kernels and provides records whenever such materials exist)
     }
     const uint32_t pos_off = obj->attr_offset[0] >> 2;
-    const float* mvp = p.matrices[oid].model_view_proj;
+    float mvp[16];
+    {
+        const float4* m4 = reinterpret_cast<const float4*>(p.matrices[oid].model_view_proj);   // 64-byte aligned: four 16-byte loads instead of sixteen 4-byte ones
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float4 c4 = __ldg(&m4[q]); mvp[4 * q] = c4.x; mvp[4 * q + 1] = c4.y; mvp[4 * q + 2] = c4.z; mvp[4 * q + 3] = c4.w; }
+    }
     const uint32_t vid[3] = {k0 & 0xFFFFFFu, k1 & 0xFFFFFFu, k2 & 0xFFFFFFu};
     float4 clip[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const uint64_t f = (uint64_t)pos_off + (uint64_t)vid[k] * 3u;
-        clip[k] = mat_point_rn(mvp, __uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));
+        if (f + 2u < p.mesh_words) clip[k] = mat_point_rn(mvp, __uint_as_float(__ldg(&p.mesh[f])), __uint_as_float(__ldg(&p.mesh[f + 1])), __uint_as_float(__ldg(&p.mesh[f + 2])));
+        else clip[k] = mat_point_rn(mvp, __uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));   // robust access at the buffer end
     }
     // trivial reject + clip need (R1)
     bool ox0 = true, ox1 = true, oy0 = true, oy1 = true, oz0 = true, oz1 = true, need_clip = false, nan = false;
@@ -767,7 +775,7 @@ int r3_blend_collect(r3_ctx* c, bool* ran) {
                           c->width));
         uint32_t used = 0;
         R3_CUDA(c, cudaMemcpyAsync(&used, (const uint32_t*)c->d_scratch + 3, 4, cudaMemcpyDeviceToHost, c->stream));
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
         if (used <= c->frag_nodes_cap) { *ran = true; return R3_OK; }
         if (attempt == 1 || used >= 0xFFFFFFF0u) break;
         R3_TRY(r3_reserve_t(c, &c->d_frag_nodes, &c->frag_nodes_cap, (uint64_t)used + (used >> 3)));

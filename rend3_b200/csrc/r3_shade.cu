@@ -769,27 +769,74 @@ __global__ void light_prep_kernel(const r3_directional_light* dir, uint32_t n_di
     }
 }
 
-// hi-Z: mip 0 = depth bits of the visibility buffer
-// (multisampled: resolve_depth_min.wgsl:18-27 keeps the MIN over the samples)
-__global__ void hiz_mip0_kernel(const unsigned long long* __restrict__ vis, float* __restrict__ out, size_t n, uint32_t samples) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float d = 1.0f;
-    for (uint32_t k = 0; k < samples; ++k) d = fminf(d, __uint_as_float((uint32_t)(vis[i * samples + k] >> 32)));
-    out[i] = d;
-}
-// hi_z.wgsl::fs_main (:18-33): MIN over a 2x2 (+1 on odd source sizes) footprint; texels outside the source are skipped
-__global__ void hiz_downsample_kernel(const float* __restrict__ src, uint32_t sw, uint32_t sh, float* __restrict__ dst, uint32_t dw, uint32_t dh) {
-    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= dw || y >= dh) return;
-    const uint32_t oddx = sw & 1u, oddy = sh & 1u;
-    float nearest = 1.0f;
-    for (uint32_t dx = 0; dx < 2u + oddx; ++dx)
-        for (uint32_t dy = 0; dy < 2u + oddy; ++dy) {
-            const uint32_t sx = 2u * x + dx, sy = 2u * y + dy;
-            if (sx < sw && sy < sh) nearest = fminf(nearest, src[(size_t)sy * sw + sx]);
+// hi-Z pyramid (hi_z.rs:161-234): mip 0 = depth bits of the visibility buffer (multisampled: resolve_depth_min.wgsl:18-27 keeps the MIN
+// over the samples); every further level = hi_z.wgsl::fs_main (:18-33): MIN over a 2 x 2 footprint, +1 column / row when the source
+// size is odd, texels outside the source skipped.  The chain runs in two launches instead of one per level (12 at 4K).
+// hiz_head_kernel: a CTA owns a 32 x 32 tile of mip 0, every thread a
+// 2 x 2 quad — mip 0 from the visibility buffer, then up to three further levels through shared memory, as long as the source level has
+// even dimensions (then the 2 x 2 footprints tile exactly and no `+1 on odd sizes` column crosses a tile).  hiz_tail_kernel: one CTA
+// walks the remaining small levels (<= 1/64 of the pixels) with a barrier between them.  Same min() over the same texels: bit-identical.
+__global__ void __launch_bounds__(256) hiz_head_kernel(const unsigned long long* __restrict__ vis, uint32_t samples, float* const* __restrict__ mips, const uint32_t* __restrict__ dims,
+                                                       uint32_t fused) {
+    __shared__ float s1[16][16];
+    __shared__ float s2[8][8];
+    const uint32_t w0 = dims[0], h0 = dims[1];
+    const uint32_t tx = threadIdx.x & 15u, ty = threadIdx.x >> 4;
+    const uint32_t x0 = blockIdx.x * 32u + tx * 2u, y0 = blockIdx.y * 32u + ty * 2u;
+    float m = 1.0f;                                    // hi_z.wgsl starts from 1.0 and takes min over the texels that exist
+#pragma unroll
+    for (uint32_t dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (uint32_t dx = 0; dx < 2; ++dx) {
+            const uint32_t x = x0 + dx, y = y0 + dy;
+            if (x < w0 && y < h0) {
+                const size_t i = (size_t)y * w0 + x;
+                float d = 1.0f;
+                for (uint32_t k = 0; k < samples; ++k) d = fminf(d, __uint_as_float((uint32_t)(vis[i * samples + k] >> 32)));
+                mips[0][i] = d;
+                m = fminf(m, d);
+            }
         }
-    dst[(size_t)y * dw + x] = nearest;
+    if (fused < 1u) return;
+    const uint32_t w1 = dims[2], h1 = dims[3], x1 = x0 >> 1, y1 = y0 >> 1;
+    if (x1 < w1 && y1 < h1) mips[1][(size_t)y1 * w1 + x1] = m;
+    if (fused < 2u) return;
+    s1[ty][tx] = m;
+    __syncthreads();
+    if (threadIdx.x < 64u) {
+        const uint32_t qx = threadIdx.x & 7u, qy = threadIdx.x >> 3;
+        const float v = fminf(fminf(s1[2 * qy][2 * qx], s1[2 * qy][2 * qx + 1]), fminf(s1[2 * qy + 1][2 * qx], s1[2 * qy + 1][2 * qx + 1]));
+        const uint32_t w2 = dims[4], h2 = dims[5], x2 = blockIdx.x * 8u + qx, y2 = blockIdx.y * 8u + qy;
+        if (x2 < w2 && y2 < h2) mips[2][(size_t)y2 * w2 + x2] = v;
+        s2[qy][qx] = v;
+    }
+    if (fused < 3u) return;
+    __syncthreads();
+    if (threadIdx.x < 16u) {
+        const uint32_t qx = threadIdx.x & 3u, qy = threadIdx.x >> 2;
+        const float v = fminf(fminf(s2[2 * qy][2 * qx], s2[2 * qy][2 * qx + 1]), fminf(s2[2 * qy + 1][2 * qx], s2[2 * qy + 1][2 * qx + 1]));
+        const uint32_t w3 = dims[6], h3 = dims[7], x3 = blockIdx.x * 4u + qx, y3 = blockIdx.y * 4u + qy;
+        if (x3 < w3 && y3 < h3) mips[3][(size_t)y3 * w3 + x3] = v;
+    }
+}
+__global__ void __launch_bounds__(1024) hiz_tail_kernel(float* const* __restrict__ mips, const uint32_t* __restrict__ dims, uint32_t first, uint32_t n_mips) {
+    for (uint32_t m = first; m < n_mips; ++m) {
+        const uint32_t sw = dims[2 * (m - 1)], sh = dims[2 * (m - 1) + 1], dw = dims[2 * m], dh = dims[2 * m + 1];
+        const float* src = mips[m - 1];
+        float* dst = mips[m];
+        const uint32_t oddx = sw & 1u, oddy = sh & 1u;
+        for (uint32_t i = threadIdx.x; i < dw * dh; i += blockDim.x) {
+            const uint32_t x = i % dw, y = i / dw;
+            float nearest = 1.0f;
+            for (uint32_t dx = 0; dx < 2u + oddx; ++dx)
+                for (uint32_t dy = 0; dy < 2u + oddy; ++dy) {
+                    const uint32_t sx = 2u * x + dx, sy = 2u * y + dy;
+                    if (sx < sw && sy < sh) nearest = fminf(nearest, src[(size_t)sy * sw + sx]);
+                }
+            dst[i] = nearest;
+        }
+        __syncthreads();   // the level just written is the next one's source (same CTA: block-scope visibility is enough)
+    }
 }
 
 // blit.wgsl: fs_main_scene into an *Srgb target (exact OETF) or fs_main_monitor (x^0.4166 approximation)
@@ -821,7 +868,7 @@ R3_EXPORT int r3_set_render_target(r3_ctx* c, uint32_t w, uint32_t h, uint32_t s
     if (samples != 1 && samples != 4) return r3_fail(c, R3_E_INVALID, "SampleCount must be One or Four");
     cudaSetDevice(c->device);
     if (w != c->width || h != c->height || samples != c->samples || !c->d_vis) {
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
         cudaFree(c->d_vis); cudaFree(c->d_hdr32); cudaFree(c->d_hdr16); cudaFree(c->d_depth); cudaFree(c->d_ldr);
         for (float* p : c->d_hiz) cudaFree(p);
         c->d_hiz.clear(); c->hiz_w.clear(); c->hiz_h.clear();
@@ -850,7 +897,7 @@ R3_EXPORT int r3_set_render_target(r3_ctx* c, uint32_t w, uint32_t h, uint32_t s
         R3_CUDA(c, cudaMalloc((void**)&c->d_hiz_dims, mips * 8));
         R3_CUDA(c, cudaMemcpyAsync(c->d_hiz_ptrs, c->d_hiz.data(), mips * sizeof(float*), cudaMemcpyHostToDevice, c->stream));
         R3_CUDA(c, cudaMemcpyAsync(c->d_hiz_dims, dims.data(), mips * 8, cudaMemcpyHostToDevice, c->stream));
-        R3_CUDA(c, cudaStreamSynchronize(c->stream));
+        R3_CUDA(c, r3_stream_sync(c));
     }
     c->width = w; c->height = h; c->samples = samples;
     memcpy(c->clear_color, clear, 16);
@@ -861,7 +908,7 @@ R3_EXPORT int r3_set_parity_target(r3_ctx* c, int enabled) {
     if (!c) return R3_E_INVALID;
     cudaSetDevice(c->device);
     c->parity_target = enabled != 0;
-    if (!c->parity_target && c->d_hdr32) { R3_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_hdr32); c->d_hdr32 = nullptr; }
+    if (!c->parity_target && c->d_hdr32) { R3_CUDA(c, r3_stream_sync(c)); cudaFree(c->d_hdr32); c->d_hdr32 = nullptr; }
     if (c->parity_target && !c->d_hdr32 && c->d_vis) {
         R3_CUDA(c, cudaMalloc((void**)&c->d_hdr32, (size_t)c->width * c->height * 16));
         R3_CUDA(c, cudaMemsetAsync(c->d_hdr32, 0, (size_t)c->width * c->height * 16, c->stream));
@@ -891,13 +938,16 @@ R3_EXPORT int r3_forward_begin(r3_ctx* c) {
 R3_EXPORT int r3_hiz_build(r3_ctx* c) {
     if (!c || !c->d_vis || c->d_hiz.empty()) return r3_fail(c, R3_E_STATE, "hiz_build before set_render_target");
     cudaSetDevice(c->device);
-    const size_t n = (size_t)c->width * c->height;
-    hiz_mip0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vis, c->d_hiz[0], n, c->samples);
-    R3_CHECK_LAUNCH(c, "hiz_mip0_kernel");
-    for (size_t m = 1; m < c->d_hiz.size(); ++m) {
-        const dim3 block(32, 8), grid((c->hiz_w[m] + 31) / 32, (c->hiz_h[m] + 7) / 8);
-        hiz_downsample_kernel<<<grid, block, 0, c->stream>>>(c->d_hiz[m - 1], c->hiz_w[m - 1], c->hiz_h[m - 1], c->d_hiz[m], c->hiz_w[m], c->hiz_h[m]);
-        R3_CHECK_LAUNCH(c, "hiz_downsample_kernel");
+    // levels fused into the head kernel: as long as the source level has even dimensions (and the level exists), at most three
+    const uint32_t n_mips = (uint32_t)c->d_hiz.size();
+    uint32_t fused = 0;
+    while (fused < 3u && fused + 1u < n_mips && !(c->hiz_w[fused] & 1u) && !(c->hiz_h[fused] & 1u)) fused++;
+    const dim3 grid((c->width + 31) / 32, (c->height + 31) / 32);
+    hiz_head_kernel<<<grid, 256, 0, c->stream>>>(c->d_vis, c->samples, c->d_hiz_ptrs, c->d_hiz_dims, fused);
+    R3_CHECK_LAUNCH(c, "hiz_head_kernel");
+    if (fused + 1u < n_mips) {
+        hiz_tail_kernel<<<1, 1024, 0, c->stream>>>(c->d_hiz_ptrs, c->d_hiz_dims, fused + 1u, n_mips);
+        R3_CHECK_LAUNCH(c, "hiz_tail_kernel");
     }
     return R3_OK;
 }
@@ -984,7 +1034,7 @@ static int copy_out(r3_ctx* c, const void* src, void* out, uint64_t cap, uint64_
     if (!out || cap < count) return r3_fail(c, R3_E_INVALID, "readback: capacity too small");
     cudaSetDevice(c->device);
     R3_CUDA(c, cudaMemcpyAsync(out, src, count * elem, cudaMemcpyDeviceToHost, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     return R3_OK;
 }
 R3_EXPORT int r3_readback_hdr_f32(r3_ctx* c, float* out, uint64_t cap) {
@@ -1007,13 +1057,13 @@ R3_EXPORT int r3_forward_light_evaluations(r3_ctx* c, uint64_t* n) {
     if (!c || !n) return R3_E_INVALID;
     cudaSetDevice(c->device);
     R3_CUDA(c, cudaMemcpyAsync(n, c->d_stats + 6, 8, cudaMemcpyDeviceToHost, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     return R3_OK;
 }
 R3_EXPORT int r3_forward_stats(r3_ctx* c, uint64_t stats[4]) {
     if (!c || !stats) return R3_E_INVALID;
     cudaSetDevice(c->device);
     R3_CUDA(c, cudaMemcpyAsync(stats, c->d_stats, 32, cudaMemcpyDeviceToHost, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     return R3_OK;
 }

@@ -107,7 +107,7 @@ R3_EXPORT int r3_skin(r3_ctx* c, const r3_skinning_input* inputs, uint32_t n_ske
     skinning_kernel<<<total_chunks, 256, 0, c->stream>>>(c->d_mesh, c->mesh_words, (const r3_skinning_input*)base, (const uint32_t*)(base + off_pre), n_skeletons,
                                                          (const float*)(base + off_j), n_joints);
     R3_CHECK_LAUNCH(c, "skinning_kernel");
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));   // host pointers are only borrowed for the call
+    R3_CUDA(c, r3_stream_sync(c));   // host pointers are only borrowed for the call
     return R3_OK;
 }
 
@@ -116,6 +116,6 @@ R3_EXPORT int r3_readback_mesh_buffer(r3_ctx* c, void* bytes, uint64_t cap) {
     if (cap < c->mesh_words * 4) return r3_fail(c, R3_E_INVALID, "readback_mesh_buffer: capacity too small");
     cudaSetDevice(c->device);
     if (c->mesh_words) R3_CUDA(c, cudaMemcpyAsync(bytes, c->d_mesh, c->mesh_words * 4, cudaMemcpyDeviceToHost, c->stream));
-    R3_CUDA(c, cudaStreamSynchronize(c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     return R3_OK;
 }

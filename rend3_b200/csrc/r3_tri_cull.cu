@@ -18,6 +18,8 @@
 //            one legal outcome of the reference's atomics, reproducible run to run.
 // (Round-1 history: a single-pass version with a per-workgroup decoupled look-back measured 1.66 ms per camera on the
 //  200k-object config — ticket + look-back latency per 256 invocations; see profiles/README.md.)
+#include <cstdlib>
+
 #include "r3_common.cuh"
 
 namespace {
@@ -31,7 +33,7 @@ constexpr int SB_WORDS = 1024;                       // words per superblock (32
 
 struct TriCullParams {
     r3_camera_header cam;
-    const uint32_t* mesh; uint64_t mesh_words;
+    const uint32_t* mesh; uint64_t mesh_words, mesh_cap_words;   // mesh_cap_words: words of the allocation (>= mesh_words + 4): bulk copies may over-read into the slack
     const r3_object* objects;
     const r3_object_matrices* matrices;
     const r3_batch_data* batches;
@@ -162,52 +164,136 @@ __device__ __forceinline__ float3 load_position(const TriCullParams& p, uint32_t
     if (f + 2u < p.mesh_words) return make_float3(__uint_as_float(__ldg(&p.mesh[f])), __uint_as_float(__ldg(&p.mesh[f + 1])), __uint_as_float(__ldg(&p.mesh[f + 2])));
     return make_float3(__uint_as_float(mesh_word(p, f)), __uint_as_float(mesh_word(p, f + 1)), __uint_as_float(mesh_word(p, f + 2)));   // robust access at the buffer end
 }
-__global__ void __launch_bounds__(TC_THREADS, 6) triangle_test_kernel(const __grid_constant__ TriCullParams p) {
+// ---- bulk-async staging of the index pulls (vertex_fetch, cull.wgsl:9-32).  The 32 invocations of a word read 96 consecutive index
+// words: one `cp.async.bulk` (the TMA unit's 1-D bulk copy, SASS UBLKCP) moves the run — widened to the enclosing 16-byte aligned 400
+// bytes — into the warp's own shared-memory slot and completes on the warp's own mbarrier (SYNCS).  Two slots per warp: the copy for the
+// NEXT workgroup is issued while the current one is being tested, so the index latency (and the three strided 4-byte loads per lane it
+// replaces) leaves the dependent chain  workgroup record -> indices -> positions -> test.
+constexpr uint32_t IDX_RUN_WORDS = 100;                        // 96 index words + up to 3 words of alignment slack, rounded to 16 bytes
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) triangle_test_kernel(const __grid_constant__ TriCullParams p) {
+    __shared__ __align__(16) uint32_t s_idx[TC_THREADS / 32][2][IDX_RUN_WORDS];
+    __shared__ __align__(8) uint64_t s_bar[TC_THREADS / 32][2];
     const uint32_t n_wg = __ldg(&p.header[3]) / TC_THREADS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool shadow = p.cam.shadow_index != R3_CAMERA_VIEWPORT;
-    for (uint32_t wg = blockIdx.x; wg < n_wg; wg += gridDim.x) {
-        const WgRec rec = load_wg(p, wg);
-        const uint32_t word = wg * (TC_THREADS / 32) + warp;                                   // global_invocation >> 5
-        const uint32_t local = warp * 32u + lane;                                              // invocation inside the workgroup
+    // Work is dealt out per WARP, not per CTA: warp g of the grid takes the workgroups g, g + G, g + 2 G, ... and walks the words of each
+    // that hold triangles (1..8) one after the other.  (Dealing a workgroup to a CTA leaves warp 0 busy in every workgroup and warp 7 in
+    // few: measured 2.4 ms instead of 2.1 ms per config-3 frame — half the resident warps idle behind the busy ones.)
+    const uint32_t total_warps = gridDim.x * (TC_THREADS / 32);
+    uint32_t wg = blockIdx.x * (TC_THREADS / 32) + warp;
+    if (wg >= n_wg) return;
+    if (lane == 0) { mbar_init(&s_bar[warp][0], 1u); mbar_init(&s_bar[warp][1], 1u); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncwarp();
+    uint32_t uses[2] = {0u, 0u};                                  // completed copies per slot: the mbarrier phase parity
+    // first index word of word `w` of the workgroup `r`, or ~0 when the run cannot be staged (it would leave the mesh allocation)
+    const auto run_start = [&](const WgRec& r, uint32_t w) -> uint64_t {
+        const uint64_t s = (uint64_t)r.first_index + ((uint64_t)r.object_invocation + w * 32u) * 3u;
+        return ((s & ~3ull) + IDX_RUN_WORDS <= p.mesh_cap_words) ? s : ~0ull;
+    };
+    const auto stage_run = [&](uint64_t s, int slot) {             // one elected lane: arm the barrier, start the copy
+        if (lane == 0 && s != ~0ull) {
+            mbar_expect_tx(&s_bar[warp][slot], IDX_RUN_WORDS * 4u);
+            bulk_copy_g2s(&s_idx[warp][slot][0], p.mesh + (s & ~3ull), IDX_RUN_WORDS * 4u, &s_bar[warp][slot]);
+        }
+    };
+    // the words of a workgroup past its last triangle: zero visibility words; non-atomic objects also need their slots INVALID
+    const auto pad_words = [&](const WgRec& r, uint32_t g, uint32_t nw) {
+        if ((uint32_t)lane >= nw && lane < TC_THREADS / 32) { p.res_out[g * (TC_THREADS / 32) + lane] = 0u; p.resid_bits[g * (TC_THREADS / 32) + lane] = 0u; }
+        if (!(r.flags & WG_ATOMIC))
+            for (uint32_t pw = nw; pw < TC_THREADS / 32; ++pw) {
+                const uint64_t o = (((uint64_t)g * (TC_THREADS / 32) + pw) * 32u + lane) * 3u;
+                p.idx_resid[o] = R3_INVALID_VERTEX; p.idx_resid[o + 1] = R3_INVALID_VERTEX; p.idx_resid[o + 2] = R3_INVALID_VERTEX;
+            }
+    };
+    // of the NEXT workgroup only the start of its first index run is kept (its record is read again, from L1 / L2, when the warp gets there)
+    const auto first_run = [&](uint32_t g) -> uint64_t {
+        const uint4 a = __ldg(&p.wg_info[2 * (size_t)g]), b = __ldg(&p.wg_info[2 * (size_t)g + 1]);
+        const uint64_t s = (uint64_t)a.y + (uint64_t)b.z * 3u;
+        return ((s & ~3ull) + IDX_RUN_WORDS <= p.mesh_cap_words) ? s : ~0ull;
+    };
+    WgRec rec = load_wg(p, wg);
+    uint32_t wg_n = wg + total_warps;
+    uint64_t run_n0 = wg_n < n_wg ? first_run(wg_n) : ~0ull;
+    uint32_t w = 0, nw = (rec.n_real + 31u) >> 5;
+    pad_words(rec, wg, nw);
+    uint64_t run = run_start(rec, 0u);
+    int slot = 0;
+    stage_run(run, slot);
+    for (;;) {
+        // the word after this one: the next word of this workgroup, or the first word of this warp's next workgroup
+        const bool same_wg = w + 1u < nw;
+        const bool has_next = same_wg || wg_n < n_wg;
+        const uint64_t run_next = has_next ? (same_wg ? run_start(rec, w + 1u) : run_n0) : ~0ull;
+
+        const uint32_t word = wg * (TC_THREADS / 32) + w;          // global_invocation >> 5
+        const uint32_t local = w * 32u + lane;                     // invocation inside the workgroup
         const bool atomic_capable = rec.flags & WG_ATOMIC;
         const bool real = local < rec.n_real;
+        const uint32_t object_invocation = rec.object_invocation + local;
+        const uint64_t ib = (uint64_t)rec.first_index + (uint64_t)object_invocation * 3u;   // vertex_fetch (cull.wgsl:9-32)
         bool passes = false, resid = false;
         uint32_t i0 = 0, i1 = 0, i2 = 0;
-        if (warp * 32u < rec.n_real) {
-            if (real) {
-                const uint32_t object_invocation = rec.object_invocation + local;
-                const uint64_t ib = (uint64_t)rec.first_index + (uint64_t)object_invocation * 3u;  // vertex_fetch (cull.wgsl:9-32)
-                if (ib + 2u < p.mesh_words) { i0 = __ldg(&p.mesh[ib]); i1 = __ldg(&p.mesh[ib + 1]); i2 = __ldg(&p.mesh[ib + 2]); }
-                else { i0 = mesh_word(p, ib); i1 = mesh_word(p, ib + 1); i2 = mesh_word(p, ib + 2); }
-                const float3 v0 = load_position(p, rec.pos_off, i0), v1 = load_position(p, rec.pos_off, i1), v2 = load_position(p, rec.pos_off, i2);
-                float mvp[16];
-                const float4* m4 = reinterpret_cast<const float4*>(p.matrices[rec.object_id].model_view_proj);   // 64-byte aligned: four 16-byte loads
+        if (run != ~0ull) {
+            mbar_wait(&s_bar[warp][slot], uses[slot] & 1u);
+            uses[slot]++;
+            const uint32_t o = (uint32_t)(run & 3ull) + (uint32_t)lane * 3u;
+            if (real) { i0 = s_idx[warp][slot][o]; i1 = s_idx[warp][slot][o + 1]; i2 = s_idx[warp][slot][o + 2]; }
+            if (real && ib + 2u >= p.mesh_words) { i0 = mesh_word(p, ib); i1 = mesh_word(p, ib + 1); i2 = mesh_word(p, ib + 2); }   // robust access at the buffer end
+        } else if (real) {
+            i0 = mesh_word(p, ib); i1 = mesh_word(p, ib + 1); i2 = mesh_word(p, ib + 2);
+        }
+        float3 v0 = make_float3(0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+        if (real) { v0 = load_position(p, rec.pos_off, i0); v1 = load_position(p, rec.pos_off, i1); v2 = load_position(p, rec.pos_off, i2); }
+        // the other slot was read one word ago by every lane (their position loads depended on it): refill it with the next word's run
+        __syncwarp();
+        stage_run(run_next, slot ^ 1);
+        if (real) {
+            float mvp[16];
+            const float4* m4 = reinterpret_cast<const float4*>(p.matrices[rec.object_id].model_view_proj);   // 64-byte aligned: four 16-byte loads
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { const float4 c4 = __ldg(&m4[k]); mvp[4 * k] = c4.x; mvp[4 * k + 1] = c4.y; mvp[4 * k + 2] = c4.z; mvp[4 * k + 3] = c4.w; }
-                passes = execute_culling(p, mvp, v0, v1, v2);
-                if (passes && !shadow && atomic_capable) {
-                    bool prev = false;                                                         // get_previous_culling_result (cull.wgsl:152-160)
-                    if (rec.prev_invocation != R3_NO_PREVIOUS) {
-                        const uint64_t pgi = (uint64_t)object_invocation + rec.prev_invocation;
-                        const uint32_t mask = (pgi >> 5) < p.res_in_words ? p.res_in[pgi >> 5] : 0u;
-                        prev = (mask >> (pgi & 31)) & 1u;
-                    }
-                    resid = !prev;
+            for (int q = 0; q < 4; ++q) { const float4 c4 = __ldg(&m4[q]); mvp[4 * q] = c4.x; mvp[4 * q + 1] = c4.y; mvp[4 * q + 2] = c4.z; mvp[4 * q + 3] = c4.w; }
+            passes = execute_culling(p, mvp, v0, v1, v2);
+            if (passes && !shadow && atomic_capable) {
+                bool prev = false;                                                             // get_previous_culling_result (cull.wgsl:152-160)
+                if (rec.prev_invocation != R3_NO_PREVIOUS) {
+                    const uint64_t pgi = (uint64_t)object_invocation + rec.prev_invocation;
+                    const uint32_t mask = (pgi >> 5) < p.res_in_words ? p.res_in[pgi >> 5] : 0u;
+                    prev = (mask >> (pgi & 31)) & 1u;
                 }
+                resid = !prev;
             }
-            const uint32_t word_pred = __ballot_sync(0xFFFFFFFFu, passes);
-            const uint32_t word_resid = __ballot_sync(0xFFFFFFFFu, resid);
-            if (lane == 0) {
-                p.res_out[word] = word_pred;                                                   // save_culling_results (cull.wgsl:229-241)
-                p.resid_bits[word] = word_resid;
-                // every visibility word is counted (atomic or not) so that the prefix over words is one consistent global scan
-                const unsigned long long t = ((unsigned long long)__popc(word_pred) << 32) | __popc(word_resid);
-                if (t) atomicAdd(&p.sb_counts[word / SB_WORDS], t);
-            }
-        } else if (lane == 0) {
-            p.res_out[word] = 0u;
-            p.resid_bits[word] = 0u;
+        }
+        const uint32_t word_pred = __ballot_sync(0xFFFFFFFFu, passes);
+        const uint32_t word_resid = __ballot_sync(0xFFFFFFFFu, resid);
+        if (lane == 0) {
+            p.res_out[word] = word_pred;                                                       // save_culling_results (cull.wgsl:229-241)
+            p.resid_bits[word] = word_resid;
+            // every visibility word is counted (atomic or not) so that the prefix over words is one consistent global scan
+            const unsigned long long t = ((unsigned long long)__popc(word_pred) << 32) | __popc(word_resid);
+            if (t) atomicAdd(&p.sb_counts[word / SB_WORDS], t);
         }
         if (!atomic_capable) {
             // non-atomic (blend) objects keep their slot: survivors in place, everything else INVALID (cull.wgsl:374-380,343-347)
@@ -217,6 +303,17 @@ __global__ void __launch_bounds__(TC_THREADS, 6) triangle_test_kernel(const __gr
             p.idx_resid[o + 1] = passes ? (hi | (i1 & 0xFFFFFFu)) : R3_INVALID_VERTEX;
             p.idx_resid[o + 2] = passes ? (hi | (i2 & 0xFFFFFFu)) : R3_INVALID_VERTEX;
         }
+        if (!has_next) break;
+        if (same_wg) {
+            w++;
+        } else {
+            wg = wg_n; rec = load_wg(p, wg); w = 0; nw = (rec.n_real + 31u) >> 5;
+            wg_n += total_warps;
+            run_n0 = wg_n < n_wg ? first_run(wg_n) : ~0ull;        // in flight while this workgroup is tested
+            pad_words(rec, wg, nw);
+        }
+        run = run_next;
+        slot ^= 1;
     }
 }
 
@@ -386,7 +483,7 @@ int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam) {
 
     TriCullParams p;
     p.cam = cam->header;
-    p.mesh = c->d_mesh; p.mesh_words = c->mesh_words;
+    p.mesh = c->d_mesh; p.mesh_words = c->mesh_words; p.mesh_cap_words = c->d_mesh ? c->mesh_cap : 0;
     p.objects = c->d_objects; p.matrices = cam->d_matrices; p.batches = j.d_batches;
     p.wg_info = wg_info; p.region_first_inv = j.d_region_first_inv; p.header = j.d_header;
     p.idx_pred = (uint32_t*)cam->index_buffer.d + cam->index_buffer.out_off();
@@ -400,13 +497,20 @@ int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam) {
     const bool viewport = cam->header.shadow_index == R3_CAMERA_VIEWPORT;
     p.hiz = c->d_hiz_ptrs; p.hiz_dims = c->d_hiz_dims; p.hiz_mips = viewport ? (uint32_t)c->d_hiz.size() : 0u;
 
-    static int test_ctas_per_sm = 0;   // resident CTAs per SM of the persistent test kernel (a property of the binary)
+    // resident CTAs per SM of the persistent test kernel (a property of the binary).  Two register budgets are compiled: 48 registers / 5 CTAs
+    // (default) and 64 / 4 (R3_TEST_CTAS=4, for experiments)
+    static int test_variant = 0, test_ctas_per_sm = 0;
     if (!test_ctas_per_sm) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&test_ctas_per_sm, triangle_test_kernel, TC_THREADS, 0) != cudaSuccess || test_ctas_per_sm < 1) test_ctas_per_sm = 4;
+        const char* e = getenv("R3_TEST_CTAS");
+        test_variant = (e && e[0] == '4') ? 4 : 5;
+        const cudaError_t rc = test_variant == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&test_ctas_per_sm, triangle_test_kernel<4>, TC_THREADS, 0)
+                                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&test_ctas_per_sm, triangle_test_kernel<5>, TC_THREADS, 0);
+        if (rc != cudaSuccess || test_ctas_per_sm < 1) test_ctas_per_sm = 4;
     }
-    const uint32_t test_grid = (uint32_t)R3_SM_COUNT * (uint32_t)test_ctas_per_sm;
+    const uint32_t test_grid = (uint32_t)R3_SM_COUNT * (uint32_t)test_ctas_per_sm, need_ctas = (n_wg + TC_THREADS / 32 - 1) / (TC_THREADS / 32);
     r3_stage_begin(c, R3_STAGE_TRIANGLE_TEST);
-    triangle_test_kernel<<<n_wg < test_grid ? n_wg : test_grid, TC_THREADS, 0, c->stream>>>(p);
+    if (test_variant == 4) triangle_test_kernel<4><<<need_ctas < test_grid ? need_ctas : test_grid, TC_THREADS, 0, c->stream>>>(p);
+    else triangle_test_kernel<5><<<need_ctas < test_grid ? need_ctas : test_grid, TC_THREADS, 0, c->stream>>>(p);
     r3_stage_end(c);
     R3_CHECK_LAUNCH(c, "triangle_test_kernel");
     superblock_scan_kernel<<<1, 1024, 0, c->stream>>>(sb_counts, j.d_header);

@@ -3,6 +3,7 @@
 // The scene file is what the engine's managers would hand over each frame (rend3_b200/scene_io.py writes it from the Python
 // scene generators); sections are  u32 tag_len | tag | u64 nbytes | payload.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -79,7 +80,9 @@ int main(int argc, char** argv) {
         const uint32_t width = tg[0], height = tg[1], frames = tg[4] ? tg[4] : 1;
 
         r3::Renderer renderer(argc > 3 ? std::atoi(argv[3]) : 0);
+        renderer.check(r3_set_parity_target(renderer.raw(), 1));   // this driver exists for the parity tests: keep the f32 shading result
         r3::BaseRenderGraph graph;
+        graph.submit_as_graph = std::getenv("R3_FRAME_GRAPH") && std::getenv("R3_FRAME_GRAPH")[0] != '0';
         renderer.upload_world(ev);
         for (uint32_t f = 0; f < frames; ++f)
             graph.add_to_graph(renderer, ev, width, height, tg[2] == 4 ? r3::SampleCount::Four : r3::SampleCount::One, settings, tg[3] != 0);

@@ -124,13 +124,18 @@ class BaseRenderGraph:
     def add_to_graph(self, ev: EvalOutput, resolution: Tuple[int, int], samples: int = 1,
                      settings: BaseRenderGraphSettings = BaseRenderGraphSettings(), srgb_target: bool = True,
                      upload: bool = True, scissor_rows: Optional[Tuple[int, int]] = None, shadow_filter=None, after_shadows=None,
-                     after_target=None, tonemap: bool = True):
+                     after_target=None, tonemap: bool = True, skinning=None, frame_graph: Optional[bool] = None):
         """One frame in the node order of base.rs:135-185.  `scissor_rows` restricts rasterisation and shading
         to a band of pixel rows (the screen-tile split of the multi-GPU forward pass); `shadow_filter(i)` selects the shadow
         maps this rank renders — it then clears only their rects, the others arrive from their owners — and `after_shadows()`
         runs once they are in the atlas (the ranks exchange their maps there); `after_target()` runs once the render target and
         the atlas exist (peer mappings are created there); `tonemap=False` leaves the blit to the caller (the assembling rank
-        runs it after the other ranks' rows have arrived)."""
+        runs it after the other ranks' rows have arrived); `frame_graph` records the frame's stream work and submits it as ONE CUDA
+        graph launch (r3_frame_begin / r3_frame_end; the reference submits once per frame, graph.rs:510) — default: the R3_FRAME_GRAPH
+        environment variable."""
+        import os
+        if frame_graph is None:
+            frame_graph = os.environ.get("R3_FRAME_GRAPH", "0") not in ("", "0")
         b, culler = self.backend, self.gpu_culler
         if upload:
             self.upload_world(ev)
@@ -141,6 +146,8 @@ class BaseRenderGraph:
             b.set_scissor_rows(scissor_rows[0], scissor_rows[1])
         if after_target is not None:
             after_target()
+        if frame_graph:
+            b.frame_begin()
         if shadow_filter is None:
             b.clear_shadow_atlas()                                                # base.rs:139
         else:
@@ -148,7 +155,8 @@ class BaseRenderGraph:
                 if shadow_filter(i):
                     b.clear_shadow_rect(s.offset[0], s.offset[1], s.size, s.size)
         b.set_frame_uniforms(frame_uniforms(ev.camera, settings.ambient_color, resolution))  # :142
-        # skinning (:145) — no animated meshes on this path
+        if skinning is not None:                                                  # :145 state.skinning: (skeleton records, joint matrices)
+            b.skin(skinning[0], skinning[1])
         mine = [(i, s) for i, s in enumerate(ev.shadows) if shadow_filter is None or shadow_filter(i)]
         for i, s in mine:                                                         # :148
             culler.object_uniform_upload(ev, s.camera, i, (s.size, s.size), 1)
@@ -169,3 +177,5 @@ class BaseRenderGraph:
         b.forward_blend()                                                         # :181 transparent objects, back to front
         if tonemap:
             b.tonemap(srgb_target)                                                # :184
+        if frame_graph:
+            b.frame_end()

@@ -713,6 +713,37 @@ def test_nan_and_signed_zero_distances_sort_like_ordered_float(cuda, monkeypatch
     host.close()
 
 
+def test_frames_submitted_as_cuda_graphs_match_oracle(monkeypatch):
+    """r3_frame_begin / r3_frame_end: the frame is recorded by stream capture and submitted as ONE graph launch (graph.rs:510: one submit
+    per frame); from the third frame on the instantiated graph of the same parity is only updated.  Five frames with a moving camera
+    (new kernel arguments every frame) and translucent objects (the blend routine reads a counter back: an early flush): every artefact
+    of every frame equals the oracle's, exactly as in eager submission."""
+    monkeypatch.setenv("R3_FRAME_GRAPH", "1")
+    from rend3_b200.world import CameraState, LEFT
+    res = (320, 200)
+    for mixed in (False, True):
+        ev = cube_field_scene(n_objects=1500, seed=3, resolution=res, n_dir_lights=1, shadow_resolution=256, shadow_distance=100.0, pull_back=8.0, extent=20.0,
+                              subdivisions=(1, 2), material_count=6 if mixed else 1, mixed_transparency=mixed)
+        b, orc = load_cuda_backend(0), load_oracle_backend()
+        graphs = {id(x): BaseRenderGraph(x) for x in (b, orc)}
+        base_view = ev.camera.view.copy()
+        for frame in range(5):
+            view = glam.mul(glam.from_rotation_y(np.float32(np.radians(0.5 * frame))), base_view)
+            ev.camera = CameraState(Camera(("perspective", 60.0, 0.1), view), LEFT, res[0] / res[1])
+            for x in (b, orc):
+                graphs[id(x)].add_to_graph(ev, res, 1, BaseRenderGraphSettings(clear_color=(0.1, 0.2, 0.3, 1.0)), upload=(frame == 0))
+            compare_frame_state(b, orc, ev, [CAMERA_VIEWPORT, 0], check_pixels=not mixed, what=f"graph frame {frame} (mixed={mixed})")
+            if mixed:
+                assert np.array_equal(b.readback_depth().view(np.uint32), orc.readback_depth().view(np.uint32))
+        st = b.frame_graph_stats()
+        assert st["frames"] == 5 and st["graphed"] == 5, st
+        if not mixed:
+            assert st["flushed"] <= 2 and st["instantiations"] <= 3, st      # steady frames: update + launch only
+        else:
+            assert st["flushed"] >= 3, st                                   # the blend routine's pool check flushes the recording
+        b.close()
+
+
 @pytest.mark.parametrize("frame_sort", ["0", "1"])
 def test_frame_wide_sort_equals_per_camera_sort(monkeypatch, frame_sort):
     """The cameras of a frame share one sort (the key does not depend on the camera, batching.rs:156-157) and take their visible

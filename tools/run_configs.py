@@ -39,6 +39,12 @@ def main():
         print(f"{name}: {n_obj} objects, {res[0]}x{res[1]}, {len(ev.shadows)} shadow maps | scene gen {gen:.1f}s first frame {first * 1e3:.1f} ms | steady frame {ms:.3f} ms"
               f" ({(b.launch_count() - l0) // frames} launches) | visible objects {b.visible_count(CAMERA_VIEWPORT)} predicted tris {tris} set-up {st[0]}"
               f" rasterised {st[1]} shaded {st[2]} -> {st[2] / ms / 1e3:.1f} Mfrag/s shaded, {n_obj / ms / 1e3:.2f} Mobj/s through the whole frame", flush=True)
+        b.set_stage_timing(True)
+        for _ in range(3):
+            g.add_to_graph(ev, res, 1, settings, upload=False)
+        st = b.stage_times()
+        b.set_stage_timing(False)
+        print("    stage ms/frame: " + ", ".join(f"{k} {v['ms'] / 3:.3f} ({v['launches'] // 3})" for k, v in st.items()), flush=True)
         b.close()
 
 
