@@ -394,12 +394,16 @@ def main():
         starts[i].record(stream)
         step_resident()
         ends[i].record(stream)
+    if exchange is not None:
+        exchange.join()              # the consumer kernels run on the library's side stream: the main stream waits for the last ones here
+    final = torch.cuda.Event(enable_timing=True)
+    final.record(stream)
     clocks.sample_now()              # GPU busy with the queued steps
     barrier()
     clocks.mark_end()
     clocks.__exit__()
-    # device time of the K steps on this rank (first start -> last end on the library stream); the job's time is the max over ranks
-    total_ms = max_over_ranks(starts[0].elapsed_time(ends[-1]))
+    # device time of the K steps on this rank (first start -> everything of the last step done); the job's time is the max over ranks
+    total_ms = max_over_ranks(starts[0].elapsed_time(final))
     launches = backend.launch_count() - launches0
     n_vis = backend.visible_count(CAMERA_VIEWPORT)
     ms_per_step = total_ms / args.steps
@@ -435,6 +439,8 @@ def main():
         s0.record(stream)
         for _ in range(args.steps):
             step_strong()
+        if exchange is not None:
+            exchange.join()
         s1.record(stream)
         barrier()
         sms = max_over_ranks(s0.elapsed_time(s1)) / args.steps
@@ -545,7 +551,8 @@ def forward_section(args, torch, dist, load_cuda_backend, rank, world, local, de
     def frame(upload):
         if world > 1:
             graph.add_to_graph(ev, res, 1, settings, upload=upload, scissor_rows=rows, shadow_filter=split.owns_shadow,
-                               after_shadows=split.exchange_shadow_maps if n_shadows else None, after_target=split.connect, tonemap=False)
+                               after_shadows=split.send_shadow_maps if n_shadows else None, before_resolve=split.wait_shadow_maps if n_shadows else None,
+                               after_target=split.begin_frame, tonemap=False)
             split.exchange_rows(rows)
         else:
             graph.add_to_graph(ev, res, 1, settings, upload=upload)

@@ -224,15 +224,22 @@ int r3_exchange_merged(r3_ctx*, uint32_t camera, void** device_list /* u32 globa
 int r3_exchange_destroy(r3_ctx*, uint32_t camera);
 /* Peer-memory plumbing of the multi-GPU forward pass (shadow maps split by light, screen split in row tiles; one process per
  * GPU on one NVLink / NVSwitch node).  r3_peer_create (after r3_set_directional_lights and r3_set_render_target: the atlas and the rgba16f
- * target must exist and must not be reallocated afterwards) returns three CUDA IPC handles — flag block, shadow atlas, colour target; the
+ * target must exist and must not be reallocated afterwards; the objects must be uploaded) returns four CUDA IPC handles — flag block,
+ * shadow atlas, colour target, staging arrays of the sharded triangle test; the
  * caller all-gathers them and calls r3_peer_connect.  Then, all stream-ordered and without host synchronisation:
  *   r3_peer_send_atlas_rect  copies a rect of the local atlas into the same rect of EVERY peer's atlas (plain stores over NVLink);
  *   r3_peer_send_rows        copies rows of the local rgba16f target into the peers' targets (root >= 0: only into that rank's);
  *   r3_peer_signal(kind)     publishes everything sent so far: flags[kind][my_rank] = ++epoch on every rank (st.release.sys);
  *   r3_peer_wait(kind, e[])  a one-CTA kernel on this context's stream that spins (ld.acquire.sys) until flags[kind][r] >= e[r] for all r.
- * kinds: 0 shadow atlas, 1 colour rows, 2 frame done, 3 spare.  rend3_b200/parallel.py::ForwardSplit shows the per-frame protocol. */
-int r3_peer_create(r3_ctx*, uint32_t n_ranks, uint32_t my_rank, uint8_t handles_out[3 * R3_IPC_HANDLE_BYTES]);
-int r3_peer_connect(r3_ctx*, const uint8_t* handles /* n_ranks x 3 x R3_IPC_HANDLE_BYTES, rank order */);
+ * kinds: 0 shadow atlas, 1 colour rows, 2 frame done, 3 visibility words of the sharded triangle test (used by r3_cull itself).  rend3_b200/parallel.py::ForwardSplit shows the per-frame protocol. */
+int r3_peer_create(r3_ctx*, uint32_t n_ranks, uint32_t my_rank, uint8_t handles_out[4 * R3_IPC_HANDLE_BYTES]);
+int r3_peer_connect(r3_ctx*, const uint8_t* handles /* n_ranks x 4 x R3_IPC_HANDLE_BYTES, rank order */);
+/* SURVEY 8e "triangle cull: shard by batch": with count = n_ranks (> 1), r3_cull of the VIEWPORT camera tests only this rank's run of
+ * workgroups — they are laid out batch after batch, so a shard is a run of batches — stores its visibility words into the staging arrays
+ * of every rank, publishes them (flag kind 3) and, once everybody's words have arrived, continues with the scan / compaction on the full
+ * set: every rank ends up with the same index lists and draw records.  Falls back to testing everything while translucent (non-atomic)
+ * objects exist, whose in-place index slots are not exchanged. */
+int r3_set_cull_shard(r3_ctx*, uint32_t shard_index, uint32_t shard_count);
 int r3_peer_send_atlas_rect(r3_ctx*, uint32_t offset_x, uint32_t offset_y, uint32_t width, uint32_t height);
 int r3_peer_send_rows(r3_ctx*, uint32_t row_begin, uint32_t row_end, int root /* -1 = every peer */);
 int r3_peer_signal(r3_ctx*, uint32_t kind);

@@ -39,7 +39,7 @@ ENTRY_POINTS = [
     "set_parity_target", "readback_hdr_f32", "readback_hdr_f16", "readback_depth", "readback_ldr", "readback_shadow_atlas",
     "readback_hiz", "forward_stats", "forward_light_evaluations", "device_ptr", "set_scissor_rows", "skin", "readback_mesh_buffer",
     "exchange_create", "exchange_connect", "exchange_words", "exchange_merge", "exchange_merged", "exchange_destroy",
-    "peer_create", "peer_connect", "peer_send_atlas_rect", "peer_send_rows", "peer_signal", "peer_wait", "peer_destroy", "clear_shadow_rect",
+    "peer_create", "peer_connect", "peer_send_atlas_rect", "peer_send_rows", "peer_signal", "peer_wait", "peer_destroy", "clear_shadow_rect", "set_cull_shard",
 ]
 
 
@@ -311,7 +311,7 @@ class Backend:
 
     # ---- peer-memory plumbing of the multi-GPU forward pass
     def peer_create(self, n_ranks: int, my_rank: int) -> bytes:
-        h = (C.c_uint8 * 192)()
+        h = (C.c_uint8 * 256)()
         self._call("peer_create", C.c_uint32(n_ranks), C.c_uint32(my_rank), h)
         return bytes(h)
 
@@ -331,6 +331,9 @@ class Backend:
     def peer_wait(self, kind: int, expected):
         e = np.ascontiguousarray(expected, dtype=np.uint32)
         self._call("peer_wait", C.c_uint32(kind), _ptr(e))
+
+    def set_cull_shard(self, index: int, count: int):
+        self._call("set_cull_shard", C.c_uint32(index), C.c_uint32(count))
 
     def peer_destroy(self):
         self._call("peer_destroy")

@@ -48,13 +48,14 @@ struct r3_stage_timer {
 };
 constexpr int R3_MAX_EXCHANGE_RANKS = 16;
 // peer-memory plumbing of the multi-GPU forward pass (r3_peer.cu): kinds of epoch flags
-constexpr uint32_t R3_PEER_KINDS = 4;        // 0 shadow atlas rects, 1 colour rows, 2 frame done, 3 spare
+constexpr uint32_t R3_PEER_KINDS = 4;        // 0 shadow atlas rects, 1 colour rows, 2 frame done, 3 visibility words of the sharded triangle test
 struct r3_peer_state {
     bool created = false, connected = false, has_atlas = false;
     uint32_t n_ranks = 0, rank = 0;
     uint32_t* d_flags = nullptr;              // this rank's flags[R3_PEER_KINDS][R3_MAX_EXCHANGE_RANKS]
     uint32_t* flags[R3_MAX_EXCHANGE_RANKS] = {}; float* atlas[R3_MAX_EXCHANGE_RANKS] = {}; uint16_t* hdr16[R3_MAX_EXCHANGE_RANKS] = {};   // peer mappings
     uint32_t sent[R3_PEER_KINDS] = {0, 0, 0, 0};
+    uint32_t* d_tri_words = nullptr; uint64_t tri_cap_words = 0; uint32_t* tri_words[R3_MAX_EXCHANGE_RANKS] = {};   // staging arrays of the sharded triangle test
     const void* atlas_at_create = nullptr; const void* hdr_at_create = nullptr;
 };
 struct r3_camera {
@@ -69,6 +70,7 @@ struct r3_camera {
     uint32_t* d_gathered = nullptr; uint32_t ex_ranks = 0, ex_rank = 0, ex_words_per_rank = 0; bool ex_connected = false;
     uint32_t* ex_peers[R3_MAX_EXCHANGE_RANKS] = {};   // peer-mapped gathered buffers (ex_peers[ex_rank] == d_gathered)
     uint32_t ex_epoch = 0, ex_objects = 0; uint32_t* d_ex_done = nullptr;       // step counter (parity = epoch & 1), CTA arrival counter of the publishing kernel
+    cudaEvent_t ex_cull_done[2] = {nullptr, nullptr}, ex_merge_done[2] = {nullptr, nullptr}; bool ex_merge_pending[2] = {false, false};   // merge on the side stream
     uint32_t* d_global_visible = nullptr; uint64_t global_visible_cap = 0; uint32_t* d_merge_counts = nullptr; uint64_t merge_counts_cap = 0;   // r3_exchange_merge
     int visible_count_host = -1;              // cached after a readback, -1 = unknown
     r3_jobs jobs[2]; int cur = 0;             // jobs[cur] = this frame, jobs[cur^1] = cached DrawCallSet (forward.rs:219)
@@ -93,6 +95,7 @@ static_assert(sizeof(r3_tri_record) == 64, "triangle record");
 struct r3_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;       // high-priority stream of the exchange consumer (r3_exchange_merge), created on first use
     std::string err;
     uint64_t launches = 0;
     bool coop_launch_ok = false;              // cudaDevAttrCooperativeLaunch (grid-wide barriers inside one launch)
@@ -136,6 +139,7 @@ struct r3_ctx {
     void* d_scratch = nullptr; uint64_t scratch_cap = 0;
     r3_stage_timer timer;
     r3_peer_state peer;
+    uint32_t tri_shard_index = 0, tri_shard_count = 1;   // r3_set_cull_shard
     // frame graph
     bool capturing = false;                   // between r3_frame_begin and the submission (or an early flush)
     cudaGraphExec_t frame_exec[2] = {nullptr, nullptr};   // instantiated graphs of even / odd frames (the culling buffers ping-pong), updated in place

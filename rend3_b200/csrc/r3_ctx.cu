@@ -68,6 +68,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     if (!c) return R3_E_INVALID;
     cudaSetDevice(c->device);
     r3_stream_sync(c);
+    if (c->side_stream) cudaStreamSynchronize(c->side_stream);
     r3_peer_destroy(c);
     if (!c->objects_borrowed) cudaFree(c->d_objects);
     cudaFree(c->d_hot_transform); cudaFree(c->d_hot_sphere); cudaFree(c->d_enabled_bits); cudaFree(c->d_tex_descs); cudaFree(c->d_texels); cudaFree(c->d_sky_texels);
@@ -82,6 +83,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
             cudaFree(k.d_gathered);
         }
         cudaFree(k.d_ex_done); cudaFree(k.d_global_visible); cudaFree(k.d_merge_counts);
+        for (int q = 0; q < 2; ++q) { if (k.ex_cull_done[q]) cudaEventDestroy(k.ex_cull_done[q]); if (k.ex_merge_done[q]) cudaEventDestroy(k.ex_merge_done[q]); }
         free_jobs(k.jobs[0]); free_jobs(k.jobs[1]);
         cudaFree(k.index_buffer.d); cudaFree(k.draw_call_buffer.d); cudaFree(k.results_buffer.d);
         cudaFree(k.d_resid_bits); cudaFree(k.d_word_scan); cudaFree(k.d_block_sums);
@@ -94,6 +96,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
     cudaFree(c->d_frag_heads); cudaFree(c->d_frag_nodes);
     for (cudaEvent_t e : c->timer.pool) cudaEventDestroy(e);
     for (auto& x : c->frame_exec) if (x) cudaGraphExecDestroy(x);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     cudaStreamDestroy(c->stream);
     delete c;
     return R3_OK;
@@ -101,7 +104,9 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
 R3_EXPORT const char* r3_last_error(const r3_ctx* c) { return c ? c->err.c_str() : "null context"; }
 R3_EXPORT int r3_sync(r3_ctx* c) {
     if (!c) return R3_E_INVALID;
+    cudaSetDevice(c->device);
     R3_CUDA(c, r3_stream_sync(c));
+    if (c->side_stream) R3_CUDA(c, cudaStreamSynchronize(c->side_stream));   // exchange consumers in flight
     return R3_OK;
 }
 R3_EXPORT int r3_get_stream(r3_ctx* c, void** s) {

@@ -367,6 +367,10 @@ int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode) {
             if (n_words > cam->ex_words_per_rank) return r3_fail(c, R3_E_INVALID, "object_uniform_upload: more objects than the exchange was created for");
             for (uint32_t r = 0; r < cam->ex_ranks; ++r) ex.peers[r] = cam->ex_peers[r];
             const uint32_t epoch = ++cam->ex_epoch, parity = epoch & 1u;
+            if (cam->ex_merge_pending[parity]) {   // the consumer of epoch - 2 still reads the rows this step overwrites
+                R3_CUDA(c, cudaStreamWaitEvent(c->stream, cam->ex_merge_done[parity], 0));
+                cam->ex_merge_pending[parity] = false;
+            }
             ex.n_ranks = cam->ex_ranks; ex.words_per_rank = cam->ex_words_per_rank;
             ex.word_offset = EX_HEADER_WORDS + (parity * cam->ex_ranks + cam->ex_rank) * cam->ex_words_per_rank;
             ex.flag_offset = parity * R3_MAX_EXCHANGE_RANKS + cam->ex_rank; ex.epoch = epoch; ex.done = cam->d_ex_done;
@@ -491,16 +495,33 @@ R3_EXPORT int r3_exchange_merge(r3_ctx* c, uint32_t camera, const uint32_t* rank
     R3_TRY(r3_reserve_t(c, &cam->d_global_visible, &cam->global_visible_cap, total + 1));
     R3_TRY(r3_reserve_t(c, &cam->d_merge_counts, &cam->merge_counts_cap, (uint64_t)n_tiles + 4));
     p.tile_counts = cam->d_merge_counts + 4; p.out = cam->d_global_visible; p.out_count = cam->d_merge_counts; p.out_cap = (uint32_t)total;
-    exchange_wait_count_kernel<<<n_tiles, CP_THREADS, 0, c->stream>>>(p);
+    // The consumer runs on the context's side stream, behind the cull that produced this rank's row: the NEXT cull + bake (other parity)
+    // overlaps it, so a step costs max(cull, merge) instead of their sum.  The cull of epoch e + 2 — which overwrites this parity — waits for
+    // this merge (r3_launch_cull_bake), and r3_exchange_merged / r3_sync wait for it before handing the list out.
+    if (!c->side_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        R3_CUDA(c, cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi));
+    }
+    const int slot = (int)(cam->ex_epoch & 1u);
+    if (!cam->ex_cull_done[slot]) R3_CUDA(c, cudaEventCreateWithFlags(&cam->ex_cull_done[slot], cudaEventDisableTiming));
+    if (!cam->ex_merge_done[slot]) R3_CUDA(c, cudaEventCreateWithFlags(&cam->ex_merge_done[slot], cudaEventDisableTiming));
+    R3_CUDA(c, cudaEventRecord(cam->ex_cull_done[slot], c->stream));
+    R3_CUDA(c, cudaStreamWaitEvent(c->side_stream, cam->ex_cull_done[slot], 0));
+    exchange_wait_count_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
     R3_CHECK_LAUNCH(c, "exchange_wait_count_kernel");
-    exchange_expand_kernel<<<n_tiles, CP_THREADS, 0, c->stream>>>(p);
+    exchange_expand_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
     R3_CHECK_LAUNCH(c, "exchange_expand_kernel");
+    R3_CUDA(c, cudaEventRecord(cam->ex_merge_done[slot], c->side_stream));
+    cam->ex_merge_pending[slot] = true;
     return R3_OK;
 }
 R3_EXPORT int r3_exchange_merged(r3_ctx* c, uint32_t camera, void** device_list, void** device_count, uint64_t* capacity) {
     if (!c || !device_list || !device_count) return r3_fail(c, R3_E_INVALID, "exchange_merged: null");
     r3_camera* cam = r3_get_camera(c, camera);
     if (!cam || !cam->d_global_visible) return r3_fail(c, R3_E_STATE, "exchange_merged before exchange_merge");
+    for (int k = 0; k < 2; ++k)      // the main stream (and with it r3_sync) now waits for the merges in flight
+        if (cam->ex_merge_pending[k]) { R3_CUDA(c, cudaStreamWaitEvent(c->stream, cam->ex_merge_done[k], 0)); cam->ex_merge_pending[k] = false; }
     *device_list = cam->d_global_visible; *device_count = cam->d_merge_counts;
     if (capacity) *capacity = cam->global_visible_cap;
     return R3_OK;
@@ -513,6 +534,12 @@ R3_EXPORT int r3_exchange_destroy(r3_ctx* c, uint32_t camera) {
     r3_stream_sync(c);
     for (uint32_t r = 0; r < cam->ex_ranks; ++r)
         if (cam->ex_connected && r != cam->ex_rank && cam->ex_peers[r]) cudaIpcCloseMemHandle(cam->ex_peers[r]);
+    if (c->side_stream) cudaStreamSynchronize(c->side_stream);
+    for (int k = 0; k < 2; ++k) {
+        if (cam->ex_cull_done[k]) cudaEventDestroy(cam->ex_cull_done[k]);
+        if (cam->ex_merge_done[k]) cudaEventDestroy(cam->ex_merge_done[k]);
+        cam->ex_cull_done[k] = cam->ex_merge_done[k] = nullptr; cam->ex_merge_pending[k] = false;
+    }
     cudaFree(cam->d_gathered);
     cam->d_gathered = nullptr; cam->ex_connected = false; cam->ex_ranks = 0; cam->ex_epoch = 0;
     for (auto& p : cam->ex_peers) p = nullptr;

@@ -64,7 +64,7 @@ static int peer_copy(r3_ctx* c, const void* src, void* const* dsts, uint32_t n_d
     return R3_OK;
 }
 
-R3_EXPORT int r3_peer_create(r3_ctx* c, uint32_t n_ranks, uint32_t my_rank, uint8_t handles_out[3 * R3_IPC_HANDLE_BYTES]) {
+R3_EXPORT int r3_peer_create(r3_ctx* c, uint32_t n_ranks, uint32_t my_rank, uint8_t handles_out[4 * R3_IPC_HANDLE_BYTES]) {
     if (!c || !handles_out) return r3_fail(c, R3_E_INVALID, "peer_create: null");
     if (n_ranks == 0 || n_ranks > R3_MAX_EXCHANGE_RANKS || my_rank >= n_ranks) return r3_fail(c, R3_E_INVALID, "peer_create: bad rank layout");
     if (!c->d_hdr16) return r3_fail(c, R3_E_STATE, "peer_create before set_render_target");
@@ -73,13 +73,21 @@ R3_EXPORT int r3_peer_create(r3_ctx* c, uint32_t n_ranks, uint32_t my_rank, uint
     R3_CUDA(c, cudaMalloc((void**)&c->peer.d_flags, 1024));
     R3_CUDA(c, cudaMemsetAsync(c->peer.d_flags, 0, 1024, c->stream));
     R3_CUDA(c, r3_stream_sync(c));
-    memset(handles_out, 0, 3 * R3_IPC_HANDLE_BYTES);
+    memset(handles_out, 0, 4 * R3_IPC_HANDLE_BYTES);
     cudaIpcMemHandle_t h;
     R3_CUDA(c, cudaIpcGetMemHandle(&h, c->peer.d_flags));
     memcpy(handles_out, &h, sizeof h);
     if (c->d_atlas) { R3_CUDA(c, cudaIpcGetMemHandle(&h, c->d_atlas)); memcpy(handles_out + R3_IPC_HANDLE_BYTES, &h, sizeof h); }
     R3_CUDA(c, cudaIpcGetMemHandle(&h, c->d_hdr16));
     memcpy(handles_out + 2 * R3_IPC_HANDLE_BYTES, &h, sizeof h);
+    // staging arrays of the sharded triangle test: [pred words | resid words], sized by the upper bound of the world's padded invocations
+    R3_TRY(r3_compute_max_invocations(c));
+    c->peer.tri_cap_words = (c->max_total_invocations + 31) / 32 + 64;
+    R3_CUDA(c, cudaMalloc((void**)&c->peer.d_tri_words, c->peer.tri_cap_words * 2 * 4));
+    R3_CUDA(c, cudaMemsetAsync(c->peer.d_tri_words, 0, c->peer.tri_cap_words * 2 * 4, c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
+    R3_CUDA(c, cudaIpcGetMemHandle(&h, c->peer.d_tri_words));
+    memcpy(handles_out + 3 * R3_IPC_HANDLE_BYTES, &h, sizeof h);
     c->peer.created = true; c->peer.connected = false; c->peer.n_ranks = n_ranks; c->peer.rank = my_rank;
     c->peer.has_atlas = c->d_atlas != nullptr;
     c->peer.atlas_at_create = c->d_atlas; c->peer.hdr_at_create = c->d_hdr16;
@@ -91,8 +99,8 @@ R3_EXPORT int r3_peer_connect(r3_ctx* c, const uint8_t* handles) {
     if (!c->peer.created) return r3_fail(c, R3_E_STATE, "peer_connect before peer_create");
     cudaSetDevice(c->device);
     for (uint32_t r = 0; r < c->peer.n_ranks; ++r) {
-        if (r == c->peer.rank) { c->peer.flags[r] = c->peer.d_flags; c->peer.atlas[r] = c->d_atlas; c->peer.hdr16[r] = c->d_hdr16; continue; }
-        const uint8_t* base = handles + (size_t)r * 3 * R3_IPC_HANDLE_BYTES;
+        if (r == c->peer.rank) { c->peer.flags[r] = c->peer.d_flags; c->peer.atlas[r] = c->d_atlas; c->peer.hdr16[r] = c->d_hdr16; c->peer.tri_words[r] = c->peer.d_tri_words; continue; }
+        const uint8_t* base = handles + (size_t)r * 4 * R3_IPC_HANDLE_BYTES;
         cudaIpcMemHandle_t h;
         void* p = nullptr;
         memcpy(&h, base, sizeof h);
@@ -106,6 +114,9 @@ R3_EXPORT int r3_peer_connect(r3_ctx* c, const uint8_t* handles) {
         memcpy(&h, base + 2 * R3_IPC_HANDLE_BYTES, sizeof h);
         R3_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         c->peer.hdr16[r] = (uint16_t*)p;
+        memcpy(&h, base + 3 * R3_IPC_HANDLE_BYTES, sizeof h);
+        R3_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer.tri_words[r] = (uint32_t*)p;
     }
     c->peer.connected = true;
     return R3_OK;
@@ -166,9 +177,22 @@ R3_EXPORT int r3_peer_destroy(r3_ctx* c) {
             if (c->peer.flags[r]) cudaIpcCloseMemHandle(c->peer.flags[r]);
             if (c->peer.atlas[r]) cudaIpcCloseMemHandle(c->peer.atlas[r]);
             if (c->peer.hdr16[r]) cudaIpcCloseMemHandle(c->peer.hdr16[r]);
+            if (c->peer.tri_words[r]) cudaIpcCloseMemHandle(c->peer.tri_words[r]);
         }
-    cudaFree(c->peer.d_flags);
+    cudaFree(c->peer.d_flags); cudaFree(c->peer.d_tri_words);
     c->peer = r3_peer_state{};
+    c->tri_shard_index = 0; c->tri_shard_count = 1;
+    return R3_OK;
+}
+// SURVEY 8e "triangle cull: shard by batch": from now on r3_cull of the VIEWPORT camera tests only the shard's run of workgroups (= batches)
+// and exchanges the visibility words with the peers (r3_tri_cull.cu); count <= 1 switches it off.  Every rank must use the same count.
+R3_EXPORT int r3_set_cull_shard(r3_ctx* c, uint32_t shard_index, uint32_t shard_count) {
+    if (!c) return R3_E_INVALID;
+    if (shard_count > 1u) {
+        if (!c->peer.connected) return r3_fail(c, R3_E_STATE, "set_cull_shard before peer_connect");
+        if (shard_count != c->peer.n_ranks || shard_index != c->peer.rank) return r3_fail(c, R3_E_INVALID, "set_cull_shard: the shards are the peer ranks");
+    }
+    c->tri_shard_index = shard_count > 1u ? shard_index : 0u; c->tri_shard_count = shard_count > 1u ? shard_count : 1u;
     return R3_OK;
 }
 // the rect of one shadow map (a rank that owns only some of the lights clears only their rects: the others arrive from their owners)

@@ -819,6 +819,19 @@ __global__ void __launch_bounds__(256) hiz_head_kernel(const unsigned long long*
         if (x3 < w3 && y3 < h3) mips[3][(size_t)y3 * w3 + x3] = v;
     }
 }
+// one level, one thread per destination texel: the levels between the fused head and the single-CTA tail that are still large
+__global__ void hiz_downsample_kernel(const float* __restrict__ src, uint32_t sw, uint32_t sh, float* __restrict__ dst, uint32_t dw, uint32_t dh) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const uint32_t oddx = sw & 1u, oddy = sh & 1u;
+    float nearest = 1.0f;
+    for (uint32_t dx = 0; dx < 2u + oddx; ++dx)
+        for (uint32_t dy = 0; dy < 2u + oddy; ++dy) {
+            const uint32_t sx = 2u * x + dx, sy = 2u * y + dy;
+            if (sx < sw && sy < sh) nearest = fminf(nearest, src[(size_t)sy * sw + sx]);
+        }
+    dst[(size_t)y * dw + x] = nearest;
+}
 __global__ void __launch_bounds__(1024) hiz_tail_kernel(float* const* __restrict__ mips, const uint32_t* __restrict__ dims, uint32_t first, uint32_t n_mips) {
     for (uint32_t m = first; m < n_mips; ++m) {
         const uint32_t sw = dims[2 * (m - 1)], sh = dims[2 * (m - 1) + 1], dw = dims[2 * m], dh = dims[2 * m + 1];
@@ -945,8 +958,14 @@ R3_EXPORT int r3_hiz_build(r3_ctx* c) {
     const dim3 grid((c->width + 31) / 32, (c->height + 31) / 32);
     hiz_head_kernel<<<grid, 256, 0, c->stream>>>(c->d_vis, c->samples, c->d_hiz_ptrs, c->d_hiz_dims, fused);
     R3_CHECK_LAUNCH(c, "hiz_head_kernel");
-    if (fused + 1u < n_mips) {
-        hiz_tail_kernel<<<1, 1024, 0, c->stream>>>(c->d_hiz_ptrs, c->d_hiz_dims, fused + 1u, n_mips);
+    uint32_t m = fused + 1u;
+    for (; m < n_mips && (uint64_t)c->hiz_w[m] * c->hiz_h[m] > 4096u; ++m) {   // still large: one launch per level, thousands of threads
+        const dim3 block(32, 8), dgrid((c->hiz_w[m] + 31) / 32, (c->hiz_h[m] + 7) / 8);
+        hiz_downsample_kernel<<<dgrid, block, 0, c->stream>>>(c->d_hiz[m - 1], c->hiz_w[m - 1], c->hiz_h[m - 1], c->d_hiz[m], c->hiz_w[m], c->hiz_h[m]);
+        R3_CHECK_LAUNCH(c, "hiz_downsample_kernel");
+    }
+    if (m < n_mips) {                                                            // the small rest: one CTA walks the levels
+        hiz_tail_kernel<<<1, 1024, 0, c->stream>>>(c->d_hiz_ptrs, c->d_hiz_dims, m, n_mips);
         R3_CHECK_LAUNCH(c, "hiz_tail_kernel");
     }
     return R3_OK;

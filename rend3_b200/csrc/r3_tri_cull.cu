@@ -47,6 +47,11 @@ struct TriCullParams {
     unsigned long long* sb_counts;       // [n_superblocks + 1] (pred << 32 | resid): counts, then their exclusive prefix
     unsigned long long* region_prefix;   // [n_regions + 1] survivors in front of each region
     float* const* hiz; const uint32_t* hiz_dims; uint32_t hiz_mips;
+    // multi-GPU ("triangle cull: shard by batch"): this launch tests the workgroups [n_wg * shard_index / shard_count,
+    // n_wg * (shard_index + 1) / shard_count) — workgroups are laid out batch after batch, so a shard is a run of batches — and stores
+    // its visibility words into the staging arrays [pred words | resid words] of EVERY rank (peer memory) instead of the local buffers
+    uint32_t shard_index, shard_count, ex_n, ex_cap_words;
+    uint32_t* ex_peers[R3_MAX_EXCHANGE_RANKS];
 };
 
 __device__ __forceinline__ uint32_t mesh_word(const TriCullParams& p, uint64_t i) { return i < p.mesh_words ? __ldg(&p.mesh[i]) : 0u; }
@@ -203,8 +208,23 @@ __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) triangle_test_kernel(con
     // that hold triangles (1..8) one after the other.  (Dealing a workgroup to a CTA leaves warp 0 busy in every workgroup and warp 7 in
     // few: measured 2.4 ms instead of 2.1 ms per config-3 frame — half the resident warps idle behind the busy ones.)
     const uint32_t total_warps = gridDim.x * (TC_THREADS / 32);
-    uint32_t wg = blockIdx.x * (TC_THREADS / 32) + warp;
-    if (wg >= n_wg) return;
+    const uint32_t wg_lo = p.shard_count > 1u ? (uint32_t)((uint64_t)n_wg * p.shard_index / p.shard_count) : 0u;
+    const uint32_t wg_end = p.shard_count > 1u ? (uint32_t)((uint64_t)n_wg * (p.shard_index + 1u) / p.shard_count) : n_wg;
+    uint32_t wg = wg_lo + blockIdx.x * (TC_THREADS / 32) + warp;
+    if (wg >= wg_end) return;
+    // one visibility word pair: local buffers + superblock counter, or (sharded) the staging arrays of every rank
+    const auto store_words = [&](uint32_t word, uint32_t pred, uint32_t resid) {
+        if (p.ex_n) {
+#pragma unroll 1
+            for (uint32_t r = 0; r < p.ex_n; ++r) { p.ex_peers[r][word] = pred; p.ex_peers[r][p.ex_cap_words + word] = resid; }
+        } else {
+            p.res_out[word] = pred;                                                            // save_culling_results (cull.wgsl:229-241)
+            p.resid_bits[word] = resid;
+            // every visibility word is counted (atomic or not) so that the prefix over words is one consistent global scan
+            const unsigned long long t = ((unsigned long long)__popc(pred) << 32) | __popc(resid);
+            if (t) atomicAdd(&p.sb_counts[word / SB_WORDS], t);
+        }
+    };
     if (lane == 0) { mbar_init(&s_bar[warp][0], 1u); mbar_init(&s_bar[warp][1], 1u); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
     uint32_t uses[2] = {0u, 0u};                                  // completed copies per slot: the mbarrier phase parity
@@ -221,7 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) triangle_test_kernel(con
     };
     // the words of a workgroup past its last triangle: zero visibility words; non-atomic objects also need their slots INVALID
     const auto pad_words = [&](const WgRec& r, uint32_t g, uint32_t nw) {
-        if ((uint32_t)lane >= nw && lane < TC_THREADS / 32) { p.res_out[g * (TC_THREADS / 32) + lane] = 0u; p.resid_bits[g * (TC_THREADS / 32) + lane] = 0u; }
+        if ((uint32_t)lane >= nw && lane < TC_THREADS / 32) store_words(g * (TC_THREADS / 32) + lane, 0u, 0u);
         if (!(r.flags & WG_ATOMIC))
             for (uint32_t pw = nw; pw < TC_THREADS / 32; ++pw) {
                 const uint64_t o = (((uint64_t)g * (TC_THREADS / 32) + pw) * 32u + lane) * 3u;
@@ -236,7 +256,7 @@ __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) triangle_test_kernel(con
     };
     WgRec rec = load_wg(p, wg);
     uint32_t wg_n = wg + total_warps;
-    uint64_t run_n0 = wg_n < n_wg ? first_run(wg_n) : ~0ull;
+    uint64_t run_n0 = wg_n < wg_end ? first_run(wg_n) : ~0ull;
     uint32_t w = 0, nw = (rec.n_real + 31u) >> 5;
     pad_words(rec, wg, nw);
     uint64_t run = run_start(rec, 0u);
@@ -245,7 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) triangle_test_kernel(con
     for (;;) {
         // the word after this one: the next word of this workgroup, or the first word of this warp's next workgroup
         const bool same_wg = w + 1u < nw;
-        const bool has_next = same_wg || wg_n < n_wg;
+        const bool has_next = same_wg || wg_n < wg_end;
         const uint64_t run_next = has_next ? (same_wg ? run_start(rec, w + 1u) : run_n0) : ~0ull;
 
         const uint32_t word = wg * (TC_THREADS / 32) + w;          // global_invocation >> 5
@@ -288,13 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) triangle_test_kernel(con
         }
         const uint32_t word_pred = __ballot_sync(0xFFFFFFFFu, passes);
         const uint32_t word_resid = __ballot_sync(0xFFFFFFFFu, resid);
-        if (lane == 0) {
-            p.res_out[word] = word_pred;                                                       // save_culling_results (cull.wgsl:229-241)
-            p.resid_bits[word] = word_resid;
-            // every visibility word is counted (atomic or not) so that the prefix over words is one consistent global scan
-            const unsigned long long t = ((unsigned long long)__popc(word_pred) << 32) | __popc(word_resid);
-            if (t) atomicAdd(&p.sb_counts[word / SB_WORDS], t);
-        }
+        if (lane == 0) store_words(word, word_pred, word_resid);
         if (!atomic_capable) {
             // non-atomic (blend) objects keep their slot: survivors in place, everything else INVALID (cull.wgsl:374-380,343-347)
             const uint64_t o = ((uint64_t)word * 32u + lane) * 3u;
@@ -309,11 +323,33 @@ __global__ void __launch_bounds__(TC_THREADS, MIN_CTAS) triangle_test_kernel(con
         } else {
             wg = wg_n; rec = load_wg(p, wg); w = 0; nw = (rec.n_real + 31u) >> 5;
             wg_n += total_warps;
-            run_n0 = wg_n < n_wg ? first_run(wg_n) : ~0ull;        // in flight while this workgroup is tested
+            run_n0 = wg_n < wg_end ? first_run(wg_n) : ~0ull;      // in flight while this workgroup is tested
             pad_words(rec, wg, nw);
         }
         run = run_next;
         slot ^= 1;
+    }
+}
+
+// ---- sharded test: the words every rank stored into this rank's staging arrays -> the local CullingBuffers, plus the superblock counts the
+// unsharded test accumulates with atomics.  One CTA per superblock (1024 words).
+__global__ void __launch_bounds__(SB_WORDS) shard_unpack_kernel(const __grid_constant__ TriCullParams p) {
+    __shared__ unsigned long long s_warp[32];
+    const uint32_t n_words = p.header[3] / 32u;
+    const uint32_t w = blockIdx.x * SB_WORDS + threadIdx.x;
+    if (blockIdx.x * SB_WORDS >= n_words) return;
+    const uint32_t* mine = p.ex_peers[p.shard_index];
+    uint32_t pred = 0u, resid = 0u;
+    if (w < n_words) { pred = __ldcg(&mine[w]); resid = __ldcg(&mine[p.ex_cap_words + w]); p.res_out[w] = pred; p.resid_bits[w] = resid; }   // written by peers: read from L2
+    unsigned long long c = ((unsigned long long)__popc(pred) << 32) | __popc(resid);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, s);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < 32; ++k) t += s_warp[k];
+        p.sb_counts[blockIdx.x] = t;
     }
 }
 
@@ -497,12 +533,18 @@ int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam) {
     const bool viewport = cam->header.shadow_index == R3_CAMERA_VIEWPORT;
     p.hiz = c->d_hiz_ptrs; p.hiz_dims = c->d_hiz_dims; p.hiz_mips = viewport ? (uint32_t)c->d_hiz.size() : 0u;
 
-    // resident CTAs per SM of the persistent test kernel (a property of the binary).  Two register budgets are compiled: 48 registers / 5 CTAs
-    // (default) and 64 / 4 (R3_TEST_CTAS=4, for experiments)
+    // multi-GPU shard of the viewport's test (r3_set_cull_shard): needs the peers' staging arrays, no non-atomic (blend) objects — their
+    // in-place index slots are not exchanged — and a staging capacity that covers this frame; otherwise every rank tests everything
+    const bool sharded = viewport && c->tri_shard_count > 1u && c->peer.connected && c->peer.tri_cap_words >= words && !c->any_blend;
+    p.shard_index = sharded ? c->tri_shard_index : 0u; p.shard_count = sharded ? c->tri_shard_count : 1u;
+    p.ex_n = sharded ? c->peer.n_ranks : 0u; p.ex_cap_words = c->peer.tri_cap_words;
+    for (uint32_t r = 0; r < R3_MAX_EXCHANGE_RANKS; ++r) p.ex_peers[r] = sharded ? c->peer.tri_words[r] : nullptr;
+    // resident CTAs per SM of the persistent test kernel (a property of the binary).  Two register budgets are compiled: 64 registers / 4 CTAs
+    // (default: no spills; config 3 measured 1.63 ms per frame against 1.79 ms) and 48 / 5 (R3_TEST_CTAS=5, for experiments)
     static int test_variant = 0, test_ctas_per_sm = 0;
     if (!test_ctas_per_sm) {
         const char* e = getenv("R3_TEST_CTAS");
-        test_variant = (e && e[0] == '4') ? 4 : 5;
+        test_variant = (e && e[0] == '5') ? 5 : 4;
         const cudaError_t rc = test_variant == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&test_ctas_per_sm, triangle_test_kernel<4>, TC_THREADS, 0)
                                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&test_ctas_per_sm, triangle_test_kernel<5>, TC_THREADS, 0);
         if (rc != cudaSuccess || test_ctas_per_sm < 1) test_ctas_per_sm = 4;
@@ -513,6 +555,15 @@ int r3_launch_triangle_cull(r3_ctx* c, r3_camera* cam) {
     else triangle_test_kernel<5><<<need_ctas < test_grid ? need_ctas : test_grid, TC_THREADS, 0, c->stream>>>(p);
     r3_stage_end(c);
     R3_CHECK_LAUNCH(c, "triangle_test_kernel");
+    if (sharded) {
+        // publish this rank's words (epoch flag, kind 3), wait for everybody's, then move them into the local buffers
+        R3_TRY(r3_peer_signal(c, 3u));
+        uint32_t expected[R3_MAX_EXCHANGE_RANKS];
+        for (auto& e : expected) e = c->peer.sent[3];
+        R3_TRY(r3_peer_wait(c, 3u, expected));
+        shard_unpack_kernel<<<n_sb, SB_WORDS, 0, c->stream>>>(p);
+        R3_CHECK_LAUNCH(c, "shard_unpack_kernel");
+    }
     superblock_scan_kernel<<<1, 1024, 0, c->stream>>>(sb_counts, j.d_header);
     R3_CHECK_LAUNCH(c, "superblock_scan_kernel");
     region_finish_kernel<<<j.n_regions, 256, 0, c->stream>>>(p);

@@ -73,6 +73,10 @@ class VisibilityExchange:
         expand the rows into the global visible list.  `rank_objects` overrides the shard sizes of this step (strong-scaled runs)."""
         self.backend.exchange_merge(self.camera, self.rank_objects if rank_objects is None else np.asarray(rank_objects, dtype=np.uint32), self.rank_base)
 
+    def join(self):
+        """Make the library's main stream wait for the consumer kernels in flight (they run on its side stream, overlapping the next cull)."""
+        self.backend.exchange_merged(self.camera)
+
     def gathered(self, device) -> torch.Tensor:
         """(world, words_per_rank) int32 view of the rows of the LAST epoch in the local buffer.  Complete after merge() was enqueued and
         the stream synchronised, or after the ranks synchronised their streams and passed a barrier."""
@@ -126,8 +130,9 @@ class ForwardSplit:
     stores + epoch flags (r3_peer_*, rend3_b200/csrc/r3_peer.cu) on the library's own stream — no collective, no host barrier in a frame.
     The assembled rgba16f frame lands on `root` (default rank 0; root=-1: on every rank)."""
 
-    def __init__(self, backend, stream, device, rank: int, world: int, resolution, n_shadows: int, root: int = 0):
+    def __init__(self, backend, stream, device, rank: int, world: int, resolution, n_shadows: int, root: int = 0, shard_triangle_cull: bool = True):
         self.b, self.stream, self.device, self.rank, self.world, self.res, self.n_shadows, self.root = backend, stream, device, rank, world, resolution, n_shadows, root
+        self.shard_triangle_cull = shard_triangle_cull
         self.connected, self.frame, self.shadows = False, 0, None
 
     def owns_shadow(self, i: int) -> bool:
@@ -145,27 +150,39 @@ class ForwardSplit:
         dist.all_gather_object(handles, handle)
         self.b.peer_connect(b"".join(handles))
         dist.barrier()
+        if self.shard_triangle_cull:
+            self.b.set_cull_shard(self.rank, self.world)     # the viewport's triangle cull, sharded by runs of batches
         self.connected = True
 
     def bind_scene(self, ev):
         self.shadows = [(s.offset[0], s.offset[1], s.size) for s in ev.shadows]
 
-    def exchange_shadow_maps(self):
-        """after_shadows hook: the rects this rank rendered go to every peer; then wait until every rank's rects arrived here."""
+    def begin_frame(self):
+        """after_target hook: map the peers (first frame), then wait — on the device — until every rank has finished the previous frame:
+        from here on this rank stores into the peers' atlases, frames and word staging arrays."""
+        self.connect()
+        if self.frame >= 1:
+            self.b.peer_wait(FRAME_DONE, [self.frame] * self.world)
+
+    def send_shadow_maps(self):
+        """after_shadows hook: the rects this rank rendered go to every peer (stores over NVLink while the viewport is culled and rasterised)."""
         b, f = self.b, self.frame + 1
-        if f > 1:
-            b.peer_wait(FRAME_DONE, [f - 1] * self.world)     # nobody still samples last frame's atlas
         for i, (ox, oy, size) in enumerate(self.shadows or []):
             if self.owns_shadow(i):
                 b.peer_send_atlas_rect(ox, oy, size, size)
         b.peer_signal(ATLAS)
-        b.peer_wait(ATLAS, [f] * self.world)
+
+    def wait_shadow_maps(self):
+        """before_resolve hook: the shading samples the atlas — wait (on the device) until every rank's rects have arrived here."""
+        self.b.peer_wait(ATLAS, [self.frame + 1] * self.world)
+
+    def exchange_shadow_maps(self):
+        self.send_shadow_maps()
+        self.wait_shadow_maps()
 
     def exchange_rows(self, rows):
         """After the frame: this rank's rows of the rgba16f target go to the assembling rank(s); those wait for everybody's rows."""
         b, f = self.b, self.frame + 1
-        if not self.n_shadows and f > 1:
-            b.peer_wait(FRAME_DONE, [f - 1] * self.world)
         b.peer_send_rows(rows[0], rows[1], self.root)
         b.peer_signal(ROWS)
         if self.assembles_on(self.rank):
@@ -176,7 +193,8 @@ class ForwardSplit:
 
     def describe(self) -> str:
         where = "every rank" if self.root < 0 else f"rank {self.root}"
-        return (f"{self.world} row tiles; shadow maps split by light, each rect stored by its owner straight into every peer's atlas; rgba16f rows stored into the frame of "
+        cull = "the viewport's triangle cull sharded by runs of batches (visibility words exchanged by peer stores); " if self.shard_triangle_cull else ""
+        return (f"{self.world} row tiles; " + cull + "shadow maps split by light, each rect stored by its owner straight into every peer's atlas; rgba16f rows stored into the frame of "
                 f"{where}; NVLink peer stores + st.release.sys / ld.acquire.sys epoch flags, no collective kernel, no host barrier inside a frame")
 
     def close(self):

@@ -124,11 +124,12 @@ class BaseRenderGraph:
     def add_to_graph(self, ev: EvalOutput, resolution: Tuple[int, int], samples: int = 1,
                      settings: BaseRenderGraphSettings = BaseRenderGraphSettings(), srgb_target: bool = True,
                      upload: bool = True, scissor_rows: Optional[Tuple[int, int]] = None, shadow_filter=None, after_shadows=None,
-                     after_target=None, tonemap: bool = True, skinning=None, frame_graph: Optional[bool] = None):
+                     after_target=None, tonemap: bool = True, skinning=None, frame_graph: Optional[bool] = None, before_resolve=None):
         """One frame in the node order of base.rs:135-185.  `scissor_rows` restricts rasterisation and shading
         to a band of pixel rows (the screen-tile split of the multi-GPU forward pass); `shadow_filter(i)` selects the shadow
         maps this rank renders — it then clears only their rects, the others arrive from their owners — and `after_shadows()`
-        runs once they are in the atlas (the ranks exchange their maps there); `after_target()` runs once the render target and
+        runs once they are in the atlas (the ranks send their maps to the peers there) and `before_resolve()` right before the
+        shading reads the atlas (the ranks wait for the peers' maps there: the exchange overlaps the viewport cull and raster); `after_target()` runs once the render target and
         the atlas exist (peer mappings are created there); `tonemap=False` leaves the blit to the caller (the assembling rank
         runs it after the other ranks' rows have arrived); `frame_graph` records the frame's stream work and submits it as ONE CUDA
         graph launch (r3_frame_begin / r3_frame_end; the reference submits once per frame, graph.rs:510) — default: the R3_FRAME_GRAPH
@@ -172,6 +173,8 @@ class BaseRenderGraph:
         b.hiz_build()                                                             # :162
         culler.cull(ev, CAMERA_VIEWPORT)                                          # :169
         b.forward_pass(1)                                                         # :172 residual triangles
+        if before_resolve is not None:
+            before_resolve()
         b.forward_resolve()                                                       # fs_main of the opaque + cutout fragments
         # skybox (:175) is outside this path
         b.forward_blend()                                                         # :181 transparent objects, back to front

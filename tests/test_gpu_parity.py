@@ -736,11 +736,13 @@ def test_frames_submitted_as_cuda_graphs_match_oracle(monkeypatch):
             if mixed:
                 assert np.array_equal(b.readback_depth().view(np.uint32), orc.readback_depth().view(np.uint32))
         st = b.frame_graph_stats()
-        assert st["frames"] == 5 and st["graphed"] == 5, st
+        assert st["frames"] == 5, st
         if not mixed:
-            assert st["flushed"] <= 2 and st["instantiations"] <= 3, st      # steady frames: update + launch only
+            # the first frame allocates (early flush, the rest of it runs eagerly); from then on every frame is one graph launch, and the
+            # instantiated graphs (one per ping-pong parity) are only updated
+            assert st["graphed"] >= 4 and st["flushed"] <= 1 and st["instantiations"] <= 2, st
         else:
-            assert st["flushed"] >= 3, st                                   # the blend routine's pool check flushes the recording
+            assert st["flushed"] >= 4, st                                   # the blend routine's pool check flushes the recording every frame
         b.close()
 
 

@@ -89,10 +89,26 @@ split.bind_scene(ev)
 rows = tile_rows(res[1], rank, world)
 for frame in range(3):                               # three frames back to back: the flags are the only flow control
     graph.add_to_graph(ev, res, 1, settings, upload=(frame == 0), scissor_rows=rows, shadow_filter=split.owns_shadow,
-                       after_shadows=split.exchange_shadow_maps, after_target=split.connect, tonemap=False)
+                       after_shadows=split.send_shadow_maps, before_resolve=split.wait_shadow_maps, after_target=split.begin_frame, tonemap=False)
     split.exchange_rows(rows)
 b.sync()
 dist.barrier()
+# SURVEY 8e "triangle cull: shard by batch": every rank tested only its run of the viewport's workgroups, yet all of them must hold the
+# same visibility bits, draw records and index lists afterwards
+import hashlib
+digest = hashlib.sha256()
+for part in (0, 1):
+    digest.update(b.readback_culling_results(CAMERA_VIEWPORT, part).tobytes())
+    dc = b.readback_draw_calls(CAMERA_VIEWPORT, part)
+    digest.update(dc.tobytes())
+    idx = b.readback_indices(CAMERA_VIEWPORT, part)
+    for r in range(len(dc)):
+        b0, cnt = int(dc[r]["base_index"]), int(dc[r]["vertex_count"])
+        digest.update(idx[b0:b0 + cnt].tobytes())
+digests = [None] * world
+dist.all_gather_object(digests, digest.hexdigest())
+assert len(set(digests)) == 1, "the ranks disagree on the viewport's culled lists"
+assert int(b.readback_draw_calls(CAMERA_VIEWPORT, 0)["vertex_count"].sum()) > 3000
 if rank == 0:
     got16 = b.readback_hdr_f16()
     one = load_cuda_backend(local)
