@@ -545,7 +545,9 @@ def forward_section(args, torch, dist, load_cuda_backend, rank, world, local, de
     split = None
     if world > 1:
         from rend3_b200.parallel import ForwardSplit
-        split = ForwardSplit(fb, fstream, dev, rank, world, res, n_shadows)
+        # the viewport's triangle test is 2% of this frame (config 5: 50 us): sharding it across the ranks (r3_set_cull_shard; exercised by
+        # tests/test_multi_gpu.py) would add a flag round trip per frame for nothing — it pays on config-3-like scenes, so it stays off here
+        split = ForwardSplit(fb, fstream, dev, rank, world, res, n_shadows, shard_triangle_cull=False)
         split.bind_scene(ev)
 
     def frame(upload):

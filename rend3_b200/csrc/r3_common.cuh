@@ -95,7 +95,7 @@ static_assert(sizeof(r3_tri_record) == 64, "triangle record");
 struct r3_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t side_stream = nullptr;       // high-priority stream of the exchange consumer (r3_exchange_merge), created on first use
+    cudaStream_t side_stream = nullptr;       // low-priority stream of the exchange consumer (r3_exchange_merge), created on first use
     std::string err;
     uint64_t launches = 0;
     bool coop_launch_ok = false;              // cudaDevAttrCooperativeLaunch (grid-wide barriers inside one launch)

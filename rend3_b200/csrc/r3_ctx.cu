@@ -50,7 +50,10 @@ R3_EXPORT int r3_ctx_create(int device, r3_ctx** out) {
     r3_ctx* c = new (std::nothrow) r3_ctx();
     if (!c) return R3_E_OOM;
     c->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // the context's stream gets the greatest priority: the exchange consumer's side stream (least priority) then only fills the SMs it leaves idle
+    int prio_least = 0, prio_greatest = 0;
+    if (cudaSetDevice(device) == cudaSuccess) cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) {
         delete c;
         cudaGetLastError();
         return R3_E_CUDA;

@@ -222,10 +222,11 @@ compact_visible_kernel(const uint32_t* __restrict__ words, const uint32_t* __res
         if ((wj >> lane) & 1u) visible[ej + __popc(wj & ((1u << lane) - 1u))] = (blockIdx.x * CP_THREADS + warp * 32 + j) * 32u + lane;
     }
     if (ex.n_ranks) {
-        // publish the row: every thread orders its peer stores at system scope, the last CTA to arrive writes the epoch flags
-        __threadfence_system();
+        // publish the row: the CTA barrier orders every thread's peer stores before thread 0's system-scope fence (cumulative), which
+        // orders them before the arrival; the last CTA to arrive writes the epoch flags with release semantics
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence_system();
             const uint32_t arrived = atomicAdd(ex.done, 1u);
             if (arrived == gridDim.x - 1u) {
                 *ex.done = 0u;                                  // next launch of this camera starts from zero (stream-ordered)
@@ -237,8 +238,8 @@ compact_visible_kernel(const uint32_t* __restrict__ words, const uint32_t* __res
 }
 
 // ---- consumer side: the GLOBAL visible list (ascending global object ids) out of the gathered rows, chained on the epoch flags.
-//   wait + count : CTA (row r, tile t): one thread spins on flags[parity][r] with ld.acquire.sys until the row's epoch arrived, then the CTA
-//                  counts the survivors of its 1024 words;
+//   wait         : one small CTA spins on flags[parity][r] with ld.acquire.sys until every row's epoch has arrived;
+//   count        : CTA (row r, tile t) counts the survivors of its 1024 words;
 //   expand       : survivors in front of the tile (sum of the counts before it), block scan, ordered expansion — as the local compaction.
 struct MergeParams {
     const uint32_t* gathered;            // this rank's buffer (flags + rows)
@@ -255,13 +256,15 @@ __device__ __forceinline__ uint32_t merge_word(const MergeParams& p, uint32_t r,
     if (n - w * 32u < 32u) word &= (1u << (n - w * 32u)) - 1u;
     return word;
 }
-__global__ void __launch_bounds__(CP_THREADS) exchange_wait_count_kernel(const __grid_constant__ MergeParams p) {
+// one small CTA waits for the flags (thread r: rank r's row); the count / expand kernels behind it on the stream then read complete rows.
+// (Spinning inside the 1024-thread count CTAs kept hundreds of them resident while a peer was late — and the next cull + bake of THIS rank
+//  off the SMs: measured 0.390 ms per weak-scaled step on 2 GPUs against 0.342 ms on one.)
+__global__ void exchange_wait_kernel(const uint32_t* __restrict__ flags, uint32_t n_ranks, uint32_t epoch) {
+    if (threadIdx.x < n_ranks)
+        while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) __nanosleep(100);
+}
+__global__ void __launch_bounds__(CP_THREADS) exchange_count_kernel(const __grid_constant__ MergeParams p) {
     const uint32_t r = blockIdx.x / p.tiles_per_rank, t = blockIdx.x % p.tiles_per_rank;
-    if (threadIdx.x == 0) {
-        const uint32_t* flag = p.gathered + p.parity * R3_MAX_EXCHANGE_RANKS + r;
-        while ((int32_t)(ld_acquire_sys(flag) - p.epoch) < 0) __nanosleep(64);
-    }
-    __syncthreads();
     const uint32_t word = merge_word(p, r, t * CP_THREADS + threadIdx.x);
     uint32_t cnt = __popc(word);
 #pragma unroll
@@ -495,21 +498,24 @@ R3_EXPORT int r3_exchange_merge(r3_ctx* c, uint32_t camera, const uint32_t* rank
     R3_TRY(r3_reserve_t(c, &cam->d_global_visible, &cam->global_visible_cap, total + 1));
     R3_TRY(r3_reserve_t(c, &cam->d_merge_counts, &cam->merge_counts_cap, (uint64_t)n_tiles + 4));
     p.tile_counts = cam->d_merge_counts + 4; p.out = cam->d_global_visible; p.out_count = cam->d_merge_counts; p.out_cap = (uint32_t)total;
-    // The consumer runs on the context's side stream, behind the cull that produced this rank's row: the NEXT cull + bake (other parity)
-    // overlaps it, so a step costs max(cull, merge) instead of their sum.  The cull of epoch e + 2 — which overwrites this parity — waits for
+    // The consumer runs on the context's LOW-priority side stream, behind the cull that produced this rank's row: the NEXT cull + bake
+    // (other parity) overlaps it and keeps the SMs — the merge CTAs fill the tail of the stream kernel and the small compaction kernel
+    // (at high priority their 1024-thread CTAs displaced the stream kernel's: 0.387 ms per weak-scaled step on 2 GPUs against 0.342 ms on one).  The cull of epoch e + 2 — which overwrites this parity — waits for
     // this merge (r3_launch_cull_bake), and r3_exchange_merged / r3_sync wait for it before handing the list out.
     if (!c->side_stream) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        R3_CUDA(c, cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi));
+        R3_CUDA(c, cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
     }
     const int slot = (int)(cam->ex_epoch & 1u);
     if (!cam->ex_cull_done[slot]) R3_CUDA(c, cudaEventCreateWithFlags(&cam->ex_cull_done[slot], cudaEventDisableTiming));
     if (!cam->ex_merge_done[slot]) R3_CUDA(c, cudaEventCreateWithFlags(&cam->ex_merge_done[slot], cudaEventDisableTiming));
     R3_CUDA(c, cudaEventRecord(cam->ex_cull_done[slot], c->stream));
     R3_CUDA(c, cudaStreamWaitEvent(c->side_stream, cam->ex_cull_done[slot], 0));
-    exchange_wait_count_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
-    R3_CHECK_LAUNCH(c, "exchange_wait_count_kernel");
+    exchange_wait_kernel<<<1, 32, 0, c->side_stream>>>(cam->d_gathered + p.parity * R3_MAX_EXCHANGE_RANKS, cam->ex_ranks, p.epoch);
+    R3_CHECK_LAUNCH(c, "exchange_wait_kernel");
+    exchange_count_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
+    R3_CHECK_LAUNCH(c, "exchange_count_kernel");
     exchange_expand_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
     R3_CHECK_LAUNCH(c, "exchange_expand_kernel");
     R3_CUDA(c, cudaEventRecord(cam->ex_merge_done[slot], c->side_stream));

@@ -10,10 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "rend3_b200", "csrc")
 CLAIMS = [
     ("r3_cull_bake.o", "cull_bake_kernel", ["LDG.E.128", "STG.E.128", "STG.E.EF.128", "LDG.E.EF.128", "LDS", "STS", "SHFL", "BAR.SYNC", "VOTE"],
-     "stream kernel: 128-bit coalesced loads / stores, operands from the constant bank, no shared memory, no shuffles"),
+     "stream kernel: 128-bit coalesced loads / stores, operands from the constant bank, no shuffles; shared memory only for the per-CTA survivor count"),
     ("r3_cull_bake.o", "compact_visible_kernel", ["ST.E.STRONG.SYS", "STG.E.STRONG.SYS", "MEMBAR.SC.SYS", "MEMBAR.ALL.SYS", "ATOMG", "RED"],
      "fused exchange: plain peer stores, system-scope fence, release store of the epoch flag by the last CTA"),
-    ("r3_cull_bake.o", "exchange_wait_count_kernel", ["LD.E.STRONG.SYS", "LDG.E.STRONG.SYS", "NANOSLEEP"], "consumer: acquire load of the epoch flag at system scope"),
+    ("r3_cull_bake.o", "exchange_wait_kernel", ["LD.E.STRONG.SYS", "LDG.E.STRONG.SYS", "NANOSLEEP"], "consumer: acquire load of the epoch flag at system scope"),
     ("r3_tri_cull.o", "triangle_test_kernel", ["UBLKCP", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK", "BAR.SYNC", "LDS", "LDG.E.128", "MUFU.RCP", "FCHK", "ATOMG", "RED"],
      "index runs staged by 1-D bulk async copies (TMA unit) on per-warp mbarriers; no block barrier"),
     ("r3_raster.o", "raster_setup_kernel", ["RED.E.MAX.64", "REDG.E.MAX.64", "RED.E.MAX", "ATOMG"], "visibility buffer: fire-and-forget 64-bit RED.MAX per covered sample"),
