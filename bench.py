@@ -8,8 +8,9 @@ One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one
   * headline workload (BASELINE config 4, the one the target metric is quoted on): fused per-object frustum cull +
     object-uniform bake over 10 M object records PER GPU (weak scaling), 1% disabled, visible list ascending;
     at N > 1 every rank receives the visible set of all shards (1 bit per object) through peer-memory stores fused into the
-    compaction kernel, published with per-row epoch flags (r3_exchange_*), and a consumer kernel chained on those flags merges
-    them into the global visible list — no host barrier, no collective kernel;
+    compaction kernel, published with per-row epoch flags (r3_exchange_*), and a consumer kernel chained on those flags counts
+    every shard's visible objects — no host barrier, no collective kernel; `with_global_list` is the same step with the rows
+    also expanded into the global visible list on every rank (an output that grows with the number of ranks);
   * `value` = objects culled+baked per second, inputs resident in HBM, CUDA events on the library's stream;
   * `strong_scaling` = BASELINE config 4 as stated: 10 M objects in TOTAL, 10 M / N per GPU;
   * `e2e`   = the same through the C ABI with HOST buffers: r3_set_objects (pinned H2D of every record) +
@@ -352,7 +353,7 @@ def main():
         from rend3_b200.parallel import VisibilityExchange
         try:
             exchange = VisibilityExchange(backend, CAMERA_VIEWPORT, n, rank, world)
-            exchange_kind = "peer-memory stores fused into the compaction kernel + per-row epoch flags + consumer merge kernel (NVLink P2P, CUDA IPC)"
+            exchange_kind = "peer-memory stores fused into the compaction kernel + per-row epoch flags + a consumer kernel chained on the flags that counts every shard's visible objects (NVLink P2P, CUDA IPC)"
         except Exception as e:   # noqa: BLE001
             print(f"[rank {rank}] peer-memory exchange unavailable ({e})", file=sys.stderr)
             exchange = None
@@ -364,12 +365,18 @@ def main():
             exchange, exchange_kind = None, "NCCL all-gather of the visibility words (peer-memory exchange unavailable on this box)"
     gathered_words = torch.empty(world * ((n + 31) // 32), dtype=torch.int32, device=dev) if world > 1 and exchange is None else None
 
-    def step_resident():
+    def step_resident(full_list=False):
         backend.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
         if world == 1:
             return
         if exchange is not None:
-            exchange.merge()          # consumer kernel: waits on the peers' epoch flags on the device, builds the global visible list
+            # consumer kernels chained on the peers' epoch flags ON THE DEVICE: the headline step counts the visible objects of every shard
+            # (it has to see every row of this epoch); `with_global_list` also expands the rows into the global visible list, whose size —
+            # 4 B per visible object of the WHOLE world on every rank — grows with the number of ranks
+            if full_list:
+                exchange.merge()
+            else:
+                exchange.count()
         else:
             wptr, wbytes = backend.device_ptr(CAMERA_VIEWPORT, 4)
             with torch.cuda.stream(stream):
@@ -383,8 +390,14 @@ def main():
     barrier()
     exchange_verified = None
     if exchange is not None:
-        # outside the timed region: the merged global list must equal the one built from an NCCL all-gather of the same words
+        # outside the timed region: the merged global list must equal the one built from an NCCL all-gather of the same words, and the
+        # light consumer's per-shard counts must add up to its length
+        step_resident(full_list=True)
         exchange_verified = exchange.verify_against_nccl(stream, dev)
+        n_list = int(exchange.merged(dev).numel())
+        step_resident()
+        counts = exchange.counts()
+        exchange_verified = bool(exchange_verified and int(counts[-1]) == n_list and int(counts[:-1].sum()) == n_list)
         barrier()
     launches0 = backend.launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -422,6 +435,24 @@ def main():
     traffic, traffic_src = measured_traffic(n)
     barrier()
 
+    # ---- the same step with the global visible list expanded on every rank (r3_exchange_merge)
+    with_list = None
+    if exchange is not None:
+        for _ in range(args.warmup):
+            step_resident(full_list=True)
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record(stream)
+        for _ in range(args.steps):
+            step_resident(full_list=True)
+        exchange.join()
+        w1.record(stream)
+        barrier()
+        wms = max_over_ranks(w0.elapsed_time(w1)) / args.steps
+        with_list = {"what": "cull + bake + exchange + the global ascending visible list built on every rank each step (4 B x visible objects of all shards)",
+                     "ms_per_step": wms, "value": world * n / (wms * 1e-3), "unit": "objects/s", "list_entries": n_list, "list_bytes_per_rank_per_step": 4 * n_list}
+        barrier()
+
     # ---- strong scaling: BASELINE config 4 as stated — 10 M objects in total, 10 M / N per GPU
     strong = None
     if world > 1:
@@ -431,7 +462,7 @@ def main():
         def step_strong():
             backend.object_uniform_upload(CAMERA_VIEWPORT, sheader, CB_BAKE | CB_CULL)   # the first 10 M / N records of this rank's buffer
             if exchange is not None:
-                exchange.merge()
+                exchange.count([ns] * world)
         for _ in range(args.warmup):
             step_strong()
         barrier()
@@ -444,7 +475,7 @@ def main():
         s1.record(stream)
         barrier()
         sms = max_over_ranks(s0.elapsed_time(s1)) / args.steps
-        strong = {"workload": f"BASELINE config 4 as stated: {ns * world} objects in total, {ns} per GPU, global visible list merged on every rank",
+        strong = {"workload": f"BASELINE config 4 as stated: {ns * world} objects in total, {ns} per GPU, visible set exchanged + counted on every rank",
                   "objects_total": ns * world, "ms_per_step": sms, "value": ns * world / (sms * 1e-3), "unit": "objects/s", "scaling": "strong"}
         for _ in range(2):   # back to the full shard (the exchange rows carry the 10 M-object words again)
             step_resident()
@@ -515,7 +546,7 @@ def main():
                          "algorithmic_bytes_per_launch": algorithmic, "step_frac": algorithmic / (ms_per_step * 1e-3) / 1e9 / peak if world == 1 else None,
                          "peak_source": peak_src},
             "cpu_baseline": cpu_baseline(n),
-            "e2e": e2e, "dynamic": dynamic, "strong_scaling": strong, "gpu_launches": launches, "clocks": clocks.summary(), "forward": forward,
+            "e2e": e2e, "dynamic": dynamic, "strong_scaling": strong, "with_global_list": with_list, "gpu_launches": launches, "clocks": clocks.summary(), "forward": forward,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
@@ -557,7 +588,9 @@ def forward_section(args, torch, dist, load_cuda_backend, rank, world, local, de
                                after_target=split.begin_frame, tonemap=False)
             split.exchange_rows(rows)
         else:
-            graph.add_to_graph(ev, res, 1, settings, upload=upload)
+            # one GPU: the frame is recorded and submitted as ONE CUDA graph launch (r3_frame_begin / r3_frame_end), like the reference's
+            # single queue submission per frame (graph.rs:510)
+            graph.add_to_graph(ev, res, 1, settings, upload=upload, frame_graph=True)
 
     split_verified = None
     if world > 1 and res[1] % world == 0:
@@ -638,7 +671,7 @@ def forward_section(args, torch, dist, load_cuda_backend, rank, world, local, de
     out = {"workload": "BASELINE config 5: 3840x2160, 4400 meshes / ~500k triangles, 64 point lights + 4 directional lights with 2048^2 shadow maps",
            "frame_ms": frame_ms, "shaded_mfrag_s": float(st[2].item()) / frame_ms / 1e3, "raster_mfrag_s": float(st[1].item()) / frame_ms / 1e3,
            "shaded_fragments": int(st[2].item()), "depth_passing_fragments": int(st[1].item()), "triangles_after_cull": tris,
-           "gpu_launches_per_frame": launches_per_frame, "batch_objects": batching,
+           "gpu_launches_per_frame": launches_per_frame, "submission": (fb.frame_graph_stats() if world == 1 else "call by call (multi-GPU split)"), "batch_objects": batching,
            "split": split.describe() if split is not None else "single GPU", "split_equals_single_gpu_frame": split_verified,
            "timing": "CUDA events on the library stream around the timed frames, max over ranks", "roofline": rooflines}
     if split is not None:
@@ -660,15 +693,15 @@ def config3_block(args, torch, load_cuda_backend, local):
     s = torch.cuda.ExternalStream(b.stream(), device=torch.device("cuda", local))
     g = BaseRenderGraph(b)
     settings = BaseRenderGraphSettings(clear_color=(0.1, 0.05, 0.1, 1.0))
-    g.add_to_graph(ev, res, 1, settings, upload=True)
+    g.add_to_graph(ev, res, 1, settings, upload=True, frame_graph=True)
     for _ in range(3):
-        g.add_to_graph(ev, res, 1, settings, upload=False)
+        g.add_to_graph(ev, res, 1, settings, upload=False, frame_graph=True)
     b.sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = b.launch_count()
     e0.record(s)
     for _ in range(args.forward_steps):
-        g.add_to_graph(ev, res, 1, settings, upload=False)
+        g.add_to_graph(ev, res, 1, settings, upload=False, frame_graph=True)
     e1.record(s)
     b.sync()
     ms = e0.elapsed_time(e1) / args.forward_steps

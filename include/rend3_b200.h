@@ -221,6 +221,11 @@ int r3_exchange_connect(r3_ctx*, uint32_t camera, const uint8_t* handles /* n_ra
 int r3_exchange_words(r3_ctx*, uint32_t camera, void** device_ptr, uint64_t* nbytes, uint32_t* words_per_rank);
 int r3_exchange_merge(r3_ctx*, uint32_t camera, const uint32_t* rank_objects /* n_ranks */, const uint32_t* rank_base /* n_ranks or NULL */);
 int r3_exchange_merged(r3_ctx*, uint32_t camera, void** device_list /* u32 global ids */, void** device_count /* u32 */, uint64_t* capacity);
+/* the light consumer: waits for the flags like r3_exchange_merge but only counts — visible objects of every shard and their total — without
+ * expanding the list (4 B per visible object of the WHOLE world on every rank: a cost that grows with the number of ranks);
+ * r3_exchange_counts reads counts[0 .. n_ranks] (the last one is the total) back, blocking */
+int r3_exchange_count(r3_ctx*, uint32_t camera, const uint32_t* rank_objects /* n_ranks */);
+int r3_exchange_counts(r3_ctx*, uint32_t camera, uint32_t* counts /* n_ranks + 1 */);
 int r3_exchange_destroy(r3_ctx*, uint32_t camera);
 /* Peer-memory plumbing of the multi-GPU forward pass (shadow maps split by light, screen split in row tiles; one process per
  * GPU on one NVLink / NVSwitch node).  r3_peer_create (after r3_set_directional_lights and r3_set_render_target: the atlas and the rgba16f

@@ -38,7 +38,7 @@ ENTRY_POINTS = [
     "shadow_pass", "forward_begin", "forward_pass", "hiz_build", "forward_resolve", "forward_blend", "tonemap",
     "set_parity_target", "readback_hdr_f32", "readback_hdr_f16", "readback_depth", "readback_ldr", "readback_shadow_atlas",
     "readback_hiz", "forward_stats", "forward_light_evaluations", "device_ptr", "set_scissor_rows", "skin", "readback_mesh_buffer",
-    "exchange_create", "exchange_connect", "exchange_words", "exchange_merge", "exchange_merged", "exchange_destroy",
+    "exchange_create", "exchange_connect", "exchange_words", "exchange_merge", "exchange_merged", "exchange_count", "exchange_counts", "exchange_destroy",
     "peer_create", "peer_connect", "peer_send_atlas_rect", "peer_send_rows", "peer_signal", "peer_wait", "peer_destroy", "clear_shadow_rect", "set_cull_shard",
 ]
 
@@ -300,6 +300,15 @@ class Backend:
         ro = np.ascontiguousarray(rank_objects, dtype=np.uint32)
         rb = None if rank_base is None else np.ascontiguousarray(rank_base, dtype=np.uint32)
         self._call("exchange_merge", C.c_uint32(camera), _ptr(ro), _ptr(rb))
+
+    def exchange_count(self, camera: int, rank_objects):
+        ro = np.ascontiguousarray(rank_objects, dtype=np.uint32)
+        self._call("exchange_count", C.c_uint32(camera), _ptr(ro))
+
+    def exchange_counts(self, camera: int, n_ranks: int) -> np.ndarray:
+        out = np.zeros(n_ranks + 1, dtype=np.uint32)
+        self._call("exchange_counts", C.c_uint32(camera), _ptr(out))
+        return out
 
     def exchange_merged(self, camera: int):
         lst, cnt, cap = C.c_void_p(), C.c_void_p(), C.c_uint64()

@@ -57,6 +57,7 @@ struct r3_peer_state {
     uint32_t sent[R3_PEER_KINDS] = {0, 0, 0, 0};
     uint32_t* d_tri_words = nullptr; uint64_t tri_cap_words = 0; uint32_t* tri_words[R3_MAX_EXCHANGE_RANKS] = {};   // staging arrays of the sharded triangle test
     const void* atlas_at_create = nullptr; const void* hdr_at_create = nullptr;
+    cudaEvent_t side_event = nullptr; bool atlas_on_side = false;   // atlas copies run on the context's side stream
 };
 struct r3_camera {
     bool header_set = false;

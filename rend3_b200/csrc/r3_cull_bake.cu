@@ -279,6 +279,27 @@ __global__ void __launch_bounds__(CP_THREADS) exchange_count_kernel(const __grid
         if (threadIdx.x == 0) p.tile_counts[blockIdx.x] = v;
     }
 }
+// per-rank survivor counts (and their total) from the tile counts: one CTA
+__global__ void __launch_bounds__(1024) exchange_rank_counts_kernel(const uint32_t* __restrict__ tile_counts, uint32_t tiles_per_rank, uint32_t n_ranks, uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_warp[32];
+    uint32_t total = 0;
+    for (uint32_t r = 0; r < n_ranks; ++r) {
+        uint32_t v = 0;
+        for (uint32_t t = threadIdx.x; t < tiles_per_rank; t += blockDim.x) v += tile_counts[r * tiles_per_rank + t];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, s);
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t sum = 0;
+            for (int k = 0; k < 32; ++k) sum += s_warp[k];
+            out[r] = sum;
+            total += sum;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n_ranks] = total;
+}
 __global__ void __launch_bounds__(CP_THREADS) exchange_expand_kernel(const __grid_constant__ MergeParams p) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_base;
@@ -476,7 +497,11 @@ R3_EXPORT int r3_exchange_words(r3_ctx* c, uint32_t camera, void** device_ptr, u
 }
 // Consumer of the exchange: the global visible list on this rank.  rank_objects[r] = slots of rank r's shard in the last step,
 // rank_base[r] = global id of its slot 0 (NULL: r * max_objects_per_rank).  Chained on the epoch flags on the device; no host barrier.
+static int r3_exchange_consume(r3_ctx* c, uint32_t camera, const uint32_t* rank_objects, const uint32_t* rank_base, bool expand);
 R3_EXPORT int r3_exchange_merge(r3_ctx* c, uint32_t camera, const uint32_t* rank_objects, const uint32_t* rank_base) {
+    return r3_exchange_consume(c, camera, rank_objects, rank_base, true);
+}
+static int r3_exchange_consume(r3_ctx* c, uint32_t camera, const uint32_t* rank_objects, const uint32_t* rank_base, bool expand) {
     if (!c || !rank_objects) return r3_fail(c, R3_E_INVALID, "exchange_merge: null");
     r3_camera* cam = r3_get_camera(c, camera);
     if (!cam || !cam->d_gathered || !cam->ex_connected) return r3_fail(c, R3_E_STATE, "exchange_merge before exchange_connect");
@@ -495,9 +520,10 @@ R3_EXPORT int r3_exchange_merge(r3_ctx* c, uint32_t camera, const uint32_t* rank
     p.epoch = cam->ex_epoch; p.parity = cam->ex_epoch & 1u;
     p.tiles_per_rank = (cam->ex_words_per_rank + CP_THREADS - 1) / CP_THREADS;
     const uint32_t n_tiles = p.tiles_per_rank * cam->ex_ranks;
-    R3_TRY(r3_reserve_t(c, &cam->d_global_visible, &cam->global_visible_cap, total + 1));
-    R3_TRY(r3_reserve_t(c, &cam->d_merge_counts, &cam->merge_counts_cap, (uint64_t)n_tiles + 4));
-    p.tile_counts = cam->d_merge_counts + 4; p.out = cam->d_global_visible; p.out_count = cam->d_merge_counts; p.out_cap = (uint32_t)total;
+    if (expand) R3_TRY(r3_reserve_t(c, &cam->d_global_visible, &cam->global_visible_cap, total + 1));
+    // scratch: [0] list length | [8 .. 8 + ranks] per-rank counts + total | [32 ..] tile counts
+    R3_TRY(r3_reserve_t(c, &cam->d_merge_counts, &cam->merge_counts_cap, (uint64_t)n_tiles + 32));
+    p.tile_counts = cam->d_merge_counts + 32; p.out = cam->d_global_visible; p.out_count = cam->d_merge_counts; p.out_cap = (uint32_t)total;
     // The consumer runs on the context's LOW-priority side stream, behind the cull that produced this rank's row: the NEXT cull + bake
     // (other parity) overlaps it and keeps the SMs — the merge CTAs fill the tail of the stream kernel and the small compaction kernel
     // (at high priority their 1024-thread CTAs displaced the stream kernel's: 0.387 ms per weak-scaled step on 2 GPUs against 0.342 ms on one).  The cull of epoch e + 2 — which overwrites this parity — waits for
@@ -516,10 +542,31 @@ R3_EXPORT int r3_exchange_merge(r3_ctx* c, uint32_t camera, const uint32_t* rank
     R3_CHECK_LAUNCH(c, "exchange_wait_kernel");
     exchange_count_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
     R3_CHECK_LAUNCH(c, "exchange_count_kernel");
-    exchange_expand_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
-    R3_CHECK_LAUNCH(c, "exchange_expand_kernel");
+    exchange_rank_counts_kernel<<<1, 1024, 0, c->side_stream>>>(p.tile_counts, p.tiles_per_rank, cam->ex_ranks, cam->d_merge_counts + 8);
+    R3_CHECK_LAUNCH(c, "exchange_rank_counts_kernel");
+    if (expand) {
+        exchange_expand_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
+        R3_CHECK_LAUNCH(c, "exchange_expand_kernel");
+    }
     R3_CUDA(c, cudaEventRecord(cam->ex_merge_done[slot], c->side_stream));
     cam->ex_merge_pending[slot] = true;
+    return R3_OK;
+}
+// Light consumer of the exchange: waits for every rank's epoch flag on the device (like r3_exchange_merge) and leaves the visible COUNT of
+// every shard — counts[r], r < n_ranks, and their total in counts[n_ranks] — without expanding the list (whose size grows with the number
+// of ranks: 4 B per visible object of the WHOLE world on every rank).  r3_exchange_counts reads them back (blocking).
+R3_EXPORT int r3_exchange_count(r3_ctx* c, uint32_t camera, const uint32_t* rank_objects) {
+    return r3_exchange_consume(c, camera, rank_objects, nullptr, false);
+}
+R3_EXPORT int r3_exchange_counts(r3_ctx* c, uint32_t camera, uint32_t* counts /* n_ranks + 1 */) {
+    if (!c || !counts) return r3_fail(c, R3_E_INVALID, "exchange_counts: null");
+    r3_camera* cam = r3_get_camera(c, camera);
+    if (!cam || !cam->d_merge_counts) return r3_fail(c, R3_E_STATE, "exchange_counts before exchange_count / exchange_merge");
+    cudaSetDevice(c->device);
+    for (int k = 0; k < 2; ++k)
+        if (cam->ex_merge_pending[k]) { R3_CUDA(c, cudaStreamWaitEvent(c->stream, cam->ex_merge_done[k], 0)); cam->ex_merge_pending[k] = false; }
+    R3_CUDA(c, cudaMemcpyAsync(counts, cam->d_merge_counts + 8, ((size_t)cam->ex_ranks + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    R3_CUDA(c, r3_stream_sync(c));
     return R3_OK;
 }
 R3_EXPORT int r3_exchange_merged(r3_ctx* c, uint32_t camera, void** device_list, void** device_count, uint64_t* capacity) {

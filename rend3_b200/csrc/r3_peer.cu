@@ -52,14 +52,22 @@ __global__ void peer_wait_kernel(const __grid_constant__ WaitParams w) {
 
 }  // namespace
 
-static int peer_copy(r3_ctx* c, const void* src, void* const* dsts, uint32_t n_dst, uint64_t first, uint64_t pitch, uint64_t row_bytes, uint32_t rows) {
+// the context's least-priority side stream (shared with the exchange consumer), created on first use
+static int peer_side_stream(r3_ctx* c) {
+    if (c->side_stream) return R3_OK;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    R3_CUDA(c, cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
+    return R3_OK;
+}
+static int peer_copy(r3_ctx* c, cudaStream_t stream, const void* src, void* const* dsts, uint32_t n_dst, uint64_t first, uint64_t pitch, uint64_t row_bytes, uint32_t rows) {
     if (!n_dst || !rows || !row_bytes) return R3_OK;
     if ((first | pitch | row_bytes) & 15u) return r3_fail(c, R3_E_INVALID, "peer copy: rect not 16-byte aligned");
     PeerPtrs d{};
     for (uint32_t k = 0; k < n_dst; ++k) d.p[k] = dsts[k];
     const uint64_t vecs = row_bytes / 16 * rows;
     const uint32_t grid = (uint32_t)((vecs + 255) / 256 < (uint64_t)R3_SM_COUNT * 8 ? (vecs + 255) / 256 : (uint64_t)R3_SM_COUNT * 8);
-    peer_copy_kernel<<<grid, 256, 0, c->stream>>>(static_cast<const uint8_t*>(src), d, n_dst, first, pitch, (uint32_t)(row_bytes / 16), rows);
+    peer_copy_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(src), d, n_dst, first, pitch, (uint32_t)(row_bytes / 16), rows);
     R3_CHECK_LAUNCH(c, "peer_copy_kernel");
     return R3_OK;
 }
@@ -135,7 +143,15 @@ R3_EXPORT int r3_peer_send_atlas_rect(r3_ctx* c, uint32_t ox, uint32_t oy, uint3
     void* dst[R3_MAX_EXCHANGE_RANKS];
     uint32_t n = 0;
     for (uint32_t r = 0; r < c->peer.n_ranks; ++r) if (r != c->peer.rank) dst[n++] = c->peer.atlas[r];
-    return peer_copy(c, c->d_atlas, dst, n, ((uint64_t)oy * c->atlas_w + ox) * 4, (uint64_t)c->atlas_w * 4, (uint64_t)w * 4, h);
+    // The copy (16.7 MB per 2048^2 map and peer) runs on the side stream behind the shadow passes recorded so far, so that this rank's
+    // viewport cull and raster do not queue behind it; r3_peer_signal(ATLAS) follows it there.  Nobody writes the rect again before every
+    // peer has signalled FRAME_DONE, which it does after it has seen the ATLAS flag, i.e. after the copy has completed.
+    R3_TRY(peer_side_stream(c));
+    if (!c->peer.side_event) R3_CUDA(c, cudaEventCreateWithFlags(&c->peer.side_event, cudaEventDisableTiming));
+    R3_CUDA(c, cudaEventRecord(c->peer.side_event, c->stream));
+    R3_CUDA(c, cudaStreamWaitEvent(c->side_stream, c->peer.side_event, 0));
+    c->peer.atlas_on_side = true;
+    return peer_copy(c, c->side_stream, c->d_atlas, dst, n, ((uint64_t)oy * c->atlas_w + ox) * 4, (uint64_t)c->atlas_w * 4, (uint64_t)w * 4, h);
 }
 R3_EXPORT int r3_peer_send_rows(r3_ctx* c, uint32_t row_begin, uint32_t row_end, int root) {
     R3_TRY(peer_ready(c, "peer_send_rows before peer_connect"));
@@ -144,7 +160,7 @@ R3_EXPORT int r3_peer_send_rows(r3_ctx* c, uint32_t row_begin, uint32_t row_end,
     uint32_t n = 0;
     for (uint32_t r = 0; r < c->peer.n_ranks; ++r) if (r != c->peer.rank && (root < 0 || (int)r == root)) dst[n++] = c->peer.hdr16[r];
     const uint64_t pitch = (uint64_t)c->width * 8;
-    return peer_copy(c, c->d_hdr16, dst, n, (uint64_t)row_begin * pitch, pitch, pitch, row_end - row_begin);
+    return peer_copy(c, c->stream, c->d_hdr16, dst, n, (uint64_t)row_begin * pitch, pitch, pitch, row_end - row_begin);
 }
 R3_EXPORT int r3_peer_signal(r3_ctx* c, uint32_t kind) {
     R3_TRY(peer_ready(c, "peer_signal before peer_connect"));
@@ -152,7 +168,9 @@ R3_EXPORT int r3_peer_signal(r3_ctx* c, uint32_t kind) {
     PeerPtrs f{};
     for (uint32_t r = 0; r < c->peer.n_ranks; ++r) f.p[r] = c->peer.flags[r];
     const uint32_t epoch = ++c->peer.sent[kind];
-    peer_signal_kernel<<<1, 32, 0, c->stream>>>(f, c->peer.n_ranks, kind * R3_MAX_EXCHANGE_RANKS + c->peer.rank, epoch);
+    cudaStream_t stream = c->stream;
+    if (kind == 0u && c->peer.atlas_on_side) { stream = c->side_stream; c->peer.atlas_on_side = false; }   // behind the atlas copies of this frame
+    peer_signal_kernel<<<1, 32, 0, stream>>>(f, c->peer.n_ranks, kind * R3_MAX_EXCHANGE_RANKS + c->peer.rank, epoch);
     R3_CHECK_LAUNCH(c, "peer_signal_kernel");
     return R3_OK;
 }
@@ -179,6 +197,8 @@ R3_EXPORT int r3_peer_destroy(r3_ctx* c) {
             if (c->peer.hdr16[r]) cudaIpcCloseMemHandle(c->peer.hdr16[r]);
             if (c->peer.tri_words[r]) cudaIpcCloseMemHandle(c->peer.tri_words[r]);
         }
+    if (c->side_stream) cudaStreamSynchronize(c->side_stream);
+    if (c->peer.side_event) cudaEventDestroy(c->peer.side_event);
     cudaFree(c->peer.d_flags); cudaFree(c->peer.d_tri_words);
     c->peer = r3_peer_state{};
     c->tri_shard_index = 0; c->tri_shard_count = 1;

@@ -73,6 +73,13 @@ class VisibilityExchange:
         expand the rows into the global visible list.  `rank_objects` overrides the shard sizes of this step (strong-scaled runs)."""
         self.backend.exchange_merge(self.camera, self.rank_objects if rank_objects is None else np.asarray(rank_objects, dtype=np.uint32), self.rank_base)
 
+    def count(self, rank_objects=None):
+        """The light consumer: waits for every rank's epoch flag on the device and counts the visible objects per shard (no list)."""
+        self.backend.exchange_count(self.camera, self.rank_objects if rank_objects is None else np.asarray(rank_objects, dtype=np.uint32))
+
+    def counts(self) -> np.ndarray:
+        return self.backend.exchange_counts(self.camera, self.world)
+
     def join(self):
         """Make the library's main stream wait for the consumer kernels in flight (they run on its side stream, overlapping the next cull)."""
         self.backend.exchange_merged(self.camera)

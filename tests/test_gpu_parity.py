@@ -592,6 +592,13 @@ def test_cpp_host_mirror_renders_the_same_frames(cuda, tmp_path):
     r = subprocess.run([exe, str(scene), str(out)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     got = load_outputs(str(out))
+    # the same frames submitted as one CUDA graph each (r3::BaseRenderGraph::submit_as_graph): identical artefacts
+    out_g = tmp_path / "out_graph.r3o"
+    r = subprocess.run([exe, str(scene), str(out_g)], capture_output=True, text=True, timeout=300, env=dict(os.environ, R3_FRAME_GRAPH="1"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    got_g = load_outputs(str(out_g))
+    for k in got:
+        assert np.array_equal(got[k], got_g[k]), f"graph submission changed `{k}`"
     orc = load_oracle_backend()
     graphs = {id(b): BaseRenderGraph(b) for b in (cuda, orc)}
     for frame in range(2):

@@ -46,6 +46,9 @@ for step, cam in enumerate(cams * 2):                # six epochs, no host barri
         want = orc.readback_visible(CAMERA_VIEWPORT).astype(np.int64)
         assert np.array_equal(got, want), (step, len(got), len(want))
         assert 0 < len(want) < n_total
+        ex.count()                                   # the light consumer on the same epoch: per-shard counts, no list
+        counts = ex.counts()
+        assert int(counts[-1]) == len(want) and [int(x) for x in counts[:-1]] == [int(((want >= l) & (want < h)).sum()) for l, h in ranges]
 # the raw rows, for a host reader: stream sync + barrier, then the words of every rank equal the oracle's bits
 b.sync()
 dist.barrier()
