@@ -206,6 +206,11 @@ enum { R3_TEX_ALBEDO = 0, R3_TEX_NORMAL, R3_TEX_ROUGHNESS, R3_TEX_METALLIC, R3_T
 #define R3_TEXFMT_RGBA8_UNORM 0u
 #define R3_TEXFMT_RGBA8_UNORM_SRGB 1u   /* rgb decoded to linear before filtering, alpha linear */
 #define R3_TEXFMT_RGBA32_FLOAT 2u
+#define R3_TEXFMT_R8_UNORM 3u           /* single channel (split AO / metallic / roughness maps): (r, 0, 0, 1) */
+#define R3_TEXFMT_RG8_UNORM 4u          /* two channels (bicomponent normal maps): (r, g, 0, 1) */
+#define R3_TEXFMT_COUNT 5u
+/* bytes per texel of a format */
+#define R3_TEXFMT_BPP(f) ((f) == R3_TEXFMT_RGBA32_FLOAT ? 16u : (f) == R3_TEXFMT_R8_UNORM ? 1u : (f) == R3_TEXFMT_RG8_UNORM ? 2u : 4u)
 typedef struct r3_texture_desc {
     uint32_t width, height, mip_count, format;
     uint64_t byte_offset;

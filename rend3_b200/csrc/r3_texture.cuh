@@ -15,13 +15,15 @@ __device__ __forceinline__ float srgb_to_linear(float e) { return e > 0.04045f ?
 // levels (coordinates, floor) follows the oracle's order without contraction; the filter weights are continuous.
 __device__ __forceinline__ float4 texel_fetch(const TexTable& p, const r3_texture_desc& d, uint32_t level, long long x, long long y) {
     unsigned long long off = d.byte_offset;
-    const unsigned long long bpp = d.format == R3_TEXFMT_RGBA32_FLOAT ? 16ull : 4ull;
+    const unsigned long long bpp = R3_TEXFMT_BPP(d.format);
     for (uint32_t l = 0; l < level; ++l) off += (unsigned long long)max(d.width >> l, 1u) * max(d.height >> l, 1u) * bpp;
     const long long w = max(d.width >> level, 1u), h = max(d.height >> level, 1u);
     if (p.clamp_to_edge) { x = x < 0 ? 0 : (x >= w ? w - 1 : x); y = y < 0 ? 0 : (y >= h ? h - 1 : y); }   // texels clamped to the cube face
     else { x = ((x % w) + w) % w; y = ((y % h) + h) % h; }                          // AddressMode::Repeat
     const uint8_t* t = p.texels + off + (unsigned long long)(y * w + x) * bpp;
     if (d.format == R3_TEXFMT_RGBA32_FLOAT) return __ldg(reinterpret_cast<const float4*>(t));
+    if (d.format == R3_TEXFMT_R8_UNORM) return make_float4((float)__ldg(t) / 255.0f, 0.0f, 0.0f, 1.0f);                     // missing channels read (0, 0, 1)
+    if (d.format == R3_TEXFMT_RG8_UNORM) { const uchar2 c2 = __ldg(reinterpret_cast<const uchar2*>(t)); return make_float4((float)c2.x / 255.0f, (float)c2.y / 255.0f, 0.0f, 1.0f); }
     const uchar4 c = __ldg(reinterpret_cast<const uchar4*>(t));
     float4 o = make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
     if (d.format == R3_TEXFMT_RGBA8_UNORM_SRGB) { o.x = srgb_to_linear(o.x); o.y = srgb_to_linear(o.y); o.z = srgb_to_linear(o.z); }

@@ -155,6 +155,8 @@ def textured_cube_scene(n_objects: int = 300, seed: int = 41, resolution: Tuple[
     normal = r.add_texture_2d(Texture(smooth((0.35, 0.35, 0.8, 0.35), (0.65, 0.65, 1.0, 0.65))))
     aomr = r.add_texture_2d(Texture(smooth((0.6, 0.3, 0.0, 0.0), (1.0, 0.9, 0.6, 1.0))))
     single = r.add_texture_2d(Texture(smooth(0.3, 0.9)))
+    single_r8 = r.add_texture_2d(Texture(smooth(0.3, 0.9), channels=1))                                   # R8Unorm: reads (r, 0, 0, 1)
+    normal_rg8 = r.add_texture_2d(Texture(smooth((0.35, 0.35, 0.0, 0.0), (0.65, 0.65, 0.0, 0.0)), channels=2))   # Rg8Unorm: bicomponent normal map
     emissive = r.add_texture_2d(Texture(smooth(0.0, 0.4), srgb=True))
     f32tex = r.add_texture_2d(Texture(rng.uniform(0.2, 0.8, (8, 8, 4)).astype(f32), mips="none"))
     ut = np.array([[2.0, 0, 0], [0, 1.5, 0], [0.25, 0.1, 1]], dtype=f32)
@@ -162,8 +164,8 @@ def textured_cube_scene(n_objects: int = 300, seed: int = 41, resolution: Tuple[
         PbrMaterial(albedo_texture=albedo, roughness_factor=0.5, sample_type=sample_type),
         PbrMaterial(albedo_texture=albedo, albedo_value=(0.9, 0.8, 0.7, 1.0), normal_texture=normal, roughness_texture=aomr, roughness_factor=0.9, metallic_factor=0.8,
                     ao_factor=0.9, sample_type=sample_type),
-        PbrMaterial(albedo_value=(0.6, 0.6, 0.6, 1.0), normal_texture=normal, normal_kind="bicomponent", normal_y_down=True, aomr_kind="bw_split",
-                    roughness_texture=single, metallic_texture=single, ao_texture=single, roughness_factor=0.8, metallic_factor=0.5, sample_type=sample_type),
+        PbrMaterial(albedo_value=(0.6, 0.6, 0.6, 1.0), normal_texture=normal_rg8, normal_kind="bicomponent", normal_y_down=True, aomr_kind="bw_split",
+                    roughness_texture=single_r8, metallic_texture=single, ao_texture=single_r8, roughness_factor=0.8, metallic_factor=0.5, sample_type=sample_type),
         PbrMaterial(albedo_texture=albedo, normal_texture=normal, normal_kind="bicomponent_swizzled", aomr_kind="swizzled_split", roughness_texture=aomr, ao_texture=single,
                     roughness_factor=1.0, metallic_factor=1.0, reflectance_texture=single, reflectance=0.8, emissive=(1.0, 0.8, 0.6), emissive_texture=emissive,
                     uv_transform0=ut, sample_type=sample_type),

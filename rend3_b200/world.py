@@ -43,6 +43,8 @@ from .layouts import (
     TEXFMT_RGBA8_UNORM,
     TEXFMT_RGBA8_UNORM_SRGB,
     TEXFMT_RGBA32_FLOAT,
+    TEXFMT_R8_UNORM,
+    TEXFMT_RG8_UNORM,
     MAT_ALBEDO_VERTEX_SRGB,
     MAT_AOMR_COMBINED,
     MAT_CC_GLTF_COMBINED,
@@ -194,6 +196,7 @@ class Texture:
     data: np.ndarray
     srgb: bool = False
     mips: str = "generated"
+    channels: int = 4          # 1 / 2: R8Unorm / Rg8Unorm — only the first channels of `data` are stored, the others read (0, 0, 1)
 
     def levels(self) -> List[np.ndarray]:
         lv = [np.ascontiguousarray(self.data)]
@@ -223,7 +226,14 @@ class Texture:
     def format(self) -> int:
         if self.data.dtype == np.float32:
             return TEXFMT_RGBA32_FLOAT
+        if self.channels in (1, 2):
+            return TEXFMT_R8_UNORM if self.channels == 1 else TEXFMT_RG8_UNORM
         return TEXFMT_RGBA8_UNORM_SRGB if self.srgb else TEXFMT_RGBA8_UNORM
+
+    def stored_levels(self) -> List[np.ndarray]:
+        """The mip levels as they are stored: narrow formats keep only their channels."""
+        lv = self.levels()
+        return [np.ascontiguousarray(l[..., : self.channels]) for l in lv] if self.channels in (1, 2) and self.data.dtype == np.uint8 else lv
 
 
 @dataclass
@@ -575,7 +585,7 @@ class Renderer:
         descs = np.zeros(len(self.textures), dtype=TEXTURE_DESC_DTYPE)
         blobs, cursor = [], 0
         for i, t in enumerate(self.textures):
-            lv = t.levels()
+            lv = t.stored_levels()
             descs[i]["width"], descs[i]["height"] = lv[0].shape[1], lv[0].shape[0]
             descs[i]["mip_count"], descs[i]["format"], descs[i]["byte_offset"] = len(lv), t.format(), cursor
             raw = np.concatenate([np.ascontiguousarray(l).view(np.uint8).reshape(-1) for l in lv])

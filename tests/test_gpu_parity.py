@@ -522,6 +522,22 @@ def test_texture_sampling_known_answers(cuda, sample_type):
             b.close()
 
 
+def test_narrow_texture_formats_known_answers(cuda):
+    """R8Unorm / Rg8Unorm entries of the bindless table on the CUDA path: stored channels as unorm, missing ones (0, 0, 1)."""
+    import texture_case as tcase
+    from rend3_b200.world import Texture
+
+    data = tcase.checker_texture(32, seed=5)
+    for channels in (1, 2):
+        b = load_cuda_backend(0)
+        tcase.build(b, Texture(data, channels=channels, mips="none"), "nearest").render_frame(32)
+        want = np.zeros((32, 32, 4))
+        want[..., :channels] = data[..., :channels].astype(np.float64) / 255.0
+        want[..., 3] = 1.0
+        assert np.abs(b.readback_hdr_f32().astype(np.float64) - want).max() < 2e-6, channels
+        b.close()
+
+
 @pytest.mark.parametrize("sample_type,samples", [("linear", 1), ("nearest", 1), ("linear", 4)])
 def test_textured_materials_match_oracle(cuda, sample_type, samples):
     """Every texture slot and layout flag of PbrMaterial (albedo sRGB / float, tri- and bi-component normal maps, combined /

@@ -449,3 +449,20 @@ def test_oracle_sort_orders_nan_distances_last_like_ordered_float():
     assert len(order) == n and list(order[-4:]) == list(bad)
     d2 = ((loc[order[:-4]].astype(np.float32)) ** 2).sum(axis=1)
     assert np.all(np.diff(d2) >= 0)
+
+
+def test_oracle_narrow_texture_formats_read_missing_channels_as_zero_zero_one():
+    """R8Unorm / Rg8Unorm in the bindless table (split AO / metallic / roughness maps, bicomponent normal maps): the stored channels
+    come back as unorm, the missing ones as (0, 0, 1) — one texel per pixel through the unlit albedo slot."""
+    import texture_case as tcase
+    from rend3_b200.world import Texture
+
+    data = tcase.checker_texture(32, seed=5)
+    for channels in (1, 2):
+        b = load_oracle_backend()
+        tcase.build(b, Texture(data, channels=channels, mips="none"), "nearest").render_frame(32)
+        want = np.zeros((32, 32, 4))
+        want[..., :channels] = data[..., :channels].astype(np.float64) / 255.0
+        want[..., 3] = 1.0
+        got = b.readback_hdr_f32().astype(np.float64)
+        assert np.abs(got - want).max() < 2e-6, channels
