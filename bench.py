@@ -199,9 +199,12 @@ def best_thread_count(oracle, backend, header, n_sample):
             continue
         oracle.set_threads(t)
         backend.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
-        t0 = time.perf_counter()
-        backend.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
-        rate = n_sample / (time.perf_counter() - t0)
+        dt = float("inf")
+        for _ in range(3):           # best of three: a single call is at the mercy of whatever else the host is doing
+            t0 = time.perf_counter()
+            backend.object_uniform_upload(CAMERA_VIEWPORT, header, CB_BAKE | CB_CULL)
+            dt = min(dt, time.perf_counter() - t0)
+        rate = n_sample / dt
         tried[t] = rate
         if rate > best_rate:
             best, best_rate = t, rate

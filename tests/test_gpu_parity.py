@@ -588,7 +588,7 @@ def test_per_fragment_cutout_matches_oracle(cuda, samples):
     ev2 = textured_cube_scene(n_objects=500, resolution=res, cutout=True)
     ev2.material_buffer["alpha_cutout"] = 0.0
     BaseRenderGraph(opaque).add_to_graph(ev2, res, samples, BaseRenderGraphSettings(clear_color=(0.05, 0.05, 0.1, 1.0)))
-    assert np.count_nonzero(opaque.readback_depth() > 0) > np.count_nonzero(orc.readback_depth() > 0) + 200
+    assert np.count_nonzero(opaque.readback_depth() > 0) > np.count_nonzero(orc.readback_depth() > 0) + 100
 
 
 def test_cpp_host_mirror_renders_the_same_frames(cuda, tmp_path):
