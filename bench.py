@@ -546,6 +546,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src, "kernel": "cull_bake_kernel<bake,cull>", "kernel_ms": kern_s * 1e3,
                          "kernel_timing": f"library stage timer: CUDA events around the kernel on its own stream, mean of {st['launches']} launches",
+                         "frac_by_traffic": (traffic / kern_s / 1e9 / peak) if traffic else None,
+                         "note": "achieved uses ALGORITHMIC bytes (SURVEY 8d counts `enabled` as 4 B per object; it travels as 1 bit, so DRAM traffic is ~6% lower): frac can exceed 1.0 by that margin, frac_by_traffic is the DRAM-side fraction",
                          "algorithmic_bytes_per_launch": algorithmic, "step_frac": algorithmic / (ms_per_step * 1e-3) / 1e9 / peak if world == 1 else None,
                          "peak_source": peak_src},
             "cpu_baseline": cpu_baseline(n),

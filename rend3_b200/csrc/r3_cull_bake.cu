@@ -279,6 +279,40 @@ __global__ void __launch_bounds__(CP_THREADS) exchange_count_kernel(const __grid
         if (threadIdx.x == 0) p.tile_counts[blockIdx.x] = v;
     }
 }
+// count-only consumer: CTA (rank r, slice s) sums the popcounts of its slice of row r with 16-byte loads and adds them to out[r] and to the
+// total out[n_ranks] — one small wave of CTAs (n_ranks x 16 of 256 threads), so that it slips into the tail of the stream kernel instead of
+// queueing thousands of CTAs behind it (8 GPUs, tile-sized count CTAs: 0.435 ms per weak-scaled step against 0.343 ms on one GPU)
+constexpr uint32_t RC_SLICES = 16;
+__global__ void __launch_bounds__(256) exchange_light_count_kernel(const __grid_constant__ MergeParams p, uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_warp[8];
+    const uint32_t r = blockIdx.x / RC_SLICES, sl = blockIdx.x % RC_SLICES;
+    const uint32_t n_words = (p.rank_objects[r] + 31u) / 32u;                        // words of the shard that can hold survivors
+    const uint32_t vecs = (p.words_per_rank + 3u) / 4u, per = (vecs + RC_SLICES - 1u) / RC_SLICES;
+    const uint32_t v0 = sl * per, v1 = min(v0 + per, vecs);
+    const uint4* row = reinterpret_cast<const uint4*>(p.gathered + EX_HEADER_WORDS + ((size_t)p.parity * p.n_ranks + r) * p.words_per_rank);   // rows are 256-byte aligned
+    const uint32_t tail_bits = p.rank_objects[r] & 31u;
+    uint32_t cnt = 0;
+    for (uint32_t v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+        const uint4 q = __ldcg(&row[v]);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+            const uint32_t wi = v * 4u + k;
+            uint32_t word = wi < n_words ? w[k] : 0u;
+            if (tail_bits && wi == n_words - 1u) word &= (1u << tail_bits) - 1u;
+            cnt += __popc(word);
+        }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, sft);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < 8; ++k) t += s_warp[k];
+        if (t) { atomicAdd(&out[r], t); atomicAdd(&out[p.n_ranks], t); }
+    }
+}
 // per-rank survivor counts (and their total) from the tile counts: one CTA
 __global__ void __launch_bounds__(1024) exchange_rank_counts_kernel(const uint32_t* __restrict__ tile_counts, uint32_t tiles_per_rank, uint32_t n_ranks, uint32_t* __restrict__ out) {
     __shared__ uint32_t s_warp[32];
@@ -540,11 +574,15 @@ static int r3_exchange_consume(r3_ctx* c, uint32_t camera, const uint32_t* rank_
     R3_CUDA(c, cudaStreamWaitEvent(c->side_stream, cam->ex_cull_done[slot], 0));
     exchange_wait_kernel<<<1, 32, 0, c->side_stream>>>(cam->d_gathered + p.parity * R3_MAX_EXCHANGE_RANKS, cam->ex_ranks, p.epoch);
     R3_CHECK_LAUNCH(c, "exchange_wait_kernel");
-    exchange_count_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
-    R3_CHECK_LAUNCH(c, "exchange_count_kernel");
-    exchange_rank_counts_kernel<<<1, 1024, 0, c->side_stream>>>(p.tile_counts, p.tiles_per_rank, cam->ex_ranks, cam->d_merge_counts + 8);
-    R3_CHECK_LAUNCH(c, "exchange_rank_counts_kernel");
-    if (expand) {
+    if (!expand) {
+        R3_CUDA(c, cudaMemsetAsync(cam->d_merge_counts + 8, 0, ((size_t)cam->ex_ranks + 1) * 4, c->side_stream));
+        exchange_light_count_kernel<<<cam->ex_ranks * RC_SLICES, 256, 0, c->side_stream>>>(p, cam->d_merge_counts + 8);
+        R3_CHECK_LAUNCH(c, "exchange_light_count_kernel");
+    } else {
+        exchange_count_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
+        R3_CHECK_LAUNCH(c, "exchange_count_kernel");
+        exchange_rank_counts_kernel<<<1, 1024, 0, c->side_stream>>>(p.tile_counts, p.tiles_per_rank, cam->ex_ranks, cam->d_merge_counts + 8);
+        R3_CHECK_LAUNCH(c, "exchange_rank_counts_kernel");
         exchange_expand_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
         R3_CHECK_LAUNCH(c, "exchange_expand_kernel");
     }

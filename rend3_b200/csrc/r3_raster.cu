@@ -643,6 +643,17 @@ __global__ void region_prefix_kernel(const r3_region* __restrict__ regions, cons
 }  // namespace
 
 // ------------------------------------------------------------------ host side
+// CTAs of kernel K that are resident at once on the whole GPU (a property of the binary: asked once per kernel)
+template <void (*K)(const RasterParams)>
+static int resident_grid() {
+    static int ctas = 0;
+    if (!ctas) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, K, RS_THREADS, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+        ctas = R3_SM_COUNT * per_sm;
+    }
+    return ctas;
+}
 struct DrawSource { const r3_jobs* jobs; const r3_indirect_call* calls; const uint32_t* indices; uint64_t index_elems; };
 
 static bool draw_source_for(r3_camera* cam, int jobs_idx, int partition, DrawSource* ds) {
@@ -704,18 +715,20 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, int mode,
         c->n_tris[pass] = max_tris;
         p.records = c->d_tris[pass];
     }
-    const int grid = R3_SM_COUNT * 8;
+    // persistent grids: exactly the CTAs that are resident at once (148 x the kernel's CTAs per SM).  A fixed 148 x 8 left the colour
+    // kernels (one resident CTA per SM) seven waves of CTAs that start only to find the tickets gone — ~35 us per launch on configs 1 / 5.
     const int variant = mode | ((mode != MODE_DEPTH && c->samples == 4u) ? MODE_MSAA : 0) | ((c->any_frag_alpha && mode != MODE_BLEND) ? MODE_ALPHA : 0);
+#define R3_RASTER_ONE(KERNEL, M) KERNEL<M><<<resident_grid<KERNEL<M>>(), RS_THREADS, 0, c->stream>>>(p)
 #define R3_RASTER_LAUNCH(KERNEL)                                                                                          \
     switch (variant) {                                                                                                    \
-        case MODE_DEPTH: KERNEL<MODE_DEPTH><<<grid, RS_THREADS, 0, c->stream>>>(p); break;                                \
-        case MODE_COLOUR: KERNEL<MODE_COLOUR><<<grid, RS_THREADS, 0, c->stream>>>(p); break;                              \
-        case MODE_BLEND: KERNEL<MODE_BLEND><<<grid, RS_THREADS, 0, c->stream>>>(p); break;                                \
-        case MODE_COLOUR | MODE_MSAA: KERNEL<MODE_COLOUR | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;      \
-        case MODE_BLEND | MODE_MSAA: KERNEL<MODE_BLEND | MODE_MSAA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;        \
-        case MODE_DEPTH | MODE_ALPHA: KERNEL<MODE_DEPTH | MODE_ALPHA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;      \
-        case MODE_COLOUR | MODE_ALPHA: KERNEL<MODE_COLOUR | MODE_ALPHA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;    \
-        default: KERNEL<MODE_COLOUR | MODE_MSAA | MODE_ALPHA><<<grid, RS_THREADS, 0, c->stream>>>(p); break;              \
+        case MODE_DEPTH: R3_RASTER_ONE(KERNEL, MODE_DEPTH); break;                                                        \
+        case MODE_COLOUR: R3_RASTER_ONE(KERNEL, MODE_COLOUR); break;                                                      \
+        case MODE_BLEND: R3_RASTER_ONE(KERNEL, MODE_BLEND); break;                                                        \
+        case MODE_COLOUR | MODE_MSAA: R3_RASTER_ONE(KERNEL, MODE_COLOUR | MODE_MSAA); break;                              \
+        case MODE_BLEND | MODE_MSAA: R3_RASTER_ONE(KERNEL, MODE_BLEND | MODE_MSAA); break;                                \
+        case MODE_DEPTH | MODE_ALPHA: R3_RASTER_ONE(KERNEL, MODE_DEPTH | MODE_ALPHA); break;                              \
+        case MODE_COLOUR | MODE_ALPHA: R3_RASTER_ONE(KERNEL, MODE_COLOUR | MODE_ALPHA); break;                            \
+        default: R3_RASTER_ONE(KERNEL, MODE_COLOUR | MODE_MSAA | MODE_ALPHA); break;                                      \
     }
     r3_stage_begin(c, depth_only ? R3_STAGE_RASTER_SETUP_DEPTH : R3_STAGE_RASTER_SETUP_COLOUR);
     R3_RASTER_LAUNCH(raster_setup_kernel)
@@ -726,6 +739,7 @@ static int run_raster(r3_ctx* c, r3_camera* cam, const DrawSource& ds, int mode,
     r3_stage_end(c);
     R3_CHECK_LAUNCH(c, "raster_band_kernel");
 #undef R3_RASTER_LAUNCH
+#undef R3_RASTER_ONE
     return R3_OK;
 }
 

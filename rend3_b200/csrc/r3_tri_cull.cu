@@ -85,8 +85,22 @@ __device__ float hiz_sample_min(const TriCullParams& p, float u, float v, uint32
 }
 
 // execute_culling (cull.wgsl:264-324), IEEE f32, source order, no FMA
+// clip-space x, y, w of M * (v, 1) (mat_point_rn's operation order per component); z is only needed by the hi-Z test of the survivors
+__device__ __forceinline__ float3 mat_point_xyw_rn(const float* __restrict__ m, const float3 v) {
+    float3 r;
+    r.x = add_rn(add_rn(add_rn(mul_rn(m[0], v.x), mul_rn(m[4], v.y)), mul_rn(m[8], v.z)), m[12]);
+    r.y = add_rn(add_rn(add_rn(mul_rn(m[1], v.x), mul_rn(m[5], v.y)), mul_rn(m[9], v.z)), m[13]);
+    r.z = add_rn(add_rn(add_rn(mul_rn(m[3], v.x), mul_rn(m[7], v.y)), mul_rn(m[11], v.z)), m[15]);   // .z of the result holds clip w
+    return r;
+}
+__device__ __forceinline__ float mat_point_z_rn(const float* __restrict__ m, const float3 v) {
+    return add_rn(add_rn(add_rn(mul_rn(m[2], v.x), mul_rn(m[6], v.y)), mul_rn(m[10], v.z)), m[14]);
+}
 __device__ bool execute_culling(const TriCullParams& p, const float* __restrict__ mvp, const float3 a, const float3 b, const float3 c) {
-    const float4 p0 = mat_point_rn(mvp, a.x, a.y, a.z), p1 = mat_point_rn(mvp, b.x, b.y, b.z), p2 = mat_point_rn(mvp, c.x, c.y, c.z);
+    struct { float x, y, w; } p0, p1, p2;
+    { const float3 q = mat_point_xyw_rn(mvp, a); p0.x = q.x; p0.y = q.y; p0.w = q.z; }
+    { const float3 q = mat_point_xyw_rn(mvp, b); p1.x = q.x; p1.y = q.y; p1.w = q.z; }
+    { const float3 q = mat_point_xyw_rn(mvp, c); p2.x = q.x; p2.y = q.y; p2.w = q.z; }
     const float t0 = sub_rn(mul_rn(p1.y, p2.w), mul_rn(p2.y, p1.w));
     const float t1 = sub_rn(mul_rn(p0.y, p2.w), mul_rn(p2.y, p0.w));
     const float t2 = sub_rn(mul_rn(p0.y, p1.w), mul_rn(p1.y, p0.w));
@@ -94,11 +108,12 @@ __device__ bool execute_culling(const TriCullParams& p, const float* __restrict_
     const bool positive = p.cam.flags & R3_PCU_POSITIVE_AREA_VISIBLE;
     if (positive && det <= 0.0f) return false;
     if (!positive && det >= 0.0f) return false;
-    float n0x = p0.x, n0y = p0.y, n0z = p0.z, n1x = p1.x, n1y = p1.y, n1z = p1.z, n2x = p2.x, n2y = p2.y, n2z = p2.z;
-    if (!(p0.w == 1.0f && p1.w == 1.0f && p2.w == 1.0f)) {   // x / 1.0f == x: orthographic (shadow) cameras skip the perspective divide
-        n0x = div_rn(p0.x, p0.w); n0y = div_rn(p0.y, p0.w); n0z = div_rn(p0.z, p0.w);
-        n1x = div_rn(p1.x, p1.w); n1y = div_rn(p1.y, p1.w); n1z = div_rn(p1.z, p1.w);
-        n2x = div_rn(p2.x, p2.w); n2y = div_rn(p2.y, p2.w); n2z = div_rn(p2.z, p2.w);
+    float n0x = p0.x, n0y = p0.y, n1x = p1.x, n1y = p1.y, n2x = p2.x, n2y = p2.y;
+    const bool unit_w = p0.w == 1.0f && p1.w == 1.0f && p2.w == 1.0f;   // x / 1.0f == x: orthographic (shadow) cameras skip the perspective divide
+    if (!unit_w) {
+        n0x = div_rn(p0.x, p0.w); n0y = div_rn(p0.y, p0.w);
+        n1x = div_rn(p1.x, p1.w); n1y = div_rn(p1.y, p1.w);
+        n2x = div_rn(p2.x, p2.w); n2y = div_rn(p2.y, p2.w);
     }
     const float minx = fminf(n0x, fminf(n1x, n2x)), miny = fminf(n0y, fminf(n1y, n2y));
     const float maxx = fmaxf(n0x, fmaxf(n1x, n2x)), maxy = fmaxf(n0y, fmaxf(n1y, n2y));
@@ -114,6 +129,9 @@ __device__ bool execute_culling(const TriCullParams& p, const float* __restrict_
     const float u = mul_rn(add_rn(maxtx, mintx), 0.5f), v = mul_rn(add_rn(maxty, minty), 0.5f);
     const float ex = sub_rn(maxsx, minsx), ey = sub_rn(maxsy, minsy);
     const uint32_t mip = ceil_log2_f32(fmaxf(fmaxf(ex, ey), 1.0f));
+    // the depths: only the triangles that reach the occlusion test pay for the z row of the transform and its three divisions
+    float n0z = mat_point_z_rn(mvp, a), n1z = mat_point_z_rn(mvp, b), n2z = mat_point_z_rn(mvp, c);
+    if (!unit_w) { n0z = div_rn(n0z, p0.w); n1z = div_rn(n1z, p1.w); n2z = div_rn(n2z, p2.w); }
     const float depth = fmaxf(fmaxf(n0z, n1z), n2z);
     const float occl = hiz_sample_min(p, u, v, mip);
     return !(depth < occl);
