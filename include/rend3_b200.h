@@ -204,15 +204,17 @@ int r3_forward_light_evaluations(r3_ctx*, uint64_t* evaluations);
  * different shadow maps merge them with an integer MAX all-reduce, the atlas being cleared to 0.0) */
 int r3_device_ptr(r3_ctx*, uint32_t camera, int which, void** device_ptr, uint64_t* nbytes);
 /* Exchange of the visible set between the GPUs of one node over NVLink / NVSwitch peer memory (one process per GPU, objects
- * sharded in contiguous ranges).  r3_exchange_create allocates this rank's buffer — epoch flags + rows[2][n_ranks][words_per_rank]
- * (1 bit per object slot, rows 256-byte aligned, two parities) — and returns its CUDA IPC handle; the caller all-gathers the handles with
- * whatever it already uses (torch.distributed, MPI) and hands them to r3_exchange_connect.  From then on every r3_object_uniform_upload(CULL)
- * on that camera is one EPOCH e: its compaction kernel also stores the visibility words into row (e & 1, my_rank) of EVERY rank's buffer and
- * publishes them with flags[e & 1][my_rank] = e (st.release.sys, after system-scope fences) — no collective kernel runs.
- * r3_exchange_merge is the consumer: two kernels on this context's stream that wait for the n_ranks flags of the current epoch with
- * ld.acquire.sys ON THE DEVICE (no host barrier) and expand the rows into the global ascending visible list (r3_exchange_merged returns its
- * device pointers; rank_base == NULL numbers the shards r * max_objects_per_rank).  Protocol: the ranks cull in lockstep; a rank consumes
- * epoch e (or meets the others at a host barrier) before issuing epoch e + 2, which reuses the parity. */
+ * sharded in contiguous ranges).  r3_exchange_create allocates this rank's buffer — epoch flags, acknowledgements and
+ * rows[4][n_ranks][words_per_rank] (1 bit per object slot, rows 256-byte aligned, four row sets) — and returns its CUDA IPC handle; the
+ * caller all-gathers the handles with whatever it already uses (torch.distributed, MPI) and hands them to r3_exchange_connect.  From then on
+ * every r3_object_uniform_upload(CULL) on that camera is one EPOCH e: its compaction kernel also stores the visibility words into row
+ * (e % 4, my_rank) of EVERY rank's buffer and publishes them with flags[e % 4][my_rank] = e (st.release.sys, after system-scope fences) —
+ * no collective kernel runs.  Consumers run on the context's least-priority side stream, chained on the flags ON THE DEVICE (ld.acquire.sys,
+ * no host barrier), overlapping the next culls: r3_exchange_count (visible objects of every shard) and r3_exchange_merge (the global
+ * ascending visible list; r3_exchange_merged hands out its device pointers, rank_base == NULL numbers the shards r * max_objects_per_rank).
+ * A consumer acknowledges its epoch to every producer; a producer that is about to overwrite a row set waits — on the device — until the
+ * epoch it held has been acknowledged by all ranks.  Protocol: the ranks cull in lockstep and an epoch that one rank consumes, every rank
+ * consumes (the acknowledgements are awaited on that assumption); consumers may lag up to three epochs before a producer blocks. */
 #define R3_IPC_HANDLE_BYTES 64
 int r3_exchange_create(r3_ctx*, uint32_t camera, uint32_t n_ranks, uint32_t my_rank, uint32_t max_objects_per_rank,
                        uint8_t handle_out[R3_IPC_HANDLE_BYTES]);

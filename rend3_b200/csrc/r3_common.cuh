@@ -47,6 +47,7 @@ struct r3_stage_timer {
     size_t used = 0;
 };
 constexpr int R3_MAX_EXCHANGE_RANKS = 16;
+constexpr int R3_EXCHANGE_SLOTS = 4;         // row sets of the visible-set exchange in flight (epoch % slots)
 // peer-memory plumbing of the multi-GPU forward pass (r3_peer.cu): kinds of epoch flags
 constexpr uint32_t R3_PEER_KINDS = 4;        // 0 shadow atlas rects, 1 colour rows, 2 frame done, 3 visibility words of the sharded triangle test
 struct r3_peer_state {
@@ -71,7 +72,7 @@ struct r3_camera {
     uint32_t* d_gathered = nullptr; uint32_t ex_ranks = 0, ex_rank = 0, ex_words_per_rank = 0; bool ex_connected = false;
     uint32_t* ex_peers[R3_MAX_EXCHANGE_RANKS] = {};   // peer-mapped gathered buffers (ex_peers[ex_rank] == d_gathered)
     uint32_t ex_epoch = 0, ex_objects = 0; uint32_t* d_ex_done = nullptr;       // step counter (parity = epoch & 1), CTA arrival counter of the publishing kernel
-    cudaEvent_t ex_cull_done[2] = {nullptr, nullptr}, ex_merge_done[2] = {nullptr, nullptr}; bool ex_merge_pending[2] = {false, false};   // merge on the side stream
+    cudaEvent_t ex_cull_done[R3_EXCHANGE_SLOTS] = {}, ex_merge_done[R3_EXCHANGE_SLOTS] = {}; bool ex_merge_pending[R3_EXCHANGE_SLOTS] = {}; uint32_t ex_consumed[R3_EXCHANGE_SLOTS] = {};   // consumers on the side stream; last epoch consumed per slot
     uint32_t* d_global_visible = nullptr; uint64_t global_visible_cap = 0; uint32_t* d_merge_counts = nullptr; uint64_t merge_counts_cap = 0;   // r3_exchange_merge
     int visible_count_host = -1;              // cached after a readback, -1 = unknown
     r3_jobs jobs[2]; int cur = 0;             // jobs[cur] = this frame, jobs[cur^1] = cached DrawCallSet (forward.rs:219)

@@ -86,7 +86,7 @@ R3_EXPORT int r3_ctx_destroy(r3_ctx* c) {
             cudaFree(k.d_gathered);
         }
         cudaFree(k.d_ex_done); cudaFree(k.d_global_visible); cudaFree(k.d_merge_counts);
-        for (int q = 0; q < 2; ++q) { if (k.ex_cull_done[q]) cudaEventDestroy(k.ex_cull_done[q]); if (k.ex_merge_done[q]) cudaEventDestroy(k.ex_merge_done[q]); }
+        for (int q = 0; q < R3_EXCHANGE_SLOTS; ++q) { if (k.ex_cull_done[q]) cudaEventDestroy(k.ex_cull_done[q]); if (k.ex_merge_done[q]) cudaEventDestroy(k.ex_merge_done[q]); }
         free_jobs(k.jobs[0]); free_jobs(k.jobs[1]);
         cudaFree(k.index_buffer.d); cudaFree(k.draw_call_buffer.d); cudaFree(k.results_buffer.d);
         cudaFree(k.d_resid_bits); cudaFree(k.d_word_scan); cudaFree(k.d_block_sums);

@@ -152,12 +152,13 @@ cull_bake_kernel(const float4* __restrict__ transforms, const float4* __restrict
 
 // visible-set exchange fused into the compaction: every word this rank produced is also stored, coalesced, into the gathered
 // buffer of every rank (its own included) through NVLink peer mappings — no collective kernel, no extra pass over the words
-// Buffer of every rank (one allocation, mapped into every process): [ flags[2][R3_MAX_EXCHANGE_RANKS] | pad to EX_HEADER_WORDS ] then
-// rows[2][n_ranks][words_per_rank].  A step with epoch e uses parity e & 1: rank r stores its words into row (e & 1, r) of every
-// buffer and then publishes them with flags[e & 1][r] = e (st.release.sys by the last CTA to finish, after every CTA fenced its stores
+// Buffer of every rank (one allocation, mapped into every process): [ flags[EX_SLOTS][R3_MAX_EXCHANGE_RANKS] | pad to EX_HEADER_WORDS ] then
+// rows[EX_SLOTS][n_ranks][words_per_rank].  A step with epoch e uses slot e % EX_SLOTS (called `parity` below): rank r stores its words into row (e & 1, r) of every
+// buffer and then publishes them with flags[e % EX_SLOTS][r] = e (st.release.sys by the last CTA to finish, after every CTA fenced its stores
 // at system scope).  A consumer waits with ld.acquire.sys on the flag of the row it needs — on the device, no host barrier — and the
-// other parity keeps epoch e - 1 intact while epoch e + 1 is written.
+// other row sets keep the previous epochs intact while the next ones are written.
 constexpr uint32_t EX_HEADER_WORDS = 256;
+constexpr uint32_t EX_SLOTS = R3_EXCHANGE_SLOTS;   // row sets in flight: epoch e uses slot e % EX_SLOTS, so a consumer may lag EX_SLOTS - 1 epochs behind the producers
 struct ExchangeParams { uint32_t* peers[R3_MAX_EXCHANGE_RANKS]; uint32_t n_ranks, word_offset, words_per_rank, flag_offset, epoch; uint32_t* done; };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -277,6 +278,15 @@ __global__ void __launch_bounds__(CP_THREADS) exchange_count_kernel(const __grid
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, s);
         if (threadIdx.x == 0) p.tile_counts[blockIdx.x] = v;
+    }
+}
+// back-pressure: a consumer that has finished reading epoch e tells every producer so (acks[my_rank] = e in every rank's buffer); a
+// producer about to overwrite the slot of epoch e waits until every consumer has acknowledged it
+constexpr uint32_t EX_ACK_WORDS = 128;              // word offset of acks[R3_MAX_EXCHANGE_RANKS] inside the buffer header
+__global__ void exchange_ack_kernel(const __grid_constant__ ExchangeParams ex, uint32_t epoch) {
+    if (threadIdx.x < ex.n_ranks) {
+        __threadfence_system();
+        st_release_sys(ex.peers[threadIdx.x] + EX_ACK_WORDS + ex.flag_offset, epoch);   // flag_offset carries my rank here
     }
 }
 // count-only consumer: CTA (rank r, slice s) sums the popcounts of its slice of row r with 16-byte loads and adds them to out[r] and to the
@@ -424,10 +434,16 @@ int r3_launch_cull_bake(r3_ctx* c, r3_camera* cam, uint32_t mode) {
         if (cam->ex_connected) {
             if (n_words > cam->ex_words_per_rank) return r3_fail(c, R3_E_INVALID, "object_uniform_upload: more objects than the exchange was created for");
             for (uint32_t r = 0; r < cam->ex_ranks; ++r) ex.peers[r] = cam->ex_peers[r];
-            const uint32_t epoch = ++cam->ex_epoch, parity = epoch & 1u;
-            if (cam->ex_merge_pending[parity]) {   // the consumer of epoch - 2 still reads the rows this step overwrites
+            const uint32_t epoch = ++cam->ex_epoch, parity = epoch % EX_SLOTS;
+            if (cam->ex_merge_pending[parity]) {   // this rank's consumer of the slot's previous epoch still reads the rows this step overwrites
                 R3_CUDA(c, cudaStreamWaitEvent(c->stream, cam->ex_merge_done[parity], 0));
                 cam->ex_merge_pending[parity] = false;
+            }
+            if (epoch > EX_SLOTS && cam->ex_consumed[parity] == epoch - EX_SLOTS) {
+                // ... and so may the PEERS' consumers (the protocol is symmetric: an epoch this rank consumed, every rank consumes): wait, on
+                // the device, until all of them have acknowledged it.  With EX_SLOTS row sets a consumer may lag three epochs before this blocks.
+                exchange_wait_kernel<<<1, 32, 0, c->stream>>>(cam->d_gathered + EX_ACK_WORDS, cam->ex_ranks, epoch - EX_SLOTS);
+                R3_CHECK_LAUNCH(c, "exchange_wait_kernel");
             }
             ex.n_ranks = cam->ex_ranks; ex.words_per_rank = cam->ex_words_per_rank;
             ex.word_offset = EX_HEADER_WORDS + (parity * cam->ex_ranks + cam->ex_rank) * cam->ex_words_per_rank;
@@ -479,7 +495,8 @@ int r3_split_slots(r3_ctx* c, const uint32_t* d_slots, uint32_t n) {
 // parity into the buffer of every rank through CUDA IPC peer mappings over NVLink / NVSwitch and publishes it with an epoch flag
 // (st.release.sys).  Consumers (r3_exchange_merge, or any kernel of the host's) wait for the flag with ld.acquire.sys on the device.
 // Protocol: the ranks call r3_object_uniform_upload(CULL) in lockstep (same number of steps); a rank consumes epoch e (or meets the
-// others at a host barrier) before it issues epoch e + 2, which reuses the parity — then no row is overwritten while it is read.
+// others at a host barrier) before it issues epoch e + EX_SLOTS, which reuses the row set; consumers acknowledge their epoch to the producers
+// (acks), which wait for the acknowledgements before they overwrite a row set — then no row is overwritten while it is read.
 R3_EXPORT int r3_exchange_create(r3_ctx* c, uint32_t camera, uint32_t n_ranks, uint32_t my_rank, uint32_t max_objects_per_rank, uint8_t handle_out[R3_IPC_HANDLE_BYTES]) {
     if (!c || !handle_out) return r3_fail(c, R3_E_INVALID, "exchange_create: null");
     if (n_ranks == 0 || n_ranks > R3_MAX_EXCHANGE_RANKS || my_rank >= n_ranks || max_objects_per_rank == 0) return r3_fail(c, R3_E_INVALID, "exchange_create: bad rank layout");
@@ -489,13 +506,14 @@ R3_EXPORT int r3_exchange_create(r3_ctx* c, uint32_t camera, uint32_t n_ranks, u
     cudaSetDevice(c->device);
     if (cam->d_gathered) return r3_fail(c, R3_E_STATE, "exchange_create: already created for this camera");
     const uint32_t wpr = (((max_objects_per_rank + 31u) / 32u) + 63u) & ~63u;   // rows start 256-byte aligned
-    const size_t total_words = EX_HEADER_WORDS + (size_t)2 * n_ranks * wpr;    // flags | two parities of n_ranks rows
+    const size_t total_words = EX_HEADER_WORDS + (size_t)EX_SLOTS * n_ranks * wpr;    // flags | EX_SLOTS sets of n_ranks rows
     R3_CUDA(c, cudaMalloc((void**)&cam->d_gathered, total_words * 4));
     R3_CUDA(c, cudaMemsetAsync(cam->d_gathered, 0, total_words * 4, c->stream));
     if (!cam->d_ex_done) R3_CUDA(c, cudaMalloc((void**)&cam->d_ex_done, 16));
     R3_CUDA(c, cudaMemsetAsync(cam->d_ex_done, 0, 16, c->stream));
     R3_CUDA(c, r3_stream_sync(c));
     cam->ex_epoch = 0; cam->ex_objects = 0;
+    for (auto& e : cam->ex_consumed) e = 0;
     cudaIpcMemHandle_t h;
     R3_CUDA(c, cudaIpcGetMemHandle(&h, cam->d_gathered));
     memcpy(handle_out, &h, sizeof h);
@@ -524,7 +542,7 @@ R3_EXPORT int r3_exchange_words(r3_ctx* c, uint32_t camera, void** device_ptr, u
     if (!cam || !cam->d_gathered) return r3_fail(c, R3_E_STATE, "exchange_words before exchange_create");
     // the rows of the LAST step (epoch parity); complete once their flags carry the epoch — r3_exchange_merge waits for that on the device,
     // a host reader synchronises its stream and meets the other ranks at a barrier first
-    *device_ptr = cam->d_gathered + EX_HEADER_WORDS + (size_t)(cam->ex_epoch & 1u) * cam->ex_ranks * cam->ex_words_per_rank;
+    *device_ptr = cam->d_gathered + EX_HEADER_WORDS + (size_t)(cam->ex_epoch % EX_SLOTS) * cam->ex_ranks * cam->ex_words_per_rank;
     *nbytes = (uint64_t)cam->ex_ranks * cam->ex_words_per_rank * 4;
     if (words_per_rank) *words_per_rank = cam->ex_words_per_rank;
     return R3_OK;
@@ -551,7 +569,7 @@ static int r3_exchange_consume(r3_ctx* c, uint32_t camera, const uint32_t* rank_
     }
     if (total >= (1ull << 32)) return r3_fail(c, R3_E_INVALID, "exchange_merge: more than 2^32 objects");
     p.gathered = cam->d_gathered; p.n_ranks = cam->ex_ranks; p.words_per_rank = cam->ex_words_per_rank;
-    p.epoch = cam->ex_epoch; p.parity = cam->ex_epoch & 1u;
+    p.epoch = cam->ex_epoch; p.parity = cam->ex_epoch % EX_SLOTS;
     p.tiles_per_rank = (cam->ex_words_per_rank + CP_THREADS - 1) / CP_THREADS;
     const uint32_t n_tiles = p.tiles_per_rank * cam->ex_ranks;
     if (expand) R3_TRY(r3_reserve_t(c, &cam->d_global_visible, &cam->global_visible_cap, total + 1));
@@ -567,7 +585,7 @@ static int r3_exchange_consume(r3_ctx* c, uint32_t camera, const uint32_t* rank_
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         R3_CUDA(c, cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, lo));
     }
-    const int slot = (int)(cam->ex_epoch & 1u);
+    const int slot = (int)(cam->ex_epoch % EX_SLOTS);
     if (!cam->ex_cull_done[slot]) R3_CUDA(c, cudaEventCreateWithFlags(&cam->ex_cull_done[slot], cudaEventDisableTiming));
     if (!cam->ex_merge_done[slot]) R3_CUDA(c, cudaEventCreateWithFlags(&cam->ex_merge_done[slot], cudaEventDisableTiming));
     R3_CUDA(c, cudaEventRecord(cam->ex_cull_done[slot], c->stream));
@@ -586,8 +604,16 @@ static int r3_exchange_consume(r3_ctx* c, uint32_t camera, const uint32_t* rank_
         exchange_expand_kernel<<<n_tiles, CP_THREADS, 0, c->side_stream>>>(p);
         R3_CHECK_LAUNCH(c, "exchange_expand_kernel");
     }
+    {   // acknowledge the epoch to every producer (their next write into this slot waits for it)
+        ExchangeParams ack{};
+        for (uint32_t r = 0; r < cam->ex_ranks; ++r) ack.peers[r] = cam->ex_peers[r];
+        ack.n_ranks = cam->ex_ranks; ack.flag_offset = cam->ex_rank;
+        exchange_ack_kernel<<<1, 32, 0, c->side_stream>>>(ack, cam->ex_epoch);
+        R3_CHECK_LAUNCH(c, "exchange_ack_kernel");
+    }
     R3_CUDA(c, cudaEventRecord(cam->ex_merge_done[slot], c->side_stream));
     cam->ex_merge_pending[slot] = true;
+    cam->ex_consumed[slot] = cam->ex_epoch;
     return R3_OK;
 }
 // Light consumer of the exchange: waits for every rank's epoch flag on the device (like r3_exchange_merge) and leaves the visible COUNT of
@@ -601,7 +627,7 @@ R3_EXPORT int r3_exchange_counts(r3_ctx* c, uint32_t camera, uint32_t* counts /*
     r3_camera* cam = r3_get_camera(c, camera);
     if (!cam || !cam->d_merge_counts) return r3_fail(c, R3_E_STATE, "exchange_counts before exchange_count / exchange_merge");
     cudaSetDevice(c->device);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < (int)EX_SLOTS; ++k)
         if (cam->ex_merge_pending[k]) { R3_CUDA(c, cudaStreamWaitEvent(c->stream, cam->ex_merge_done[k], 0)); cam->ex_merge_pending[k] = false; }
     R3_CUDA(c, cudaMemcpyAsync(counts, cam->d_merge_counts + 8, ((size_t)cam->ex_ranks + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
     R3_CUDA(c, r3_stream_sync(c));
@@ -611,7 +637,7 @@ R3_EXPORT int r3_exchange_merged(r3_ctx* c, uint32_t camera, void** device_list,
     if (!c || !device_list || !device_count) return r3_fail(c, R3_E_INVALID, "exchange_merged: null");
     r3_camera* cam = r3_get_camera(c, camera);
     if (!cam || !cam->d_global_visible) return r3_fail(c, R3_E_STATE, "exchange_merged before exchange_merge");
-    for (int k = 0; k < 2; ++k)      // the main stream (and with it r3_sync) now waits for the merges in flight
+    for (int k = 0; k < (int)EX_SLOTS; ++k)      // the main stream (and with it r3_sync) now waits for the merges in flight
         if (cam->ex_merge_pending[k]) { R3_CUDA(c, cudaStreamWaitEvent(c->stream, cam->ex_merge_done[k], 0)); cam->ex_merge_pending[k] = false; }
     *device_list = cam->d_global_visible; *device_count = cam->d_merge_counts;
     if (capacity) *capacity = cam->global_visible_cap;
@@ -626,7 +652,7 @@ R3_EXPORT int r3_exchange_destroy(r3_ctx* c, uint32_t camera) {
     for (uint32_t r = 0; r < cam->ex_ranks; ++r)
         if (cam->ex_connected && r != cam->ex_rank && cam->ex_peers[r]) cudaIpcCloseMemHandle(cam->ex_peers[r]);
     if (c->side_stream) cudaStreamSynchronize(c->side_stream);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < (int)EX_SLOTS; ++k) {
         if (cam->ex_cull_done[k]) cudaEventDestroy(cam->ex_cull_done[k]);
         if (cam->ex_merge_done[k]) cudaEventDestroy(cam->ex_merge_done[k]);
         cam->ex_cull_done[k] = cam->ex_merge_done[k] = nullptr; cam->ex_merge_pending[k] = false;

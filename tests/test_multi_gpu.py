@@ -49,6 +49,18 @@ for step, cam in enumerate(cams * 2):                # six epochs, no host barri
         ex.count()                                   # the light consumer on the same epoch: per-shard counts, no list
         counts = ex.counts()
         assert int(counts[-1]) == len(want) and [int(x) for x in counts[:-1]] == [int(((want >= l) & (want < h)).sum()) for l, h in ranges]
+# forty more epochs without ever joining the consumers (they lag behind the culls on the side stream): the acknowledgement / back-pressure
+# protocol must neither deadlock nor let a row be overwritten under a reader — the last epoch's list is still exact
+for step in range(40):
+    cam = cams[step % 3]
+    b.object_uniform_upload(CAMERA_VIEWPORT, per_camera_header(cam, CAMERA_VIEWPORT, (1920, 1080), 1, hi - lo), CB_BAKE | CB_CULL)
+    (ex.merge if step % 2 else ex.count)()
+b.object_uniform_upload(CAMERA_VIEWPORT, per_camera_header(cams[1], CAMERA_VIEWPORT, (1920, 1080), 1, hi - lo), CB_BAKE | CB_CULL)
+ex.merge()
+got = ex.merged(f"cuda:{local}").cpu().numpy().view(np.uint32).astype(np.int64)
+orc.object_uniform_upload(CAMERA_VIEWPORT, per_camera_header(cams[1], CAMERA_VIEWPORT, (1920, 1080), 1, n_total), CB_CULL)
+want = orc.readback_visible(CAMERA_VIEWPORT).astype(np.int64)
+assert np.array_equal(got, want), ("after 41 unjoined epochs", len(got), len(want))
 # the raw rows, for a host reader: stream sync + barrier, then the words of every rank equal the oracle's bits
 b.sync()
 dist.barrier()
