@@ -532,7 +532,12 @@ def main():
     # ---- forward: BASELINE config 5
     forward = None
     if not args.no_forward:
-        forward = forward_section(args, torch, dist, load_cuda_backend, rank, world, local, dev, barrier, max_over_ranks)
+        try:
+            forward = forward_section(args, torch, dist, load_cuda_backend, rank, world, local, dev, barrier, max_over_ranks)
+        except Exception as e:   # noqa: BLE001 — the headline line must survive a failure of the secondary workload
+            if world > 1:
+                raise            # ranks must fail together: a half-finished collective would hang the others
+            forward = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         line = {
