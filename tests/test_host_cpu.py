@@ -308,6 +308,13 @@ def test_shard_and_tile_partitions_cover_everything():
         for world in (1, 2, 4, 8):
             rows = [tile_rows(h, r, world) for r in range(world)]
             assert rows[0][0] == 0 and rows[-1][1] == h and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+    # shadow maps split by light: every light has exactly one owner, whatever the ratio of lights to ranks
+    from rend3_b200.parallel import ForwardSplit
+    for world in (1, 2, 4, 8):
+        splits = [ForwardSplit(None, None, None, r, world, (64, 64), 5) for r in range(world)]
+        for light in range(11):
+            assert sum(1 for sp in splits if sp.owns_shadow(light)) == 1
+        assert [sp.assembles_on(sp.rank) for sp in splits].count(True) == 1
 
 
 def test_oracle_frustum_boundary_and_degenerate_records():
