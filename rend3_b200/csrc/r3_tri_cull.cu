@@ -8,9 +8,13 @@
 // B200 design.  The reference launches one dispatch per 256-object batch and appends survivors with a global
 // atomicAdd per triangle on a handful of contended counters, which also makes the list order nondeterministic.
 // Here every batch is handled by the same launches, all of them plain streaming kernels without inter-CTA waits:
-//   test     one CTA per reference workgroup (256 invocations), one warp per 32: the cull test; the warp ballot IS the
-//            32-bit visibility word the reference assembles with workgroup atomics (1 bit per invocation to HBM), a
-//            second word marks the residual triangles; per-superblock (1024 words) survivor counts by one atomic per CTA;
+//   test     persistent grid sized by the occupancy API; the reference workgroups (256 invocations) are dealt to WARPS
+//            (warp g takes workgroups g, g + warps, ...), each warp stages the 400-byte run of indices of its next word
+//            with cp.async.bulk + an mbarrier while it tests the current one; the warp ballot IS the 32-bit visibility
+//            word the reference assembles with workgroup atomics (1 bit per invocation to HBM), a second word marks
+//            the residual triangles; per-superblock (1024 words) survivor counts by one 64-bit RED per word.
+//            With r3_set_cull_shard the viewport's workgroups are split in runs across ranks and the words travel
+//            over NVLink peer stores (r3_peer.cu);
 //   scan     one block: exclusive prefix of the superblock counts;
 //   regions  one CTA per region: survivors in front of the region -> its two IndirectCall records;
 //   compact  one CTA per superblock: block scan of the word popcounts, then each surviving triangle re-reads its three
