@@ -208,9 +208,29 @@ enum { R3_TEX_ALBEDO = 0, R3_TEX_NORMAL, R3_TEX_ROUGHNESS, R3_TEX_METALLIC, R3_T
 #define R3_TEXFMT_RGBA32_FLOAT 2u
 #define R3_TEXFMT_R8_UNORM 3u           /* single channel (split AO / metallic / roughness maps): (r, 0, 0, 1) */
 #define R3_TEXFMT_RG8_UNORM 4u          /* two channels (bicomponent normal maps): (r, g, 0, 1) */
-#define R3_TEXFMT_COUNT 5u
-/* bytes per texel of a format */
+/* Block-compressed formats (what rend3-gltf's ktx2 / dds loaders hand to add_texture_2d, rend3-gltf/src/lib.rs:1300-1335, 1455-1476,
+ * 1556-1602): 4x4-texel blocks, row-major, level l stores ceil(w_l / 4) x ceil(h_l / 4) blocks of 8 (BC1, BC4) or 16 bytes.  The decode is
+ * rule R11 of the oracle (oracle/r3_oracle_forward.inc): the ideal palette of the format as ONE IEEE division of two exact integers per
+ * channel, e.g. BC1 code 2 red = (2 r0 + r1) / 93 with the 5-bit endpoints r0, r1.  BC6H / BC7 are not implemented (r3_set_textures
+ * rejects them like any unknown format). */
+#define R3_TEXFMT_BC1_RGBA_UNORM 5u
+#define R3_TEXFMT_BC1_RGBA_UNORM_SRGB 6u
+#define R3_TEXFMT_BC2_RGBA_UNORM 7u
+#define R3_TEXFMT_BC2_RGBA_UNORM_SRGB 8u
+#define R3_TEXFMT_BC3_RGBA_UNORM 9u
+#define R3_TEXFMT_BC3_RGBA_UNORM_SRGB 10u
+#define R3_TEXFMT_BC4_R_UNORM 11u        /* (r, 0, 0, 1) */
+#define R3_TEXFMT_BC4_R_SNORM 12u
+#define R3_TEXFMT_BC5_RG_UNORM 13u       /* (r, g, 0, 1) */
+#define R3_TEXFMT_BC5_RG_SNORM 14u
+#define R3_TEXFMT_COUNT 15u
+#define R3_TEXFMT_IS_BLOCK(f) ((f) >= R3_TEXFMT_BC1_RGBA_UNORM && (f) <= R3_TEXFMT_BC5_RG_SNORM)
+#define R3_TEXFMT_BLOCK_BYTES(f) (((f) <= R3_TEXFMT_BC1_RGBA_UNORM_SRGB || (f) == R3_TEXFMT_BC4_R_UNORM || (f) == R3_TEXFMT_BC4_R_SNORM) ? 8u : 16u)
+/* bytes per texel of an uncompressed format */
 #define R3_TEXFMT_BPP(f) ((f) == R3_TEXFMT_RGBA32_FLOAT ? 16u : (f) == R3_TEXFMT_R8_UNORM ? 1u : (f) == R3_TEXFMT_RG8_UNORM ? 2u : 4u)
+/* bytes of one w x h level */
+#define R3_TEXFMT_LEVEL_BYTES(f, w, h) \
+    (R3_TEXFMT_IS_BLOCK(f) ? (uint64_t)(((w) + 3u) / 4u) * (((h) + 3u) / 4u) * R3_TEXFMT_BLOCK_BYTES(f) : (uint64_t)(w) * (h) * R3_TEXFMT_BPP(f))
 typedef struct r3_texture_desc {
     uint32_t width, height, mip_count, format;
     uint64_t byte_offset;

@@ -188,10 +188,10 @@ API int r3o_set_textures(r3o_ctx* c, const r3_texture_desc* descs, uint32_t n, c
     for (uint32_t i = 0; i < n; ++i) {
         const r3_texture_desc* d = &descs[i];
         if (!d->width || !d->height || !d->mip_count || d->mip_count > 32 || d->format >= R3_TEXFMT_COUNT) return fail(c, R3_E_INVALID, "textures: bad descriptor");
-        uint64_t bpp = R3_TEXFMT_BPP(d->format), total = 0;
+        uint64_t total = 0;
         for (uint32_t l = 0; l < d->mip_count; ++l) {
-            uint64_t w = (d->width >> l) ? (d->width >> l) : 1, h = (d->height >> l) ? (d->height >> l) : 1;
-            total += w * h * bpp;
+            uint32_t w = (d->width >> l) ? (d->width >> l) : 1, h = (d->height >> l) ? (d->height >> l) : 1;
+            total += R3_TEXFMT_LEVEL_BYTES(d->format, w, h);
         }
         if (d->byte_offset % 16 || d->byte_offset + total > nbytes) return fail(c, R3_E_INVALID, "textures: mip chain outside the texel blob");
     }

@@ -345,9 +345,8 @@ R3_EXPORT int r3_set_textures(r3_ctx* c, const r3_texture_desc* descs, uint32_t 
     for (uint32_t i = 0; i < n; ++i) {   // validated once here so the samplers index without checks
         const r3_texture_desc& d = descs[i];
         if (!d.width || !d.height || !d.mip_count || d.mip_count > 32 || d.format >= R3_TEXFMT_COUNT) return r3_fail(c, R3_E_INVALID, "set_textures: bad descriptor");
-        const uint64_t bpp = R3_TEXFMT_BPP(d.format);
         uint64_t total = 0;
-        for (uint32_t l = 0; l < d.mip_count; ++l) total += (uint64_t)((d.width >> l) ? (d.width >> l) : 1u) * ((d.height >> l) ? (d.height >> l) : 1u) * bpp;
+        for (uint32_t l = 0; l < d.mip_count; ++l) total += R3_TEXFMT_LEVEL_BYTES(d.format, (d.width >> l) ? (d.width >> l) : 1u, (d.height >> l) ? (d.height >> l) : 1u);
         if (d.byte_offset % 16 || d.byte_offset + total > nbytes) return r3_fail(c, R3_E_INVALID, "set_textures: mip chain outside the texel blob");
     }
     cudaSetDevice(c->device);

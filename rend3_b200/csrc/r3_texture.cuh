@@ -13,13 +13,56 @@ __device__ __forceinline__ float srgb_to_linear(float e) { return e > 0.04045f ?
 // ------------------------------------------------------------------ material textures (rule R9 of the oracle)
 // textureSampleGrad with the linear / nearest Repeat sampler of common/samplers.rs:42-56.  Everything that SELECTS texels or
 // levels (coordinates, floor) follows the oracle's order without contraction; the filter weights are continuous.
+// Block-compressed texels, rule R11 (include/r3_layouts.h, oracle/r3_oracle_forward.inc): every palette entry is ONE correctly rounded
+// division of two exact integers, so a texel has the same bit pattern as in the oracle.  The block is read with one or two 8-byte loads.
+__device__ __forceinline__ float3 bc_colour(uint2 blk, uint32_t t, bool bc1, float& alpha) {
+    const uint32_t c0 = blk.x & 0xFFFFu, c1 = blk.x >> 16, code = (blk.y >> (2u * t)) & 3u;
+    const int r0 = (int)(c0 >> 11), g0 = (int)((c0 >> 5) & 63u), b0 = (int)(c0 & 31u), r1 = (int)(c1 >> 11), g1 = (int)((c1 >> 5) & 63u), b1 = (int)(c1 & 31u);
+    const bool four = !bc1 || c0 > c1;
+    int wa = 1, wb = 0, den = 1;                                     // numerator wa * e0 + wb * e1, denominator den * full
+    if (code == 1u) { wa = 0; wb = 1; }
+    else if (code == 2u) { if (four) { wa = 2; wb = 1; den = 3; } else { wa = 1; wb = 1; den = 2; } }
+    else if (code == 3u) { if (four) { wa = 1; wb = 2; den = 3; } else { wa = 0; wb = 0; alpha = 0.0f; } }
+    const float d5 = (float)(den * 31), d6 = (float)(den * 63);
+    return make_float3(div_rn((float)(wa * r0 + wb * r1), d5), div_rn((float)(wa * g0 + wb * g1), d6), div_rn((float)(wa * b0 + wb * b1), d5));
+}
+__device__ __forceinline__ float bc_channel(uint2 blk, uint32_t t, bool snorm) {
+    const unsigned long long bits = (((unsigned long long)blk.y << 32) | blk.x) >> 16;
+    const int code = (int)((bits >> (3u * t)) & 7ull);
+    int r0 = snorm ? (int)(signed char)(blk.x & 0xFFu) : (int)(blk.x & 0xFFu), r1 = snorm ? (int)(signed char)((blk.x >> 8) & 0xFFu) : (int)((blk.x >> 8) & 0xFFu);
+    const bool wide = r0 > r1;
+    if (snorm) { r0 = max(r0, -127); r1 = max(r1, -127); }
+    const int full = snorm ? 127 : 255;
+    if (code == 0) return div_rn((float)r0, (float)full);
+    if (code == 1) return div_rn((float)r1, (float)full);
+    if (wide) return div_rn((float)((8 - code) * r0 + (code - 1) * r1), (float)(7 * full));
+    if (code < 6) return div_rn((float)((6 - code) * r0 + (code - 1) * r1), (float)(5 * full));
+    return code == 6 ? (snorm ? -1.0f : 0.0f) : 1.0f;
+}
+__device__ __noinline__ float4 block_texel_fetch(const uint8_t* level_base, uint32_t f, long long w, long long x, long long y) {
+    const uint8_t* b = level_base + (unsigned long long)((y >> 2) * ((w + 3) >> 2) + (x >> 2)) * R3_TEXFMT_BLOCK_BYTES(f);
+    const uint32_t t = (uint32_t)((y & 3) * 4 + (x & 3));
+    const uint2 first = __ldg(reinterpret_cast<const uint2*>(b));
+    if (f == R3_TEXFMT_BC4_R_UNORM || f == R3_TEXFMT_BC4_R_SNORM) return make_float4(bc_channel(first, t, f == R3_TEXFMT_BC4_R_SNORM), 0.0f, 0.0f, 1.0f);
+    const bool bc1 = f == R3_TEXFMT_BC1_RGBA_UNORM || f == R3_TEXFMT_BC1_RGBA_UNORM_SRGB;
+    const uint2 second = bc1 ? first : __ldg(reinterpret_cast<const uint2*>(b + 8));
+    if (f == R3_TEXFMT_BC5_RG_UNORM || f == R3_TEXFMT_BC5_RG_SNORM)
+        return make_float4(bc_channel(first, t, f == R3_TEXFMT_BC5_RG_SNORM), bc_channel(second, t, f == R3_TEXFMT_BC5_RG_SNORM), 0.0f, 1.0f);
+    float alpha = 1.0f;
+    float3 c = bc_colour(second, t, bc1, alpha);
+    if (f == R3_TEXFMT_BC2_RGBA_UNORM || f == R3_TEXFMT_BC2_RGBA_UNORM_SRGB) alpha = div_rn((float)(((t < 8u ? first.x : first.y) >> (4u * (t & 7u))) & 15u), 15.0f);
+    else if (!bc1) alpha = bc_channel(first, t, false);
+    if (f == R3_TEXFMT_BC1_RGBA_UNORM_SRGB || f == R3_TEXFMT_BC2_RGBA_UNORM_SRGB || f == R3_TEXFMT_BC3_RGBA_UNORM_SRGB) { c.x = srgb_to_linear(c.x); c.y = srgb_to_linear(c.y); c.z = srgb_to_linear(c.z); }
+    return make_float4(c.x, c.y, c.z, alpha);
+}
 __device__ __forceinline__ float4 texel_fetch(const TexTable& p, const r3_texture_desc& d, uint32_t level, long long x, long long y) {
     unsigned long long off = d.byte_offset;
-    const unsigned long long bpp = R3_TEXFMT_BPP(d.format);
-    for (uint32_t l = 0; l < level; ++l) off += (unsigned long long)max(d.width >> l, 1u) * max(d.height >> l, 1u) * bpp;
+    for (uint32_t l = 0; l < level; ++l) off += R3_TEXFMT_LEVEL_BYTES(d.format, max(d.width >> l, 1u), max(d.height >> l, 1u));
     const long long w = max(d.width >> level, 1u), h = max(d.height >> level, 1u);
     if (p.clamp_to_edge) { x = x < 0 ? 0 : (x >= w ? w - 1 : x); y = y < 0 ? 0 : (y >= h ? h - 1 : y); }   // texels clamped to the cube face
     else { x = ((x % w) + w) % w; y = ((y % h) + h) % h; }                          // AddressMode::Repeat
+    if (R3_TEXFMT_IS_BLOCK(d.format)) return block_texel_fetch(p.texels + off, d.format, w, x, y);
+    const unsigned long long bpp = R3_TEXFMT_BPP(d.format);
     const uint8_t* t = p.texels + off + (unsigned long long)(y * w + x) * bpp;
     if (d.format == R3_TEXFMT_RGBA32_FLOAT) return __ldg(reinterpret_cast<const float4*>(t));
     if (d.format == R3_TEXFMT_R8_UNORM) return make_float4((float)__ldg(t) / 255.0f, 0.0f, 0.0f, 1.0f);                     // missing channels read (0, 0, 1)

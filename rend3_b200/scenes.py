@@ -132,7 +132,7 @@ def subdivided_cube_mesh(k: int, with_uv: bool = False, vertex_alpha_seed: Optio
 
 
 def textured_cube_scene(n_objects: int = 300, seed: int = 41, resolution: Tuple[int, int] = (320, 180), texture_size: int = 32,
-                        sample_type: str = "linear", cutout: bool = False) -> EvalOutput:
+                        sample_type: str = "linear", cutout: bool = False, block_compressed: bool = False) -> EvalOutput:
     """Cubes with texture coordinates and materials that exercise every texture slot and layout flag of PbrMaterial
     (opaque.wgsl:203-424): sRGB albedo, tri- and bi-component normal maps, combined / split AO-metallic-roughness, reflectance,
     clear coat, emissive, a scaled uv_transform0; one shadowed directional light and two point lights."""
@@ -187,6 +187,13 @@ def textured_cube_scene(n_objects: int = 300, seed: int = 41, resolution: Tuple[
             PbrMaterial(albedo_texture=alpha_tex, albedo_value=(1.0, 1.0, 1.0, 1.3), albedo_vertex="srgb", roughness_factor=0.6, transparency=CUTOUT, alpha_cutout=0.4,
                         sample_type=sample_type),
         ]
+    if block_compressed:
+        # the same images as the ktx2 / dds assets rend3-gltf would load (rend3-gltf/src/lib.rs:1300-1335): BC1 / BC3 sRGB colour maps, BC1 / BC2
+        # linear maps, BC4 single-channel and BC5 two-channel maps; the float texture stays uncompressed
+        for handle, name in ((albedo, "bc1"), (normal, "bc3"), (aomr, "bc2"), (single, "bc1"), (single_r8, "bc4"), (normal_rg8, "bc5"), (emissive, "bc3")):
+            r.textures[handle].block_format = name
+        if cutout:
+            r.textures[alpha_tex].block_format = "bc3"
     mat_ids = [r.add_material(m) for m in mats]
     r.set_camera_data(cube_example_camera(8.0))
     r.add_directional_light(DirectionalLight(color=(1, 1, 1), intensity=1.0, direction=(-1.0, -4.0, 2.0), distance=80.0, resolution=256))

@@ -197,6 +197,9 @@ class Texture:
     srgb: bool = False
     mips: str = "generated"
     channels: int = 4          # 1 / 2: R8Unorm / Rg8Unorm — only the first channels of `data` are stored, the others read (0, 0, 1)
+    block_format: Optional[str] = None   # "bc1" | "bc2" | "bc3" | "bc4" | "bc4s" | "bc5" | "bc5s": the levels are stored as 4x4 blocks (bc.py stands in
+                                         # for the ktx2 / dds asset rend3-gltf would load); `srgb` picks the *UnormSrgb variant of bc1 - bc3
+    block_levels: Optional[List[np.ndarray]] = None   # the asset's own blocks per level (flat uint8); then `data` only carries the level-0 shape
 
     def levels(self) -> List[np.ndarray]:
         lv = [np.ascontiguousarray(self.data)]
@@ -224,6 +227,10 @@ class Texture:
         return lv
 
     def format(self) -> int:
+        if self.block_format is not None:
+            from .bc import BLOCK_FORMATS
+            plain, srgb, _ = BLOCK_FORMATS[self.block_format]
+            return srgb if (self.srgb and srgb is not None) else plain
         if self.data.dtype == np.float32:
             return TEXFMT_RGBA32_FLOAT
         if self.channels in (1, 2):
@@ -233,6 +240,11 @@ class Texture:
     def stored_levels(self) -> List[np.ndarray]:
         """The mip levels as they are stored: narrow formats keep only their channels."""
         lv = self.levels()
+        if self.block_format is not None:
+            from .bc import encode
+            if self.block_levels is not None:
+                return [np.ascontiguousarray(l, dtype=np.uint8).reshape(-1) for l in self.block_levels]
+            return [encode(self.block_format, l) for l in lv]
         return [np.ascontiguousarray(l[..., : self.channels]) for l in lv] if self.channels in (1, 2) and self.data.dtype == np.uint8 else lv
 
 
@@ -586,7 +598,7 @@ class Renderer:
         blobs, cursor = [], 0
         for i, t in enumerate(self.textures):
             lv = t.stored_levels()
-            descs[i]["width"], descs[i]["height"] = lv[0].shape[1], lv[0].shape[0]
+            descs[i]["width"], descs[i]["height"] = t.data.shape[1], t.data.shape[0]
             descs[i]["mip_count"], descs[i]["format"], descs[i]["byte_offset"] = len(lv), t.format(), cursor
             raw = np.concatenate([np.ascontiguousarray(l).view(np.uint8).reshape(-1) for l in lv])
             pad = (-len(raw)) % 16

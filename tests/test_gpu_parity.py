@@ -431,9 +431,13 @@ def test_error_paths(cuda):
     d["width"], d["height"], d["mip_count"], d["format"] = 8, 8, 4, 0
     with pytest.raises(R3Error):
         cuda.set_textures(d, np.zeros(8 * 8 * 4, dtype=np.uint8))          # levels 1..3 missing
-    d["mip_count"], d["format"] = 1, 7
+    d["mip_count"], d["format"] = 1, 15                                         # past BC5: BC6H / BC7 and anything unknown
     with pytest.raises(R3Error):
         cuda.set_textures(d, np.zeros(8 * 8 * 4, dtype=np.uint8))
+    d["width"], d["height"], d["mip_count"], d["format"] = 10, 6, 3, 9           # BC3: 3x2 + 2x1 + 1x1 blocks of 16 bytes
+    cuda.set_textures(d, np.zeros(9 * 16, dtype=np.uint8))
+    with pytest.raises(R3Error):
+        cuda.set_textures(d, np.zeros(8 * 16, dtype=np.uint8))
     # exchange: connect before create, bad rank layout, more objects than announced
     with pytest.raises(R3Error):
         cuda.exchange_connect(CAMERA_VIEWPORT, bytes(64))
@@ -536,6 +540,70 @@ def test_narrow_texture_formats_known_answers(cuda):
         want[..., 3] = 1.0
         assert np.abs(b.readback_hdr_f32().astype(np.float64) - want).max() < 2e-6, channels
         b.close()
+
+
+def test_block_compressed_formats_match_oracle_bit_for_bit():
+    """BC1 - BC5 entries of the bindless table on the CUDA path (rule R11: one IEEE division of two exact integers per channel): every format
+    drawn one texel per pixel — random images with punch-through BC1 blocks, both BC4 palettes, signed and sRGB variants, a size that is not
+    a multiple of the block — against the float64 decode of the same blocks and, texel for texel, against the oracle."""
+    import texture_case as tcase
+    from rend3_b200 import bc
+    from rend3_b200.world import Texture
+
+    for size in (32, 30):
+        data = tcase.checker_texture(size, seed=5)
+        for name, (_, srgb_format, _) in bc.BLOCK_FORMATS.items():
+            for srgb in ((False, True) if srgb_format is not None else (False,)):
+                t = Texture(data, srgb=srgb, mips="none", block_format=name)
+                b, orc = load_cuda_backend(0), load_oracle_backend()
+                for be in (b, orc):
+                    tcase.build(be, t, "nearest").render_frame(size)
+                got, ref = b.readback_hdr_f32(), orc.readback_hdr_f32()
+                want = bc.decode(name, t.stored_levels()[0], size, size, srgb)
+                assert np.abs(got.astype(np.float64) - want).max() < 5e-7, (size, name, srgb)
+                if not srgb:   # the linear formats go through no transcendental: identical bits (the sRGB curve's powf is within the pixel tolerance)
+                    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (size, name)
+                else:
+                    assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() < 1e-6, (size, name)
+                b.close()
+    # a mip chain of blocks: levels of 8x8 .. 1x1 texels are 2x2, 1x1, 1x1, 1x1 blocks; minified 4x with the linear sampler
+    data = tcase.checker_texture(32, seed=9)
+    for name in ("bc1", "bc3", "bc5s"):
+        t = Texture(data, srgb=False, block_format=name)
+        b, orc = load_cuda_backend(0), load_oracle_backend()
+        for be in (b, orc):
+            tcase.build(be, t, "linear", uv_scale=4.0).render_frame(32)
+        assert np.abs(b.readback_hdr_f32().astype(np.float64) - orc.readback_hdr_f32().astype(np.float64)).max() < 1e-6, name
+        b.close()
+
+
+@pytest.mark.parametrize("sample_type,cutout", [("linear", False), ("nearest", False), ("linear", True)])
+def test_block_compressed_materials_match_oracle(cuda, sample_type, cutout):
+    """The textured scene with its maps stored as BC1 / BC2 / BC3 / BC4 / BC5 blocks (the ktx2 / dds path of rend3-gltf): every slot of
+    get_pixel_data_inner reads decoded blocks, and with `cutout` the BC3 alpha decides the discard in the forward AND the shadow passes —
+    depth and shadow atlas bit-identical, pixels within the tolerance."""
+    from rend3_b200.scenes import textured_cube_scene
+
+    res = (320, 180)
+    ev = textured_cube_scene(n_objects=500, resolution=res, sample_type=sample_type, cutout=cutout, block_compressed=True)
+    from rend3_b200.layouts import TEXFMT_BC1_RGBA_UNORM
+    assert np.count_nonzero(ev.texture_descs["format"] >= TEXFMT_BC1_RGBA_UNORM) >= 7
+    orc = load_oracle_backend()
+    for b in (cuda, orc):
+        BaseRenderGraph(b).add_to_graph(ev, res, 1, BaseRenderGraphSettings(clear_color=(0.05, 0.05, 0.1, 1.0)))
+    compare_frame_state(cuda, orc, ev, [CAMERA_VIEWPORT, 0], check_pixels=False, what="block compressed")
+    w, h = ev.shadow_target_size
+    assert np.array_equal(cuda.readback_shadow_atlas(w, h).view(np.uint32), orc.readback_shadow_atlas(w, h).view(np.uint32))
+    assert np.array_equal(cuda.readback_depth().view(np.uint32), orc.readback_depth().view(np.uint32))
+    assert cuda.forward_stats()[:3] == orc.forward_stats()[:3] and orc.forward_stats()[2] > 10000
+    a, o = cuda.readback_hdr_f32().astype(np.float64), orc.readback_hdr_f32().astype(np.float64)
+    off = np.abs(a - o) > TOL * np.maximum(1.0, np.abs(o))
+    assert not off.any(), f"{off.sum()} channel values differ (max {np.abs(a - o).max():.3e})"
+    # the blocks are really sampled: the same scene with uncompressed maps gives a (slightly) different image
+    plain = load_oracle_backend()
+    BaseRenderGraph(plain).add_to_graph(textured_cube_scene(n_objects=500, resolution=res, sample_type=sample_type, cutout=cutout), res, 1,
+                                        BaseRenderGraphSettings(clear_color=(0.05, 0.05, 0.1, 1.0)))
+    assert np.abs(plain.readback_hdr_f32().astype(np.float64) - o).max() > 1e-3
 
 
 @pytest.mark.parametrize("sample_type,samples", [("linear", 1), ("nearest", 1), ("linear", 4)])

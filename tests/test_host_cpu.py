@@ -473,3 +473,96 @@ def test_oracle_narrow_texture_formats_read_missing_channels_as_zero_zero_one():
         want[..., 3] = 1.0
         got = b.readback_hdr_f32().astype(np.float64)
         assert np.abs(got - want).max() < 2e-6, channels
+
+
+def _known_blocks():
+    """Hand-assembled blocks and the texels the published palettes give (D3D11 functional spec 19.5 / Khronos Data Format 1.3 ch. 18-20)."""
+    import struct
+
+    codes = [0, 1, 2, 3] * 4                                              # texel t = 4 py + px uses code t % 4
+    two = sum(c << (2 * t) for t, c in enumerate(codes))
+    cases = []
+    # BC1, c0 = pure red 0xF800 > c1 = pure blue 0x001F: four-colour mode
+    cases.append(("bc1", struct.pack("<HHI", 0xF800, 0x001F, two), [(1, 0, 0, 1), (0, 0, 1, 1), (2 / 3, 0, 1 / 3, 1), (1 / 3, 0, 2 / 3, 1)]))
+    # BC1, c0 <= c1: three-colour mode, code 3 = transparent black
+    cases.append(("bc1", struct.pack("<HHI", 0x001F, 0xF800, two), [(0, 0, 1, 1), (1, 0, 0, 1), (0.5, 0, 0.5, 1), (0, 0, 0, 0)]))
+    # BC2 ignores the endpoint order (always four colours); alpha nibble of texel t = t
+    alpha4 = sum(t << (4 * t) for t in range(16))
+    cases.append(("bc2", struct.pack("<QHHI", alpha4, 0x001F, 0xF800, two), [((0, 0, 1), (1, 0, 0), (1 / 3, 0, 2 / 3), (2 / 3, 0, 1 / 3))[t % 4] + (t / 15,) for t in range(16)]))
+    # BC4 unorm, e0 = 255 > e1 = 0: eight values; texel t uses code t % 8
+    three = sum((t % 8) << (3 * t) for t in range(16))
+    cases.append(("bc4", bytes([255, 0]) + three.to_bytes(6, "little"), [(v, 0, 0, 1) for v in (1, 0, 6 / 7, 5 / 7, 4 / 7, 3 / 7, 2 / 7, 1 / 7)]))
+    # BC4 unorm, e0 = 50 <= e1 = 150: six values, then 0 and 1
+    cases.append(("bc4", bytes([50, 150]) + three.to_bytes(6, "little"), [(v / 255, 0, 0, 1) for v in (50, 150, 70, 90, 110, 130)] + [(0, 0, 0, 1), (1, 0, 0, 1)]))
+    # BC4 snorm: -128 reads as -1 like -127; e0 = 127 > e1 = -128
+    cases.append(("bc4s", bytes([127, 0x80]) + three.to_bytes(6, "little"), [(v, 0, 0, 1) for v in (1, -1, 5 / 7, 3 / 7, 1 / 7, -1 / 7, -3 / 7, -5 / 7)]))
+    # BC4 snorm six-value mode: e0 = -64 <= e1 = 64, code 6 = -1, code 7 = +1
+    cases.append(("bc4s", bytes([0xC0, 0x40]) + three.to_bytes(6, "little"), [(v / 127, 0, 0, 1) for v in (-64, 64, -38.4, -12.8, 12.8, 38.4)] + [(-1, 0, 0, 1), (1, 0, 0, 1)]))
+    # BC3 = BC4 alpha block + four-colour block; BC5 = two BC4 blocks
+    cases.append(("bc3", bytes([255, 0]) + three.to_bytes(6, "little") + struct.pack("<HHI", 0x001F, 0xF800, two), None))
+    cases.append(("bc5", bytes([255, 0]) + three.to_bytes(6, "little") + bytes([50, 150]) + three.to_bytes(6, "little"), None))
+    return cases
+
+
+def test_block_decode_known_answers():
+    """Rule R11 on hand-assembled blocks: the numpy decoder of rend3_b200/bc.py and the ORACLE's texel fetch (through a 4 x 4 texture drawn
+    one texel per pixel) both give the palettes of the published format descriptions."""
+    import texture_case as tcase
+    from rend3_b200 import bc
+    from rend3_b200.world import Texture
+
+    for name, block, palette in _known_blocks():
+        img = bc.decode(name, np.frombuffer(block, dtype=np.uint8), 4, 4)
+        if palette is not None:
+            want = np.array([palette[t % len(palette)] for t in range(16)], dtype=np.float64).reshape(4, 4, 4)
+            assert np.abs(img - want).max() < 1e-12, name
+        elif name == "bc3":
+            assert np.allclose(img[..., 3].reshape(-1)[:8], [1, 0, 6 / 7, 5 / 7, 4 / 7, 3 / 7, 2 / 7, 1 / 7]) and np.allclose(img[0, 2, :3], [1 / 3, 0, 2 / 3])
+        else:
+            assert np.allclose(img[..., 0].reshape(-1)[:8], [1, 0, 6 / 7, 5 / 7, 4 / 7, 3 / 7, 2 / 7, 1 / 7]) and np.allclose(img[..., 1].reshape(-1)[6:8], [0, 1])
+        b = load_oracle_backend()
+        tex = Texture(np.zeros((4, 4, 4), dtype=np.uint8), mips="none", block_format=name, block_levels=[np.frombuffer(block, dtype=np.uint8)])
+        tcase.build(b, tex, "nearest").render_frame(4)
+        assert np.abs(b.readback_hdr_f32().astype(np.float64) - img).max() < 1e-7, name
+
+
+def test_oracle_block_compressed_formats_match_the_published_palettes():
+    """BC1 - BC5 entries of the bindless table (what rend3-gltf's ktx2 / dds loaders pass to add_texture_2d): random images — punch-through
+    BC1 blocks, both BC4 palettes, signed variants, sRGB variants, a size that is not a multiple of the block — encoded by bc.py, drawn one
+    texel per pixel by the oracle and compared with the float64 decode of the same blocks."""
+    import texture_case as tcase
+    from rend3_b200 import bc
+    from rend3_b200.world import Texture
+
+    for size in (32, 30):
+        data = tcase.checker_texture(size, seed=5)
+        for name, (_, srgb_format, _) in bc.BLOCK_FORMATS.items():
+            for srgb in ((False, True) if srgb_format is not None else (False,)):
+                t = Texture(data, srgb=srgb, mips="none", block_format=name)
+                b = load_oracle_backend()
+                tcase.build(b, t, "nearest").render_frame(size)
+                want = bc.decode(name, t.stored_levels()[0], size, size, srgb)
+                assert np.abs(b.readback_hdr_f32().astype(np.float64) - want).max() < 5e-7, (size, name, srgb)
+    # the encoder is good enough that the scenes keep their look: the decode stays close to the source image
+    img = np.clip(np.rint(np.add.outer(np.linspace(0, 200, 32), np.linspace(0, 55, 32))), 0, 255).astype(np.uint8)
+    rgba = np.stack([img, img[::-1], img.T, 255 - img // 2], axis=-1)
+    for name in ("bc1", "bc3", "bc5"):
+        dec = bc.decode(name, bc.encode(name, rgba), 32, 32)
+        ch = {"bc1": 3, "bc3": 4, "bc5": 2}[name]
+        assert np.abs(dec[..., :ch] - rgba[..., :ch] / 255.0).max() < 0.1, name
+
+
+def test_block_compressed_mip_chains_are_validated():
+    """r3o_set_textures sizes the chain of a block format in blocks (ceil(w / 4) x ceil(h / 4) x 8 or 16 bytes per level)."""
+    from rend3_b200 import layouts
+
+    b = load_oracle_backend()
+    d = np.zeros(1, dtype=layouts.TEXTURE_DESC_DTYPE)
+    d["width"], d["height"], d["mip_count"], d["format"] = 10, 6, 3, layouts.TEXFMT_BC3_RGBA_UNORM          # 3x2 + 2x1 + 1x1 blocks of 16 bytes
+    need = (6 + 2 + 1) * 16
+    b.set_textures(d, np.zeros(need, dtype=np.uint8))
+    with pytest.raises(Exception):
+        b.set_textures(d, np.zeros(need - 16, dtype=np.uint8))
+    d["format"] = 15                                                                                         # BC6H / BC7 and beyond: rejected
+    with pytest.raises(Exception):
+        b.set_textures(d, np.zeros(4096, dtype=np.uint8))
