@@ -211,8 +211,9 @@ enum { R3_TEX_ALBEDO = 0, R3_TEX_NORMAL, R3_TEX_ROUGHNESS, R3_TEX_METALLIC, R3_T
 /* Block-compressed formats (what rend3-gltf's ktx2 / dds loaders hand to add_texture_2d, rend3-gltf/src/lib.rs:1300-1335, 1455-1476,
  * 1556-1602): 4x4-texel blocks, row-major, level l stores ceil(w_l / 4) x ceil(h_l / 4) blocks of 8 (BC1, BC4) or 16 bytes.  The decode is
  * rule R11 of the oracle (oracle/r3_oracle_forward.inc): the ideal palette of the format as ONE IEEE division of two exact integers per
- * channel, e.g. BC1 code 2 red = (2 r0 + r1) / 93 with the 5-bit endpoints r0, r1.  BC6H / BC7 are not implemented (r3_set_textures
- * rejects them like any unknown format). */
+ * channel, e.g. BC1 code 2 red = (2 r0 + r1) / 93 with the 5-bit endpoints r0, r1.  BC7 is integer-exact by its specification (8-bit texels
+ * from the interpolation ((64 - w) e0 + w e1 + 32) >> 6, then / 255); a block of the reserved mode reads (0, 0, 0, 0).  BC6H is not
+ * implemented (r3_set_textures rejects it like any unknown format). */
 #define R3_TEXFMT_BC1_RGBA_UNORM 5u
 #define R3_TEXFMT_BC1_RGBA_UNORM_SRGB 6u
 #define R3_TEXFMT_BC2_RGBA_UNORM 7u
@@ -223,8 +224,10 @@ enum { R3_TEX_ALBEDO = 0, R3_TEX_NORMAL, R3_TEX_ROUGHNESS, R3_TEX_METALLIC, R3_T
 #define R3_TEXFMT_BC4_R_SNORM 12u
 #define R3_TEXFMT_BC5_RG_UNORM 13u       /* (r, g, 0, 1) */
 #define R3_TEXFMT_BC5_RG_SNORM 14u
-#define R3_TEXFMT_COUNT 15u
-#define R3_TEXFMT_IS_BLOCK(f) ((f) >= R3_TEXFMT_BC1_RGBA_UNORM && (f) <= R3_TEXFMT_BC5_RG_SNORM)
+#define R3_TEXFMT_BC7_RGBA_UNORM 15u
+#define R3_TEXFMT_BC7_RGBA_UNORM_SRGB 16u
+#define R3_TEXFMT_COUNT 17u
+#define R3_TEXFMT_IS_BLOCK(f) ((f) >= R3_TEXFMT_BC1_RGBA_UNORM && (f) <= R3_TEXFMT_BC7_RGBA_UNORM_SRGB)
 #define R3_TEXFMT_BLOCK_BYTES(f) (((f) <= R3_TEXFMT_BC1_RGBA_UNORM_SRGB || (f) == R3_TEXFMT_BC4_R_UNORM || (f) == R3_TEXFMT_BC4_R_SNORM) ? 8u : 16u)
 /* bytes per texel of an uncompressed format */
 #define R3_TEXFMT_BPP(f) ((f) == R3_TEXFMT_RGBA32_FLOAT ? 16u : (f) == R3_TEXFMT_R8_UNORM ? 1u : (f) == R3_TEXFMT_RG8_UNORM ? 2u : 4u)

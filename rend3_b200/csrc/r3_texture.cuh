@@ -3,6 +3,8 @@
 #ifndef R3_TEXTURE_CUH
 #define R3_TEXTURE_CUH
 #include "r3_common.cuh"
+#define R3_BC7_TABLE __device__ const
+#include "../../include/r3_bc7_tables.h"
 
 namespace {
 
@@ -39,9 +41,69 @@ __device__ __forceinline__ float bc_channel(uint2 blk, uint32_t t, bool snorm) {
     if (code < 6) return div_rn((float)((6 - code) * r0 + (code - 1) * r1), (float)(5 * full));
     return code == 6 ? (snorm ? -1.0f : 0.0f) : 1.0f;
 }
+// BC7: the format fixes the 8-bit texel (include/r3_bc7_tables.h, rule R11); instead of unpacking the block field after field like the oracle,
+// the one texel asked for reads its fields at offsets computed from the mode row.
+__device__ __forceinline__ uint32_t bc7_bits(unsigned long long lo, unsigned long long hi, uint32_t pos, uint32_t width) {   // width 0..8
+    const unsigned long long v = pos >= 64u ? hi >> (pos - 64u) : (lo >> pos) | ((hi << 1) << (63u - pos));
+    return (uint32_t)v & ((1u << width) - 1u);
+}
+__device__ __forceinline__ uint32_t bc7_widen(uint32_t v, uint32_t bits) { return ((v << (8u - bits)) | (v >> (2u * bits - 8u))) & 255u; }
+__device__ __forceinline__ uint32_t bc7_weight(uint32_t index, uint32_t bits) { const uint32_t m = (1u << bits) - 1u; return (index * 64u + (m >> 1)) / m; }   // {0,21,43,64}, {0,9,...,64}, {0,4,...,64}
+__device__ __noinline__ uchar4 bc7_texel(uint4 blk, uint32_t t) {
+    const int mode = __ffs((int)(blk.x & 0xFFu)) - 1;
+    if (mode < 0) return make_uchar4(0, 0, 0, 0);                                    // reserved mode
+    const unsigned long long lo = ((unsigned long long)blk.y << 32) | blk.x, hi = ((unsigned long long)blk.w << 32) | blk.z;
+    const uint8_t* m = r3_bc7_modes[mode];
+    const uint32_t ns = m[0], pb = m[1], rb = m[2], isb = m[3], cb = m[4], ab = m[5], epb = m[6], spb = m[7], ib = m[8], ib2 = m[9];
+    uint32_t pos = (uint32_t)mode + 1u;
+    const uint32_t partition = bc7_bits(lo, hi, pos, pb); pos += pb;
+    const uint32_t rotation = bc7_bits(lo, hi, pos, rb); pos += rb;
+    const uint32_t idxsel = bc7_bits(lo, hi, pos, isb); pos += isb;
+    uint32_t subset = 0u, a1 = 16u, a2 = 16u;                                       // a1, a2: the other anchor texels (16 = none)
+    if (ns == 2u) { subset = (r3_bc7_partition2[partition] >> t) & 1u; a1 = r3_bc7_anchor2[partition]; }
+    else if (ns == 3u) { subset = (r3_bc7_partition3[partition] >> (2u * t)) & 3u; a1 = r3_bc7_anchor3a[partition]; a2 = r3_bc7_anchor3b[partition]; }
+    const uint32_t e0 = 2u * subset, e1 = e0 + 1u, alpha_base = pos + 6u * ns * cb, p_base = alpha_base + 2u * ns * ab;
+    uint32_t lo_ep[4], hi_ep[4];
+#pragma unroll
+    for (uint32_t ch = 0; ch < 3u; ++ch) {
+        lo_ep[ch] = bc7_bits(lo, hi, pos + (ch * 2u * ns + e0) * cb, cb);
+        hi_ep[ch] = bc7_bits(lo, hi, pos + (ch * 2u * ns + e1) * cb, cb);
+    }
+    lo_ep[3] = bc7_bits(lo, hi, alpha_base + e0 * ab, ab);
+    hi_ep[3] = bc7_bits(lo, hi, alpha_base + e1 * ab, ab);
+    uint32_t index_base = p_base, cbits = cb, abits = ab;
+    if (epb | spb) {
+        const uint32_t p0 = bc7_bits(lo, hi, epb ? p_base + e0 : p_base + subset, 1u), p1 = epb ? bc7_bits(lo, hi, p_base + e1, 1u) : p0;
+#pragma unroll
+        for (uint32_t ch = 0; ch < 4u; ++ch) { lo_ep[ch] = (lo_ep[ch] << 1) | p0; hi_ep[ch] = (hi_ep[ch] << 1) | p1; }
+        index_base += epb ? 2u * ns : ns;
+        ++cbits; ++abits;
+    }
+#pragma unroll
+    for (uint32_t ch = 0; ch < 3u; ++ch) { lo_ep[ch] = bc7_widen(lo_ep[ch], cbits); hi_ep[ch] = bc7_widen(hi_ep[ch], cbits); }
+    if (ab) { lo_ep[3] = bc7_widen(lo_ep[3], abits); hi_ep[3] = bc7_widen(hi_ep[3], abits); } else { lo_ep[3] = 255u; hi_ep[3] = 255u; }
+    // the texel's index: every anchor in front of it shortens the offset by one bit, and an anchor's own index is one bit short
+    const uint32_t before = (t > 0u) + (t > a1) + (t > a2), is_anchor = (t == 0u) | (t == a1) | (t == a2);
+    uint32_t ci = bc7_bits(lo, hi, index_base + t * ib - before, ib - is_anchor), cw = ib, ai = ci, aw = ib;
+    if (ib2) {
+        const uint32_t second = bc7_bits(lo, hi, index_base + 16u * ib - 1u + t * ib2 - (t > 0u), ib2 - (t == 0u));
+        if (idxsel) { ai = ci; aw = ib; ci = second; cw = ib2; } else { ai = second; aw = ib2; }
+    }
+    const uint32_t wc = bc7_weight(ci, cw), wa = bc7_weight(ai, aw);
+    uint32_t r = ((64u - wc) * lo_ep[0] + wc * hi_ep[0] + 32u) >> 6, g = ((64u - wc) * lo_ep[1] + wc * hi_ep[1] + 32u) >> 6,
+             b = ((64u - wc) * lo_ep[2] + wc * hi_ep[2] + 32u) >> 6, a = ((64u - wa) * lo_ep[3] + wa * hi_ep[3] + 32u) >> 6;
+    if (rotation == 1u) { const uint32_t s = r; r = a; a = s; } else if (rotation == 2u) { const uint32_t s = g; g = a; a = s; } else if (rotation == 3u) { const uint32_t s = b; b = a; a = s; }
+    return make_uchar4((unsigned char)r, (unsigned char)g, (unsigned char)b, (unsigned char)a);
+}
 __device__ __noinline__ float4 block_texel_fetch(const uint8_t* level_base, uint32_t f, long long w, long long x, long long y) {
     const uint8_t* b = level_base + (unsigned long long)((y >> 2) * ((w + 3) >> 2) + (x >> 2)) * R3_TEXFMT_BLOCK_BYTES(f);
     const uint32_t t = (uint32_t)((y & 3) * 4 + (x & 3));
+    if (f == R3_TEXFMT_BC7_RGBA_UNORM || f == R3_TEXFMT_BC7_RGBA_UNORM_SRGB) {
+        const uchar4 c8 = bc7_texel(__ldg(reinterpret_cast<const uint4*>(b)), t);
+        float4 o = make_float4(div_rn((float)c8.x, 255.0f), div_rn((float)c8.y, 255.0f), div_rn((float)c8.z, 255.0f), div_rn((float)c8.w, 255.0f));
+        if (f == R3_TEXFMT_BC7_RGBA_UNORM_SRGB) { o.x = srgb_to_linear(o.x); o.y = srgb_to_linear(o.y); o.z = srgb_to_linear(o.z); }
+        return o;
+    }
     const uint2 first = __ldg(reinterpret_cast<const uint2*>(b));
     if (f == R3_TEXFMT_BC4_R_UNORM || f == R3_TEXFMT_BC4_R_SNORM) return make_float4(bc_channel(first, t, f == R3_TEXFMT_BC4_R_SNORM), 0.0f, 0.0f, 1.0f);
     const bool bc1 = f == R3_TEXFMT_BC1_RGBA_UNORM || f == R3_TEXFMT_BC1_RGBA_UNORM_SRGB;

@@ -189,8 +189,8 @@ def textured_cube_scene(n_objects: int = 300, seed: int = 41, resolution: Tuple[
         ]
     if block_compressed:
         # the same images as the ktx2 / dds assets rend3-gltf would load (rend3-gltf/src/lib.rs:1300-1335): BC1 / BC3 sRGB colour maps, BC1 / BC2
-        # linear maps, BC4 single-channel and BC5 two-channel maps; the float texture stays uncompressed
-        for handle, name in ((albedo, "bc1"), (normal, "bc3"), (aomr, "bc2"), (single, "bc1"), (single_r8, "bc4"), (normal_rg8, "bc5"), (emissive, "bc3")):
+        # linear maps, BC4 single-channel and BC5 two-channel maps, BC7 (mode 6) for a linear and an sRGB map; the float texture stays uncompressed
+        for handle, name in ((albedo, "bc1"), (normal, "bc3"), (aomr, "bc2"), (single, "bc7"), (single_r8, "bc4"), (normal_rg8, "bc5"), (emissive, "bc7")):
             r.textures[handle].block_format = name
         if cutout:
             r.textures[alpha_tex].block_format = "bc3"

@@ -431,7 +431,7 @@ def test_error_paths(cuda):
     d["width"], d["height"], d["mip_count"], d["format"] = 8, 8, 4, 0
     with pytest.raises(R3Error):
         cuda.set_textures(d, np.zeros(8 * 8 * 4, dtype=np.uint8))          # levels 1..3 missing
-    d["mip_count"], d["format"] = 1, 15                                         # past BC5: BC6H / BC7 and anything unknown
+    d["mip_count"], d["format"] = 1, 17                                         # past BC7: BC6H and anything unknown
     with pytest.raises(R3Error):
         cuda.set_textures(d, np.zeros(8 * 8 * 4, dtype=np.uint8))
     d["width"], d["height"], d["mip_count"], d["format"] = 10, 6, 3, 9           # BC3: 3x2 + 2x1 + 1x1 blocks of 16 bytes
@@ -566,9 +566,20 @@ def test_block_compressed_formats_match_oracle_bit_for_bit():
                 else:
                     assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() < 1e-6, (size, name)
                 b.close()
+    # BC7: random blocks of every mode (and the reserved one) -> the same 8-bit texels, hence the same floats, as the oracle
+    blocks = tcase.random_bc7_blocks(64 * 9, seed=3).reshape(-1)
+    for srgb in (False, True):
+        t = Texture(np.zeros((96, 96, 4), dtype=np.uint8), srgb=srgb, mips="none", block_format="bc7", block_levels=[blocks])
+        b, orc = load_cuda_backend(0), load_oracle_backend()
+        for be in (b, orc):
+            tcase.build(be, t, "nearest").render_frame(96)
+        got, ref = b.readback_hdr_f32(), orc.readback_hdr_f32()
+        assert np.abs(got.astype(np.float64) - bc.decode("bc7", blocks, 96, 96, srgb)).max() < 5e-7, srgb
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)) if not srgb else np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() < 1e-6
+        b.close()
     # a mip chain of blocks: levels of 8x8 .. 1x1 texels are 2x2, 1x1, 1x1, 1x1 blocks; minified 4x with the linear sampler
     data = tcase.checker_texture(32, seed=9)
-    for name in ("bc1", "bc3", "bc5s"):
+    for name in ("bc1", "bc3", "bc5s", "bc7"):
         t = Texture(data, srgb=False, block_format=name)
         b, orc = load_cuda_backend(0), load_oracle_backend()
         for be in (b, orc):
@@ -579,7 +590,7 @@ def test_block_compressed_formats_match_oracle_bit_for_bit():
 
 @pytest.mark.parametrize("sample_type,cutout", [("linear", False), ("nearest", False), ("linear", True)])
 def test_block_compressed_materials_match_oracle(cuda, sample_type, cutout):
-    """The textured scene with its maps stored as BC1 / BC2 / BC3 / BC4 / BC5 blocks (the ktx2 / dds path of rend3-gltf): every slot of
+    """The textured scene with its maps stored as BC1 / BC2 / BC3 / BC4 / BC5 / BC7 blocks (the ktx2 / dds path of rend3-gltf): every slot of
     get_pixel_data_inner reads decoded blocks, and with `cutout` the BC3 alpha decides the discard in the forward AND the shadow passes —
     depth and shadow atlas bit-identical, pixels within the tolerance."""
     from rend3_b200.scenes import textured_cube_scene

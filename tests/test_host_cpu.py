@@ -563,6 +563,80 @@ def test_block_compressed_mip_chains_are_validated():
     b.set_textures(d, np.zeros(need, dtype=np.uint8))
     with pytest.raises(Exception):
         b.set_textures(d, np.zeros(need - 16, dtype=np.uint8))
-    d["format"] = 15                                                                                         # BC6H / BC7 and beyond: rejected
+    d["format"] = 17                                                                                         # BC6H and anything unknown: rejected
     with pytest.raises(Exception):
         b.set_textures(d, np.zeros(4096, dtype=np.uint8))
+
+
+def _pillow_decode(name, blocks, w, h):
+    """Pillow's DDS reader as an independent BCn decoder (8-bit texels): the blocks wrapped in a DX10 DDS header."""
+    import io
+    import struct
+
+    Image = pytest.importorskip("PIL.Image")
+    code = {"bc1": 71, "bc2": 74, "bc3": 77, "bc4": 80, "bc5": 83, "bc7": 98}[name]
+    pf = struct.pack("<II4sIIIII", 32, 0x4, b"DX10", 0, 0, 0, 0, 0)
+    hdr = struct.pack("<IIIIIII44x", 124, 0x1 | 0x2 | 0x4 | 0x1000 | 0x80000, h, w, len(bytes(blocks)), 0, 1) + pf + struct.pack("<IIIII", 0x1000, 0, 0, 0, 0)
+    im = Image.open(io.BytesIO(b"DDS " + hdr + struct.pack("<IIIII", code, 3, 0, 1, 0) + bytes(blocks)))
+    im.load()
+    a = np.asarray(im)
+    return a[..., None] if a.ndim == 2 else a
+
+
+def test_block_decoders_agree_with_pillow():
+    """The decode rules pinned on an implementation that is not ours: Pillow's BCn decoder.  BC7 is specified to the integer, so the 8-bit
+    texels of random blocks of every mode are IDENTICAL; BC1 - BC5 are decoded by Pillow in 8-bit integer arithmetic, so rule R11's exact
+    ratios agree with it to within one 8-bit step."""
+    import texture_case as tcase
+    from rend3_b200 import bc
+
+    blocks = tcase.random_bc7_blocks(8 * 360, seed=7)                       # modes 0..7 (the reserved mode: the specification says zeros)
+    blocks = blocks[np.arange(len(blocks)) % 9 != 8]
+    n = len(blocks)
+    got = _pillow_decode("bc7", blocks.reshape(-1), 4 * n, 4)
+    mine = np.stack([bc.decode_bc7_block(bytes(b)) for b in blocks]).reshape(n, 4, 4, 4).transpose(1, 0, 2, 3).reshape(4, 4 * n, 4)
+    assert np.array_equal(got, mine)
+    assert not bc.decode_bc7_block(bytes(16)).any()
+    img = tcase.checker_texture(32, seed=11)
+    for name in ("bc1", "bc2", "bc3", "bc4", "bc5", "bc7"):
+        data = bc.encode(name, img)
+        ref = _pillow_decode(name, data, 32, 32).astype(np.float64) / 255.0
+        assert np.abs(bc.decode(name, data, 32, 32)[..., : ref.shape[-1]] - ref).max() <= 1.0 / 255.0 + 1e-12, name
+
+
+def test_bc7_tables_of_the_header_match_the_python_copy_and_the_probe():
+    """include/r3_bc7_tables.h (what the CUDA code and the oracle decode with) holds the same constants as rend3_b200/bc.py, and both equal
+    what tools/derive_bc7_tables.py reads off Pillow's decoder block by block."""
+    import re
+    from rend3_b200 import bc
+
+    text = open(os.path.join(ROOT, "include", "r3_bc7_tables.h")).read()
+
+    def table(name):
+        body = re.search(name + r"\[[^=]*=\s*\{(.*?)\};", text, re.S).group(1)
+        return [int(x.rstrip("u"), 0) for x in re.findall(r"0x[0-9A-Fa-f]+u?|\d+", body)]
+
+    assert table("r3_bc7_partition2") == list(bc.BC7_P2) and table("r3_bc7_partition3") == list(bc.BC7_P3)
+    assert table("r3_bc7_anchor2") == list(bc.BC7_A2) and table("r3_bc7_anchor3a") == list(bc.BC7_A3A) and table("r3_bc7_anchor3b") == list(bc.BC7_A3B)
+    assert table("r3_bc7_modes") == [x for m in bc.BC7_MODES for x in m]
+    pytest.importorskip("PIL.Image")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import derive_bc7_tables
+
+    p2, p3, a2, a3a, a3b = derive_bc7_tables.derive()
+    assert (p2, p3, a2, a3a, a3b) == (list(bc.BC7_P2), list(bc.BC7_P3), list(bc.BC7_A2), list(bc.BC7_A3A), list(bc.BC7_A3B))
+
+
+def test_oracle_bc7_blocks_of_every_mode():
+    """Random BC7 blocks (every mode, the reserved one included) in the bindless table, drawn one texel per pixel by the oracle, against
+    the Python statement of the format; linear and sRGB variant."""
+    import texture_case as tcase
+    from rend3_b200 import bc
+    from rend3_b200.world import Texture
+
+    blocks = tcase.random_bc7_blocks(64, seed=3).reshape(-1)
+    for srgb in (False, True):
+        t = Texture(np.zeros((32, 32, 4), dtype=np.uint8), srgb=srgb, mips="none", block_format="bc7", block_levels=[blocks])
+        b = load_oracle_backend()
+        tcase.build(b, t, "nearest").render_frame(32)
+        assert np.abs(b.readback_hdr_f32().astype(np.float64) - bc.decode("bc7", blocks, 32, 32, srgb)).max() < 5e-7, srgb

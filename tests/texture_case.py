@@ -30,3 +30,15 @@ def build(backend, texture: Texture, sample_type="linear", uv_scale=1.0):
     r.renderer.add_object(Object(r.renderer.add_mesh(mesh), mat, glam.identity()))
     r.renderer.set_camera_data(Camera(("raw", glam.identity()), glam.identity()))
     return r
+
+
+def random_bc7_blocks(n: int, seed: int) -> np.ndarray:
+    """n random 16-byte BC7 blocks, block i forced into mode i % 9 (8 = the reserved mode: no mode bit in byte 0): any bit pattern is a valid
+    block, so random bits reach every partition, rotation, index selection and p bit of every mode."""
+    rng = np.random.default_rng(seed)
+    blocks = rng.integers(0, 256, (n, 16), dtype=np.uint8)
+    for i, b in enumerate(blocks):
+        mode, v = i % 9, int.from_bytes(bytes(b), "little")
+        v = (v & ~0xFF) if mode == 8 else ((v & ~((1 << (mode + 1)) - 1)) | (1 << mode))
+        b[:] = np.frombuffer(v.to_bytes(16, "little"), dtype=np.uint8)
+    return blocks
