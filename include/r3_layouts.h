@@ -226,11 +226,32 @@ enum { R3_TEX_ALBEDO = 0, R3_TEX_NORMAL, R3_TEX_ROUGHNESS, R3_TEX_METALLIC, R3_T
 #define R3_TEXFMT_BC5_RG_SNORM 14u
 #define R3_TEXFMT_BC7_RGBA_UNORM 15u
 #define R3_TEXFMT_BC7_RGBA_UNORM_SRGB 16u
-#define R3_TEXFMT_COUNT 17u
+/* The other filterable uncompressed formats the ktx2 path can hand over (rend3-gltf/src/lib.rs:1195-1285).  Missing channels read (0, 0, 1);
+ * snorm: max(v, -127) / 127; unorm16: v / 65535; Rgb10a2: 10-bit channels / 1023 from bit 0, alpha / 3; Bgra8: the bytes are b, g, r, a.
+ * The integer (Uint / Sint) formats cannot be bound to a filtering sampler and are rejected. */
+#define R3_TEXFMT_R8_SNORM 17u
+#define R3_TEXFMT_RG8_SNORM 18u
+#define R3_TEXFMT_RGBA8_SNORM 19u
+#define R3_TEXFMT_BGRA8_UNORM 20u
+#define R3_TEXFMT_BGRA8_UNORM_SRGB 21u
+#define R3_TEXFMT_RGB10A2_UNORM 22u
+#define R3_TEXFMT_R16_FLOAT 23u
+#define R3_TEXFMT_RG16_FLOAT 24u
+#define R3_TEXFMT_RGBA16_FLOAT 25u
+#define R3_TEXFMT_R32_FLOAT 26u
+#define R3_TEXFMT_RG32_FLOAT 27u
+#define R3_TEXFMT_R16_UNORM 28u
+#define R3_TEXFMT_RG16_UNORM 29u
+#define R3_TEXFMT_RGBA16_UNORM 30u
+#define R3_TEXFMT_COUNT 31u
 #define R3_TEXFMT_IS_BLOCK(f) ((f) >= R3_TEXFMT_BC1_RGBA_UNORM && (f) <= R3_TEXFMT_BC7_RGBA_UNORM_SRGB)
 #define R3_TEXFMT_BLOCK_BYTES(f) (((f) <= R3_TEXFMT_BC1_RGBA_UNORM_SRGB || (f) == R3_TEXFMT_BC4_R_UNORM || (f) == R3_TEXFMT_BC4_R_SNORM) ? 8u : 16u)
 /* bytes per texel of an uncompressed format */
-#define R3_TEXFMT_BPP(f) ((f) == R3_TEXFMT_RGBA32_FLOAT ? 16u : (f) == R3_TEXFMT_R8_UNORM ? 1u : (f) == R3_TEXFMT_RG8_UNORM ? 2u : 4u)
+#define R3_TEXFMT_BPP(f) \
+    ((f) == R3_TEXFMT_RGBA32_FLOAT ? 16u : \
+     ((f) == R3_TEXFMT_RGBA16_FLOAT || (f) == R3_TEXFMT_RG32_FLOAT || (f) == R3_TEXFMT_RGBA16_UNORM) ? 8u : \
+     ((f) == R3_TEXFMT_RG8_UNORM || (f) == R3_TEXFMT_RG8_SNORM || (f) == R3_TEXFMT_R16_FLOAT || (f) == R3_TEXFMT_R16_UNORM) ? 2u : \
+     ((f) == R3_TEXFMT_R8_UNORM || (f) == R3_TEXFMT_R8_SNORM) ? 1u : 4u)
 /* bytes of one w x h level */
 #define R3_TEXFMT_LEVEL_BYTES(f, w, h) \
     (R3_TEXFMT_IS_BLOCK(f) ? (uint64_t)(((w) + 3u) / 4u) * (((h) + 3u) / 4u) * R3_TEXFMT_BLOCK_BYTES(f) : (uint64_t)(w) * (h) * R3_TEXFMT_BPP(f))

@@ -2,6 +2,8 @@
 // (r3_shade.cu) and the per-fragment alpha cutout of the rasteriser (r3_raster.cu).
 #ifndef R3_TEXTURE_CUH
 #define R3_TEXTURE_CUH
+#include <cuda_fp16.h>
+
 #include "r3_common.cuh"
 #define R3_BC7_TABLE __device__ const
 #include "../../include/r3_bc7_tables.h"
@@ -117,6 +119,36 @@ __device__ __noinline__ float4 block_texel_fetch(const uint8_t* level_base, uint
     if (f == R3_TEXFMT_BC1_RGBA_UNORM_SRGB || f == R3_TEXFMT_BC2_RGBA_UNORM_SRGB || f == R3_TEXFMT_BC3_RGBA_UNORM_SRGB) { c.x = srgb_to_linear(c.x); c.y = srgb_to_linear(c.y); c.z = srgb_to_linear(c.z); }
     return make_float4(c.x, c.y, c.z, alpha);
 }
+// the uncompressed formats beyond the five common ones (include/r3_layouts.h): one aligned load of the texel, missing channels (0, 0, 1)
+__device__ __forceinline__ float snorm8(int v) { return div_rn((float)max(v, -127), 127.0f); }
+__device__ __forceinline__ float half_bits(unsigned short h) { return __half2float(__ushort_as_half(h)); }
+__device__ __noinline__ float4 wide_texel_fetch(const uint8_t* t, uint32_t f) {
+    switch (f) {
+    case R3_TEXFMT_R8_SNORM: return make_float4(snorm8((signed char)__ldg(t)), 0.0f, 0.0f, 1.0f);
+    case R3_TEXFMT_RG8_SNORM: { const char2 c = __ldg(reinterpret_cast<const char2*>(t)); return make_float4(snorm8(c.x), snorm8(c.y), 0.0f, 1.0f); }
+    case R3_TEXFMT_RGBA8_SNORM: { const char4 c = __ldg(reinterpret_cast<const char4*>(t)); return make_float4(snorm8(c.x), snorm8(c.y), snorm8(c.z), snorm8(c.w)); }
+    case R3_TEXFMT_BGRA8_UNORM:
+    case R3_TEXFMT_BGRA8_UNORM_SRGB: {
+        const uchar4 c = __ldg(reinterpret_cast<const uchar4*>(t));
+        float4 o = make_float4(div_rn((float)c.z, 255.0f), div_rn((float)c.y, 255.0f), div_rn((float)c.x, 255.0f), div_rn((float)c.w, 255.0f));
+        if (f == R3_TEXFMT_BGRA8_UNORM_SRGB) { o.x = srgb_to_linear(o.x); o.y = srgb_to_linear(o.y); o.z = srgb_to_linear(o.z); }
+        return o;
+    }
+    case R3_TEXFMT_RGB10A2_UNORM: {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(t));
+        return make_float4(div_rn((float)(v & 1023u), 1023.0f), div_rn((float)((v >> 10) & 1023u), 1023.0f), div_rn((float)((v >> 20) & 1023u), 1023.0f), div_rn((float)(v >> 30), 3.0f));
+    }
+    case R3_TEXFMT_R16_FLOAT: return make_float4(half_bits(__ldg(reinterpret_cast<const unsigned short*>(t))), 0.0f, 0.0f, 1.0f);
+    case R3_TEXFMT_RG16_FLOAT: { const ushort2 h = __ldg(reinterpret_cast<const ushort2*>(t)); return make_float4(half_bits(h.x), half_bits(h.y), 0.0f, 1.0f); }
+    case R3_TEXFMT_RGBA16_FLOAT: { const ushort4 h = __ldg(reinterpret_cast<const ushort4*>(t)); return make_float4(half_bits(h.x), half_bits(h.y), half_bits(h.z), half_bits(h.w)); }
+    case R3_TEXFMT_R32_FLOAT: return make_float4(__ldg(reinterpret_cast<const float*>(t)), 0.0f, 0.0f, 1.0f);
+    case R3_TEXFMT_RG32_FLOAT: { const float2 v = __ldg(reinterpret_cast<const float2*>(t)); return make_float4(v.x, v.y, 0.0f, 1.0f); }
+    case R3_TEXFMT_R16_UNORM: return make_float4(div_rn((float)__ldg(reinterpret_cast<const unsigned short*>(t)), 65535.0f), 0.0f, 0.0f, 1.0f);
+    case R3_TEXFMT_RG16_UNORM: { const ushort2 h = __ldg(reinterpret_cast<const ushort2*>(t)); return make_float4(div_rn((float)h.x, 65535.0f), div_rn((float)h.y, 65535.0f), 0.0f, 1.0f); }
+    default: { const ushort4 h = __ldg(reinterpret_cast<const ushort4*>(t));          // R3_TEXFMT_RGBA16_UNORM (r3_set_textures validated the format)
+        return make_float4(div_rn((float)h.x, 65535.0f), div_rn((float)h.y, 65535.0f), div_rn((float)h.z, 65535.0f), div_rn((float)h.w, 65535.0f)); }
+    }
+}
 __device__ __forceinline__ float4 texel_fetch(const TexTable& p, const r3_texture_desc& d, uint32_t level, long long x, long long y) {
     unsigned long long off = d.byte_offset;
     for (uint32_t l = 0; l < level; ++l) off += R3_TEXFMT_LEVEL_BYTES(d.format, max(d.width >> l, 1u), max(d.height >> l, 1u));
@@ -126,6 +158,7 @@ __device__ __forceinline__ float4 texel_fetch(const TexTable& p, const r3_textur
     if (R3_TEXFMT_IS_BLOCK(d.format)) return block_texel_fetch(p.texels + off, d.format, w, x, y);
     const unsigned long long bpp = R3_TEXFMT_BPP(d.format);
     const uint8_t* t = p.texels + off + (unsigned long long)(y * w + x) * bpp;
+    if (d.format >= R3_TEXFMT_R8_SNORM) return wide_texel_fetch(t, d.format);
     if (d.format == R3_TEXFMT_RGBA32_FLOAT) return __ldg(reinterpret_cast<const float4*>(t));
     if (d.format == R3_TEXFMT_R8_UNORM) return make_float4((float)__ldg(t) / 255.0f, 0.0f, 0.0f, 1.0f);                     // missing channels read (0, 0, 1)
     if (d.format == R3_TEXFMT_RG8_UNORM) { const uchar2 c2 = __ldg(reinterpret_cast<const uchar2*>(t)); return make_float4((float)c2.x / 255.0f, (float)c2.y / 255.0f, 0.0f, 1.0f); }

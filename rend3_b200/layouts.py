@@ -159,6 +159,8 @@ TEXTURE_DESC_DTYPE = _dt([("width", u4, 0), ("height", u4, 4), ("mip_count", u4,
 TEXFMT_RGBA8_UNORM, TEXFMT_RGBA8_UNORM_SRGB, TEXFMT_RGBA32_FLOAT, TEXFMT_R8_UNORM, TEXFMT_RG8_UNORM = 0, 1, 2, 3, 4
 (TEXFMT_BC1_RGBA_UNORM, TEXFMT_BC1_RGBA_UNORM_SRGB, TEXFMT_BC2_RGBA_UNORM, TEXFMT_BC2_RGBA_UNORM_SRGB, TEXFMT_BC3_RGBA_UNORM, TEXFMT_BC3_RGBA_UNORM_SRGB,
  TEXFMT_BC4_R_UNORM, TEXFMT_BC4_R_SNORM, TEXFMT_BC5_RG_UNORM, TEXFMT_BC5_RG_SNORM, TEXFMT_BC7_RGBA_UNORM, TEXFMT_BC7_RGBA_UNORM_SRGB) = range(5, 17)   # 4x4 blocks, rule R11 (include/r3_layouts.h)
+(TEXFMT_R8_SNORM, TEXFMT_RG8_SNORM, TEXFMT_RGBA8_SNORM, TEXFMT_BGRA8_UNORM, TEXFMT_BGRA8_UNORM_SRGB, TEXFMT_RGB10A2_UNORM, TEXFMT_R16_FLOAT, TEXFMT_RG16_FLOAT,
+ TEXFMT_RGBA16_FLOAT, TEXFMT_R32_FLOAT, TEXFMT_RG32_FLOAT, TEXFMT_R16_UNORM, TEXFMT_RG16_UNORM, TEXFMT_RGBA16_UNORM) = range(17, 31)
 (TEX_ALBEDO, TEX_NORMAL, TEX_ROUGHNESS, TEX_METALLIC, TEX_REFLECTANCE, TEX_CLEAR_COAT, TEX_CLEAR_COAT_ROUGHNESS, TEX_EMISSIVE, TEX_ANISOTROPY,
  TEX_AMBIENT_OCCLUSION) = range(10)
 

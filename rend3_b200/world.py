@@ -199,6 +199,7 @@ class Texture:
     channels: int = 4          # 1 / 2: R8Unorm / Rg8Unorm — only the first channels of `data` are stored, the others read (0, 0, 1)
     block_format: Optional[str] = None   # "bc1" | "bc2" | "bc3" | "bc4" | "bc4s" | "bc5" | "bc5s": the levels are stored as 4x4 blocks (bc.py stands in
                                          # for the ktx2 / dds asset rend3-gltf would load); `srgb` picks the *UnormSrgb variant of bc1 - bc3
+    storage: Optional[str] = None        # one of texformats.STORAGE ("rgba16f", "bgra8_srgb", "rgb10a2", "rg8s", ...): the levels are stored in that format
     block_levels: Optional[List[np.ndarray]] = None   # the asset's own blocks per level (flat uint8); then `data` only carries the level-0 shape
 
     def levels(self) -> List[np.ndarray]:
@@ -227,6 +228,9 @@ class Texture:
         return lv
 
     def format(self) -> int:
+        if self.storage is not None:
+            from .texformats import STORAGE
+            return STORAGE[self.storage][0]
         if self.block_format is not None:
             from .bc import BLOCK_FORMATS
             plain, srgb, _ = BLOCK_FORMATS[self.block_format]
@@ -240,6 +244,9 @@ class Texture:
     def stored_levels(self) -> List[np.ndarray]:
         """The mip levels as they are stored: narrow formats keep only their channels."""
         lv = self.levels()
+        if self.storage is not None:
+            from .texformats import pack
+            return [pack(self.storage, l) for l in lv]
         if self.block_format is not None:
             from .bc import encode
             if self.block_levels is not None:

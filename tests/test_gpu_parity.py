@@ -431,7 +431,7 @@ def test_error_paths(cuda):
     d["width"], d["height"], d["mip_count"], d["format"] = 8, 8, 4, 0
     with pytest.raises(R3Error):
         cuda.set_textures(d, np.zeros(8 * 8 * 4, dtype=np.uint8))          # levels 1..3 missing
-    d["mip_count"], d["format"] = 1, 17                                         # past BC7: BC6H and anything unknown
+    d["mip_count"], d["format"] = 1, 31                                         # past the last format: BC6H, the integer formats, anything unknown
     with pytest.raises(R3Error):
         cuda.set_textures(d, np.zeros(8 * 8 * 4, dtype=np.uint8))
     d["width"], d["height"], d["mip_count"], d["format"] = 10, 6, 3, 9           # BC3: 3x2 + 2x1 + 1x1 blocks of 16 bytes
@@ -585,6 +585,35 @@ def test_block_compressed_formats_match_oracle_bit_for_bit():
         for be in (b, orc):
             tcase.build(be, t, "linear", uv_scale=4.0).render_frame(32)
         assert np.abs(b.readback_hdr_f32().astype(np.float64) - orc.readback_hdr_f32().astype(np.float64)).max() < 1e-6, name
+        b.close()
+
+
+def test_ktx2_formats_match_oracle_bit_for_bit():
+    """Formats 17 - 30 (snorm8, Bgra8 / sRGB, Rgb10a2, 16 / 32-bit float, unorm16) on the CUDA path: one texel per pixel against the float64
+    unpack of the stored bytes and, bit for bit, against the oracle; then minified 4x through a generated mip chain with the linear sampler."""
+    import texture_case as tcase
+    from rend3_b200 import texformats as tf
+    from rend3_b200.world import Texture
+
+    data = tcase.checker_texture(32, seed=5)
+    data[0, 0], data[0, 1] = 0, 7
+    for name in tf.STORAGE:
+        t = Texture(data, mips="none", storage=name)
+        b, orc = load_cuda_backend(0), load_oracle_backend()
+        for be in (b, orc):
+            tcase.build(be, t, "nearest").render_frame(32)
+        got, ref = b.readback_hdr_f32(), orc.readback_hdr_f32()
+        assert np.abs(got.astype(np.float64) - tf.unpack(name, t.stored_levels()[0], 32, 32)).max() < 5e-7, name
+        if name != "bgra8_srgb":
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), name
+        b.close()
+    for name in ("rgba8s", "rgb10a2", "rgba16f", "rg32f", "rgba16", "bgra8_srgb"):
+        t = Texture(data, storage=name)
+        b, orc = load_cuda_backend(0), load_oracle_backend()
+        for be in (b, orc):
+            tcase.build(be, t, "linear", uv_scale=4.0).render_frame(32)
+        o = orc.readback_hdr_f32().astype(np.float64)
+        assert np.abs(b.readback_hdr_f32().astype(np.float64) - o).max() < 1e-6 * max(1.0, np.abs(o).max()), name
         b.close()
 
 

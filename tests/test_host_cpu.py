@@ -563,7 +563,7 @@ def test_block_compressed_mip_chains_are_validated():
     b.set_textures(d, np.zeros(need, dtype=np.uint8))
     with pytest.raises(Exception):
         b.set_textures(d, np.zeros(need - 16, dtype=np.uint8))
-    d["format"] = 17                                                                                         # BC6H and anything unknown: rejected
+    d["format"] = 31                                                                                         # BC6H and anything unknown: rejected
     with pytest.raises(Exception):
         b.set_textures(d, np.zeros(4096, dtype=np.uint8))
 
@@ -640,3 +640,35 @@ def test_oracle_bc7_blocks_of_every_mode():
         b = load_oracle_backend()
         tcase.build(b, t, "nearest").render_frame(32)
         assert np.abs(b.readback_hdr_f32().astype(np.float64) - bc.decode("bc7", blocks, 32, 32, srgb)).max() < 5e-7, srgb
+
+
+def test_oracle_ktx2_formats_read_back_as_the_sampler_defines():
+    """Formats 17 - 30 of include/r3_layouts.h (snorm8, Bgra8 / sRGB, Rgb10a2, 16 / 32-bit float, unorm16; what the ktx2 loader can pass,
+    rend3-gltf/src/lib.rs:1195-1285): drawn one texel per pixel by the oracle against the float64 unpack of the stored bytes — -128 snorm
+    reads -1, subnormal halves survive, missing channels read (0, 0, 1)."""
+    import texture_case as tcase
+    from rend3_b200 import texformats as tf
+    from rend3_b200.world import Texture
+
+    data = tcase.checker_texture(32, seed=5)
+    data[0, 0], data[0, 1] = 0, 7                                            # -128 for the snorm formats, the subnormal marker of the half formats
+    for name, (fmt, bpp) in tf.STORAGE.items():
+        t = Texture(data, mips="none", storage=name)
+        stored = t.stored_levels()[0]
+        assert len(stored) == 32 * 32 * bpp and t.format() == fmt
+        b = load_oracle_backend()
+        tcase.build(b, t, "nearest").render_frame(32)
+        want = tf.unpack(name, stored, 32, 32)
+        assert np.abs(b.readback_hdr_f32().astype(np.float64) - want).max() < 5e-7, name
+        if name.endswith("8s"):
+            assert want[0, 0, 0] == -1.0
+    from rend3_b200 import layouts
+    d = np.zeros(1, dtype=layouts.TEXTURE_DESC_DTYPE)
+    d["width"], d["height"], d["mip_count"], d["format"] = 4, 4, 3, layouts.TEXFMT_RGBA16_FLOAT            # 16 + 4 + 1 texels of 8 bytes
+    b = load_oracle_backend()
+    b.set_textures(d, np.zeros(21 * 8, dtype=np.uint8))
+    with pytest.raises(Exception):
+        b.set_textures(d, np.zeros(21 * 8 - 8, dtype=np.uint8))
+    d["format"] = 31                                                                                         # integer formats and anything unknown
+    with pytest.raises(Exception):
+        b.set_textures(d, np.zeros(4096, dtype=np.uint8))
